@@ -1,0 +1,200 @@
+/*
+ * libunetb200 — C ABI of the B200 (sm_100a) U-Net training / inference hot path.
+ *
+ * Drop-in boundary for SaurabhIndi/unet-segmentation: everything below sits UNDER the reference's
+ * `UNet` nn.Module (models/unet_model.py:65-146) and `WeightedCrossEntropyLoss`
+ * (utils/losses.py:6-57) and under `get_instance_masks` (utils/metrics.py:42-72). The reference has
+ * no FFI of its own (it dispatches to ATen/cuDNN through torch.nn); the ctypes binding a
+ * maintainer would add is shown in INTEGRATION.md and shipped in unet_segmentation_b200/_lib.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative ub_status; ub_last_error() gives the text
+ *     (thread-local). No C++ exception crosses this boundary. There is NO CPU fallback: without a
+ *     CUDA device every compute entry point fails with UB_ERR_CUDA.
+ *   - all pointers are DEVICE pointers unless stated otherwise; `stream` is a cudaStream_t passed
+ *     as void*; no entry point synchronises the device or allocates after plan creation.
+ *   - activations inside the library are NHWC bf16; the tensors that cross the boundary keep the
+ *     reference's layouts: images / logits NCHW fp32, parameters and gradients in torch layout fp32,
+ *     targets int64, masks uint8, instance labels uint16.
+ */
+#ifndef UNET_B200_H_
+#define UNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ub_status {
+    UB_OK = 0,
+    UB_ERR_CUDA = -1,        /* CUDA runtime / driver failure (includes "no device") */
+    UB_ERR_ARG = -2,         /* invalid argument */
+    UB_ERR_UNSUPPORTED = -3, /* configuration outside the supported envelope (e.g. bilinear=True) */
+    UB_ERR_TMAP = -4,        /* TMA descriptor encoding failed */
+    UB_ERR_NOMEM = -5
+} ub_status;
+
+/* NHWC bf16 view: element strides, channel stride 1. A centre crop (reference
+ * models/unet_model.py:88-102) or a channel slice of a concat buffer (:131-143) is just a view. */
+typedef struct ub_view {
+    const void* ptr;
+    int32_t N, H, W, C;
+    int64_t sN, sH, sW;
+} ub_view;
+
+const char* ub_last_error(void);
+int ub_version(void);
+int ub_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Network executor ("plan"): replaces UNet.forward (models/unet_model.py:105-146) and its autograd
+ * backward for a fixed input shape. levels = 5 and base_channels = 64 reproduce the reference
+ * (:73-85); other values are the optional trailing keyword arguments of the drop-in constructor.
+ *
+ * Parameter order (ub_plan_num_params entries) = reference named_parameters() order:
+ *   inc.{conv0.w, conv0.b, bn0.w, bn0.b, conv1.w, conv1.b, bn1.w, bn1.b}, down1..down{L-1} (same 8),
+ *   up1..up{L-1}.{up.w, up.b, conv0.w, conv0.b, bn0.w, bn0.b, conv1.w, conv1.b, bn1.w, bn1.b},
+ *   outc.{w, b}.
+ * BN buffer order (ub_plan_num_bn entries): the BatchNorm2d modules in the same traversal order.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ub_plan ub_plan;
+
+int ub_plan_create(ub_plan** plan, int N, int n_channels, int H, int W, int base_channels,
+                   int levels, int n_classes, int training);
+int ub_plan_destroy(ub_plan* plan);
+int ub_plan_out_hw(const ub_plan* plan, int* out_h, int* out_w);
+int ub_plan_num_params(const ub_plan* plan);
+int ub_plan_num_bn(const ub_plan* plan);
+int64_t ub_plan_param_numel(const ub_plan* plan, int index);
+int64_t ub_plan_device_bytes(const ub_plan* plan);
+
+/* Bind the torch-owned fp32 master parameters / BN buffers (device pointers, kept by reference). */
+int ub_plan_bind_params(ub_plan* plan, const float* const* params, int count);
+int ub_plan_bind_bn_buffers(ub_plan* plan, float* const* running_mean, float* const* running_var,
+                            int64_t* const* num_batches_tracked, int count);
+/* Refresh the packed bf16 operand caches from the bound masters (after optimizer.step() /
+ * load_state_dict()). */
+int ub_plan_pack_weights(ub_plan* plan, void* stream);
+
+/* x: [N][n_channels][H][W] fp32; logits: [N][n_classes][out_h][out_w] fp32.
+ * training plan: batch statistics, running-stat update (momentum 0.1, unbiased variance),
+ * activations saved for backward. eval plan: running statistics folded into the conv epilogues;
+ * `mask` (optional, may be NULL; [N][out_h][out_w] uint8) receives 255 where logit1 > logit0,
+ * i.e. softmax(logits)[:,1] > 0.5 (reference scripts/predict.py:85-92). */
+int ub_plan_forward(ub_plan* plan, const float* x, float* logits, uint8_t* mask, void* stream);
+
+/* Backward, split into stages so that a data-parallel caller can all-reduce the gradients of a
+ * finished stage while the next one runs. Stage 0 = outc + last up block, then the remaining up
+ * blocks deepest-last, then the down blocks bottom-up, last stage = inc.
+ * grads[i] receives d(loss)/d(param i) (fp32, torch layout, overwritten) for the parameters of the
+ * stage only; ub_plan_stage_params reports which. dlogits: [N][n_classes][out_h][out_w] fp32.
+ * x must still be the tensor given to the last ub_plan_forward. */
+int ub_plan_num_stages(const ub_plan* plan);
+int ub_plan_stage_params(const ub_plan* plan, int stage, int* first_param, int* num_params);
+int ub_plan_backward_stage(ub_plan* plan, int stage, const float* dlogits, float* const* grads,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * WeightedCrossEntropyLoss.forward (utils/losses.py:29-57) + its gradient, one pass.
+ * Strides are in elements; inputs may be non-contiguous views (scripts/train.py:118-126).
+ * dlogits (optional): contiguous [N][C][H][W], = d(loss)/d(logits) for grad_output == 1.
+ * err_flag (device int, caller zeroes it): set to 1 if a target is outside [0, C) and != -100.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t ub_wce_workspace_floats(void);
+int ub_wce_forward(const float* logits, const int64_t logit_strides[4], const int64_t* targets,
+                   const int64_t target_strides[3], const float* weight_maps,
+                   const int64_t weight_strides[3], int N, int C, int H, int W, float* loss,
+                   float* dlogits, float* workspace, int* err_flag, void* stream);
+/* out[i] = in[i] * (*scalar) — applies the upstream grad_output (a device scalar). */
+int ub_scale_by_device_scalar(const float* in, const float* scalar, float* out, int64_t n,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * get_instance_masks (utils/metrics.py:42-72): 8-connected labelling in raster order, components
+ * smaller than min_size zeroed, ids not compacted, uint16 output. Bit-exact.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t ub_ccl_workspace_bytes(int H, int W);
+int ub_ccl_label(const uint8_t* mask, int H, int W, int min_size, uint16_t* labels, void* workspace,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Operator-level entry points (teacher-forced per-layer parity tests). bf16 NHWC
+ * views in, the same kernels the plan launches.
+ * ---------------------------------------------------------------------------------------------- */
+/* nn.Conv2d(k=3,p=0).weight [Co][Ci][3][3] fp32 -> forward operand wf [Co][9][Ci] bf16 and
+ * data-gradient operand wd [Ci][9][Co] bf16 (taps rotated by 180 degrees). wd may be NULL. */
+int ub_op_pack_conv3x3(const float* w, int Co, int Ci, void* wf, void* wd, void* stream);
+/* nn.ConvTranspose2d(k=2,s=2).weight [Ci][Co][2][2] -> wf [4*Co][Ci], wb [Ci][4*Co] (bf16);
+ * bias [Co] -> bias4 [4*Co]. wb / bias / bias4 may be NULL. */
+int ub_op_pack_convT(const float* w, int Ci, int Co, void* wf, void* wb, const float* bias,
+                     float* bias4, void* stream);
+
+int64_t ub_op_conv_stats_floats(int Co);
+/* Valid 3x3 convolution over the channel concat [src0, src1] (src1 may be NULL).
+ * epilogue 0: y = acc + bias (bf16) and per-channel (sum, sumsq) partials -> stats, launch
+ *             geometry -> info[4] = {grid, n_tiles, BN, M} (host ints) for ub_op_bn_finalize;
+ * epilogue 1: y = acc + bias;   epilogue 2: y = relu(acc*scale + shift). */
+int ub_op_conv3x3_forward(const ub_view* src0, const ub_view* src1, const void* wf,
+                          const float* bias, int Co, int epilogue, const float* scale,
+                          const float* shift, void* y, float* stats, int* info, void* stream);
+/* dx[N][H+2][W+2][Ci] = full correlation of dy[N][H][W][Co] with the rotated weights wd. */
+int ub_op_conv3x3_dgrad(const ub_view* dy, const void* wd, int Ci, void* dx, void* stream);
+int64_t ub_op_wgrad_workspace_floats(int rows, int cols, int64_t pixels);
+/* dw[Co][C0+C1][3][3] fp32 = sum over pixels of x (concat of src0, src1) * dy[N][H-2][W-2][Co]. */
+int ub_op_conv3x3_wgrad(const ub_view* src0, const ub_view* src1, const void* dy, int Co,
+                        float* workspace, int64_t workspace_floats, float* dw, void* stream);
+/* ConvTranspose2d(k=2,s=2): x[N][H][W][Ci] -> dst view [N][2H][2W][Co] (may be a channel slice). */
+int ub_op_convT_forward(const ub_view* x, const void* wf, const float* bias4, int Co,
+                        const ub_view* dst, void* stream);
+/* dx[N][H][W][Ci] from dup view [N][2H][2W][Co]. */
+int ub_op_convT_dgrad(const ub_view* dup, const void* wb, int Ci, void* dx, void* stream);
+/* dw[Ci][Co][2][2] fp32. x is contiguous [N][H][W][Ci]. */
+int ub_op_convT_wgrad(const ub_view* dup, const void* x, int Ci, float* workspace,
+                      int64_t workspace_floats, float* dw, void* stream);
+
+int ub_op_bn_finalize(const float* stats, const int* info, int C, const float* gamma,
+                      const float* beta, float* running_mean, float* running_var,
+                      int64_t* num_batches_tracked, float momentum, float eps, float* scale,
+                      float* shift, float* mean, float* rstd, void* stream);
+/* a = relu(y*scale + shift); pooled (optional) = 2x2/2 floor-mode max-pool of a. */
+int ub_op_bn_apply_relu(const void* y, void* a, void* pooled, int N, int H, int W, int C,
+                        const float* scale, const float* shift, void* stream);
+int64_t ub_op_bn_bwd_workspace_floats(int C);
+/* BN+ReLU backward. Upstream gradient of a: `g` (direct), or — when g == NULL — gathered from the
+ * pooled-tensor gradient gp (2x2 max-pool backward, first arg-max) plus the skip-connection
+ * gradient gs placed at (crop_h, crop_w) (gs may be NULL). Outputs dgamma, dbeta (fp32) and
+ * dy (bf16 [N][H][W][C], gradient of the conv output). */
+int ub_op_bn_relu_backward(const void* y, int N, int H, int W, int C, const float* scale,
+                           const float* shift, const float* mean, const float* rstd,
+                           const ub_view* g, const ub_view* gp, const ub_view* gs, int crop_h,
+                           int crop_w, float* workspace, float* dgamma, float* dbeta, void* dy,
+                           void* stream);
+
+/* First convolution (fp32, C_in = n_channels): training forward = statistics + finalize + apply. */
+int64_t ub_op_first_conv_workspace_floats(int Co);
+int ub_op_first_conv_forward(const float* x, int N, int Ci, int H, int W, const float* w,
+                             const float* bias, int Co, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var,
+                             int64_t* num_batches_tracked, float momentum, float eps,
+                             float* workspace, float* scale, float* shift, float* mean,
+                             float* rstd, void* a, void* stream);
+int ub_op_first_conv_backward(const float* x, int N, int Ci, int H, int W, const float* w,
+                              const float* bias, int Co, const float* scale, const float* shift,
+                              const float* mean, const float* rstd, const ub_view* g,
+                              float* workspace, float* dgamma, float* dbeta, float* dw,
+                              void* stream);
+
+/* 1x1 head: a[N][H][W][K] bf16 -> logits NCHW fp32 (+ optional 2-class mask). */
+int ub_op_head_forward(const void* a, int N, int H, int W, int K, int n_classes, const float* w,
+                       const float* b, float* logits, uint8_t* mask, void* stream);
+int64_t ub_op_head_bwd_workspace_floats(int K, int n_classes);
+int ub_op_head_backward(const float* dlogits, const void* a, int N, int H, int W, int K,
+                        int n_classes, const float* w, void* da, float* workspace, float* dw,
+                        float* db, void* stream);
+int ub_op_maxpool2(const void* a, void* pooled, int N, int H, int W, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNET_B200_H_ */

@@ -1,0 +1,303 @@
+"""Teacher-forced per-layer parity (tier T0): every CUDA kernel, called through the C
+ABI, against the single torch op it replaces, in fp32 on the same bf16-rounded inputs. Only the
+accumulation order differs, so the bars are tight: rel-L2 <= 4e-3 for bf16 outputs (one bf16
+rounding), <= 1e-3 and cosine >= 0.999 for fp32 gradients."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 4e-3
+F32_TOL = 1e-3
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cosine(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from unet_segmentation_b200 import _lib, ops as _ops
+
+    _lib.require_cuda()
+    return _ops
+
+
+def rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed + sum(shape))
+    return torch.randn(*shape, device="cuda", generator=g) * scale
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", [
+    (1, 12, 12, 64, 64),       # less than one M tile
+    (2, 37, 29, 64, 128),      # odd sizes, tiles straddle rows and images
+    (2, 23, 23, 128, 256),
+    (1, 19, 21, 256, 512),     # two N tiles
+    (3, 30, 30, 64, 64),
+])
+def test_conv3x3_forward(ops, n, h, w, ci, co):
+    x = bf(rand(n, ci, h, w))
+    wt = bf(rand(co, ci, 3, 3, scale=(2.0 / (9 * ci)) ** 0.5, seed=1))
+    b = rand(co, seed=2)
+    wf, _ = ops.pack_conv3x3(wt)
+    y, _, _ = ops.conv3x3_forward(ops.nhwc(x), None, wf, b, epilogue=1)
+    ref = F.conv2d(x, wt, b)
+    torch.cuda.synchronize()
+    assert rel_l2(ops.nchw(y), ref) < BF16_TOL
+
+
+def test_conv3x3_forward_stats_and_bn(ops):
+    n, h, w, ci, co = 2, 41, 33, 64, 128
+    x = bf(rand(n, ci, h, w)) + 0.3
+    wt = bf(rand(co, ci, 3, 3, scale=0.05, seed=1))
+    b = rand(co, seed=2)
+    gamma, beta = rand(co, seed=3) + 1.5, rand(co, seed=4)
+    rm, rv = torch.zeros(co, device="cuda"), torch.ones(co, device="cuda")
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    wf, _ = ops.pack_conv3x3(wt)
+    y, stats, info = ops.conv3x3_forward(ops.nhwc(x), None, wf, b, epilogue=0)
+    scale, shift, mean, rstd = ops.bn_finalize(stats, info, gamma, beta, rm, rv, nbt)
+    a, p = ops.bn_apply_relu(y, scale, shift, pool=True)
+    ref_y = F.conv2d(x, wt, b)
+    bn = torch.nn.BatchNorm2d(co).cuda().train()
+    with torch.no_grad():
+        bn.weight.copy_(gamma); bn.bias.copy_(beta)
+    ref_a = F.relu(bn(ref_y))
+    torch.cuda.synchronize()
+    assert rel_l2(mean, ref_y.mean((0, 2, 3))) < 1e-3
+    assert rel_l2(1 / rstd ** 2, ref_y.var((0, 2, 3), unbiased=False) + 1e-5) < 2e-3
+    assert rel_l2(rm, bn.running_mean) < 1e-3 and rel_l2(rv, bn.running_var) < 2e-3
+    assert int(nbt) == 1
+    assert rel_l2(ops.nchw(a), ref_a) < 6e-3   # two bf16 roundings (y and a)
+    # pooling is exact given a
+    assert torch.equal(ops.nchw(p), F.max_pool2d(ops.nchw(a), 2))
+
+
+def test_conv3x3_concat_sources(ops):
+    """Zero-copy crop + concat: src0 = centre crop of a larger skip tensor, src1 = up-sampled."""
+    n, hs, ws_, cs, h, w, cu, co = 2, 30, 28, 64, 20, 18, 64, 128
+    skip = bf(rand(n, cs, hs, ws_))
+    up = bf(rand(n, cu, h, w, seed=5))
+    ch, cw = (hs - h) // 2, (ws_ - w) // 2
+    wt = bf(rand(co, cs + cu, 3, 3, scale=0.04, seed=1))
+    wf, _ = ops.pack_conv3x3(wt)
+    skip_nhwc = ops.nhwc(skip)
+    y, _, _ = ops.conv3x3_forward(skip_nhwc[:, ch:ch + h, cw:cw + w, :], ops.nhwc(up), wf, None)
+    ref = F.conv2d(torch.cat([skip[:, :, ch:ch + h, cw:cw + w], up], 1), wt)
+    torch.cuda.synchronize()
+    assert rel_l2(ops.nchw(y), ref) < BF16_TOL
+    # weight gradient over the same two sources
+    dy = bf(rand(n, co, h - 2, w - 2, seed=7))
+    dw = ops.conv3x3_wgrad(skip_nhwc[:, ch:ch + h, cw:cw + w, :], ops.nhwc(up), ops.nhwc(dy))
+    ref_dw = torch.nn.grad.conv2d_weight(
+        torch.cat([skip[:, :, ch:ch + h, cw:cw + w], up], 1), wt.shape, dy)
+    torch.cuda.synchronize()
+    assert rel_l2(dw, ref_dw) < F32_TOL and cosine(dw, ref_dw) > 0.9999
+
+
+def test_conv3x3_eval_epilogue(ops):
+    n, h, w, ci, co = 1, 25, 25, 64, 64
+    x = bf(rand(n, ci, h, w))
+    wt = bf(rand(co, ci, 3, 3, scale=0.06, seed=1))
+    scale, shift = rand(co, seed=2).abs() + 0.5, rand(co, seed=3)
+    wf, _ = ops.pack_conv3x3(wt)
+    y, _, _ = ops.conv3x3_forward(ops.nhwc(x), None, wf, None, epilogue=2, scale=scale, shift=shift)
+    ref = F.relu(F.conv2d(x, wt) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    torch.cuda.synchronize()
+    assert rel_l2(ops.nchw(y), ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", [(1, 10, 10, 64, 64), (2, 21, 17, 128, 64), (2, 14, 14, 256, 512)])
+def test_conv3x3_dgrad(ops, n, h, w, ci, co):
+    dy = bf(rand(n, co, h, w))
+    wt = bf(rand(co, ci, 3, 3, scale=0.05, seed=1))
+    _, wd = ops.pack_conv3x3(wt)
+    dx = ops.conv3x3_dgrad(ops.nhwc(dy), wd)
+    ref = torch.nn.grad.conv2d_input((n, ci, h + 2, w + 2), wt, dy)
+    torch.cuda.synchronize()
+    assert rel_l2(ops.nchw(dx), ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", [(1, 12, 12, 64, 64), (2, 35, 27, 64, 128), (2, 18, 18, 256, 256),
+                                         (1, 50, 50, 128, 64)])
+def test_conv3x3_wgrad(ops, n, h, w, ci, co):
+    x = bf(rand(n, ci, h, w))
+    dy = bf(rand(n, co, h - 2, w - 2, seed=3))
+    dw = ops.conv3x3_wgrad(ops.nhwc(x), None, ops.nhwc(dy))
+    ref = torch.nn.grad.conv2d_weight(x, (co, ci, 3, 3), dy)
+    torch.cuda.synchronize()
+    assert rel_l2(dw, ref) < F32_TOL and cosine(dw, ref) > 0.9999
+
+
+@pytest.mark.parametrize("n,h,w,ci", [(1, 6, 6, 128), (2, 11, 9, 256), (1, 24, 24, 1024)])
+def test_conv_transpose(ops, n, h, w, ci):
+    co = ci // 2
+    x = bf(rand(n, ci, h, w))
+    wt = bf(rand(ci, co, 2, 2, scale=0.05, seed=1))
+    b = rand(co, seed=2)
+    wf, wb, b4 = ops.pack_convT(wt, b)
+    # write into the second channel range of a wider (concat-like) buffer
+    buf = torch.zeros(n, 2 * h, 2 * w, 2 * co, dtype=torch.bfloat16, device="cuda")
+    ops.convT_forward(ops.nhwc(x), wf, b4, buf[..., co:])
+    ref = F.conv_transpose2d(x, wt, b, stride=2)
+    torch.cuda.synchronize()
+    assert rel_l2(ops.nchw(buf[..., co:]), ref) < BF16_TOL
+    assert float(buf[..., :co].float().abs().max()) == 0.0
+    # backward: gradient arrives as a channel slice of d(concat)
+    dbuf = ops.nhwc(bf(rand(n, 2 * co, 2 * h, 2 * w, seed=4)))
+    dup = dbuf[..., co:]
+    dx = ops.convT_dgrad(dup, wb)
+    dw = ops.convT_wgrad(dup, ops.nhwc(x))
+    dup_nchw = ops.nchw(dup)
+    ref_dx = F.conv2d(dup_nchw, wt, stride=2)
+    xr = x.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    F.conv_transpose2d(xr, wr, None, stride=2).backward(dup_nchw)
+    torch.cuda.synchronize()
+    assert rel_l2(ops.nchw(dx), xr.grad) < BF16_TOL
+    assert rel_l2(ops.nchw(dx), ref_dx) < BF16_TOL
+    assert rel_l2(dw, wr.grad) < F32_TOL and cosine(dw, wr.grad) > 0.9999
+
+
+def _bn_relu_ref(y, gamma, beta, g_fn):
+    yr = y.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    a = F.relu(F.batch_norm(yr, None, None, gr, br, True, 0.1, 1e-5))
+    g_fn(a)
+    return yr.grad, gr.grad, br.grad
+
+
+def test_bn_relu_backward_direct(ops):
+    n, h, w, c = 2, 19, 23, 128
+    y = bf(rand(n, c, h, w) * 1.3 + 0.2)
+    gamma, beta = rand(c, seed=1) + 1.2, rand(c, seed=2) * 0.3
+    g = bf(rand(n, c, h, w, seed=3))
+    mean = y.mean((0, 2, 3)); var = y.var((0, 2, 3), unbiased=False)
+    rstd = (var + 1e-5).rsqrt(); scale = gamma * rstd; shift = beta - mean * scale
+    dy, dgamma, dbeta = ops.bn_relu_backward(ops.nhwc(y), scale, shift, mean, rstd, g=ops.nhwc(g))
+    ry, rg, rb = _bn_relu_ref(y, gamma, beta, lambda a: a.backward(g))
+    torch.cuda.synchronize()
+    assert rel_l2(dgamma, rg) < F32_TOL and rel_l2(dbeta, rb) < F32_TOL
+    assert rel_l2(ops.nchw(dy), ry) < BF16_TOL
+
+
+@pytest.mark.parametrize("h,w", [(20, 20), (21, 19)])
+def test_bn_relu_backward_pool_skip(ops, h, w):
+    """Upstream = max-pool backward (first arg-max) + centre-cropped skip gradient (channel slice)."""
+    n, c, th, tw = 2, 64, 8, 10
+    y = bf(rand(n, c, h, w) + 0.1)
+    gamma, beta = rand(c, seed=1) + 1.0, rand(c, seed=2) * 0.2
+    mean = y.mean((0, 2, 3)); var = y.var((0, 2, 3), unbiased=False)
+    rstd = (var + 1e-5).rsqrt(); scale = gamma * rstd; shift = beta - mean * scale
+    gp = bf(rand(n, c, h // 2, w // 2, seed=3))
+    dcat = bf(rand(n, 2 * c, th, tw, seed=4))          # d(concat); first c channels -> skip
+    ch, cw = (h - th) // 2, (w - tw) // 2
+    dcat_nhwc = ops.nhwc(dcat)
+    dy, dgamma, dbeta = ops.bn_relu_backward(ops.nhwc(y), scale, shift, mean, rstd, g=None,
+                                             gp=ops.nhwc(gp), gs=dcat_nhwc[..., :c], crop=(ch, cw))
+
+    def g_fn(a):
+        # forward rounding of a to bf16 decides the arg-max, as in the kernel
+        a_r = a + (bf(a.detach()) - a.detach())
+        pooled = F.max_pool2d(a_r, 2)
+        skip = a_r[:, :, ch:ch + th, cw:cw + tw]
+        ((pooled * gp).sum() + (skip * dcat[:, :c]).sum()).backward()
+
+    ry, rg, rb = _bn_relu_ref(y, gamma, beta, g_fn)
+    torch.cuda.synchronize()
+    assert rel_l2(dgamma, rg) < F32_TOL and rel_l2(dbeta, rb) < F32_TOL
+    assert rel_l2(ops.nchw(dy), ry) < BF16_TOL
+
+
+@pytest.mark.parametrize("ci", [1, 3])
+def test_first_conv(ops, ci):
+    n, h, w, co = 2, 40, 36, 64
+    x = 0.4 + 0.2 * torch.rand(n, ci, h, w, device="cuda")
+    wt = rand(co, ci, 3, 3, scale=0.3, seed=1)
+    b = rand(co, seed=2) * 0.1
+    gamma, beta = rand(co, seed=3) + 1.0, rand(co, seed=4) * 0.2
+    rm, rv = torch.zeros(co, device="cuda"), torch.ones(co, device="cuda")
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    a, st = ops.first_conv_forward(x, wt, b, gamma, beta, rm, rv, nbt)
+    wr = wt.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    bn_rm, bn_rv = torch.zeros(co, device="cuda"), torch.ones(co, device="cuda")
+    ref_a = F.relu(F.batch_norm(F.conv2d(x, wr, b), bn_rm, bn_rv, gr, br, True, 0.1, 1e-5))
+    g = bf(rand(n, co, h - 2, w - 2, seed=5))
+    ref_a.backward(g)
+    dw, dgamma, dbeta = ops.first_conv_backward(x, wt, b, st, ops.nhwc(g))
+    torch.cuda.synchronize()
+    assert rel_l2(ops.nchw(a), ref_a) < BF16_TOL
+    assert rel_l2(rm, bn_rm) < 1e-4 and rel_l2(rv, bn_rv) < 1e-3 and int(nbt) == 1
+    assert rel_l2(dgamma, gr.grad) < F32_TOL and rel_l2(dbeta, br.grad) < F32_TOL
+    assert rel_l2(dw, wr.grad) < F32_TOL and cosine(dw, wr.grad) > 0.9999
+
+
+@pytest.mark.parametrize("nc", [1, 2, 3])
+def test_head(ops, nc):
+    n, h, w, k = 2, 17, 13, 64
+    a = bf(rand(n, k, h, w).relu())
+    wt, b = rand(nc, k, scale=0.2, seed=1), rand(nc, seed=2)
+    logits, mask = ops.head_forward(ops.nhwc(a), wt, b, want_mask=True)
+    ar = a.clone().requires_grad_(True); wr = wt.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = F.conv2d(ar, wr.view(nc, k, 1, 1), br)
+    dl = rand(n, nc, h, w, seed=3)
+    ref.backward(dl)
+    da, dw, db = ops.head_backward(dl, ops.nhwc(a), wt)
+    torch.cuda.synchronize()
+    assert rel_l2(logits, ref) < 1e-5
+    if nc == 2:
+        assert torch.equal(mask > 0, logits[:, 1] > logits[:, 0])
+    assert rel_l2(ops.nchw(da), ar.grad) < BF16_TOL
+    assert rel_l2(dw, wr.grad) < F32_TOL and rel_l2(db, br.grad) < F32_TOL
+
+
+@pytest.mark.parametrize("nc", [2, 4])
+def test_weighted_cross_entropy(ops, nc):
+    """Reference formula (utils/losses.py:49,54,57) on non-contiguous cropped views
+    (scripts/train.py:118-126)."""
+    n, hh, th = 3, 40, 24
+    logits = rand(n, nc, th, th, scale=2.0).requires_grad_(True)
+    full_t = torch.randint(0, nc, (n, 1, hh, hh), device="cuda")
+    full_w = torch.rand(n, 1, hh, hh, device="cuda") * 3 + 10
+    s = (hh - th) // 2
+    t = full_t[:, :, s:s + th, s:s + th].squeeze(1)
+    wm = full_w[:, :, s:s + th, s:s + th].squeeze(1)
+    assert not t.is_contiguous()
+    loss, dz, err = ops.wce_forward(logits.detach(), t, wm)
+    ref = (torch.nn.CrossEntropyLoss(reduction="none")(logits, t) * wm).mean()
+    ref.backward()
+    torch.cuda.synchronize()
+    assert int(err) == 0
+    assert abs(float(loss) - float(ref)) / abs(float(ref)) < 1e-5
+    assert rel_l2(dz, logits.grad) < 1e-5
+
+
+def test_ccl_matches_scipy(ops):
+    from scipy import ndimage
+
+    rng = np.random.default_rng(0)
+    for h, w, p in [(64, 64, 0.45), (324, 324, 0.55), (37, 1050, 0.5), (5, 5, 1.0), (16, 16, 0.0)]:
+        m = (rng.random((h, w)) < p).astype(np.uint8) * 255
+        lab, _ = ndimage.label(m > 0, structure=np.ones((3, 3)))
+        area = np.bincount(lab.ravel())
+        small = area < 15
+        small[0] = False
+        ref = lab.copy()
+        ref[small[lab]] = 0
+        ref = ref.astype(np.uint16)
+        out = ops.ccl_label(torch.from_numpy(m).cuda(), 15).cpu().numpy()
+        assert np.array_equal(out, ref), (h, w, p)

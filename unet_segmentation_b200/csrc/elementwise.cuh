@@ -1,0 +1,458 @@
+// HBM-bound kernels between the tensor-core convolutions: batch-norm statistics finalisation,
+// BN-apply + ReLU (+ 2x2 max-pool), their backward (with the max-pool scatter and the
+// skip-connection gradient gathered on the fly), weight packing, and the split-K reduction of
+// weight gradients. All activations are NHWC bf16 with C % 8 == 0; one thread moves 16 bytes.
+//
+// Reference ops replaced: nn.BatchNorm2d train/eval (models/unet_model.py:12,16),
+// nn.ReLU (:13,17), nn.MaxPool2d(2) (:28), _center_crop + torch.cat backward (:88-102,131-143).
+#pragma once
+#include "common.cuh"
+
+namespace ub {
+
+struct Vec8 {
+    float v[8];
+};
+__device__ __forceinline__ Vec8 unpack8(const uint4& u) {
+    Vec8 r;
+    r.v[0] = bf16_lo(u.x); r.v[1] = bf16_hi(u.x);
+    r.v[2] = bf16_lo(u.y); r.v[3] = bf16_hi(u.y);
+    r.v[4] = bf16_lo(u.z); r.v[5] = bf16_hi(u.z);
+    r.v[6] = bf16_lo(u.w); r.v[7] = bf16_hi(u.w);
+    return r;
+}
+__device__ __forceinline__ uint4 pack8(const Vec8& r) {
+    uint4 u;
+    u.x = pack_bf16x2(r.v[0], r.v[1]);
+    u.y = pack_bf16x2(r.v[2], r.v[3]);
+    u.z = pack_bf16x2(r.v[4], r.v[5]);
+    u.w = pack_bf16x2(r.v[6], r.v[7]);
+    return u;
+}
+__device__ __forceinline__ uint4 ldg16(const void* p) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
+}
+// bf16 rounding of relu(y*scale+shift): the exact arithmetic of the forward pass, so that the
+// backward pass can recompute activations (ReLU mask, pool arg-max) bit-identically.
+__device__ __forceinline__ float bn_relu_bf16(float y, float sc, float sh) {
+    return __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(y, sc, sh), 0.f)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// BN statistics finalisation (train mode). Partials come from the conv epilogue:
+// stats[(cta*4 + warp)][2][BN]; CTA b covers channel tile (b % n_tiles).
+// Biased variance normalises, unbiased variance updates running_var (torch semantics).
+// ---------------------------------------------------------------------------------------------
+static __global__ void bn_finalize_kernel(const float* __restrict__ stats, int grid_ctas, int n_tiles,
+                                   int BN, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean,
+                                   float* running_var, long long* num_batches_tracked,
+                                   float momentum, float eps, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ save_mean,
+                                   float* __restrict__ save_rstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    if (c >= C) return;
+    const int tile = c / BN, col = c % BN;
+    double s = 0.0, q = 0.0;
+    for (int b = tile; b < grid_ctas; b += n_tiles) {
+        for (int w = 0; w < 4; ++w) {
+            const float* p = stats + ((long long)b * 4 + w) * (2 * BN);
+            s += (double)p[col];
+            q += (double)p[BN + col];
+        }
+    }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    save_mean[c] = (float)mean;
+    save_rstd[c] = rstd;
+    if (running_mean) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// Generic variant: partials[blocks][2][C] (first-layer statistics, BN backward sums).
+static __global__ void bn_finalize_flat_kernel(const float* __restrict__ part, int blocks, int C,
+                                        double count, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float* running_mean,
+                                        float* running_var, long long* num_batches_tracked,
+                                        float momentum, float eps, float* __restrict__ scale,
+                                        float* __restrict__ shift, float* __restrict__ save_mean,
+                                        float* __restrict__ save_rstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < blocks; ++b) {
+        s += (double)part[(long long)b * 2 * C + c];
+        q += (double)part[(long long)b * 2 * C + C + c];
+    }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    save_mean[c] = (float)mean;
+    save_rstd[c] = rstd;
+    if (running_mean) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// Eval mode: fold conv bias + running statistics into a per-channel affine.
+static __global__ void bn_fold_eval_kernel(int C, const float* __restrict__ conv_bias,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ rm, const float* __restrict__ rv,
+                                    float eps, float* __restrict__ scale,
+                                    float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sc = gamma[c] / sqrtf(rv[c] + eps);
+    scale[c] = sc;
+    shift[c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * sc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BN-apply + ReLU (+ fused 2x2/2 floor-mode max-pool).   y -> a (and pooled p)
+// ---------------------------------------------------------------------------------------------
+template <bool POOL>
+static __global__ void __launch_bounds__(256)
+bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
+                     __nv_bfloat16* __restrict__ pooled, int N, int H, int W, int C,
+                     const float* __restrict__ scale, const float* __restrict__ shift) {
+    const int CG = C >> 3;
+    if (!POOL) {
+        const long long total = (long long)N * H * W * CG;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += (long long)gridDim.x * blockDim.x) {
+            const int cg = (int)(i % CG);
+            Vec8 x = unpack8(ldg16(y + i * 8));
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + 4));
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8));
+            const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + 4));
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            Vec8 o;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(fmaf(x.v[k], sc[k], sh[k]), 0.f);
+            *reinterpret_cast<uint4*>(a + i * 8) = pack8(o);
+        }
+    } else {
+        const int HW2 = (H + 1) >> 1, WW2 = (W + 1) >> 1;
+        const int Hp = H >> 1, Wp = W >> 1;
+        const long long total = (long long)N * HW2 * WW2 * CG;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += (long long)gridDim.x * blockDim.x) {
+            const int cg = (int)(i % CG);
+            long long t = i / CG;
+            const int wp = (int)(t % WW2); t /= WW2;
+            const int hp = (int)(t % HW2);
+            const int n = (int)(t / HW2);
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + 4));
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8));
+            const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + 4));
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            Vec8 mx;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mx.v[k] = 0.f;  // post-ReLU values are >= 0
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int h = hp * 2 + (d >> 1), w = wp * 2 + (d & 1);
+                if (h < H && w < W) {
+                    const long long off = (((long long)n * H + h) * W + w) * C + cg * 8;
+                    Vec8 x = unpack8(ldg16(y + off));
+                    Vec8 o;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        o.v[k] = bn_relu_bf16(x.v[k], sc[k], sh[k]);
+                        mx.v[k] = fmaxf(mx.v[k], o.v[k]);
+                    }
+                    *reinterpret_cast<uint4*>(a + off) = pack8(o);
+                }
+            }
+            if (hp < Hp && wp < Wp) {
+                const long long off = (((long long)n * Hp + hp) * Wp + wp) * C + cg * 8;
+                *reinterpret_cast<uint4*>(pooled + off) = pack8(mx);
+            }
+        }
+    }
+}
+
+// Stand-alone 2x2 max-pool (eval path, where BN+ReLU is folded into the conv epilogue).
+static __global__ void __launch_bounds__(256)
+maxpool2_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ pooled, int N,
+                int H, int W, int C) {
+    const int CG = C >> 3, Hp = H >> 1, Wp = W >> 1;
+    const long long total = (long long)N * Hp * Wp * CG;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % CG);
+        long long t = i / CG;
+        const int wp = (int)(t % Wp); t /= Wp;
+        const int hp = (int)(t % Hp);
+        const int n = (int)(t / Hp);
+        Vec8 mx;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int h = hp * 2 + (d >> 1), w = wp * 2 + (d & 1);
+            Vec8 x = unpack8(ldg16(a + (((long long)n * H + h) * W + w) * C + cg * 8));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mx.v[k] = d == 0 ? x.v[k] : fmaxf(mx.v[k], x.v[k]);
+        }
+        *reinterpret_cast<uint4*>(pooled + i * 8) = pack8(mx);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BN + ReLU backward. Upstream gradient of the post-ReLU activation a[N,H,W,C] is either
+//   DIRECT: a tensor view g (possibly a channel slice of a wider buffer), or
+//   POOL_SKIP: gathered on the fly from the gradient of the pooled tensor (routed to the first
+//     arg-max of each 2x2 window, recomputed from y) plus the gradient of the centre-cropped skip
+//     connection (a channel slice of d(concat)), so d(a) is never materialised.
+// Pass 1 (reduce): per-block partial sums of dyh = g*[a>0] and dyh*xhat.
+// Pass 2 (apply):  dy = scale*(dyh - mean(dyh) - xhat*mean(dyh*xhat)), written as bf16.
+// ---------------------------------------------------------------------------------------------
+struct BnBwdArgs {
+    const __nv_bfloat16* y;  // pre-BN conv output [N,H,W,C]
+    int N, H, W, C;
+    const float* scale;      // gamma*rstd
+    const float* shift;      // beta - mean*scale
+    const float* mean;
+    const float* rstd;
+    View g;                  // DIRECT
+    View gp;                 // POOL_SKIP: grad of pooled [N,H/2,W/2,C]
+    View gs;                 // POOL_SKIP: grad of cropped skip [N,th,tw,C] (may be a slice)
+    int crop_h, crop_w;
+    int has_skip;
+    float* partial;          // reduce: [gridDim.x][2][C]
+    const float* dgamma;     // apply
+    const float* dbeta;
+    float inv_count;
+    __nv_bfloat16* dy;       // apply: [N,H,W,C]
+};
+
+template <bool POOL_SKIP, bool APPLY>
+static __global__ void __launch_bounds__(256)
+bn_bwd_kernel(const BnBwdArgs A) {
+    const int C = A.C, CG = C >> 3, H = A.H, W = A.W;
+    const int cg = threadIdx.x % CG;  // host guarantees 256 % CG == 0 and grid stride % CG == 0
+    float sc[8], sh[8], mu[8], rs[8], kb[8], kg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        sc[k] = A.scale[cg * 8 + k];
+        sh[k] = A.shift[cg * 8 + k];
+        mu[k] = A.mean[cg * 8 + k];
+        rs[k] = A.rstd[cg * 8 + k];
+        if (APPLY) {
+            kb[k] = A.dbeta[cg * 8 + k] * A.inv_count;
+            kg[k] = A.dgamma[cg * 8 + k] * A.inv_count;
+        }
+    }
+    float acc_b[8], acc_g[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc_b[k] = 0.f; acc_g[k] = 0.f; }
+
+    const int HW2 = POOL_SKIP ? (H + 1) >> 1 : H, WW2 = POOL_SKIP ? (W + 1) >> 1 : W;
+    const long long total = (long long)A.N * HW2 * WW2 * CG;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long t = i / CG;
+        const int wq = (int)(t % WW2); t /= WW2;
+        const int hq = (int)(t % HW2);
+        const int n = (int)(t / HW2);
+
+        auto process = [&](int h, int w, const Vec8& yv, const Vec8& gv) {
+            Vec8 o;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float act = fmaf(yv.v[k], sc[k], sh[k]);
+                const float dyh = act > 0.f ? gv.v[k] : 0.f;
+                const float xh = (yv.v[k] - mu[k]) * rs[k];
+                if (APPLY) {
+                    o.v[k] = sc[k] * (dyh - kb[k] - xh * kg[k]);
+                } else {
+                    acc_b[k] += dyh;
+                    acc_g[k] = fmaf(dyh, xh, acc_g[k]);
+                }
+            }
+            if (APPLY)
+                *reinterpret_cast<uint4*>(A.dy + (((long long)n * H + h) * W + w) * C + cg * 8) =
+                    pack8(o);
+        };
+
+        if (!POOL_SKIP) {
+            const Vec8 yv = unpack8(ldg16(A.y + (((long long)n * H + hq) * W + wq) * C + cg * 8));
+            const __nv_bfloat16* gptr = reinterpret_cast<const __nv_bfloat16*>(A.g.ptr) +
+                                        n * A.g.sN + hq * A.g.sH + wq * A.g.sW + cg * 8;
+            const Vec8 gv = unpack8(ldg16(gptr));
+            process(hq, wq, yv, gv);
+        } else {
+            Vec8 yv[4], av[4];
+            bool inb[4];
+            Vec8 mx;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mx.v[k] = 0.f;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int h = hq * 2 + (d >> 1), w = wq * 2 + (d & 1);
+                inb[d] = h < H && w < W;
+                if (inb[d]) {
+                    yv[d] = unpack8(ldg16(A.y + (((long long)n * H + h) * W + w) * C + cg * 8));
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        av[d].v[k] = bn_relu_bf16(yv[d].v[k], sc[k], sh[k]);
+                        mx.v[k] = fmaxf(mx.v[k], av[d].v[k]);
+                    }
+                }
+            }
+            const bool full = (hq < (H >> 1)) && (wq < (W >> 1));
+            Vec8 gpv;
+            if (full) {
+                const __nv_bfloat16* gptr = reinterpret_cast<const __nv_bfloat16*>(A.gp.ptr) +
+                                            n * A.gp.sN + hq * A.gp.sH + wq * A.gp.sW + cg * 8;
+                gpv = unpack8(ldg16(gptr));
+            }
+            bool taken[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) taken[k] = false;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                if (!inb[d]) continue;
+                const int h = hq * 2 + (d >> 1), w = wq * 2 + (d & 1);
+                Vec8 gv;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float g = 0.f;
+                    if (full && !taken[k] && av[d].v[k] == mx.v[k]) {
+                        g = gpv.v[k];
+                        taken[k] = true;
+                    }
+                    gv.v[k] = g;
+                }
+                if (A.has_skip) {
+                    const int hs = h - A.crop_h, ws = w - A.crop_w;
+                    if (hs >= 0 && hs < A.gs.H && ws >= 0 && ws < A.gs.W) {
+                        const __nv_bfloat16* sptr =
+                            reinterpret_cast<const __nv_bfloat16*>(A.gs.ptr) + n * A.gs.sN +
+                            hs * A.gs.sH + ws * A.gs.sW + cg * 8;
+                        const Vec8 sv = unpack8(ldg16(sptr));
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) gv.v[k] += sv.v[k];
+                    }
+                }
+                process(h, w, yv[d], gv);
+            }
+        }
+    }
+
+    if (!APPLY) {
+        // block reduction over the 256/CG threads that share a channel group
+        __shared__ float red[256 * 16];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            red[threadIdx.x * 16 + k] = acc_b[k];
+            red[threadIdx.x * 16 + 8 + k] = acc_g[k];
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < CG * 16; j += blockDim.x) {
+            const int g2 = j / 16, e = j % 16;
+            float s = 0.f;
+            for (int tt = g2; tt < 256; tt += CG) s += red[tt * 16 + e];
+            const int c = g2 * 8 + (e & 7);
+            A.partial[(long long)blockIdx.x * 2 * C + (e < 8 ? 0 : C) + c] = s;
+        }
+    }
+}
+
+// dbeta/dgamma = sum over blocks of the partials (fixed order => deterministic).
+static __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double b = 0.0, g = 0.0;
+    for (int k = 0; k < blocks; ++k) {
+        b += (double)part[(long long)k * 2 * C + c];
+        g += (double)part[(long long)k * 2 * C + C + c];
+    }
+    dbeta[c] = (float)b;
+    dgamma[c] = (float)g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight packing (fp32 torch layouts -> bf16 GEMM operands)
+// ---------------------------------------------------------------------------------------------
+// conv [Co][Ci][3][3] -> fprop B [Co][tap][Ci]   and   dgrad B [Ci][tap'][Co], tap' = 8 - tap
+static __global__ void pack_conv3x3_kernel(const float* __restrict__ w, int Co, int Ci,
+                                    __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+    const long long total = (long long)Co * Ci * 9;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        // i indexes the fprop layout (coalesced writes)
+        const int ci = (int)(i % Ci);
+        const int tap = (int)((i / Ci) % 9);
+        const int co = (int)(i / ((long long)Ci * 9));
+        const __nv_bfloat16 v = __float2bfloat16_rn(w[((long long)co * Ci + ci) * 9 + tap]);
+        wf[i] = v;
+        if (wd) wd[((long long)ci * 9 + (8 - tap)) * Co + co] = v;
+    }
+}
+// convT [Ci][Co][2][2] -> fwd B [(q*Co+co)][Ci]   and   bwd-data B [Ci][(q*Co+co)]
+static __global__ void pack_convT2x2_kernel(const float* __restrict__ w, int Ci, int Co,
+                                     __nv_bfloat16* __restrict__ wf,
+                                     __nv_bfloat16* __restrict__ wb) {
+    const long long total = (long long)Ci * Co * 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Ci);
+        const int co = (int)((i / Ci) % Co);
+        const int q = (int)(i / ((long long)Ci * Co));
+        const __nv_bfloat16 v = __float2bfloat16_rn(w[((long long)ci * Co + co) * 4 + q]);
+        wf[i] = v;
+        if (wb) wb[(long long)ci * 4 * Co + (long long)q * Co + co] = v;
+    }
+}
+// bias of the transposed conv replicated over the 4 sub-pixel positions (GEMM column order)
+static __global__ void tile_bias4_kernel(const float* __restrict__ b, int Co, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4 * Co) out[i] = b[i % Co];
+}
+
+// Split-K reduction of weight-gradient partial tiles + permutation into the torch layout:
+//   ws[split][row = tap*RC + rc][col]  ->  out[(col*RC + rc)*T + tap]
+//   conv3x3: RC = Ci, col = co, T = 9;   convT2x2: RC = Co, col = ci, T = 4
+static __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits,
+                                    long long split_stride, int rows, int cols, int RC, int T,
+                                    float* __restrict__ out) {
+    const long long total = (long long)rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % cols);
+        const int row = (int)(i / cols);
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += ws[(long long)k * split_stride + i];
+        const int tap = row / RC, rc = row % RC;
+        out[((long long)col * RC + rc) * T + tap] = s;
+    }
+}
+
+static __global__ void fill_zero_kernel(float* p, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        p[i] = 0.f;
+}
+
+}  // namespace ub

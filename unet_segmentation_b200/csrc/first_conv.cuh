@@ -1,0 +1,171 @@
+// First DoubleConv convolution (inc.double_conv.0, reference models/unet_model.py:73 -> :11-13):
+// C_in = n_channels (1 for DIC-C2DH-HeLa), K = 9*C_in, arithmetic intensity ~9 FLOP/B. It stays in
+// fp32 on CUDA cores (rounding the low-contrast input image to bf16 is 75 % of the
+// end-to-end bf16 drift) and its pre-BN output is never stored: statistics, BN-apply, and the
+// backward pass recompute the 9-tap convolution from the fp32 input (HBM traffic = input read +
+// one bf16 activation write).
+//
+// Thread mapping: one thread = one output pixel x 8 output channels (16 B bf16 store); the channel
+// group of a thread is fixed (threadIdx.x % (Co/8)) so per-channel sums live in registers.
+#pragma once
+#include "common.cuh"
+#include "elementwise.cuh"
+
+namespace ub {
+
+struct FirstConvArgs {
+    const float* x;   // [N][Ci][H][W] fp32 (NCHW, as handed over by the caller)
+    int N, Ci, H, W;  // input dims; output is (H-2) x (W-2)
+    int Co;           // output channels (64); Co % 8 == 0, 256 % (Co/8) == 0
+    const float* w;   // [Co][Ci][3][3] fp32 master weights
+    const float* bias;   // [Co] or null
+    const float* scale;  // apply / backward
+    const float* shift;
+    const float* mean;
+    const float* rstd;
+    __nv_bfloat16* a;    // apply: [N][H-2][W-2][Co] bf16
+    float* partial;      // stats / bwd reduce: [gridDim.x][2][Co]
+    View g;              // backward: gradient of a (direct view)
+    const float* dgamma;
+    const float* dbeta;
+    float inv_count;
+    float* wpartial;     // wgrad: [gridDim.x][Co][9] for input channel `ci_sel`
+    int ci_sel;
+};
+
+enum : int { FC_STATS = 0, FC_APPLY = 1, FC_BWD_REDUCE = 2, FC_BWD_WGRAD = 3 };
+
+template <int MODE>
+static __global__ void __launch_bounds__(256)
+first_conv_kernel(const FirstConvArgs A) {
+    extern __shared__ float wsm[];  // [Ci*9][Co] weights, transposed for 8-wide reads
+    const int Co = A.Co, CG = Co >> 3, Ci = A.Ci;
+    for (int i = threadIdx.x; i < Co * Ci * 9; i += blockDim.x) {
+        const int co = i / (Ci * 9), r = i % (Ci * 9);
+        wsm[r * Co + co] = A.w[i];
+    }
+    __syncthreads();
+    const int cg = threadIdx.x % CG;
+    const int Ho = A.H - 2, Wo = A.W - 2;
+
+    float bi[8], sc[8], sh[8], mu[8], rs[8], kb[8], kg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = cg * 8 + k;
+        bi[k] = A.bias ? A.bias[c] : 0.f;
+        if (MODE != FC_STATS) { sc[k] = A.scale[c]; sh[k] = A.shift[c]; }
+        if (MODE >= FC_BWD_REDUCE) { mu[k] = A.mean[c]; rs[k] = A.rstd[c]; }
+        if (MODE == FC_BWD_WGRAD) {
+            kb[k] = A.dbeta[c] * A.inv_count;
+            kg[k] = A.dgamma[c] * A.inv_count;
+        }
+    }
+    float acc0[8], acc1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
+    float wacc[9][8];
+    if (MODE == FC_BWD_WGRAD) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wacc[t][k] = 0.f;
+    }
+
+    const long long total = (long long)A.N * Ho * Wo * CG;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long t = i / CG;
+        const int wq = (int)(t % Wo); t /= Wo;
+        const int hq = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        float y[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = bi[k];
+        float xsel[9];
+        for (int ci = 0; ci < Ci; ++ci) {
+            const float* xp = A.x + (((long long)n * Ci + ci) * A.H + hq) * A.W + wq;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const float xv = __ldg(xp + (tap / 3) * A.W + (tap % 3));
+                if (MODE == FC_BWD_WGRAD && ci == A.ci_sel) xsel[tap] = xv;
+                const float4 w0 = *reinterpret_cast<const float4*>(&wsm[(ci * 9 + tap) * Co + cg * 8]);
+                const float4 w1 =
+                    *reinterpret_cast<const float4*>(&wsm[(ci * 9 + tap) * Co + cg * 8 + 4]);
+                y[0] = fmaf(xv, w0.x, y[0]); y[1] = fmaf(xv, w0.y, y[1]);
+                y[2] = fmaf(xv, w0.z, y[2]); y[3] = fmaf(xv, w0.w, y[3]);
+                y[4] = fmaf(xv, w1.x, y[4]); y[5] = fmaf(xv, w1.y, y[5]);
+                y[6] = fmaf(xv, w1.z, y[6]); y[7] = fmaf(xv, w1.w, y[7]);
+            }
+        }
+        if (MODE == FC_STATS) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { acc0[k] += y[k]; acc1[k] = fmaf(y[k], y[k], acc1[k]); }
+        } else if (MODE == FC_APPLY) {
+            Vec8 o;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(fmaf(y[k], sc[k], sh[k]), 0.f);
+            *reinterpret_cast<uint4*>(A.a + i * 8) = pack8(o);
+        } else {
+            const __nv_bfloat16* gptr = reinterpret_cast<const __nv_bfloat16*>(A.g.ptr) +
+                                        n * A.g.sN + hq * A.g.sH + wq * A.g.sW + cg * 8;
+            const Vec8 gv = unpack8(ldg16(gptr));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float act = fmaf(y[k], sc[k], sh[k]);
+                const float dyh = act > 0.f ? gv.v[k] : 0.f;
+                const float xh = (y[k] - mu[k]) * rs[k];
+                if (MODE == FC_BWD_REDUCE) {
+                    acc0[k] += dyh;
+                    acc1[k] = fmaf(dyh, xh, acc1[k]);
+                } else {
+                    const float dy = sc[k] * (dyh - kb[k] - xh * kg[k]);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) wacc[tap][k] = fmaf(dy, xsel[tap], wacc[tap][k]);
+                }
+            }
+        }
+    }
+
+    if (MODE == FC_STATS || MODE == FC_BWD_REDUCE) {
+        __shared__ float red[256 * 16];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            red[threadIdx.x * 16 + k] = acc0[k];
+            red[threadIdx.x * 16 + 8 + k] = acc1[k];
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < CG * 16; j += blockDim.x) {
+            const int g2 = j / 16, e = j % 16;
+            float s = 0.f;
+            for (int tt = g2; tt < 256; tt += CG) s += red[tt * 16 + e];
+            A.partial[(long long)blockIdx.x * 2 * Co + (e < 8 ? 0 : Co) + g2 * 8 + (e & 7)] = s;
+        }
+    } else if (MODE == FC_BWD_WGRAD) {
+        __shared__ float red[256 * 9];
+        for (int k = 0; k < 8; ++k) {
+            __syncthreads();
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) red[threadIdx.x * 9 + tap] = wacc[tap][k];
+            __syncthreads();
+            for (int j = threadIdx.x; j < CG * 9; j += blockDim.x) {
+                const int g2 = j / 9, tap = j % 9;
+                float s = 0.f;
+                for (int tt = g2; tt < 256; tt += CG) s += red[tt * 9 + tap];
+                A.wpartial[((long long)blockIdx.x * Co + g2 * 8 + k) * 9 + tap] = s;
+            }
+        }
+    }
+}
+
+// out[co][ci_sel][tap] = sum over blocks of wpartial[b][co][tap]
+static __global__ void first_wgrad_finalize_kernel(const float* __restrict__ wpartial, int blocks, int Co,
+                                            int Ci, int ci_sel, float* __restrict__ dw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Co * 9) return;
+    double s = 0.0;
+    for (int b = 0; b < blocks; ++b) s += (double)wpartial[(long long)b * Co * 9 + i];
+    const int co = i / 9, tap = i % 9;
+    dw[((long long)co * Ci + ci_sel) * 9 + tap] = (float)s;
+}
+
+}  // namespace ub

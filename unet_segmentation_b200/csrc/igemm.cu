@@ -1,0 +1,250 @@
+// Host-side launchers of the tcgen05 implicit-GEMM kernels (see igemm.cuh).
+#include "igemm.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "elementwise.cuh"
+#include "tmaps.cuh"
+#include "ub_internal.h"
+
+namespace ub {
+
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+static int pick_bn(int ncols) {
+    if (ncols % 256 == 0) return 256;
+    if (ncols % 128 == 0) return 128;
+    if (ncols % 64 == 0) return 64;
+    return 0;
+}
+
+size_t igemm_stats_floats(int ncols) {
+    int bn = pick_bn(ncols);
+    if (!bn) return 0;
+    return (size_t)num_sms() * 4 * 2 * bn;
+}
+
+template <int BN, int EPI>
+static int launch_igemm_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                          const IgemmParams& p, int grid, cudaStream_t stream) {
+    using Cfg = IgemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel<BN, EPI>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    igemm_kmajor_kernel<BN, EPI><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, p);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+
+template <int BN>
+static int launch_igemm_bn(int epi, const CUtensorMap& a0, const CUtensorMap& a1,
+                           const CUtensorMap& b, const IgemmParams& p, int grid,
+                           cudaStream_t stream) {
+    switch (epi) {
+        case EPI_CONV_STATS: return launch_igemm_t<BN, EPI_CONV_STATS>(a0, a1, b, p, grid, stream);
+        case EPI_STORE: return launch_igemm_t<BN, EPI_STORE>(a0, a1, b, p, grid, stream);
+        case EPI_AFFINE_RELU: return launch_igemm_t<BN, EPI_AFFINE_RELU>(a0, a1, b, p, grid, stream);
+        case EPI_CONVT: return launch_igemm_t<BN, EPI_CONVT>(a0, a1, b, p, grid, stream);
+    }
+    set_last_error("unknown epilogue kind %d", epi);
+    return UB_ERR_ARG;
+}
+
+static int check_view(const View& v, const char* what) {
+    if (v.C % 64 != 0 || v.C <= 0) {
+        set_last_error("%s: channel count %d is not a positive multiple of 64", what, v.C);
+        return UB_ERR_UNSUPPORTED;
+    }
+    if ((reinterpret_cast<uintptr_t>(v.ptr) & 15) || (v.sW % 8) || (v.sH % 8) || (v.sN % 8)) {
+        set_last_error("%s: view is not 16-byte aligned", what);
+        return UB_ERR_ARG;
+    }
+    return UB_OK;
+}
+
+int launch_igemm(const View& src0, const View* src1, int lower, int upper, int tstride, int taps,
+                 int tapw, const __nv_bfloat16* wB, int ncols, const IgemmEpilogue& epi,
+                 IgemmLaunchInfo* info, cudaStream_t stream) {
+    UB_TRY(check_view(src0, "igemm source 0"));
+    if (src1) {
+        UB_TRY(check_view(*src1, "igemm source 1"));
+        if (src1->N != src0.N || src1->H != src0.H || src1->W != src0.W) {
+            set_last_error("igemm: concat sources differ in shape");
+            return UB_ERR_ARG;
+        }
+    }
+    const int BN = pick_bn(ncols);
+    if (!BN) {
+        set_last_error("igemm: %d output columns is not a multiple of 64", ncols);
+        return UB_ERR_UNSUPPORTED;
+    }
+    const int Wo = (src0.W + upper - lower - 1) / tstride + 1;
+    const int Ho = (src0.H + upper - lower - 1) / tstride + 1;
+    if (Wo <= 0 || Ho <= 0) {
+        set_last_error("igemm: empty output (%d x %d)", Ho, Wo);
+        return UB_ERR_ARG;
+    }
+    const long long M = (long long)src0.N * Ho * Wo;
+    if (M > 0x7FFFFF00LL) {
+        set_last_error("igemm: too many rows");
+        return UB_ERR_UNSUPPORTED;
+    }
+    const int ctot = src0.C + (src1 ? src1->C : 0);
+    const long long K = (long long)taps * ctot;
+
+    CUtensorMap mA0, mA1, mB;
+    int r = make_tmap_im2col(&mA0, src0, lower, upper, tstride, 128);
+    if (r) { set_last_error("igemm: im2col tensor map (source 0) failed: %d", r); return UB_ERR_TMAP; }
+    if (src1) {
+        r = make_tmap_im2col(&mA1, *src1, lower, upper, tstride, 128);
+        if (r) { set_last_error("igemm: im2col tensor map (source 1) failed: %d", r); return UB_ERR_TMAP; }
+    } else {
+        mA1 = mA0;
+    }
+    r = make_tmap_2d(&mB, wB, (unsigned long long)K, (unsigned long long)ncols,
+                     (unsigned long long)K * 2, (unsigned)BN);
+    if (r) { set_last_error("igemm: weight tensor map failed: %d", r); return UB_ERR_TMAP; }
+
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)M; p.Wo = Wo; p.Ho = Ho; p.lower = lower; p.tstride = tstride;
+    p.taps = taps; p.tapw = tapw;
+    p.cchunks0 = src0.C / 64; p.cchunks1 = src1 ? src1->C / 64 : 0;
+    p.m_tiles = (int)((M + 127) / 128);
+    p.n_tiles = ncols / BN;
+    p.out = epi.out; p.ldo = epi.ldo; p.bias = epi.bias; p.scale = epi.scale; p.shift = epi.shift;
+    p.stats = epi.stats;
+    if (epi.kind == EPI_CONVT) {
+        p.out = (__nv_bfloat16*)epi.ct_dst.ptr;
+        p.ct_cout = ncols / 4; p.ct_H = src0.H; p.ct_W = src0.W;
+        p.ct_sN = epi.ct_dst.sN; p.ct_sH = epi.ct_dst.sH; p.ct_sW = epi.ct_dst.sW;
+    }
+    int grid = (num_sms() / p.n_tiles) * p.n_tiles;
+    if (grid <= 0) grid = p.n_tiles;
+    const long long tiles = (long long)p.m_tiles * p.n_tiles;
+    if (grid > tiles) grid = (int)tiles;
+    if (info) { info->grid = grid; info->n_tiles = p.n_tiles; info->BN = BN; info->M = (int)M; }
+    switch (BN) {
+        case 256: return launch_igemm_bn<256>(epi.kind, mA0, mA1, mB, p, grid, stream);
+        case 128: return launch_igemm_bn<128>(epi.kind, mA0, mA1, mB, p, grid, stream);
+        default: return launch_igemm_bn<64>(epi.kind, mA0, mA1, mB, p, grid, stream);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+static int wgrad_splits(int rows, int cols, long long mpix) {
+    const int bn = pick_bn(cols);
+    if (!bn) return 1;
+    const int m_tiles = (rows + 127) / 128, n_tiles = cols / bn;
+    const int units = m_tiles * n_tiles;
+    const long long kblocks = (mpix + 63) / 64;
+    long long s = (2LL * num_sms() + units - 1) / units;
+    const long long smax = kblocks / 8 > 1 ? kblocks / 8 : 1;
+    if (s > smax) s = smax;
+    if (s < 1) s = 1;
+    return (int)s;
+}
+size_t wgrad_ws_floats(int rows, int cols, long long mpix) {
+    return (size_t)wgrad_splits(rows, cols, mpix) * (size_t)rows * (size_t)cols;
+}
+
+template <int BN>
+static int launch_wgrad_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                          const WgradParams& p, dim3 grid, cudaStream_t stream) {
+    using Cfg = WgradCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<BN>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    igemm_wgrad_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, p);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+
+int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int tstride, int taps,
+                 int tapw, const __nv_bfloat16* B, long long ldb, int cols, float* ws,
+                 size_t ws_floats, float* out, cudaStream_t stream) {
+    UB_TRY(check_view(src0, "wgrad source 0"));
+    if (src1) UB_TRY(check_view(*src1, "wgrad source 1"));
+    const int BN = pick_bn(cols);
+    if (!BN) {
+        set_last_error("wgrad: %d columns is not a multiple of 64", cols);
+        return UB_ERR_UNSUPPORTED;
+    }
+    const int Wo = (src0.W + upper - lower - 1) / tstride + 1;
+    const int Ho = (src0.H + upper - lower - 1) / tstride + 1;
+    const long long mpix = (long long)src0.N * Ho * Wo;
+    const int ctot = src0.C + (src1 ? src1->C : 0);
+    const int rows = taps * ctot;
+    const int splits = wgrad_splits(rows, cols, mpix);
+    if ((size_t)splits * rows * cols > ws_floats) {
+        set_last_error("wgrad: workspace too small");
+        return UB_ERR_ARG;
+    }
+    CUtensorMap mA0, mA1, mB;
+    int r = make_tmap_im2col(&mA0, src0, lower, upper, tstride, 64);
+    if (r) { set_last_error("wgrad: im2col tensor map failed: %d", r); return UB_ERR_TMAP; }
+    if (src1) {
+        r = make_tmap_im2col(&mA1, *src1, lower, upper, tstride, 64);
+        if (r) { set_last_error("wgrad: im2col tensor map (source 1) failed: %d", r); return UB_ERR_TMAP; }
+    } else {
+        mA1 = mA0;
+    }
+    r = make_tmap_2d(&mB, B, (unsigned long long)cols, (unsigned long long)mpix,
+                     (unsigned long long)ldb * 2, 64);
+    if (r) { set_last_error("wgrad: matrix tensor map failed: %d", r); return UB_ERR_TMAP; }
+
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.Mpix = (int)mpix; p.Wo = Wo; p.Ho = Ho; p.lower = lower; p.tstride = tstride;
+    p.taps = taps; p.tapw = tapw;
+    p.cchunks0 = src0.C / 64; p.cchunks1 = src1 ? src1->C / 64 : 0;
+    p.a_chunks_total = rows / 64;
+    p.n_tiles = cols / BN; p.splits = splits;
+    p.kblocks_total = (int)((mpix + 63) / 64);
+    p.ws = ws; p.ldw = cols; p.split_stride = (long long)rows * cols;
+    const int m_tiles = (rows + 127) / 128;
+    dim3 grid(m_tiles * p.n_tiles, splits);
+    int rc;
+    switch (BN) {
+        case 256: rc = launch_wgrad_t<256>(mA0, mA1, mB, p, grid, stream); break;
+        case 128: rc = launch_wgrad_t<128>(mA0, mA1, mB, p, grid, stream); break;
+        default: rc = launch_wgrad_t<64>(mA0, mA1, mB, p, grid, stream); break;
+    }
+    UB_TRY(rc);
+    const long long total = (long long)rows * cols;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, splits, p.split_stride, rows, cols, ctot,
+                                                    taps, out);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+
+}  // namespace ub

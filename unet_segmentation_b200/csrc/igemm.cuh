@@ -1,0 +1,427 @@
+// Implicit-GEMM convolution kernels on tcgen05 tensor cores (sm_100a).
+//
+//  * igemm_kmajor_kernel  — forward 3x3 valid conv, its data gradient, the 2x2/stride-2
+//    transposed conv and its data gradient. A operand = im2col TMA tiles of an NHWC bf16 view
+//    (up to two sources: zero-copy channel concat), B operand = packed bf16 weights, both K-major,
+//    fp32 accumulators in TMEM, persistent CTAs, warp-specialised (TMA / MMA / 4 epilogue warps).
+//  * igemm_wgrad_kernel   — weight gradients: reduction over pixels, both operands MN-major,
+//    split-K over CTAs with fp32 partial tiles reduced in a fixed order afterwards.
+//
+// Reference ops replaced: nn.Conv2d(k=3,p=0) fwd/bwd (models/unet_model.py:11,15),
+// nn.ConvTranspose2d(k=2,s=2) fwd/bwd (:45), torch.cat of the cropped skip (:131-143).
+#pragma once
+#include "common.cuh"
+
+namespace ub {
+
+enum : int { EPI_CONV_STATS = 0, EPI_STORE = 1, EPI_AFFINE_RELU = 2, EPI_CONVT = 3 };
+
+struct IgemmParams {
+    int M;               // GEMM rows = base pixels = N*Ho*Wo
+    int Wo, Ho;          // traversal extents of the im2col bounding box
+    int lower;           // lower corner of the bounding box (same for w and h)
+    int tstride;         // traversal stride
+    int taps, tapw;      // filter taps and taps per filter row
+    int cchunks0, cchunks1;  // 64-channel chunks per tap taken from source 0 / source 1
+    int m_tiles, n_tiles;
+    __nv_bfloat16* out;  // [M][ldo] (EPI_CONV_STATS / STORE / AFFINE_RELU)
+    long long ldo;
+    const float* bias;   // per GEMM column, may be null
+    const float* scale;  // EPI_AFFINE_RELU: y = relu(acc*scale + shift)
+    const float* shift;
+    float* stats;        // EPI_CONV_STATS: [gridDim.x*4][2][BN] per-warp partial (sum, sumsq)
+    // EPI_CONVT: GEMM column = q*ct_cout + co, q = dy*2+dx; row = (n,h,w) of the input
+    int ct_cout, ct_H, ct_W;
+    long long ct_sN, ct_sH, ct_sW;  // element strides of the destination [N,2H,2W,*] view
+};
+
+template <int BN>
+struct IgemmCfg {
+    static constexpr int A_BYTES = 128 * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(192, 1)
+igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
+                    const __grid_constant__ CUtensorMap mapA1,
+                    const __grid_constant__ CUtensorMap mapB, const IgemmParams p) {
+    using Cfg = IgemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - raw);
+    const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+    volatile uint32_t* tmem_slot_g =
+        reinterpret_cast<volatile uint32_t*>(gbase + Cfg::STAGES * Cfg::STAGE_BYTES +
+                                             8 * (2 * Cfg::STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA0);
+        tma_prefetch_desc(&mapA1);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_g;
+
+    const int cchunks = p.cchunks0 + p.cchunks1;
+    const int kblocks = p.taps * cchunks;
+    const int cta_n = blockIdx.x % p.n_tiles;
+    const int m_first = blockIdx.x / p.n_tiles;
+    const int m_step = gridDim.x / p.n_tiles;
+    const int n0 = cta_n * BN;
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+            const int m0 = mt * 128;
+            const int q = m0 % p.Wo;
+            const int t = m0 / p.Wo;
+            const int pr = t % p.Ho;
+            const int n = t / p.Ho;
+            const int cw = p.lower + q * p.tstride;
+            const int ch = p.lower + pr * p.tstride;
+            int tap = 0, cc = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+                const uint32_t sb = sa + Cfg::A_BYTES;
+                const uint16_t offw = (uint16_t)(tap % p.tapw);
+                const uint16_t offh = (uint16_t)(tap / p.tapw);
+                if (cc < p.cchunks0)
+                    tma_load_im2col(sa, &mapA0, full_bar(stage), cc * 64, cw, ch, n, offw, offh);
+                else
+                    tma_load_im2col(sa, &mapA1, full_bar(stage), (cc - p.cchunks0) * 64, cw, ch, n,
+                                    offw, offh);
+                tma_load_2d(sb, &mapB, full_bar(stage), kb * 64, n0);
+                if (++cc == cchunks) { cc = 0; ++tap; }
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------ MMA issuer ------------------------------
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+            mbar_wait(tempty_bar(as), aphase ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+                const uint32_t sb = sa + Cfg::A_BYTES;
+                const uint64_t da = make_smem_desc(sa, 0, 1024);
+                const uint64_t db = make_smem_desc(sb, 0, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // 16 bf16 = 32 B along K => +2 in 16-byte units
+                    umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                              (uint32_t)((kb | k) != 0));
+                umma_commit(empty_bar(stage));
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(tfull_bar(as));
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+    } else if (warp >= 2) {
+        // ------------------------------ epilogue ------------------------------
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        const int row_in_tile = quad * 32 + lane;
+        int as = 0;
+        uint32_t aphase = 0;
+        float ssum[BN / 32], ssq[BN / 32];
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+
+        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+            const long long m = (long long)mt * 128 + row_in_tile;
+            const bool valid = m < p.M;
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+
+            long long ct_row = 0;
+            if (EPI == EPI_CONVT) {
+                const int w = (int)(m % p.ct_W);
+                const long long t = m / p.ct_W;
+                const int h = (int)(t % p.ct_H);
+                const long long n = t / p.ct_H;
+                ct_row = n * p.ct_sN + (long long)(2 * h) * p.ct_sH + (long long)(2 * w) * p.ct_sW;
+            }
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(trow + (uint32_t)(c * 32), r);
+                tmem_ld_wait();
+                const int col0 = n0 + c * 32;
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                if (EPI == EPI_AFFINE_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        v[i] = fmaxf(fmaf(v[i], __ldg(p.scale + col0 + i), __ldg(p.shift + col0 + i)),
+                                     0.f);
+                } else if (p.bias != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col0 + i);
+                }
+                if (valid) {
+                    __nv_bfloat16* dst;
+                    if (EPI == EPI_CONVT) {
+                        const int qd = col0 / p.ct_cout;
+                        const int co = col0 - qd * p.ct_cout;
+                        dst = p.out + ct_row + (long long)(qd >> 1) * p.ct_sH +
+                              (long long)(qd & 1) * p.ct_sW + co;
+                    } else {
+                        dst = p.out + m * p.ldo + col0;
+                    }
+                    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                        o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                        o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                        o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                        d4[j] = o;
+                    }
+                }
+                if (EPI == EPI_CONV_STATS) {
+                    float s2[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        v[i] = valid ? v[i] : 0.f;
+                        s2[i] = v[i] * v[i];
+                    }
+                    ssum[c] += warp_column_sum(v, lane);
+                    ssq[c] += warp_column_sum(s2, lane);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+        if (EPI == EPI_CONV_STATS) {
+            float* dst = p.stats + ((long long)blockIdx.x * 4 + quad) * (2 * BN);
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                dst[c * 32 + lane] = ssum[c];
+                dst[BN + c * 32 + lane] = ssq[c];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+// =================================================================================================
+// Weight gradient: D[(tap, ca), cb] = sum_pix  Aact[pix + tap, ca] * Bmat[pix, cb]
+//   A side ("im2col'd activations", up to two sources): 64-row chunks indexed (tap, channel chunk)
+//   B side: plain [pixels][channels] matrix. Both MN-major; K = pixels, 64 per pipeline stage.
+//   conv3x3:  A = layer input x,  B = dY       -> D[(tap,ci), co]
+//   convT2x2: A = d(up) (stride 2, 4 taps),  B = layer input x -> D[(q,co), ci]
+// =================================================================================================
+struct WgradParams {
+    int Mpix;
+    int Wo, Ho, lower, tstride, taps, tapw;
+    int cchunks0, cchunks1;
+    int a_chunks_total;  // taps * (cchunks0 + cchunks1)
+    int n_tiles, splits;
+    int kblocks_total;   // ceil(Mpix / 64)
+    float* ws;           // [splits][a_chunks_total*64][ldw]
+    long long ldw;
+    long long split_stride;
+};
+
+template <int BN>
+struct WgradCfg {
+    static constexpr int A_BYTES = 2 * 8192;
+    static constexpr int B_BYTES = (BN / 64) * 8192;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+    static constexpr uint32_t TMEM_COLS = BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
+                   const __grid_constant__ CUtensorMap mapA1,
+                   const __grid_constant__ CUtensorMap mapB, const WgradParams p) {
+    using Cfg = WgradCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - raw);
+    const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
+    volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(
+        gbase + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 1));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA0);
+        tma_prefetch_desc(&mapA1);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tfull_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_g;
+
+    const int m_tile = blockIdx.x / p.n_tiles;
+    const int n_tile = blockIdx.x % p.n_tiles;
+    const int split = blockIdx.y;
+    const int kb_begin = (int)((long long)p.kblocks_total * split / p.splits);
+    const int kb_end = (int)((long long)p.kblocks_total * (split + 1) / p.splits);
+    const int cchunks = p.cchunks0 + p.cchunks1;
+    const int n0 = n_tile * BN;
+
+    if (warp == 0 && lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        // the (at most) two 64-row chunks of this CTA's M' tile
+        int a_tap[2], a_cc[2];
+        bool a_ok[2];
+        for (int j = 0; j < 2; ++j) {
+            const int c = m_tile * 2 + j;
+            a_ok[j] = c < p.a_chunks_total;
+            a_tap[j] = a_ok[j] ? c / cchunks : 0;
+            a_cc[j] = a_ok[j] ? c % cchunks : 0;
+        }
+        const uint32_t tx = (a_ok[1] ? 2u : 1u) * 8192u + Cfg::B_BYTES;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+            const int m0 = kb * 64;
+            const int q = m0 % p.Wo;
+            const int t = m0 / p.Wo;
+            const int pr = t % p.Ho;
+            const int n = t / p.Ho;
+            const int cw = p.lower + q * p.tstride;
+            const int ch = p.lower + pr * p.tstride;
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), tx);
+            const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+            const uint32_t sb = sa + Cfg::A_BYTES;
+            for (int j = 0; j < 2; ++j) {
+                if (!a_ok[j]) continue;
+                const uint16_t offw = (uint16_t)(a_tap[j] % p.tapw);
+                const uint16_t offh = (uint16_t)(a_tap[j] / p.tapw);
+                if (a_cc[j] < p.cchunks0)
+                    tma_load_im2col(sa + j * 8192, &mapA0, full_bar(stage), a_cc[j] * 64, cw, ch, n,
+                                    offw, offh);
+                else
+                    tma_load_im2col(sa + j * 8192, &mapA1, full_bar(stage),
+                                    (a_cc[j] - p.cchunks0) * 64, cw, ch, n, offw, offh);
+            }
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(sb + j * 8192, &mapB, full_bar(stage), n0 + j * 64, m0);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+            const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // 16 pixels = 16 rows of 128 B
+                const uint64_t da = make_smem_desc(sa + k * 2048, 8192, 1024);
+                const uint64_t db = make_smem_desc(sb + k * 2048, 8192, 1024);
+                umma_bf16(tmem_base, da, db, idesc, (uint32_t)((kb != kb_begin) || (k != 0)));
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar);
+    } else if (warp >= 2) {
+        const int quad = warp & 3;
+        const int row = m_tile * 128 + quad * 32 + lane;
+        const bool valid = row < p.a_chunks_total * 64;
+        float* dst = p.ws + (long long)split * p.split_stride + (long long)row * p.ldw + n0;
+        if (kb_end > kb_begin) {
+            mbar_wait(tfull_bar, 0);
+            tc_fence_after();
+        }
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            if (kb_end > kb_begin) {
+                tmem_ld_32x32(trow + (uint32_t)(c * 32), r);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = 0u;
+            }
+            if (valid) {
+                uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    d4[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace ub

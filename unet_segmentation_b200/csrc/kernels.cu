@@ -1,0 +1,295 @@
+// Host-side launchers of the HBM-bound kernels (elementwise.cuh, first_conv.cuh, head_loss.cuh,
+// ccl.cuh). Grids are sized in multiples of the SM count; no launcher synchronises.
+#include "ccl.cuh"
+#include "elementwise.cuh"
+#include "first_conv.cuh"
+#include "head_loss.cuh"
+#include "igemm.cuh"
+#include "ub_internal.h"
+
+namespace ub {
+
+static inline int ew_blocks(long long items, int per_sm = 8) {
+    long long b = (items + 255) / 256;
+    const long long cap = (long long)num_sms() * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+// Grid for the "fixed channel group per thread" kernels: 4 CTAs per SM.
+static inline int red_blocks(long long items) {
+    long long b = (items + 255) / 256;
+    const long long cap = (long long)num_sms() * 4;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+static int check_cg(int C, const char* what) {
+    if (C % 8 != 0 || C <= 0 || 256 % (C / 8) != 0) {
+        set_last_error("%s: channel count %d unsupported (need C/8 to divide 256)", what, C);
+        return UB_ERR_UNSUPPORTED;
+    }
+    return UB_OK;
+}
+
+int launch_pack_conv3x3(const float* w, int Co, int Ci, __nv_bfloat16* wf, __nv_bfloat16* wd,
+                        cudaStream_t s) {
+    pack_conv3x3_kernel<<<ew_blocks((long long)Co * Ci * 9), 256, 0, s>>>(w, Co, Ci, wf, wd);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+int launch_pack_convT(const float* w, int Ci, int Co, __nv_bfloat16* wf, __nv_bfloat16* wb,
+                      const float* bias, float* bias4, cudaStream_t s) {
+    pack_convT2x2_kernel<<<ew_blocks((long long)Co * Ci * 4), 256, 0, s>>>(w, Ci, Co, wf, wb);
+    UB_CHECK_CUDA(cudaGetLastError());
+    if (bias && bias4) {
+        tile_bias4_kernel<<<(4 * Co + 255) / 256, 256, 0, s>>>(bias, Co, bias4);
+        UB_CHECK_CUDA(cudaGetLastError());
+    }
+    return UB_OK;
+}
+
+int launch_bn_finalize(const float* stats, const IgemmLaunchInfo& info, int C, double count,
+                       const float* gamma, const float* beta, float* rm, float* rv,
+                       long long* nbt, float momentum, float eps, float* scale, float* shift,
+                       float* mean, float* rstd, cudaStream_t s) {
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, info.grid, info.n_tiles, info.BN, C,
+                                                       count, gamma, beta, rm, rv, nbt, momentum,
+                                                       eps, scale, shift, mean, rstd);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+int launch_bn_finalize_flat(const float* part, int blocks, int C, double count, const float* gamma,
+                            const float* beta, float* rm, float* rv, long long* nbt,
+                            float momentum, float eps, float* scale, float* shift, float* mean,
+                            float* rstd, cudaStream_t s) {
+    bn_finalize_flat_kernel<<<(C + 127) / 128, 128, 0, s>>>(part, blocks, C, count, gamma, beta, rm,
+                                                            rv, nbt, momentum, eps, scale, shift,
+                                                            mean, rstd);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+int launch_bn_fold_eval(int C, const float* conv_bias, const float* gamma, const float* beta,
+                        const float* rm, const float* rv, float eps, float* scale, float* shift,
+                        cudaStream_t s) {
+    bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, conv_bias, gamma, beta, rm, rv, eps,
+                                                        scale, shift);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+
+int launch_bn_apply_relu(const __nv_bfloat16* y, __nv_bfloat16* a, __nv_bfloat16* pooled, int N,
+                         int H, int W, int C, const float* scale, const float* shift,
+                         cudaStream_t s) {
+    if (C % 8) { set_last_error("bn_apply: C %% 8 != 0"); return UB_ERR_UNSUPPORTED; }
+    if (pooled) {
+        const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+        bn_apply_relu_kernel<true><<<ew_blocks(items), 256, 0, s>>>(y, a, pooled, N, H, W, C, scale,
+                                                                    shift);
+    } else {
+        const long long items = (long long)N * H * W * (C / 8);
+        bn_apply_relu_kernel<false><<<ew_blocks(items), 256, 0, s>>>(y, a, nullptr, N, H, W, C,
+                                                                     scale, shift);
+    }
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+int launch_maxpool2(const __nv_bfloat16* a, __nv_bfloat16* pooled, int N, int H, int W, int C,
+                    cudaStream_t s) {
+    const long long items = (long long)N * (H / 2) * (W / 2) * (C / 8);
+    maxpool2_kernel<<<ew_blocks(items), 256, 0, s>>>(a, pooled, N, H, W, C);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+
+size_t bn_bwd_partial_floats(int C) { return (size_t)num_sms() * 4 * 2 * C; }
+
+int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
+    UB_TRY(check_cg(d.C, "bn_bwd"));
+    BnBwdArgs A;
+    memset(&A, 0, sizeof(A));
+    A.y = d.y; A.N = d.N; A.H = d.H; A.W = d.W; A.C = d.C;
+    A.scale = d.scale; A.shift = d.shift; A.mean = d.mean; A.rstd = d.rstd;
+    A.g = d.g; A.gp = d.gp; A.gs = d.gs; A.crop_h = d.crop_h; A.crop_w = d.crop_w;
+    A.has_skip = d.has_skip ? 1 : 0;
+    A.partial = d.partial;
+    A.dgamma = d.dgamma; A.dbeta = d.dbeta; A.dy = d.dy;
+    const long long count = (long long)d.N * d.H * d.W;
+    A.inv_count = (float)(1.0 / (double)count);
+    const long long items = d.pool_skip
+                                ? (long long)d.N * ((d.H + 1) / 2) * ((d.W + 1) / 2) * (d.C / 8)
+                                : count * (d.C / 8);
+    const int blocks = red_blocks(items);
+    if (d.pool_skip) bn_bwd_kernel<true, false><<<blocks, 256, 0, s>>>(A);
+    else bn_bwd_kernel<false, false><<<blocks, 256, 0, s>>>(A);
+    UB_CHECK_CUDA(cudaGetLastError());
+    bn_bwd_finalize_kernel<<<(d.C + 127) / 128, 128, 0, s>>>(d.partial, blocks, d.C, d.dgamma,
+                                                             d.dbeta);
+    UB_CHECK_CUDA(cudaGetLastError());
+    const int ablocks = ew_blocks(items);
+    if (d.pool_skip) bn_bwd_kernel<true, true><<<ablocks, 256, 0, s>>>(A);
+    else bn_bwd_kernel<false, true><<<ablocks, 256, 0, s>>>(A);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t first_conv_partial_floats(int Co) {
+    const size_t a = (size_t)num_sms() * 4 * 2 * Co;
+    const size_t b = (size_t)num_sms() * 4 * Co * 9;
+    return a > b ? a : b;
+}
+static int fc_fill(const FirstConvDesc& d, FirstConvArgs& A) {
+    UB_TRY(check_cg(d.Co, "first conv"));
+    if (d.H < 3 || d.W < 3) { set_last_error("first conv: input smaller than 3x3"); return UB_ERR_ARG; }
+    if ((size_t)d.Co * d.Ci * 9 * 4 > 96 * 1024) {
+        set_last_error("first conv: n_channels=%d too large for the fp32 direct kernel", d.Ci);
+        return UB_ERR_UNSUPPORTED;
+    }
+    memset(&A, 0, sizeof(A));
+    A.x = d.x; A.N = d.N; A.Ci = d.Ci; A.H = d.H; A.W = d.W; A.Co = d.Co; A.w = d.w; A.bias = d.bias;
+    return UB_OK;
+}
+template <int MODE>
+static int fc_launch(const FirstConvArgs& A, int blocks, cudaStream_t s) {
+    const size_t smem = (size_t)A.Co * A.Ci * 9 * 4;
+    if (smem > 48 * 1024)
+        UB_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<MODE>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    first_conv_kernel<MODE><<<blocks, 256, smem, s>>>(A);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+int launch_first_conv_stats(const FirstConvDesc& d, float* partial, int* blocks_out,
+                            cudaStream_t s) {
+    FirstConvArgs A;
+    UB_TRY(fc_fill(d, A));
+    A.partial = partial;
+    const long long items = (long long)d.N * (d.H - 2) * (d.W - 2) * (d.Co / 8);
+    const int blocks = red_blocks(items);
+    *blocks_out = blocks;
+    return fc_launch<FC_STATS>(A, blocks, s);
+}
+int launch_first_conv_apply(const FirstConvDesc& d, const float* scale, const float* shift,
+                            __nv_bfloat16* a, cudaStream_t s) {
+    FirstConvArgs A;
+    UB_TRY(fc_fill(d, A));
+    A.scale = scale; A.shift = shift; A.a = a;
+    const long long items = (long long)d.N * (d.H - 2) * (d.W - 2) * (d.Co / 8);
+    return fc_launch<FC_APPLY>(A, ew_blocks(items), s);
+}
+int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const float* shift,
+                          const float* mean, const float* rstd, const View& g, float* partial,
+                          float* dgamma, float* dbeta, float* dw, cudaStream_t s) {
+    FirstConvArgs A;
+    UB_TRY(fc_fill(d, A));
+    A.scale = scale; A.shift = shift; A.mean = mean; A.rstd = rstd; A.g = g;
+    A.partial = partial;
+    const long long count = (long long)d.N * (d.H - 2) * (d.W - 2);
+    const long long items = count * (d.Co / 8);
+    const int blocks = red_blocks(items);
+    UB_TRY(fc_launch<FC_BWD_REDUCE>(A, blocks, s));
+    bn_bwd_finalize_kernel<<<(d.Co + 127) / 128, 128, 0, s>>>(partial, blocks, d.Co, dgamma, dbeta);
+    UB_CHECK_CUDA(cudaGetLastError());
+    A.dgamma = dgamma; A.dbeta = dbeta; A.inv_count = (float)(1.0 / (double)count);
+    A.wpartial = partial;
+    for (int ci = 0; ci < d.Ci; ++ci) {
+        A.ci_sel = ci;
+        UB_TRY(fc_launch<FC_BWD_WGRAD>(A, blocks, s));
+        first_wgrad_finalize_kernel<<<(d.Co * 9 + 127) / 128, 128, 0, s>>>(partial, blocks, d.Co,
+                                                                           d.Ci, ci, dw);
+        UB_CHECK_CUDA(cudaGetLastError());
+    }
+    return UB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int launch_head_fwd(const __nv_bfloat16* a, int N, int H, int W, int K, int NC, const float* w,
+                    const float* b, float* logits, unsigned char* mask, cudaStream_t s) {
+    if (NC < 1 || NC > HEAD_MAX_CLASSES || K % 8) {
+        set_last_error("head: n_classes=%d (max %d) / K=%d unsupported", NC, HEAD_MAX_CLASSES, K);
+        return UB_ERR_UNSUPPORTED;
+    }
+    const long long P = (long long)N * H * W;
+    head_fwd_kernel<<<ew_blocks(P), 256, (size_t)(NC * K + NC) * 4, s>>>(
+        a, P, (long long)H * W, K, NC, w, b, logits, mask);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+size_t head_bwd_partial_floats(int K, int NC) { return (size_t)num_sms() * 4 * (NC * K + NC); }
+int launch_head_bwd(const float* dlogits, const __nv_bfloat16* a, int N, int H, int W, int K,
+                    int NC, const float* w, __nv_bfloat16* da, float* partial, float* dw, float* db,
+                    cudaStream_t s) {
+    if (NC < 1 || NC > HEAD_MAX_CLASSES) {
+        set_last_error("head: n_classes=%d unsupported", NC);
+        return UB_ERR_UNSUPPORTED;
+    }
+    UB_TRY(check_cg(K, "head_bwd"));
+    const long long P = (long long)N * H * W;
+    const int blocks = red_blocks(P * (K / 8));
+    head_bwd_kernel<<<blocks, 256, 0, s>>>(dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
+    UB_CHECK_CUDA(cudaGetLastError());
+    const int len = NC * K + NC;
+    reduce_partials_kernel<<<(len + 127) / 128, 128, 0, s>>>(partial, blocks, len, dw, NC * K, db);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+
+size_t wce_partial_floats() { return (size_t)num_sms() * 8; }
+int launch_wce(const WceDesc& d, float* loss, float* dz, float* partial, int* err,
+               cudaStream_t s) {
+    WceArgs A;
+    A.z = d.z; A.zN = d.zs[0]; A.zC = d.zs[1]; A.zH = d.zs[2]; A.zW = d.zs[3];
+    A.t = d.t; A.tN = d.ts[0]; A.tH = d.ts[1]; A.tW = d.ts[2];
+    A.wm = d.w; A.wN = d.ws[0]; A.wH = d.ws[1]; A.wW = d.ws[2];
+    A.N = d.N; A.C = d.C; A.H = d.H; A.W = d.W;
+    A.dz = dz; A.partial = partial; A.err = err;
+    const long long P = (long long)d.N * d.H * d.W;
+    if (P <= 0 || d.C < 1) { set_last_error("wce: empty input"); return UB_ERR_ARG; }
+    const int blocks = ew_blocks(P);
+    wce_fwd_bwd_kernel<<<blocks, 256, 0, s>>>(A);
+    UB_CHECK_CUDA(cudaGetLastError());
+    wce_finalize_kernel<<<1, 256, 0, s>>>(partial, blocks, (double)P, loss);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+int launch_scale_by_scalar(const float* in, const float* scalar, float* out, long long n,
+                           cudaStream_t s) {
+    scale_by_scalar_kernel<<<ew_blocks(n), 256, 0, s>>>(in, scalar, out, n);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+int launch_fill_zero(float* p, long long n, cudaStream_t s) {
+    if (n <= 0) return UB_OK;
+    fill_zero_kernel<<<ew_blocks(n), 256, 0, s>>>(p, n);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t ccl_ws_bytes(int H, int W) {
+    const size_t n = (size_t)H * W;
+    const size_t nb = (n + 1023) / 1024;
+    return (3 * n + nb + 16) * sizeof(int);
+}
+int launch_ccl(const unsigned char* mask, int H, int W, int min_size, unsigned short* out, void* ws,
+               cudaStream_t s) {
+    const long long n = (long long)H * W;
+    if (n <= 0) return UB_OK;
+    if (n > 0x7FFFFFFFLL) { set_last_error("ccl: image too large"); return UB_ERR_UNSUPPORTED; }
+    const int nb = (int)((n + 1023) / 1024);
+    int* L = reinterpret_cast<int*>(ws);
+    int* area = L + n;
+    int* rank = area + n;
+    int* block_roots = rank + n;
+    ccl_init_kernel<<<ew_blocks(n), 256, 0, s>>>(mask, L, area, n);
+    ccl_merge_kernel<<<ew_blocks(n), 256, 0, s>>>(mask, L, H, W);
+    ccl_flatten_kernel<<<nb, 1024, 0, s>>>(L, area, block_roots, n);
+    ccl_scan_kernel<<<1, 1024, 0, s>>>(block_roots, nb);
+    ccl_rank_kernel<<<nb, 1024, 0, s>>>(L, block_roots, rank, n);
+    ccl_emit_kernel<<<ew_blocks(n), 256, 0, s>>>(L, area, rank, min_size, out, n);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+
+}  // namespace ub

@@ -1,0 +1,579 @@
+// Network executor: the whole UNet.forward (reference models/unet_model.py:105-146) and its
+// backward as a fixed sequence of kernel launches over a pre-allocated NHWC bf16 activation arena.
+// No allocation, no host synchronisation and no tensor-map-independent host work happens after
+// ub_plan_create, so a step can be captured into a CUDA graph.
+#include <vector>
+
+#include "../../include/unet_b200.h"
+#include "igemm.cuh"
+#include "ub_internal.h"
+
+using namespace ub;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+struct ConvUnit {
+    int Ci = 0, Co = 0, Hin = 0, Win = 0;  // output is (Hin-2) x (Win-2)
+    int p_w = 0, p_b = 0, p_g = 0, p_be = 0, bn = 0;
+    bool first = false;
+    bf16 *wf = nullptr, *wd = nullptr;
+    bf16 *y = nullptr, *a = nullptr, *dy = nullptr;
+    float *scale = nullptr, *shift = nullptr, *mean = nullptr, *rstd = nullptr;
+    IgemmLaunchInfo info{};
+    int Ho() const { return Hin - 2; }
+    int Wo() const { return Win - 2; }
+};
+struct Block {
+    ConvUnit u[2];
+    View in0{}, in1{};
+    bool two = false;
+    bool pool = false;
+    bf16* pooled = nullptr;  // [N, Ho/2, Wo/2, Co]
+    bf16* da0 = nullptr;     // gradient of u[0].a
+    bf16* din = nullptr;     // gradient of the block input [N, Hin, Win, Ci] (contiguous)
+};
+struct UpT {
+    int Ci = 0, Co = 0, Hin = 0, Win = 0;
+    int p_w = 0, p_b = 0;
+    bf16 *wf = nullptr, *wb = nullptr;
+    float* bias4 = nullptr;
+    bf16* out = nullptr;  // [N, 2Hin, 2Win, Co]
+    bf16* dx = nullptr;   // [N, Hin, Win, Ci]
+};
+
+}  // namespace
+
+struct ub_plan {
+    int N = 0, Cin = 0, H = 0, W = 0, base = 0, L = 0, NC = 0;
+    bool training = false;
+    int outH = 0, outW = 0;
+    std::vector<Block> enc, dec;
+    std::vector<UpT> ups;
+    std::vector<int> crop;  // crop start of the skip of dec[j]
+    std::vector<const float*> params;
+    std::vector<long long> param_numel;
+    std::vector<float*> rm, rv;
+    std::vector<long long*> nbt;
+    std::vector<void*> allocs;
+    size_t bytes = 0;
+    float* scratch = nullptr;   // stats / reduction partials
+    float* wgrad_ws = nullptr;
+    size_t wgrad_ws_floats = 0;
+    bf16* head_da = nullptr;
+    const float* x = nullptr;   // input of the last forward (kept by the caller)
+    bool packed = false;
+    float momentum = 0.1f, eps = 1e-5f;
+
+    template <typename T>
+    int alloc(T** p, size_t count) {
+        void* q = nullptr;
+        const size_t b = ((count * sizeof(T) + 255) / 256) * 256;
+        cudaError_t e = cudaMalloc(&q, b ? b : 256);
+        if (e != cudaSuccess) {
+            set_last_error("cudaMalloc of %zu bytes failed: %s", b, cudaGetErrorString(e));
+            cudaGetLastError();
+            return ub::UB_ERR_NOMEM;
+        }
+        allocs.push_back(q);
+        bytes += b;
+        *p = reinterpret_cast<T*>(q);
+        return 0;
+    }
+    ~ub_plan() {
+        for (void* q : allocs) cudaFree(q);
+    }
+};
+
+static int alloc_unit(ub_plan* P, ConvUnit& u) {
+    const size_t out = (size_t)P->N * u.Ho() * u.Wo() * u.Co;
+    UB_TRY(P->alloc(&u.a, out));
+    UB_TRY(P->alloc(&u.scale, u.Co));
+    UB_TRY(P->alloc(&u.shift, u.Co));
+    UB_TRY(P->alloc(&u.mean, u.Co));
+    UB_TRY(P->alloc(&u.rstd, u.Co));
+    if (!u.first) {
+        UB_TRY(P->alloc(&u.wf, (size_t)u.Co * 9 * u.Ci));
+        if (P->training) UB_TRY(P->alloc(&u.wd, (size_t)u.Co * 9 * u.Ci));
+    }
+    if (P->training) {
+        if (!u.first) {
+            UB_TRY(P->alloc(&u.y, out));
+            UB_TRY(P->alloc(&u.dy, out));
+        }
+    }
+    return 0;
+}
+
+extern "C" {
+
+int ub_plan_create(ub_plan** out, int N, int n_channels, int H, int W, int base, int levels,
+                   int n_classes, int training) {
+    if (!out) return ub::UB_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        set_last_error("no CUDA device available (libunetb200 has no CPU fallback)");
+        return ub::UB_ERR_CUDA;
+    }
+    if (N < 1 || n_channels < 1 || levels < 2 || levels > 7 || n_classes < 1 ||
+        n_classes > 8 || base < 64 || base % 64 != 0) {
+        set_last_error("plan: unsupported configuration (N=%d n_channels=%d base=%d levels=%d "
+                       "n_classes=%d); base must be a multiple of 64, n_classes <= 8",
+                       N, n_channels, base, levels, n_classes);
+        return ub::UB_ERR_UNSUPPORTED;
+    }
+    if ((base & (base - 1)) != 0 || (base << (levels - 1)) > 2048) {
+        set_last_error("plan: base_channels=%d must be a power of two and the widest layer (%d) "
+                       "at most 2048 channels", base, base << (levels - 1));
+        return ub::UB_ERR_UNSUPPORTED;
+    }
+    ub_plan* P = new ub_plan();
+    P->N = N; P->Cin = n_channels; P->H = H; P->W = W; P->base = base; P->L = levels;
+    P->NC = n_classes; P->training = training != 0;
+    const int L = levels;
+    P->enc.resize(L);
+    P->dec.resize(L - 1);
+    P->ups.resize(L - 1);
+    P->crop.resize(L - 1);
+    const int nparams = 8 * L + 10 * (L - 1) + 2;
+    P->params.assign(nparams, nullptr);
+    P->param_numel.assign(nparams, 0);
+    P->rm.assign(2 * L + 2 * (L - 1), nullptr);
+    P->rv.assign(2 * L + 2 * (L - 1), nullptr);
+    P->nbt.assign(2 * L + 2 * (L - 1), nullptr);
+
+    auto fail = [&](int code) { delete P; return code; };
+    auto set_unit_params = [&](ConvUnit& u, int pbase, int bn) {
+        u.p_w = pbase; u.p_b = pbase + 1; u.p_g = pbase + 2; u.p_be = pbase + 3; u.bn = bn;
+        P->param_numel[u.p_w] = (long long)u.Co * u.Ci * 9;
+        P->param_numel[u.p_b] = u.Co; P->param_numel[u.p_g] = u.Co; P->param_numel[u.p_be] = u.Co;
+    };
+
+    // ---- geometry: encoder ----
+    int h = H, w = W;
+    for (int i = 0; i < L; ++i) {
+        Block& b = P->enc[i];
+        const int co = base << i;
+        b.u[0].Ci = i == 0 ? n_channels : base << (i - 1);
+        b.u[0].Co = co; b.u[0].Hin = h; b.u[0].Win = w; b.u[0].first = (i == 0);
+        b.u[1].Ci = co; b.u[1].Co = co; b.u[1].Hin = h - 2; b.u[1].Win = w - 2;
+        set_unit_params(b.u[0], 8 * i, 2 * i);
+        set_unit_params(b.u[1], 8 * i + 4, 2 * i + 1);
+        h -= 4; w -= 4;
+        if (h < 1 || w < 1) {
+            set_last_error("plan: input %dx%d too small for %d levels", H, W, L);
+            return fail(ub::UB_ERR_ARG);
+        }
+        b.pool = i < L - 1;
+        if (b.pool) { h /= 2; w /= 2; }
+        if (b.pool && (h < 5 || w < 5)) {
+            set_last_error("plan: input %dx%d too small for %d levels", H, W, L);
+            return fail(ub::UB_ERR_ARG);
+        }
+    }
+    // ---- geometry: decoder ----
+    for (int j = 0; j < L - 1; ++j) {
+        UpT& t = P->ups[j];
+        Block& b = P->dec[j];
+        const int cp = base << (L - 1 - j);
+        t.Ci = cp; t.Co = cp / 2; t.Hin = h; t.Win = w;
+        const int pb = 8 * L + 10 * j;
+        t.p_w = pb; t.p_b = pb + 1;
+        P->param_numel[t.p_w] = (long long)t.Ci * t.Co * 4;
+        P->param_numel[t.p_b] = t.Co;
+        h *= 2; w *= 2;
+        const Block& sk = P->enc[L - 2 - j];
+        const int sh = sk.u[1].Ho(), sw = sk.u[1].Wo();
+        if (sh < h || sw < w) {
+            set_last_error("plan: skip connection (%dx%d) smaller than up-sampled map (%dx%d)", sh,
+                           sw, h, w);
+            return fail(ub::UB_ERR_ARG);
+        }
+        b.two = true;
+        b.u[0].Ci = cp; b.u[0].Co = cp / 2; b.u[0].Hin = h; b.u[0].Win = w;
+        b.u[1].Ci = cp / 2; b.u[1].Co = cp / 2; b.u[1].Hin = h - 2; b.u[1].Win = w - 2;
+        set_unit_params(b.u[0], pb + 2, 2 * L + 2 * j);
+        set_unit_params(b.u[1], pb + 6, 2 * L + 2 * j + 1);
+        h -= 4; w -= 4;
+        if (h < 1 || w < 1) {
+            set_last_error("plan: input %dx%d too small for %d levels", H, W, L);
+            return fail(ub::UB_ERR_ARG);
+        }
+    }
+    P->outH = h; P->outW = w;
+    P->param_numel[nparams - 2] = (long long)n_classes * base;
+    P->param_numel[nparams - 1] = n_classes;
+
+    // ---- allocation ----
+    size_t scratch = wce_partial_floats();
+    size_t wws = 0;
+    auto upd = [](size_t& a, size_t b) { if (b > a) a = b; };
+    for (int i = 0; i < L; ++i) {
+        Block& b = P->enc[i];
+        for (int k = 0; k < 2; ++k) {
+            ConvUnit& u = b.u[k];
+            if (int r = alloc_unit(P, u)) return fail(r);
+            if (u.first) upd(scratch, first_conv_partial_floats(u.Co));
+            else upd(scratch, igemm_stats_floats(u.Co));
+            upd(scratch, bn_bwd_partial_floats(u.Co));
+            if (!u.first)
+                upd(wws, wgrad_ws_floats(9 * u.Ci, u.Co, (long long)N * u.Ho() * u.Wo()));
+        }
+        if (b.pool) {
+            const int ph = b.u[1].Ho() / 2, pw = b.u[1].Wo() / 2;
+            if (int r = P->alloc(&b.pooled, (size_t)N * ph * pw * b.u[1].Co)) return fail(r);
+        }
+        if (P->training) {
+            if (int r = P->alloc(&b.da0, (size_t)N * b.u[0].Ho() * b.u[0].Wo() * b.u[0].Co))
+                return fail(r);
+            if (i > 0)
+                if (int r = P->alloc(&b.din, (size_t)N * b.u[0].Hin * b.u[0].Win * b.u[0].Ci))
+                    return fail(r);
+        }
+    }
+    for (int j = 0; j < L - 1; ++j) {
+        UpT& t = P->ups[j];
+        Block& b = P->dec[j];
+        if (int r = P->alloc(&t.wf, (size_t)4 * t.Co * t.Ci)) return fail(r);
+        if (int r = P->alloc(&t.bias4, (size_t)4 * t.Co)) return fail(r);
+        if (int r = P->alloc(&t.out, (size_t)N * 4 * t.Hin * t.Win * t.Co)) return fail(r);
+        if (P->training) {
+            if (int r = P->alloc(&t.wb, (size_t)4 * t.Co * t.Ci)) return fail(r);
+            if (int r = P->alloc(&t.dx, (size_t)N * t.Hin * t.Win * t.Ci)) return fail(r);
+            upd(wws, wgrad_ws_floats(4 * t.Co, t.Ci, (long long)N * t.Hin * t.Win));
+        }
+        for (int k = 0; k < 2; ++k) {
+            ConvUnit& u = b.u[k];
+            if (int r = alloc_unit(P, u)) return fail(r);
+            upd(scratch, igemm_stats_floats(u.Co));
+            upd(scratch, bn_bwd_partial_floats(u.Co));
+            upd(wws, wgrad_ws_floats(9 * u.Ci, u.Co, (long long)N * u.Ho() * u.Wo()));
+        }
+        if (P->training) {
+            if (int r = P->alloc(&b.da0, (size_t)N * b.u[0].Ho() * b.u[0].Wo() * b.u[0].Co))
+                return fail(r);
+            if (int r = P->alloc(&b.din, (size_t)N * b.u[0].Hin * b.u[0].Win * b.u[0].Ci))
+                return fail(r);
+        }
+        // sources of the zero-copy concat: [cropped skip, up-sampled]
+        const Block& sk = P->enc[L - 2 - j];
+        const int sh = sk.u[1].Ho(), sw = sk.u[1].Wo(), sc = sk.u[1].Co;
+        const int uh = b.u[0].Hin, uw = b.u[0].Win;
+        const int ch = (sh - uh) / 2, cw = (sw - uw) / 2;
+        P->crop[j] = ch;
+        View full = make_view(sk.u[1].a, N, sh, sw, sc);
+        View v = full;
+        v.ptr = sk.u[1].a + ((long long)ch * sw + cw) * sc;
+        v.H = uh; v.W = uw;
+        b.in0 = v;
+        b.in1 = make_view(t.out, N, uh, uw, t.Co);
+        // remember the column crop in the view itself (crop_w may differ from crop_h)
+        (void)cw;
+    }
+    for (int i = 1; i < L; ++i) {
+        Block& b = P->enc[i];
+        const Block& pr = P->enc[i - 1];
+        b.in0 = make_view(pr.pooled, N, b.u[0].Hin, b.u[0].Win, b.u[0].Ci);
+    }
+    upd(scratch, head_bwd_partial_floats(base, n_classes));
+    if (int r = P->alloc(&P->scratch, scratch)) return fail(r);
+    if (P->training) {
+        P->wgrad_ws_floats = wws;
+        if (int r = P->alloc(&P->wgrad_ws, wws)) return fail(r);
+        if (int r = P->alloc(&P->head_da, (size_t)N * P->outH * P->outW * base)) return fail(r);
+    }
+    *out = P;
+    return 0;
+}
+
+int ub_plan_destroy(ub_plan* P) {
+    delete P;
+    return 0;
+}
+int ub_plan_out_hw(const ub_plan* P, int* oh, int* ow) {
+    if (!P) return ub::UB_ERR_ARG;
+    if (oh) *oh = P->outH;
+    if (ow) *ow = P->outW;
+    return 0;
+}
+int ub_plan_num_params(const ub_plan* P) { return P ? (int)P->params.size() : ub::UB_ERR_ARG; }
+int ub_plan_num_bn(const ub_plan* P) { return P ? (int)P->rm.size() : ub::UB_ERR_ARG; }
+int64_t ub_plan_param_numel(const ub_plan* P, int i) {
+    if (!P || i < 0 || i >= (int)P->param_numel.size()) return ub::UB_ERR_ARG;
+    return P->param_numel[i];
+}
+int64_t ub_plan_device_bytes(const ub_plan* P) { return P ? (int64_t)P->bytes : 0; }
+
+int ub_plan_bind_params(ub_plan* P, const float* const* params, int count) {
+    if (!P || !params || count != (int)P->params.size()) {
+        set_last_error("bind_params: expected %d parameters, got %d",
+                       P ? (int)P->params.size() : -1, count);
+        return ub::UB_ERR_ARG;
+    }
+    for (int i = 0; i < count; ++i) {
+        if (!params[i]) { set_last_error("bind_params: parameter %d is null", i); return ub::UB_ERR_ARG; }
+        P->params[i] = params[i];
+    }
+    P->packed = false;
+    return 0;
+}
+int ub_plan_bind_bn_buffers(ub_plan* P, float* const* rm, float* const* rv,
+                            int64_t* const* nbt, int count) {
+    if (!P || !rm || !rv || count != (int)P->rm.size()) {
+        set_last_error("bind_bn_buffers: expected %d BatchNorm layers, got %d",
+                       P ? (int)P->rm.size() : -1, count);
+        return ub::UB_ERR_ARG;
+    }
+    for (int i = 0; i < count; ++i) {
+        P->rm[i] = rm[i]; P->rv[i] = rv[i];
+        P->nbt[i] = nbt ? (long long*)nbt[i] : nullptr;
+    }
+    return 0;
+}
+
+int ub_plan_pack_weights(ub_plan* P, void* stream) {
+    if (!P) return ub::UB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (size_t i = 0; i < P->params.size(); ++i)
+        if (!P->params[i]) { set_last_error("pack_weights: parameters not bound"); return ub::UB_ERR_ARG; }
+    auto pack_block = [&](Block& b) -> int {
+        for (int k = 0; k < 2; ++k) {
+            ConvUnit& u = b.u[k];
+            if (u.first) continue;
+            UB_TRY(launch_pack_conv3x3(P->params[u.p_w], u.Co, u.Ci, u.wf, u.wd, s));
+        }
+        return 0;
+    };
+    for (auto& b : P->enc) UB_TRY(pack_block(b));
+    for (auto& b : P->dec) UB_TRY(pack_block(b));
+    for (auto& t : P->ups)
+        UB_TRY(launch_pack_convT(P->params[t.p_w], t.Ci, t.Co, t.wf, t.wb, P->params[t.p_b], t.bias4,
+                                 s));
+    P->packed = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const View* in1,
+                             bf16* pooled, cudaStream_t s) {
+    const int N = P->N;
+    if (u.first) {
+        FirstConvDesc d;
+        d.x = P->x; d.N = N; d.Ci = u.Ci; d.H = u.Hin; d.W = u.Win; d.Co = u.Co;
+        d.w = P->params[u.p_w];
+        if (P->training) {
+            d.bias = P->params[u.p_b];
+            int blocks = 0;
+            UB_TRY(launch_first_conv_stats(d, P->scratch, &blocks, s));
+            UB_TRY(launch_bn_finalize_flat(P->scratch, blocks, u.Co, (double)N * u.Ho() * u.Wo(),
+                                           P->params[u.p_g], P->params[u.p_be], P->rm[u.bn],
+                                           P->rv[u.bn], P->nbt[u.bn], P->momentum, P->eps, u.scale,
+                                           u.shift, u.mean, u.rstd, s));
+        } else {
+            d.bias = nullptr;
+            UB_TRY(launch_bn_fold_eval(u.Co, P->params[u.p_b], P->params[u.p_g], P->params[u.p_be],
+                                       P->rm[u.bn], P->rv[u.bn], P->eps, u.scale, u.shift, s));
+        }
+        return launch_first_conv_apply(d, u.scale, u.shift, u.a, s);
+    }
+    IgemmEpilogue e;
+    memset(&e, 0, sizeof(e));
+    e.ldo = u.Co;
+    if (P->training) {
+        e.kind = EPI_CONV_STATS; e.out = u.y; e.bias = P->params[u.p_b]; e.stats = P->scratch;
+        UB_TRY(launch_igemm(in0, in1, 0, -2, 1, 9, 3, u.wf, u.Co, e, &u.info, s));
+        UB_TRY(launch_bn_finalize(P->scratch, u.info, u.Co, (double)u.info.M, P->params[u.p_g],
+                                  P->params[u.p_be], P->rm[u.bn], P->rv[u.bn], P->nbt[u.bn],
+                                  P->momentum, P->eps, u.scale, u.shift, u.mean, u.rstd, s));
+        return launch_bn_apply_relu(u.y, u.a, pooled, N, u.Ho(), u.Wo(), u.Co, u.scale, u.shift, s);
+    }
+    UB_TRY(launch_bn_fold_eval(u.Co, P->params[u.p_b], P->params[u.p_g], P->params[u.p_be],
+                               P->rm[u.bn], P->rv[u.bn], P->eps, u.scale, u.shift, s));
+    e.kind = EPI_AFFINE_RELU; e.out = u.a; e.scale = u.scale; e.shift = u.shift;
+    UB_TRY(launch_igemm(in0, in1, 0, -2, 1, 9, 3, u.wf, u.Co, e, &u.info, s));
+    if (pooled) return launch_maxpool2(u.a, pooled, N, u.Ho(), u.Wo(), u.Co, s);
+    return 0;
+}
+
+static int block_forward(ub_plan* P, Block& b, cudaStream_t s) {
+    UB_TRY(conv_unit_forward(P, b.u[0], b.in0, b.two ? &b.in1 : nullptr, nullptr, s));
+    View mid = make_view(b.u[0].a, P->N, b.u[0].Ho(), b.u[0].Wo(), b.u[0].Co);
+    return conv_unit_forward(P, b.u[1], mid, nullptr, b.pool ? b.pooled : nullptr, s);
+}
+
+int ub_plan_forward(ub_plan* P, const float* x, float* logits, uint8_t* mask, void* stream) {
+    if (!P || !x || !logits) { set_last_error("forward: null pointer"); return ub::UB_ERR_ARG; }
+    if (!P->packed) { set_last_error("forward: call ub_plan_pack_weights first"); return ub::UB_ERR_ARG; }
+    for (size_t i = 0; i < P->rm.size(); ++i)
+        if (!P->rm[i] || !P->rv[i]) { set_last_error("forward: BN buffers not bound"); return ub::UB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    P->x = x;
+    const int L = P->L;
+    for (int i = 0; i < L; ++i) UB_TRY(block_forward(P, P->enc[i], s));
+    for (int j = 0; j < L - 1; ++j) {
+        UpT& t = P->ups[j];
+        const ConvUnit& prev = j == 0 ? P->enc[L - 1].u[1] : P->dec[j - 1].u[1];
+        View xin = make_view(prev.a, P->N, t.Hin, t.Win, t.Ci);
+        IgemmEpilogue e;
+        memset(&e, 0, sizeof(e));
+        e.kind = EPI_CONVT; e.bias = t.bias4;
+        e.ct_dst = make_view(t.out, P->N, 2 * t.Hin, 2 * t.Win, t.Co);
+        UB_TRY(launch_igemm(xin, nullptr, 0, 0, 1, 1, 1, t.wf, 4 * t.Co, e, nullptr, s));
+        UB_TRY(block_forward(P, P->dec[j], s));
+    }
+    const ConvUnit& last = P->dec[L - 2].u[1];
+    const int np = (int)P->params.size();
+    return launch_head_fwd(last.a, P->N, P->outH, P->outW, P->base, P->NC, P->params[np - 2],
+                           P->params[np - 1], logits, P->training ? nullptr : mask, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+int ub_plan_num_stages(const ub_plan* P) { return P ? 2 * P->L - 1 : ub::UB_ERR_ARG; }
+
+int ub_plan_stage_params(const ub_plan* P, int stage, int* first, int* count) {
+    if (!P || stage < 0 || stage >= 2 * P->L - 1) return ub::UB_ERR_ARG;
+    const int L = P->L;
+    int f, c;
+    if (stage < L - 1) {
+        const int j = L - 2 - stage;  // decoder block index
+        f = 8 * L + 10 * j;
+        c = 10 + (stage == 0 ? 2 : 0);  // the head's two parameters follow the last up block
+    } else {
+        const int i = 2 * L - 2 - stage;  // encoder block index
+        f = 8 * i;
+        c = 8;
+    }
+    if (first) *first = f;
+    if (count) *count = c;
+    return 0;
+}
+
+struct Upstream {
+    bool pool_skip = false;
+    View g{}, gp{}, gs{};
+    int crop_h = 0, crop_w = 0;
+    bool has_skip = false;
+};
+
+static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const* grads,
+                          cudaStream_t s) {
+    const int N = P->N;
+    ConvUnit& u1 = b.u[1];
+    ConvUnit& u0 = b.u[0];
+    // ---- second conv unit ----
+    BnBwdDesc d;
+    memset(&d, 0, sizeof(d));
+    d.y = u1.y; d.N = N; d.H = u1.Ho(); d.W = u1.Wo(); d.C = u1.Co;
+    d.scale = u1.scale; d.shift = u1.shift; d.mean = u1.mean; d.rstd = u1.rstd;
+    d.pool_skip = up.pool_skip; d.g = up.g; d.gp = up.gp; d.gs = up.gs;
+    d.crop_h = up.crop_h; d.crop_w = up.crop_w; d.has_skip = up.has_skip;
+    d.partial = P->scratch; d.dgamma = grads[u1.p_g]; d.dbeta = grads[u1.p_be]; d.dy = u1.dy;
+    UB_TRY(launch_bn_bwd(d, s));
+    View a0 = make_view(u0.a, N, u0.Ho(), u0.Wo(), u0.Co);
+    UB_TRY(launch_wgrad(a0, nullptr, 0, -2, 1, 9, 3, u1.dy, u1.Co, u1.Co, P->wgrad_ws,
+                        P->wgrad_ws_floats, grads[u1.p_w], s));
+    UB_TRY(launch_fill_zero(grads[u1.p_b], u1.Co, s));  // analytically zero ahead of a BatchNorm
+    {
+        IgemmEpilogue e;
+        memset(&e, 0, sizeof(e));
+        e.kind = EPI_STORE; e.out = b.da0; e.ldo = u1.Ci;
+        View dyv = make_view(u1.dy, N, u1.Ho(), u1.Wo(), u1.Co);
+        UB_TRY(launch_igemm(dyv, nullptr, -2, 0, 1, 9, 3, u1.wd, u1.Ci, e, nullptr, s));
+    }
+    // ---- first conv unit ----
+    View g0 = make_view(b.da0, N, u0.Ho(), u0.Wo(), u0.Co);
+    UB_TRY(launch_fill_zero(grads[u0.p_b], u0.Co, s));
+    if (u0.first) {
+        FirstConvDesc f;
+        f.x = P->x; f.N = N; f.Ci = u0.Ci; f.H = u0.Hin; f.W = u0.Win; f.Co = u0.Co;
+        f.w = P->params[u0.p_w]; f.bias = P->params[u0.p_b];
+        return launch_first_conv_bwd(f, u0.scale, u0.shift, u0.mean, u0.rstd, g0, P->scratch,
+                                     grads[u0.p_g], grads[u0.p_be], grads[u0.p_w], s);
+    }
+    memset(&d, 0, sizeof(d));
+    d.y = u0.y; d.N = N; d.H = u0.Ho(); d.W = u0.Wo(); d.C = u0.Co;
+    d.scale = u0.scale; d.shift = u0.shift; d.mean = u0.mean; d.rstd = u0.rstd;
+    d.pool_skip = false; d.g = g0;
+    d.partial = P->scratch; d.dgamma = grads[u0.p_g]; d.dbeta = grads[u0.p_be]; d.dy = u0.dy;
+    UB_TRY(launch_bn_bwd(d, s));
+    UB_TRY(launch_wgrad(b.in0, b.two ? &b.in1 : nullptr, 0, -2, 1, 9, 3, u0.dy, u0.Co, u0.Co,
+                        P->wgrad_ws, P->wgrad_ws_floats, grads[u0.p_w], s));
+    IgemmEpilogue e;
+    memset(&e, 0, sizeof(e));
+    e.kind = EPI_STORE; e.out = b.din; e.ldo = u0.Ci;
+    View dyv = make_view(u0.dy, N, u0.Ho(), u0.Wo(), u0.Co);
+    return launch_igemm(dyv, nullptr, -2, 0, 1, 9, 3, u0.wd, u0.Ci, e, nullptr, s);
+}
+
+int ub_plan_backward_stage(ub_plan* P, int stage, const float* dlogits, float* const* grads,
+                           void* stream) {
+    if (!P || !grads) { set_last_error("backward: null pointer"); return ub::UB_ERR_ARG; }
+    if (!P->training) {
+        set_last_error("backward: plan was created for inference (training=0)");
+        return ub::UB_ERR_ARG;
+    }
+    if (stage < 0 || stage >= 2 * P->L - 1) { set_last_error("backward: bad stage"); return ub::UB_ERR_ARG; }
+    if (!P->x) { set_last_error("backward: no forward pass recorded"); return ub::UB_ERR_ARG; }
+    int first = 0, cnt = 0;
+    ub_plan_stage_params(P, stage, &first, &cnt);
+    for (int i = first; i < first + cnt; ++i)
+        if (!grads[i]) { set_last_error("backward: gradient buffer %d is null", i); return ub::UB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int L = P->L, N = P->N;
+
+    if (stage < L - 1) {
+        const int j = L - 2 - stage;
+        Block& b = P->dec[j];
+        UpT& t = P->ups[j];
+        Upstream up;
+        if (stage == 0) {
+            if (!dlogits) { set_last_error("backward: dlogits is null"); return ub::UB_ERR_ARG; }
+            const int np = (int)P->params.size();
+            UB_TRY(launch_head_bwd(dlogits, b.u[1].a, N, P->outH, P->outW, P->base, P->NC,
+                                   P->params[np - 2], P->head_da, P->scratch, grads[np - 2],
+                                   grads[np - 1], s));
+            up.g = make_view(P->head_da, N, P->outH, P->outW, P->base);
+        } else {
+            const UpT& nt = P->ups[j + 1];
+            up.g = make_view(nt.dx, N, nt.Hin, nt.Win, nt.Ci);
+        }
+        UB_TRY(block_backward(P, b, up, grads, s));
+        // transposed conv: the second channel range of d(concat) is d(up)
+        const int cs = b.u[0].Ci - t.Co;  // skip channels
+        View dup = make_view(b.din, N, b.u[0].Hin, b.u[0].Win, b.u[0].Ci);
+        dup.ptr = b.din + cs;
+        dup.C = t.Co;
+        IgemmEpilogue e;
+        memset(&e, 0, sizeof(e));
+        e.kind = EPI_STORE; e.out = t.dx; e.ldo = t.Ci;
+        UB_TRY(launch_igemm(dup, nullptr, 0, -1, 2, 4, 2, t.wb, t.Ci, e, nullptr, s));
+        const ConvUnit& prev = j == 0 ? P->enc[L - 1].u[1] : P->dec[j - 1].u[1];
+        UB_TRY(launch_wgrad(dup, nullptr, 0, -1, 2, 4, 2, prev.a, t.Ci, t.Ci, P->wgrad_ws,
+                            P->wgrad_ws_floats, grads[t.p_w], s));
+        return launch_fill_zero(grads[t.p_b], t.Co, s);  // removed by the following BatchNorm
+    }
+    const int i = 2 * L - 2 - stage;
+    Block& b = P->enc[i];
+    Upstream up;
+    if (i == L - 1) {
+        const UpT& t0 = P->ups[0];
+        up.g = make_view(t0.dx, N, t0.Hin, t0.Win, t0.Ci);
+    } else {
+        const Block& nx = P->enc[i + 1];
+        const int j = L - 2 - i;
+        const Block& db = P->dec[j];
+        up.pool_skip = true;
+        up.gp = make_view(nx.din, N, nx.u[0].Hin, nx.u[0].Win, nx.u[0].Ci);
+        View gs = make_view(db.din, N, db.u[0].Hin, db.u[0].Win, db.u[0].Ci);
+        gs.C = b.u[1].Co;  // first channel range of d(concat) = gradient of the cropped skip
+        up.gs = gs;
+        up.has_skip = true;
+        up.crop_h = (b.u[1].Ho() - db.u[0].Hin) / 2;
+        up.crop_w = (b.u[1].Wo() - db.u[0].Win) / 2;
+    }
+    return block_backward(P, b, up, grads, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// Internal C++ launch API shared by the op-level C ABI (capi_ops.cu) and the network executor
+// (plan.cu). Every function enqueues work on `stream` and returns 0 or a negative ub error code;
+// nothing synchronises the device.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace ub {
+
+enum : int {
+    UB_OK = 0,
+    UB_ERR_CUDA = -1,
+    UB_ERR_ARG = -2,
+    UB_ERR_UNSUPPORTED = -3,
+    UB_ERR_TMAP = -4,
+    UB_ERR_NOMEM = -5,
+};
+
+void set_last_error(const char* fmt, ...);
+const char* last_error();
+int num_sms();
+
+#define UB_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ub::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                               __LINE__);                                                     \
+            return ub::UB_ERR_CUDA;                                                           \
+        }                                                                                     \
+    } while (0)
+#define UB_TRY(expr)              \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != 0) return _r;   \
+    } while (0)
+
+// ---- igemm.cu -------------------------------------------------------------------------------
+struct IgemmEpilogue {
+    int kind;                 // EPI_*
+    __nv_bfloat16* out;       // plain kinds: [M][ldo]
+    long long ldo;
+    const float* bias;
+    const float* scale;
+    const float* shift;
+    float* stats;             // EPI_CONV_STATS partials; layout reported through stats_* below
+    View ct_dst;              // EPI_CONVT destination view [N,2H,2W,>=Cout] (ptr at channel 0)
+};
+struct IgemmLaunchInfo {
+    int grid, n_tiles, BN, M;
+};
+// A operand: im2col over src0 (and optionally src1 = second channel range of a zero-copy concat).
+// B operand: packed weights [ncols][taps*(C0+C1)] bf16, K-major.
+int launch_igemm(const View& src0, const View* src1, int lower, int upper, int tstride, int taps,
+                 int tapw, const __nv_bfloat16* wB, int ncols, const IgemmEpilogue& epi,
+                 IgemmLaunchInfo* info, cudaStream_t stream);
+size_t igemm_stats_floats(int ncols);  // upper bound of the stats partial buffer
+
+// Weight gradient. A side: im2col'd activations (rows = taps * (C0+C1)); B side: [Mpix][cols]
+// matrix with row pitch ldb. Result (fp32, torch layout, see wgrad_reduce_kernel) in `out`.
+int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int tstride, int taps,
+                 int tapw, const __nv_bfloat16* B, long long ldb, int cols, float* ws,
+                 size_t ws_floats, float* out, cudaStream_t stream);
+size_t wgrad_ws_floats(int rows, int cols, long long mpix);
+
+// ---- kernels.cu ------------------------------------------------------------------------------
+int launch_pack_conv3x3(const float* w, int Co, int Ci, __nv_bfloat16* wf, __nv_bfloat16* wd,
+                        cudaStream_t s);
+int launch_pack_convT(const float* w, int Ci, int Co, __nv_bfloat16* wf, __nv_bfloat16* wb,
+                      const float* bias, float* bias4, cudaStream_t s);
+int launch_bn_finalize(const float* stats, const IgemmLaunchInfo& info, int C, double count,
+                       const float* gamma, const float* beta, float* rm, float* rv,
+                       long long* nbt, float momentum, float eps, float* scale, float* shift,
+                       float* mean, float* rstd, cudaStream_t s);
+int launch_bn_finalize_flat(const float* part, int blocks, int C, double count, const float* gamma,
+                            const float* beta, float* rm, float* rv, long long* nbt,
+                            float momentum, float eps, float* scale, float* shift, float* mean,
+                            float* rstd, cudaStream_t s);
+int launch_bn_fold_eval(int C, const float* conv_bias, const float* gamma, const float* beta,
+                        const float* rm, const float* rv, float eps, float* scale, float* shift,
+                        cudaStream_t s);
+int launch_bn_apply_relu(const __nv_bfloat16* y, __nv_bfloat16* a, __nv_bfloat16* pooled, int N,
+                         int H, int W, int C, const float* scale, const float* shift,
+                         cudaStream_t s);
+int launch_maxpool2(const __nv_bfloat16* a, __nv_bfloat16* pooled, int N, int H, int W, int C,
+                    cudaStream_t s);
+struct BnBwdDesc {
+    const __nv_bfloat16* y;
+    int N, H, W, C;
+    const float *scale, *shift, *mean, *rstd;
+    bool pool_skip;
+    View g;        // direct
+    View gp;       // pooled grad
+    View gs;       // skip grad
+    int crop_h, crop_w;
+    bool has_skip;
+    float* partial;        // workspace, >= bn_bwd_partial_floats(C)
+    float* dgamma;         // out [C]
+    float* dbeta;          // out [C]
+    __nv_bfloat16* dy;     // out [N,H,W,C]
+};
+size_t bn_bwd_partial_floats(int C);
+int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s);
+
+struct FirstConvDesc {
+    const float* x;
+    int N, Ci, H, W, Co;
+    const float* w;
+    const float* bias;
+};
+size_t first_conv_partial_floats(int Co);
+int launch_first_conv_stats(const FirstConvDesc& d, float* partial, int* blocks, cudaStream_t s);
+int launch_first_conv_apply(const FirstConvDesc& d, const float* scale, const float* shift,
+                            __nv_bfloat16* a, cudaStream_t s);
+int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const float* shift,
+                          const float* mean, const float* rstd, const View& g, float* partial,
+                          float* dgamma, float* dbeta, float* dw, cudaStream_t s);
+
+int launch_head_fwd(const __nv_bfloat16* a, int N, int H, int W, int K, int NC, const float* w,
+                    const float* b, float* logits, unsigned char* mask, cudaStream_t s);
+size_t head_bwd_partial_floats(int K, int NC);
+int launch_head_bwd(const float* dlogits, const __nv_bfloat16* a, int N, int H, int W, int K,
+                    int NC, const float* w, __nv_bfloat16* da, float* partial, float* dw, float* db,
+                    cudaStream_t s);
+
+struct WceDesc {
+    const float* z; long long zs[4];
+    const long long* t; long long ts[3];
+    const float* w; long long ws[3];
+    int N, C, H, W;
+};
+size_t wce_partial_floats();
+int launch_wce(const WceDesc& d, float* loss, float* dz, float* partial, int* err, cudaStream_t s);
+int launch_scale_by_scalar(const float* in, const float* scalar, float* out, long long n,
+                           cudaStream_t s);
+int launch_fill_zero(float* p, long long n, cudaStream_t s);
+
+size_t ccl_ws_bytes(int H, int W);
+int launch_ccl(const unsigned char* mask, int H, int W, int min_size, unsigned short* out, void* ws,
+               cudaStream_t s);
+
+}  // namespace ub
