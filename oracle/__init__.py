@@ -1,0 +1,18 @@
+"""TEST INFRASTRUCTURE ONLY — CPU/torch-fp32 restatements of the reference's hot path.
+
+Nothing under ``oracle/`` is part of the product: only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s CPU-baseline / ``--impl reference`` legs may import it, and only as the checker or
+the timed CPU baseline — never as a fallback for the CUDA library.
+
+Pinning status:
+  * UNet forward/backward + WeightedCrossEntropyLoss: the reference holds no value tests (only a
+    shape assert, models/unet_model.py:219-222). The restatement in ``unet_ref.py`` is pinned
+    against the reference ITSELF, imported from /root/reference in the authoring container
+    (tests/test_oracle.py) and through golden vectors generated from it
+    (oracle/make_golden.py -> tests/golden/unet_golden.npz).
+  * get_instance_masks: pinned by 84 shipped mask -> instance pairs of the reference
+    (data/raw/processed/predictions/DIC-C2DH-HeLa/01_RES{,_INST}); a subset is committed as
+    tests/golden/ccl_golden.npz.
+  * overlap-tile inference: absent from the reference -> PARITY UNPINNED; semantics
+    are defined in ``overlap_tile_ref.py`` and checked through the aligned-tile invariant.
+"""

@@ -1,0 +1,151 @@
+"""Functional fp32 restatement of the reference U-Net and its loss (TEST INFRASTRUCTURE ONLY).
+
+Follows /root/reference/models/unet_model.py line by line but as pure functions over a
+reference-keyed ``state_dict`` (so it travels to the GPU box where /root/reference is absent):
+
+  DoubleConv      models/unet_model.py:11-17   conv3x3(p=0)+BN+ReLU twice
+  Down            :28                          MaxPool2d(2) then DoubleConv
+  Up (.up/.conv)  :45-46, 129-143              ConvTranspose2d(k=2,s=2), centre-crop skip, cat [skip, up]
+  _center_crop    :88-102
+  OutConv         :60
+  UNet.forward    :105-146
+  WeightedCrossEntropyLoss.forward  utils/losses.py:49,54,57
+  center_crop_tensor / init_weights scripts/train.py:39-51, 54-61
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+def center_crop(t: torch.Tensor, size) -> torch.Tensor:
+    """models/unet_model.py:88-102 and scripts/train.py:39-51 (identical arithmetic)."""
+    h, w = t.shape[-2:]
+    th, tw = size
+    hs, ws = max(0, (h - th) // 2), max(0, (w - tw) // 2)
+    return t[..., hs:hs + th, ws:ws + tw]
+
+
+def _conv_bn_relu(x, sd, conv, bn, training, buffers_out, momentum=0.1, eps=1e-5):
+    x = F.conv2d(x, sd[f"{conv}.weight"], sd[f"{conv}.bias"])
+    rm, rv = sd[f"{bn}.running_mean"], sd[f"{bn}.running_var"]
+    if training and buffers_out is not None:
+        rm, rv = rm.clone(), rv.clone()
+        buffers_out[f"{bn}.running_mean"], buffers_out[f"{bn}.running_var"] = rm, rv
+        buffers_out[f"{bn}.num_batches_tracked"] = sd[f"{bn}.num_batches_tracked"] + 1
+    elif training:
+        rm = rv = None
+    x = F.batch_norm(x, rm, rv, sd[f"{bn}.weight"], sd[f"{bn}.bias"], training, momentum, eps)
+    return F.relu(x)
+
+
+def _double_conv(x, sd, prefix, training, buffers_out):
+    x = _conv_bn_relu(x, sd, f"{prefix}.0", f"{prefix}.1", training, buffers_out)
+    return _conv_bn_relu(x, sd, f"{prefix}.3", f"{prefix}.4", training, buffers_out)
+
+
+def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = False,
+                 levels: int = 5, buffers_out: Optional[dict] = None,
+                 capture: Optional[dict] = None) -> torch.Tensor:
+    """logits = UNet(x). ``buffers_out`` (dict) receives the updated BN buffers in training mode;
+    ``capture`` (dict) receives the intermediate block outputs (teacher forcing)."""
+    feats = [_double_conv(x, sd, "inc.double_conv", training, buffers_out)]
+    for i in range(1, levels):
+        p = F.max_pool2d(feats[-1], 2)
+        feats.append(_double_conv(p, sd, f"down{i}.maxpool_conv.1.double_conv", training,
+                                  buffers_out))
+    y = feats[-1]
+    for j in range(1, levels):
+        up = F.conv_transpose2d(y, sd[f"up{j}.up.weight"], sd[f"up{j}.up.bias"], stride=2)
+        skip = center_crop(feats[levels - 1 - j], up.shape[-2:])
+        y = _double_conv(torch.cat([skip, up], dim=1), sd, f"up{j}.conv.double_conv", training,
+                         buffers_out)
+        if capture is not None:
+            capture[f"up{j}"] = y
+    if capture is not None:
+        for i, f in enumerate(feats):
+            capture[f"x{i + 1}"] = f
+    return F.conv2d(y, sd["outc.conv.weight"], sd["outc.conv.bias"])
+
+
+def weighted_cross_entropy(logits, targets, weight_maps):
+    """utils/losses.py:49 (CE reduction='none'), :54 (* w), :57 (.mean())."""
+    return (F.cross_entropy(logits, targets, reduction="none") * weight_maps).mean()
+
+
+def out_size(h: int, levels: int = 5) -> int:
+    """Spatial size of the logits for an input of size h (floor-mode pooling)."""
+    for i in range(levels):
+        h -= 4
+        if i < levels - 1:
+            h //= 2
+    for _ in range(levels - 1):
+        h = h * 2 - 4
+    return h
+
+
+# ------------------------------------------------------------------------------------------------
+# Reference-identical construction of a random-init state_dict. The module tree is declared in the
+# reference's order (models/unet_model.py:73-85) with stock torch layers, so that
+# ``torch.manual_seed(s)`` consumes the RNG exactly like ``UNet(n_channels, n_classes)`` there,
+# followed by ``model.apply(init_weights)`` (scripts/train.py:54-61,94).
+# ------------------------------------------------------------------------------------------------
+def _double_conv_modules(cin, cout):
+    import torch.nn as nn
+
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, padding=0), nn.BatchNorm2d(cout), nn.ReLU(True),
+                         nn.Conv2d(cout, cout, 3, padding=0), nn.BatchNorm2d(cout), nn.ReLU(True))
+
+
+def make_state_dict(n_channels=1, n_classes=2, seed=0, base=64, levels=5, init=True,
+                    device="cpu"):
+    import torch.nn as nn
+
+    torch.manual_seed(seed)
+    c = [base << i for i in range(levels)]
+    mods = {"inc.double_conv": _double_conv_modules(n_channels, c[0])}
+    for i in range(1, levels):
+        mods[f"down{i}.maxpool_conv.1.double_conv"] = _double_conv_modules(c[i - 1], c[i])
+    for j in range(1, levels):
+        cp = c[levels - j]
+        mods[f"up{j}.up"] = nn.ConvTranspose2d(cp, cp // 2, kernel_size=2, stride=2)
+        mods[f"up{j}.conv.double_conv"] = _double_conv_modules(cp, cp // 2)
+    mods["outc.conv"] = nn.Conv2d(c[0], n_classes, kernel_size=1)
+    if init:  # scripts/train.py:54-61 — nn.Conv2d only (ConvTranspose2d keeps torch's default)
+        for m in mods.values():
+            for sub in m.modules():
+                if isinstance(sub, nn.Conv2d):
+                    nn.init.kaiming_normal_(sub.weight, mode="fan_out", nonlinearity="relu")
+                    if sub.bias is not None:
+                        nn.init.constant_(sub.bias, 0)
+                elif isinstance(sub, nn.BatchNorm2d):
+                    nn.init.constant_(sub.weight, 1)
+                    nn.init.constant_(sub.bias, 0)
+    sd = {}
+    for prefix, m in mods.items():
+        for k, v in m.state_dict().items():
+            sd[f"{prefix}.{k}"] = v.detach().to(device)
+    return sd
+
+
+def synthetic_batch(n, size=512, out=None, seed=1234, levels=5, device="cpu"):
+    """DIC-C2DH-HeLa-shaped synthetic sample: low-contrast image in [0,1], target =
+    union of random ellipses (fg ~0.45), two-valued class-balance weight map, target and
+    weights centre-cropped + squeezed exactly like scripts/train.py:118-126 (non-contiguous)."""
+    g = torch.Generator().manual_seed(seed)
+    out = out_size(size, levels) if out is None else out
+    img = 0.4 + 0.2 * torch.rand(n, 1, size, size, generator=g)
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing="ij")
+    mask = torch.zeros(n, 1, size, size, dtype=torch.bool)
+    for b in range(n):
+        for _ in range(10):
+            cy, cx = (torch.rand(2, generator=g) * size).tolist()
+            ry, rx = (size * (0.08 + 0.12 * torch.rand(2, generator=g))).tolist()
+            mask[b, 0] |= ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1.0
+    f_fg = mask.float().mean().clamp(0.05, 0.95)
+    wmap = torch.where(mask, 10 + 1 / f_fg, 10 + 1 / (1 - f_fg)).float()
+    t = center_crop(mask.long(), (out, out)).squeeze(1)
+    w = center_crop(wmap, (out, out)).squeeze(1)
+    return img.to(device), t.to(device), w.to(device)

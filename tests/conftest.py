@@ -8,7 +8,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _exact_fp32_references():
+    """torch references must be true fp32: cuDNN / cuBLAS default to TF32 on Blackwell."""
+    try:
+        import torch
+
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:  # pragma: no cover
+        pass
+
+
 def pytest_configure(config):
+    _exact_fp32_references()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 
 

@@ -1,0 +1,337 @@
+"""Drop-in ``UNet`` for the reference's models/unet_model.py.
+
+Same constructor, attributes, sub-module tree and ``state_dict`` keys as the reference
+(models/unet_model.py:5-85: ``inc.double_conv.{0,1,3,4}``, ``downK.maxpool_conv.1.double_conv.*``,
+``upK.up``, ``upK.conv.double_conv.*``, ``outc.conv``; 82 parameters, 54 buffers), so
+``model.apply(init_weights)``, ``.to()``, ``load_state_dict`` and ``optim.SGD(model.parameters())``
+(scripts/train.py:93-97, scripts/predict.py:120-123) work unchanged. The sub-modules are genuine
+``nn.Conv2d / nn.BatchNorm2d / nn.ConvTranspose2d`` *parameter holders*; ``forward`` is a single
+``torch.autograd.Function`` over the C-ABI network executor of libunetb200 (sm_100a). There is no
+CPU path and no cuDNN/cuBLAS dispatch: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check
+
+_NO_SUBMODULE_FWD = ("only UNet.forward is implemented by the B200 library; the building blocks "
+                     "are parameter holders (there is no ATen/cuDNN fallback path)")
+
+
+class DoubleConv(nn.Module):
+    """[Conv3x3(valid) -> BatchNorm2d -> ReLU] x 2 — parameter holder (reference :5-21)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        layers = []
+        for cin in (in_channels, out_channels):
+            layers += [nn.Conv2d(cin, out_channels, kernel_size=3, padding=0),
+                       nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True)]
+        self.double_conv = nn.Sequential(*layers)
+
+    def forward(self, x):  # pragma: no cover - never on the product path
+        raise NotImplementedError(_NO_SUBMODULE_FWD)
+
+
+class Down(nn.Module):
+    """MaxPool2d(2) then DoubleConv — parameter holder (reference :23-33)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), DoubleConv(in_channels, out_channels))
+
+    def forward(self, x):  # pragma: no cover
+        raise NotImplementedError(_NO_SUBMODULE_FWD)
+
+
+class Up(nn.Module):
+    """ConvTranspose2d(k=2,s=2) then DoubleConv over [cropped skip, up] (reference :35-54)."""
+
+    def __init__(self, in_channels_from_prev_decoder: int, skip_channels: int, out_channels: int,
+                 bilinear: bool = True):
+        super().__init__()
+        if bilinear:
+            raise NotImplementedError(
+                "bilinear=True (nn.Upsample) is outside the B200 hot path; the reference's "
+                "train.py / predict.py use the transposed-convolution branch")
+        half = in_channels_from_prev_decoder // 2
+        self.up = nn.ConvTranspose2d(in_channels_from_prev_decoder, half, kernel_size=2, stride=2)
+        self.conv = DoubleConv(half + skip_channels, out_channels)
+
+    def forward(self, x1, x2_cropped):  # pragma: no cover
+        raise NotImplementedError(_NO_SUBMODULE_FWD)
+
+
+class OutConv(nn.Module):
+    """1x1 convolution to n_classes logits (reference :56-63)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
+
+    def forward(self, x):  # pragma: no cover
+        raise NotImplementedError(_NO_SUBMODULE_FWD)
+
+
+# ------------------------------------------------------------------------------------------------
+class _Plan:
+    """Python handle of a ``ub_plan`` (one per input shape / mode / device)."""
+
+    def __init__(self, n, cin, h, w, base, levels, n_classes, training, device):
+        self.lib = _lib.load()
+        self.device = device
+        self.training = training
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            check(self.lib.ub_plan_create(C.byref(handle), n, cin, h, w, base, levels, n_classes,
+                                          1 if training else 0), "ub_plan_create")
+        self.handle = handle
+        oh, ow = C.c_int(), C.c_int()
+        check(self.lib.ub_plan_out_hw(handle, C.byref(oh), C.byref(ow)))
+        self.out_hw = (oh.value, ow.value)
+        self.n, self.n_classes = n, n_classes
+        self.num_params = self.lib.ub_plan_num_params(handle)
+        self.num_stages = self.lib.ub_plan_num_stages(handle)
+        self.numels = [int(self.lib.ub_plan_param_numel(handle, i)) for i in range(self.num_params)]
+        self.offsets = [0]
+        for k in self.numels:
+            self.offsets.append(self.offsets[-1] + k)
+        self.stage_ranges = []
+        for s in range(self.num_stages):
+            f, c = C.c_int(), C.c_int()
+            check(self.lib.ub_plan_stage_params(handle, s, C.byref(f), C.byref(c)))
+            self.stage_ranges.append((f.value, c.value))
+        self.bound_ptrs = None
+        self.bound_buf_ptrs = None
+        self.packed_versions = None
+        self.generation = 0
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.ub_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def device_bytes(self) -> int:
+        return int(self.lib.ub_plan_device_bytes(self.handle))
+
+    def bind(self, params, bn_modules):
+        ptrs = tuple(p.data_ptr() for p in params)
+        if ptrs != self.bound_ptrs:
+            arr = (C.c_void_p * len(ptrs))(*ptrs)
+            check(self.lib.ub_plan_bind_params(self.handle, arr, len(ptrs)), "ub_plan_bind_params")
+            self.bound_ptrs = ptrs
+            self.packed_versions = None
+        bptrs = tuple((m.running_mean.data_ptr(), m.running_var.data_ptr(),
+                       m.num_batches_tracked.data_ptr()) for m in bn_modules)
+        if bptrs != self.bound_buf_ptrs:
+            k = len(bptrs)
+            rm = (C.c_void_p * k)(*[b[0] for b in bptrs])
+            rv = (C.c_void_p * k)(*[b[1] for b in bptrs])
+            nb = (C.c_void_p * k)(*[b[2] for b in bptrs])
+            check(self.lib.ub_plan_bind_bn_buffers(self.handle, rm, rv, nb, k),
+                  "ub_plan_bind_bn_buffers")
+            self.bound_buf_ptrs = bptrs
+        versions = tuple(p._version for p in params)
+        if versions != self.packed_versions:
+            check(self.lib.ub_plan_pack_weights(self.handle, _stream()), "ub_plan_pack_weights")
+            self.packed_versions = versions
+
+    def forward(self, x, want_mask=False):
+        oh, ow = self.out_hw
+        logits = torch.empty(self.n, self.n_classes, oh, ow, dtype=torch.float32, device=x.device)
+        mask = (torch.empty(self.n, oh, ow, dtype=torch.uint8, device=x.device)
+                if want_mask else None)
+        check(self.lib.ub_plan_forward(self.handle, C.c_void_p(x.data_ptr()),
+                                       C.c_void_p(logits.data_ptr()),
+                                       C.c_void_p(mask.data_ptr() if mask is not None else 0),
+                                       _stream()), "ub_plan_forward")
+        self.generation += 1
+        return logits, mask
+
+    def backward(self, dlogits, stage_hook: Optional[Callable] = None):
+        flat = torch.empty(self.offsets[-1], dtype=torch.float32, device=dlogits.device)
+        views = [flat[self.offsets[i]:self.offsets[i + 1]] for i in range(self.num_params)]
+        arr = (C.c_void_p * self.num_params)(*[v.data_ptr() for v in views])
+        dl = C.c_void_p(dlogits.data_ptr())
+        for s in range(self.num_stages):
+            check(self.lib.ub_plan_backward_stage(self.handle, s, dl, arr, _stream()),
+                  f"ub_plan_backward_stage({s})")
+            if stage_hook is not None:
+                f, c = self.stage_ranges[s]
+                stage_hook(s, flat[self.offsets[f]:self.offsets[f + c]])
+        return flat, views
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _UNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        plan = module._plan_for(x, training=True)
+        logits, _ = plan.forward(x)
+        ctx.plan = plan
+        ctx.generation = plan.generation
+        ctx.module = module
+        ctx.shapes = [p.shape for p in params]
+        ctx.save_for_backward(x)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        plan = ctx.plan
+        if plan.generation != ctx.generation:
+            raise RuntimeError("UNet (B200): the saved activations of this forward pass were "
+                               "overwritten by a later forward of the same shape; call backward "
+                               "before the next training-mode forward")
+        (x,) = ctx.saved_tensors  # keeps the input alive: the first conv recomputes from it
+        dlogits = dlogits.contiguous().float()
+        module = ctx.module
+        _, views = plan.backward(dlogits, stage_hook=module._stage_hook)
+        if module._backward_done_hook is not None:
+            module._backward_done_hook()
+        grads = [v.view(s) for v, s in zip(views, ctx.shapes)]
+        return (None, None, *grads)
+
+
+class UNet(nn.Module):
+    """``UNet(n_channels, n_classes, bilinear=False)`` — reference signature
+    (models/unet_model.py:65-66). ``base_channels`` / ``levels`` are trailing keyword knobs with the
+    reference's hard-coded values (64-128-256-512-1024, :73-82) as defaults."""
+
+    def __init__(self, n_channels, n_classes, bilinear=False, *, base_channels: int = 64,
+                 levels: int = 5):
+        super().__init__()
+        self.n_channels = n_channels
+        self.n_classes = n_classes
+        self.bilinear = bilinear
+        self.base_channels = base_channels
+        self.levels = levels
+        if levels == 5:
+            c = [base_channels << i for i in range(5)]
+            self.inc = DoubleConv(n_channels, c[0])
+            self.down1 = Down(c[0], c[1])
+            self.down2 = Down(c[1], c[2])
+            self.down3 = Down(c[2], c[3])
+            self.down4 = Down(c[3], c[4])
+            self.up1 = Up(c[4], c[3], c[3], bilinear)
+            self.up2 = Up(c[3], c[2], c[2], bilinear)
+            self.up3 = Up(c[2], c[1], c[1], bilinear)
+            self.up4 = Up(c[1], c[0], c[0], bilinear)
+            self.outc = OutConv(c[0], n_classes)
+        else:
+            c = [base_channels << i for i in range(levels)]
+            self.inc = DoubleConv(n_channels, c[0])
+            for i in range(1, levels):
+                setattr(self, f"down{i}", Down(c[i - 1], c[i]))
+            for j in range(1, levels):
+                cp = c[levels - j]
+                setattr(self, f"up{j}", Up(cp, cp // 2, cp // 2, bilinear))
+            self.outc = OutConv(c[0], n_classes)
+        self._plans: dict = {}
+        self._stage_hook: Optional[Callable] = None
+        self._backward_done_hook: Optional[Callable] = None
+
+    # -- reference helper kept for API parity (models/unet_model.py:88-102) -------------------
+    def _center_crop(self, feature_map, target_size):
+        _, _, h, w = feature_map.size()
+        th, tw = target_size
+        hs, ws = max(0, (h - th) // 2), max(0, (w - tw) // 2)
+        return feature_map[:, :, hs:hs + th, ws:ws + tw]
+
+    # -- parameter / buffer traversal in the library's canonical order --------------------------
+    def _blocks(self):
+        enc = [self.inc] + [getattr(self, f"down{i}").maxpool_conv[1] for i in range(1, self.levels)]
+        ups = [getattr(self, f"up{j}") for j in range(1, self.levels)]
+        return enc, ups
+
+    def _ordered_params(self):
+        enc, ups = self._blocks()
+        out = []
+
+        def dc(block):
+            seq = block.double_conv
+            for conv, bn in ((seq[0], seq[1]), (seq[3], seq[4])):
+                out.extend([conv.weight, conv.bias, bn.weight, bn.bias])
+
+        for b in enc:
+            dc(b)
+        for u in ups:
+            out.extend([u.up.weight, u.up.bias])
+            dc(u.conv)
+        out.extend([self.outc.conv.weight, self.outc.conv.bias])
+        return out
+
+    def _ordered_bns(self):
+        enc, ups = self._blocks()
+        out = []
+        for b in enc + [u.conv for u in ups]:
+            out.extend([b.double_conv[1], b.double_conv[4]])
+        return out
+
+    def _plan_for(self, x: torch.Tensor, training: bool) -> _Plan:
+        n, c, h, w = x.shape
+        key = (n, c, h, w, training, x.device.index)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 8:  # keep the arena bounded when shapes vary
+                self._plans.pop(next(iter(self._plans)))
+            plan = _Plan(n, c, h, w, self.base_channels, self.levels, self.n_classes, training,
+                         x.device)
+            self._plans[key] = plan
+        plan.bind(self._ordered_params(), self._ordered_bns())
+        return plan
+
+    def _check_input(self, x):
+        if not isinstance(x, torch.Tensor) or x.dim() != 4:
+            raise ValueError("UNet expects a (N, C, H, W) tensor")
+        if not x.is_cuda:
+            raise RuntimeError("UNet (B200) runs only on a CUDA device (sm_100a); move the model "
+                               "and input to 'cuda' — there is no CPU fallback")
+        if x.shape[1] != self.n_channels:
+            raise ValueError(f"expected {self.n_channels} input channels, got {x.shape[1]}")
+        p = self.outc.conv.weight
+        if p.device != x.device or p.dtype != torch.float32:
+            raise RuntimeError("UNet (B200): parameters must be fp32 on the same CUDA device as the "
+                               "input (bf16 operand copies are kept internally)")
+        return x.contiguous().float()
+
+    def forward(self, x):
+        x = self._check_input(x)
+        with torch.cuda.device(x.device):
+            if self.training and torch.is_grad_enabled():
+                return _UNetFunction.apply(self, x, *self._ordered_params())
+            plan = self._plan_for(x, training=self.training)
+            logits, _ = plan.forward(x)
+            return logits
+
+    @torch.no_grad()
+    def predict_mask(self, x):
+        """Eval-mode forward returning (logits, uint8 mask) with mask = 255 where
+        softmax(logits)[:,1] > 0.5 (reference scripts/predict.py:81-92), fused in the head kernel."""
+        if self.training:
+            raise RuntimeError("predict_mask needs model.eval()")
+        x = self._check_input(x)
+        with torch.cuda.device(x.device):
+            plan = self._plan_for(x, training=False)
+            return plan.forward(x, want_mask=True)
+
+    # -- data-parallel support -----------------------------------------------------------------
+    def set_backward_hooks(self, stage_hook: Optional[Callable], done_hook: Optional[Callable]):
+        """stage_hook(stage_index, flat_fp32_grad_slice) runs right after the kernels of a backward
+        stage were enqueued; done_hook() after the last stage (see parallel.py)."""
+        self._stage_hook = stage_hook
+        self._backward_done_hook = done_hook
+
+    def arena_bytes(self) -> int:
+        return sum(p.device_bytes() for p in self._plans.values())
