@@ -1,0 +1,163 @@
+"""CPU tests: the oracle restatements against the reference's golden vectors (and against the live
+reference when /root/reference is mounted), and the C-ABI surface. No GPU needed."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+
+from oracle import ccl_ref, unet_ref  # noqa: E402
+
+
+def _case(blob, name):
+    return {k[len(name) + 1:]: blob[k] for k in blob.files if k.startswith(name + "/")}
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(GOLD, "unet_golden.npz"))
+
+
+@pytest.mark.parametrize("name", ["train_n2_s188", "train_n1_s220", "eval_n1_s252"])
+def test_unet_oracle_matches_reference_golden(golden, name):
+    c = _case(golden, name)
+    n, size, sw, sx, training = [int(v) for v in c["meta"]]
+    sd = unet_ref.make_state_dict(1, 2, seed=sw)
+    img, t, w = unet_ref.synthetic_batch(n, size=size, seed=sx)
+    if training:
+        params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()
+                  and "running" not in k}
+        full = dict(sd)
+        full.update(params)
+        bufs = {}
+        logits = unet_ref.unet_forward(full, img, training=True, buffers_out=bufs)
+        loss = unet_ref.weighted_cross_entropy(logits, t, w)
+        loss.backward()
+        assert abs(float(loss) - float(c["loss"])) <= 1e-6 * abs(float(c["loss"]))
+        for k, p in params.items():
+            g = p.grad.flatten()
+            ref_norm = float(c[f"gnorm/{k}"])
+            assert abs(float(g.double().norm()) - ref_norm) <= 1e-4 * ref_norm + 1e-9, k
+            np.testing.assert_allclose(g[torch.from_numpy(c[f"gidx/{k}"])].numpy(), c[f"gval/{k}"],
+                                       rtol=1e-3, atol=1e-5 * ref_norm + 1e-9)
+        for k in [k for k in c if k.startswith("buf/")]:
+            np.testing.assert_allclose(bufs[k[4:]].numpy(), c[k], rtol=1e-5, atol=1e-6)
+    else:
+        g = torch.Generator().manual_seed(99)
+        for k in [k for k in sd if k.endswith("running_mean")]:
+            nf = sd[k].numel()
+            sd[k] = torch.randn(nf, generator=g) * 0.1
+            sd[k.replace("running_mean", "running_var")] = 0.5 + torch.rand(nf, generator=g)
+        with torch.no_grad():
+            logits = unet_ref.unet_forward(sd, img, training=False)
+    np.testing.assert_allclose(logits.detach().numpy(), c["logits"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_unet_oracle_matches_live_reference():
+    sys.dont_write_bytecode = True
+    spec = importlib.util.spec_from_file_location("ref_unet_model_live",
+                                                  os.path.join(REF, "models", "unet_model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(5)
+    model = mod.UNet(1, 2).train()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = torch.rand(1, 1, 204, 204)
+    bufs = {}
+    mine = unet_ref.unet_forward(sd, x, training=True, buffers_out=bufs)
+    ref = model(x)
+    assert torch.allclose(mine, ref, rtol=1e-5, atol=1e-6)
+    new = model.state_dict()
+    for k, v in bufs.items():
+        assert torch.allclose(v.float(), new[k].float(), rtol=1e-5, atol=1e-6), k
+    model.eval()
+    with torch.no_grad():
+        assert torch.allclose(unet_ref.unet_forward(new, x, training=False), model(x), rtol=1e-5,
+                              atol=1e-6)
+    assert unet_ref.out_size(512) == 324 and unet_ref.out_size(572) == 388
+
+
+def test_drop_in_module_tree_matches_reference_state_dict():
+    """Same keys, shapes and dtypes as the reference module tree and same seeded init."""
+    from unet_segmentation_b200.unet import UNet
+
+    torch.manual_seed(0)
+    m = UNet(1, 2)
+    ours = m.state_dict()
+    ref = unet_ref.make_state_dict(1, 2, seed=0, init=False)
+    assert list(ours.keys()) == list(ref.keys())
+    assert len(list(m.parameters())) == 82 and len(list(m.buffers())) == 54
+    for k in ref:
+        assert ours[k].shape == ref[k].shape and ours[k].dtype == ref[k].dtype, k
+        assert torch.equal(ours[k], ref[k]), k
+    assert sum(p.numel() for p in m.parameters()) == 31_042_434
+    # canonical order handed to the C library == named_parameters order
+    assert [id(p) for p in m._ordered_params()] == [id(p) for p in m.parameters()]
+    bn_names = [n for n, mod in m.named_modules() if isinstance(mod, torch.nn.BatchNorm2d)]
+    assert [id(b) for b in m._ordered_bns()] == [id(dict(m.named_modules())[n]) for n in bn_names]
+
+
+def test_drop_in_rejects_cpu_and_bilinear():
+    from unet_segmentation_b200.loss import WeightedCrossEntropyLoss
+    from unet_segmentation_b200.unet import UNet
+
+    m = UNet(1, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 1, 188, 188))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        WeightedCrossEntropyLoss()(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, dtype=torch.long),
+                                   torch.ones(1, 4, 4))
+    with pytest.raises(NotImplementedError):
+        UNet(1, 2, bilinear=True)
+
+
+def test_ccl_oracle_matches_reference_golden_pairs():
+    blob = np.load(os.path.join(GOLD, "ccl_golden.npz"))
+    ids = sorted(k[4:] for k in blob.files if k.startswith("mask"))
+    assert len(ids) >= 4
+    for i in ids:
+        out = ccl_ref.get_instance_masks(blob[f"mask{i}"], min_size=15)
+        assert out.dtype == np.uint16
+        assert np.array_equal(out, blob[f"inst{i}"]), i
+
+
+def test_ccl_pure_python_agrees_on_small_cases():
+    rng = np.random.default_rng(3)
+    for shape, p in [((9, 13), 0.5), ((16, 16), 0.7), ((1, 30), 0.6), ((12, 12), 0.0)]:
+        m = (rng.random(shape) < p).astype(np.uint8) * 255
+        for ms in (1, 4, 15):
+            assert np.array_equal(ccl_ref.get_instance_masks(m, ms),
+                                  ccl_ref.get_instance_masks_pure(m, ms))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_ccl_oracle_matches_all_shipped_pairs():
+    from PIL import Image
+
+    base = os.path.join(REF, "data/raw/processed/predictions/DIC-C2DH-HeLa")
+    n = 0
+    for i in range(0, 84, 7):
+        m = np.array(Image.open(os.path.join(base, "01_RES", f"mask{i:03d}.tif")))
+        inst = np.array(Image.open(os.path.join(base, "01_RES_INST", f"m{i:03d}.tif")))
+        assert np.array_equal(ccl_ref.get_instance_masks(m, 15), inst.astype(np.uint16))
+        n += 1
+    assert n == 12
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from unet_segmentation_b200 import _lib
+
+    lib = _lib.load()
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(lib, name), f"libunetb200.so does not export {name}"
+    assert set(declared) == set(_lib._SIGNATURES)
+    assert lib.ub_version() >= 100
