@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 U-Net hot path (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one reference training iteration (scripts/train.py:108-133): zero_grad -> UNet forward ->
+centre-crop + squeeze of target / weight map -> WeightedCrossEntropyLoss -> backward ->
+SGD(lr 1e-4, momentum 0.99) step, on BASELINE.json configs[1]: batch 16 x 1 x 512 x 512 synthetic
+DIC-C2DH-HeLa-shaped images with weight maps per GPU (weak scaling), bf16 tensor-core operands
+with fp32 accumulation and fp32 master weights. Rank 0 prints ONE JSON line.
+
+  value     img/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e       img/s through the public API with HOST (pinned) buffers: H2D of image / mask / weight
+            map and D2H of the loss inside the timed region, every step
+  roofline  the dominant kernel class timed in-step with CUDA events on the launching stream
+            (ub_plan_profile_*), algorithmic FLOPs / duration against MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference (fp32 torch on the host cores), bounded sample
+  --impl reference  times that CPU path alone (rank 0 only) and prints the same line shape
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "unet_512x512_train_images_per_sec"
+UNIT = "img/s"
+BATCH_PER_GPU = 16
+SIZE = 512
+FLOP_PER_IMG_STEP = 671.28e9      # 3 x fwd - first-layer dgrad
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        d["_source"] = "measured"
+        return d
+    except Exception:
+        d = dict(FALLBACK_PEAKS)
+        d["_source"] = "fallback"
+        return d
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for p in self.samples:
+            try:
+                sm.append(float(p[0])); smax.append(float(p[1])); power.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(steps: int, warmup: int, threads: int | None = None):
+    """The reference's CPU path (oracle port, fp32 torch): BASELINE.json configs[0], one
+    1x1x512x512 sample per step: zero_grad -> forward -> loss -> backward."""
+    import torch
+
+    from oracle import unet_ref
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = unet_ref.make_state_dict(1, 2, seed=0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and "running" not in k}
+    full = dict(sd)
+    full.update(params)
+    img, t, w = unet_ref.synthetic_batch(1, size=SIZE, seed=1234)
+    times = []
+    for it in range(warmup + steps):
+        for p in params.values():
+            p.grad = None
+        t0 = time.perf_counter()
+        bufs = {}
+        logits = unet_ref.unet_forward(full, img, training=True, buffers_out=bufs)
+        loss = unet_ref.weighted_cross_entropy(logits, t, w)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    return med, sum(times), torch.get_num_threads()
+
+
+def run_reference_arm(args, rank: int):
+    if rank != 0:
+        return
+    med, total, threads = cpu_reference_step_time(args.steps, max(args.warmup, 1))
+    value = 1.0 / med
+    sample = (f"{args.steps} timed steps of one 1x1x{SIZE}x{SIZE} sample (batch-16 workload sampled "
+              f"at 1 image/step), fp32 torch CPU, median step {med:.3f} s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": med * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "UNet(1,2) 64->1024 train step (fwd + weighted CE + bwd), 512x512, "
+                               "CPU oracle port of the reference", "batch_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-infer", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0 and world > 1:
+        print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    warmup = max(args.warmup, 3)
+
+    from oracle import unet_ref  # synthetic data generator + seeded init only (not timed)
+    from unet_segmentation_b200 import _lib, parallel
+    from unet_segmentation_b200.loss import WeightedCrossEntropyLoss
+    from unet_segmentation_b200.unet import UNet
+
+    lib = _lib.load()
+    N = args.batch
+    model = UNet(1, 2)
+    model.load_state_dict(unet_ref.make_state_dict(1, 2, seed=0))   # reference ctor + init_weights
+    model = model.to(dev).train()
+    parallel.broadcast_parameters(model)
+    reducer = parallel.StageGradAllReducer(model) if world > 1 else None
+    criterion = WeightedCrossEntropyLoss()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.99)   # scripts/train.py:97
+
+    # synthetic data, seed = 1234 + rank; full-size mask / weight map as the dataset
+    # hands them over (scripts/train.py:108-112), cropped on the device like train.py:118-126
+    g = torch.Generator().manual_seed(1234 + rank)
+    img_h = (0.4 + 0.2 * torch.rand(N, 1, SIZE, SIZE, generator=g)).pin_memory()
+    yy, xx = torch.meshgrid(torch.arange(SIZE), torch.arange(SIZE), indexing="ij")
+    m = torch.zeros(N, 1, SIZE, SIZE, dtype=torch.bool)
+    for b in range(N):
+        for _ in range(10):
+            cy, cx = (torch.rand(2, generator=g) * SIZE).tolist()
+            ry, rx = (SIZE * (0.08 + 0.12 * torch.rand(2, generator=g))).tolist()
+            m[b, 0] |= ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1.0
+    f_fg = m.float().mean().clamp(0.05, 0.95)
+    mask_h = m.long().pin_memory()
+    wmap_h = torch.where(m, 10 + 1 / f_fg, 10 + 1 / (1 - f_fg)).float().pin_memory()
+    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+    h2d_bytes = img_h.numel() * 4 + mask_h.numel() * 8 + wmap_h.numel() * 4
+    d2h_bytes = 4
+
+    out_hw = unet_ref.out_size(SIZE)
+    s0 = (SIZE - out_hw) // 2
+
+    def crop(t):
+        return t[:, :, s0:s0 + out_hw, s0:s0 + out_hw].squeeze(1)
+
+    def step(img, mask, wmap):
+        opt.zero_grad(set_to_none=True)
+        logits = model(img)
+        loss = criterion(logits, crop(mask), crop(wmap))
+        loss.backward()
+        opt.step()
+        return loss
+
+    img_d, mask_d, wmap_d = img_h.to(dev), mask_h.to(dev), wmap_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput (value) ----------------
+    for _ in range(warmup):
+        loss = step(img_d, mask_d, wmap_d)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = int(lib.ub_launch_count())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(img_d, mask_d, wmap_d)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = int(lib.ub_launch_count()) - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(loss)
+    ms_per_step = ms_total / args.steps
+    value = world * N * args.steps / (ms_total * 1e-3)
+
+    # ---------------- end-to-end with host buffers (e2e) ----------------
+    def e2e_step():
+        img = img_h.to(dev, non_blocking=True)
+        mask = mask_h.to(dev, non_blocking=True)
+        wmap = wmap_h.to(dev, non_blocking=True)
+        loss = step(img, mask, wmap)
+        loss_h.copy_(loss.detach(), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * N * args.steps / (e2e_ms * 1e-3)
+
+    # ---------------- in-step kernel timing (roofline) ----------------
+    roofline, breakdown = None, None
+    peaks = load_peaks()
+    if rank == 0:
+        plan = next(p for k, p in model._plans.items() if k[4])   # the training plan
+        ncls = lib.ub_plan_profile_classes()
+        import ctypes as C
+
+        lib.ub_plan_profile_enable(plan.handle, 1)
+    prof_steps = min(args.steps, 5)
+    for _ in range(prof_steps):
+        step(img_d, mask_d, wmap_d)
+    barrier()
+    if rank == 0:
+        ms = (C.c_double * ncls)(); fl = (C.c_double * ncls)(); by = (C.c_double * ncls)()
+        ln = (C.c_int * ncls)()
+        _lib.check(lib.ub_plan_profile_collect(plan.handle, ms, fl, by, ln), "profile_collect")
+        lib.ub_plan_profile_enable(plan.handle, 0)
+        breakdown = {}
+        for c in range(ncls):
+            name = lib.ub_plan_profile_class_name(c).decode()
+            if ln[c]:
+                breakdown[name] = {"ms_per_step": ms[c] / prof_steps,
+                                   "groups_per_step": ln[c] / prof_steps,
+                                   "tflops": (fl[c] / (ms[c] * 1e-3) / 1e12) if fl[c] else None,
+                                   "gbs": by[c] / (ms[c] * 1e-3) / 1e9}
+        dom = max(breakdown, key=lambda k: breakdown[k]["ms_per_step"])
+        d = breakdown[dom]
+        tensor_bound = d["tflops"] is not None
+        if tensor_bound:
+            peak = float(peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"])
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": d["tflops"], "peak": peak,
+                        "unit": "TFLOP/s", "frac": d["tflops"] / peak, "traffic": None,
+                        "peak_source": f"{peaks['_source']} sustained bf16 (kernel timed in-step)",
+                        "share_of_step": d["ms_per_step"] / ms_per_step}
+        else:
+            peak = float(peaks["hbm_gbs"])
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": peak,
+                        "unit": "GB/s", "frac": d["gbs"] / peak, "traffic": None,
+                        "peak_source": f"{peaks['_source']} HBM copy",
+                        "share_of_step": d["ms_per_step"] / ms_per_step}
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        med, total, threads = cpu_reference_step_time(steps=5, warmup=2)
+        cpu_baseline = {"value": 1.0 / med, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"5 timed + 2 warm-up steps of one 1x1x{SIZE}x{SIZE} sample "
+                                  f"(configs[0]); oracle port of the reference on "
+                                  f"{os.cpu_count()} host CPUs, median {med:.3f} s/step"}
+
+    if rank == 0:
+        sus = float(peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"UNet(1,2) 64->1024 bf16 training step, batch {N}/GPU x 1x"
+                                   f"{SIZE}x{SIZE} + weight maps (BASELINE configs[1]"
+                                   f"{'/[2]' if world > 1 else ''})",
+                       "global_batch": world * N, "parallelism": f"dp{world}",
+                       "optimizer": "SGD(lr=1e-4, momentum=0.99) torch foreach, inside the step",
+                       "bn": "per-rank batch statistics", "l2": "per-step working set 11 GB >> 126 MB L2",
+                       "first_conv": "fp32 CUDA-core (SURVEY F4)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "step_tflops": world * N * FLOP_PER_IMG_STEP / (ms_per_step * 1e-3) / 1e12,
+            "step_frac_of_bf16_sustained": N * FLOP_PER_IMG_STEP / (ms_per_step * 1e-3) / 1e12 / sus,
+            "kernel_breakdown": breakdown,
+            "final_loss": final_loss,
+            "allreduce": ({"collectives_per_step": reducer.n_collectives /
+                           (args.steps * 2 + warmup + 2 + prof_steps),
+                           "bytes_per_step": reducer.bytes_reduced /
+                           (args.steps * 2 + warmup + 2 + prof_steps)} if reducer else None),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

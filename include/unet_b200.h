@@ -95,6 +95,17 @@ int ub_plan_stage_params(const ub_plan* plan, int stage, int* first_param, int* 
 int ub_plan_backward_stage(ub_plan* plan, int stage, const float* dlogits, float* const* grads,
                            void* stream);
 
+/* Measurement support (bench.py): total number of kernels the library has launched so far, and
+ * optional in-step timing: while enabled, every kernel group the plan launches is bracketed by two
+ * CUDA events on the launching stream; collect() synchronises them and returns, per kernel class
+ * (ub_plan_profile_class_name), the summed duration [ms], algorithmic FLOPs / bytes and the number
+ * of timed groups. Arrays hold ub_plan_profile_classes() entries. */
+int64_t ub_launch_count(void);
+int ub_plan_profile_enable(ub_plan* plan, int on);
+int ub_plan_profile_classes(void);
+const char* ub_plan_profile_class_name(int cls);
+int ub_plan_profile_collect(ub_plan* plan, double* ms, double* flops, double* bytes, int* launches);
+
 /* ------------------------------------------------------------------------------------------------
  * WeightedCrossEntropyLoss.forward (utils/losses.py:29-57) + its gradient, one pass.
  * Strides are in elements; inputs may be non-contiguous views (scripts/train.py:118-126).

@@ -47,6 +47,12 @@ _SIGNATURES = {
     "ub_plan_num_stages": (c_int, [_P]),
     "ub_plan_stage_params": (c_int, [_P, c_int, C.POINTER(c_int), C.POINTER(c_int)]),
     "ub_plan_backward_stage": (c_int, [_P, c_int, _P, C.POINTER(c_void_p), _P]),
+    "ub_launch_count": (c_int64, []),
+    "ub_plan_profile_enable": (c_int, [_P, c_int]),
+    "ub_plan_profile_classes": (c_int, []),
+    "ub_plan_profile_class_name": (C.c_char_p, [c_int]),
+    "ub_plan_profile_collect": (c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double), C.POINTER(c_int)]),
     "ub_wce_workspace_floats": (c_int64, []),
     "ub_wce_forward": (c_int, [_P, C.POINTER(c_int64), _P, C.POINTER(c_int64), _P,
                                C.POINTER(c_int64), c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),

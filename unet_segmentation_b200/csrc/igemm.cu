@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "elementwise.cuh"
 #include "tmaps.cuh"
 #include "ub_internal.h"
@@ -18,6 +20,10 @@ void set_last_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
     static int n = 0;
@@ -55,7 +61,7 @@ static int launch_igemm_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
         attr_set = true;
     }
     igemm_kmajor_kernel<BN, EPI><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, p);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 
@@ -183,7 +189,7 @@ static int launch_wgrad_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
         attr_set = true;
     }
     igemm_wgrad_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, p);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 
@@ -243,7 +249,7 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, splits, p.split_stride, rows, cols, ctot,
                                                     taps, out);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 

@@ -35,16 +35,16 @@ static int check_cg(int C, const char* what) {
 int launch_pack_conv3x3(const float* w, int Co, int Ci, __nv_bfloat16* wf, __nv_bfloat16* wd,
                         cudaStream_t s) {
     pack_conv3x3_kernel<<<ew_blocks((long long)Co * Ci * 9), 256, 0, s>>>(w, Co, Ci, wf, wd);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 int launch_pack_convT(const float* w, int Ci, int Co, __nv_bfloat16* wf, __nv_bfloat16* wb,
                       const float* bias, float* bias4, cudaStream_t s) {
     pack_convT2x2_kernel<<<ew_blocks((long long)Co * Ci * 4), 256, 0, s>>>(w, Ci, Co, wf, wb);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     if (bias && bias4) {
         tile_bias4_kernel<<<(4 * Co + 255) / 256, 256, 0, s>>>(bias, Co, bias4);
-        UB_CHECK_CUDA(cudaGetLastError());
+        UB_POST_LAUNCH();
     }
     return UB_OK;
 }
@@ -56,7 +56,7 @@ int launch_bn_finalize(const float* stats, const IgemmLaunchInfo& info, int C, d
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, info.grid, info.n_tiles, info.BN, C,
                                                        count, gamma, beta, rm, rv, nbt, momentum,
                                                        eps, scale, shift, mean, rstd);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 int launch_bn_finalize_flat(const float* part, int blocks, int C, double count, const float* gamma,
@@ -66,7 +66,7 @@ int launch_bn_finalize_flat(const float* part, int blocks, int C, double count, 
     bn_finalize_flat_kernel<<<(C + 127) / 128, 128, 0, s>>>(part, blocks, C, count, gamma, beta, rm,
                                                             rv, nbt, momentum, eps, scale, shift,
                                                             mean, rstd);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 int launch_bn_fold_eval(int C, const float* conv_bias, const float* gamma, const float* beta,
@@ -74,7 +74,7 @@ int launch_bn_fold_eval(int C, const float* conv_bias, const float* gamma, const
                         cudaStream_t s) {
     bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, conv_bias, gamma, beta, rm, rv, eps,
                                                         scale, shift);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 
@@ -91,14 +91,14 @@ int launch_bn_apply_relu(const __nv_bfloat16* y, __nv_bfloat16* a, __nv_bfloat16
         bn_apply_relu_kernel<false><<<ew_blocks(items), 256, 0, s>>>(y, a, nullptr, N, H, W, C,
                                                                      scale, shift);
     }
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 int launch_maxpool2(const __nv_bfloat16* a, __nv_bfloat16* pooled, int N, int H, int W, int C,
                     cudaStream_t s) {
     const long long items = (long long)N * (H / 2) * (W / 2) * (C / 8);
     maxpool2_kernel<<<ew_blocks(items), 256, 0, s>>>(a, pooled, N, H, W, C);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 
@@ -122,14 +122,14 @@ int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
     const int blocks = red_blocks(items);
     if (d.pool_skip) bn_bwd_kernel<true, false><<<blocks, 256, 0, s>>>(A);
     else bn_bwd_kernel<false, false><<<blocks, 256, 0, s>>>(A);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     bn_bwd_finalize_kernel<<<(d.C + 127) / 128, 128, 0, s>>>(d.partial, blocks, d.C, d.dgamma,
                                                              d.dbeta);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     const int ablocks = ew_blocks(items);
     if (d.pool_skip) bn_bwd_kernel<true, true><<<ablocks, 256, 0, s>>>(A);
     else bn_bwd_kernel<false, true><<<ablocks, 256, 0, s>>>(A);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 
@@ -157,7 +157,7 @@ static int fc_launch(const FirstConvArgs& A, int blocks, cudaStream_t s) {
         UB_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<MODE>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     first_conv_kernel<MODE><<<blocks, 256, smem, s>>>(A);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 int launch_first_conv_stats(const FirstConvDesc& d, float* partial, int* blocks_out,
@@ -190,7 +190,7 @@ int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const floa
     const int blocks = red_blocks(items);
     UB_TRY(fc_launch<FC_BWD_REDUCE>(A, blocks, s));
     bn_bwd_finalize_kernel<<<(d.Co + 127) / 128, 128, 0, s>>>(partial, blocks, d.Co, dgamma, dbeta);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     A.dgamma = dgamma; A.dbeta = dbeta; A.inv_count = (float)(1.0 / (double)count);
     A.wpartial = partial;
     for (int ci = 0; ci < d.Ci; ++ci) {
@@ -198,7 +198,7 @@ int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const floa
         UB_TRY(fc_launch<FC_BWD_WGRAD>(A, blocks, s));
         first_wgrad_finalize_kernel<<<(d.Co * 9 + 127) / 128, 128, 0, s>>>(partial, blocks, d.Co,
                                                                            d.Ci, ci, dw);
-        UB_CHECK_CUDA(cudaGetLastError());
+        UB_POST_LAUNCH();
     }
     return UB_OK;
 }
@@ -213,7 +213,7 @@ int launch_head_fwd(const __nv_bfloat16* a, int N, int H, int W, int K, int NC, 
     const long long P = (long long)N * H * W;
     head_fwd_kernel<<<ew_blocks(P), 256, (size_t)(NC * K + NC) * 4, s>>>(
         a, P, (long long)H * W, K, NC, w, b, logits, mask);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 size_t head_bwd_partial_floats(int K, int NC) { return (size_t)num_sms() * 4 * (NC * K + NC); }
@@ -228,10 +228,10 @@ int launch_head_bwd(const float* dlogits, const __nv_bfloat16* a, int N, int H, 
     const long long P = (long long)N * H * W;
     const int blocks = red_blocks(P * (K / 8));
     head_bwd_kernel<<<blocks, 256, 0, s>>>(dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     const int len = NC * K + NC;
     reduce_partials_kernel<<<(len + 127) / 128, 128, 0, s>>>(partial, blocks, len, dw, NC * K, db);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 
@@ -248,21 +248,21 @@ int launch_wce(const WceDesc& d, float* loss, float* dz, float* partial, int* er
     if (P <= 0 || d.C < 1) { set_last_error("wce: empty input"); return UB_ERR_ARG; }
     const int blocks = ew_blocks(P);
     wce_fwd_bwd_kernel<<<blocks, 256, 0, s>>>(A);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     wce_finalize_kernel<<<1, 256, 0, s>>>(partial, blocks, (double)P, loss);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 int launch_scale_by_scalar(const float* in, const float* scalar, float* out, long long n,
                            cudaStream_t s) {
     scale_by_scalar_kernel<<<ew_blocks(n), 256, 0, s>>>(in, scalar, out, n);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 int launch_fill_zero(float* p, long long n, cudaStream_t s) {
     if (n <= 0) return UB_OK;
     fill_zero_kernel<<<ew_blocks(n), 256, 0, s>>>(p, n);
-    UB_CHECK_CUDA(cudaGetLastError());
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 
@@ -288,7 +288,8 @@ int launch_ccl(const unsigned char* mask, int H, int W, int min_size, unsigned s
     ccl_scan_kernel<<<1, 1024, 0, s>>>(block_roots, nb);
     ccl_rank_kernel<<<nb, 1024, 0, s>>>(L, block_roots, rank, n);
     ccl_emit_kernel<<<ew_blocks(n), 256, 0, s>>>(L, area, rank, min_size, out, n);
-    UB_CHECK_CUDA(cudaGetLastError());
+    count_launch(5);
+    UB_POST_LAUNCH();
     return UB_OK;
 }
 

@@ -64,6 +64,10 @@ struct ub_plan {
     const float* x = nullptr;   // input of the last forward (kept by the caller)
     bool packed = false;
     float momentum = 0.1f, eps = 1e-5f;
+    // optional in-step kernel timing (CUDA events on the launching stream)
+    struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
+    bool prof_on = false;
+    std::vector<ProfRec> prof;
 
     template <typename T>
     int alloc(T** p, size_t count) {
@@ -82,8 +86,30 @@ struct ub_plan {
     }
     ~ub_plan() {
         for (void* q : allocs) cudaFree(q);
+        for (auto& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     }
 };
+
+enum : int { CLS_FPROP = 0, CLS_DGRAD, CLS_WGRAD, CLS_CT_FPROP, CLS_CT_DGRAD, CLS_CT_WGRAD,
+             CLS_BN_APPLY, CLS_BN_BWD, CLS_FIRST, CLS_HEAD, CLS_COUNT };
+
+// Brackets the launches issued inside its scope with two CUDA events when profiling is enabled.
+struct ProfScope {
+    ub_plan* P; cudaStream_t s; cudaEvent_t e1 = nullptr;
+    ProfScope(ub_plan* P_, int cls, double flops, double bytes, cudaStream_t s_) : P(P_), s(s_) {
+        if (!P->prof_on) return;
+        ub_plan::ProfRec r;
+        r.cls = cls; r.flops = flops; r.bytes = bytes;
+        if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+        cudaEventRecord(r.e0, s);
+        e1 = r.e1;
+        P->prof.push_back(r);
+    }
+    ~ProfScope() { if (e1) cudaEventRecord(e1, s); }
+};
+static inline double gemm_bytes(double rows_in, double cin, double cout, double taps, double rows_out) {
+    return 2.0 * (rows_in * cin + cout * taps * cin + rows_out * cout);
+}
 
 static int alloc_unit(ub_plan* P, ConvUnit& u) {
     const size_t out = (size_t)P->N * u.Ho() * u.Wo() * u.Co;
@@ -359,7 +385,10 @@ int ub_plan_pack_weights(ub_plan* P, void* stream) {
 static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const View* in1,
                              bf16* pooled, cudaStream_t s) {
     const int N = P->N;
+    const double pix_out = (double)N * u.Ho() * u.Wo(), pix_in = (double)N * u.Hin * u.Win;
     if (u.first) {
+        ProfScope ps(P, CLS_FIRST, 2.0 * pix_out * u.Co * 9 * u.Ci * (P->training ? 2 : 1),
+                     4.0 * pix_in * u.Ci * (P->training ? 2 : 1) + 2.0 * pix_out * u.Co, s);
         FirstConvDesc d;
         d.x = P->x; d.N = N; d.Ci = u.Ci; d.H = u.Hin; d.W = u.Win; d.Co = u.Co;
         d.w = P->params[u.p_w];
@@ -381,9 +410,15 @@ static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const Vie
     IgemmEpilogue e;
     memset(&e, 0, sizeof(e));
     e.ldo = u.Co;
+    const double fl = 2.0 * pix_out * u.Co * 9.0 * u.Ci;
+    const double by = gemm_bytes(pix_in, u.Ci, u.Co, 9, pix_out);
     if (P->training) {
         e.kind = EPI_CONV_STATS; e.out = u.y; e.bias = P->params[u.p_b]; e.stats = P->scratch;
-        UB_TRY(launch_igemm(in0, in1, 0, -2, 1, 9, 3, u.wf, u.Co, e, &u.info, s));
+        {
+            ProfScope ps(P, CLS_FPROP, fl, by, s);
+            UB_TRY(launch_igemm(in0, in1, 0, -2, 1, 9, 3, u.wf, u.Co, e, &u.info, s));
+        }
+        ProfScope ps(P, CLS_BN_APPLY, 0, pix_out * u.Co * (pooled ? 4.5 : 4.0), s);
         UB_TRY(launch_bn_finalize(P->scratch, u.info, u.Co, (double)u.info.M, P->params[u.p_g],
                                   P->params[u.p_be], P->rm[u.bn], P->rv[u.bn], P->nbt[u.bn],
                                   P->momentum, P->eps, u.scale, u.shift, u.mean, u.rstd, s));
@@ -392,8 +427,14 @@ static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const Vie
     UB_TRY(launch_bn_fold_eval(u.Co, P->params[u.p_b], P->params[u.p_g], P->params[u.p_be],
                                P->rm[u.bn], P->rv[u.bn], P->eps, u.scale, u.shift, s));
     e.kind = EPI_AFFINE_RELU; e.out = u.a; e.scale = u.scale; e.shift = u.shift;
-    UB_TRY(launch_igemm(in0, in1, 0, -2, 1, 9, 3, u.wf, u.Co, e, &u.info, s));
-    if (pooled) return launch_maxpool2(u.a, pooled, N, u.Ho(), u.Wo(), u.Co, s);
+    {
+        ProfScope ps(P, CLS_FPROP, fl, by, s);
+        UB_TRY(launch_igemm(in0, in1, 0, -2, 1, 9, 3, u.wf, u.Co, e, &u.info, s));
+    }
+    if (pooled) {
+        ProfScope ps(P, CLS_BN_APPLY, 0, pix_out * u.Co * 2.5, s);
+        return launch_maxpool2(u.a, pooled, N, u.Ho(), u.Wo(), u.Co, s);
+    }
     return 0;
 }
 
@@ -420,11 +461,18 @@ int ub_plan_forward(ub_plan* P, const float* x, float* logits, uint8_t* mask, vo
         memset(&e, 0, sizeof(e));
         e.kind = EPI_CONVT; e.bias = t.bias4;
         e.ct_dst = make_view(t.out, P->N, 2 * t.Hin, 2 * t.Win, t.Co);
-        UB_TRY(launch_igemm(xin, nullptr, 0, 0, 1, 1, 1, t.wf, 4 * t.Co, e, nullptr, s));
+        {
+            const double m = (double)P->N * t.Hin * t.Win;
+            ProfScope ps(P, CLS_CT_FPROP, 2.0 * m * 4 * t.Co * t.Ci,
+                         gemm_bytes(m, t.Ci, 4.0 * t.Co, 1, m), s);
+            UB_TRY(launch_igemm(xin, nullptr, 0, 0, 1, 1, 1, t.wf, 4 * t.Co, e, nullptr, s));
+        }
         UB_TRY(block_forward(P, P->dec[j], s));
     }
     const ConvUnit& last = P->dec[L - 2].u[1];
     const int np = (int)P->params.size();
+    ProfScope ps(P, CLS_HEAD, 2.0 * P->N * P->outH * P->outW * P->base * P->NC,
+                 (double)P->N * P->outH * P->outW * (2.0 * P->base + 4.0 * P->NC), s);
     return launch_head_fwd(last.a, P->N, P->outH, P->outW, P->base, P->NC, P->params[np - 2],
                            P->params[np - 1], logits, P->training ? nullptr : mask, s);
 }
@@ -470,16 +518,25 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
     d.pool_skip = up.pool_skip; d.g = up.g; d.gp = up.gp; d.gs = up.gs;
     d.crop_h = up.crop_h; d.crop_w = up.crop_w; d.has_skip = up.has_skip;
     d.partial = P->scratch; d.dgamma = grads[u1.p_g]; d.dbeta = grads[u1.p_be]; d.dy = u1.dy;
-    UB_TRY(launch_bn_bwd(d, s));
+    const double po1 = (double)N * u1.Ho() * u1.Wo(), pi1 = (double)N * u1.Hin * u1.Win;
+    const double fl1 = 2.0 * po1 * u1.Co * 9.0 * u1.Ci;
+    {
+        ProfScope ps(P, CLS_BN_BWD, 0, po1 * u1.Co * 10.0, s);
+        UB_TRY(launch_bn_bwd(d, s));
+    }
     View a0 = make_view(u0.a, N, u0.Ho(), u0.Wo(), u0.Co);
-    UB_TRY(launch_wgrad(a0, nullptr, 0, -2, 1, 9, 3, u1.dy, u1.Co, u1.Co, P->wgrad_ws,
-                        P->wgrad_ws_floats, grads[u1.p_w], s));
+    {
+        ProfScope ps(P, CLS_WGRAD, fl1, 2.0 * (pi1 * u1.Ci + po1 * u1.Co) + 4.0 * 9 * u1.Ci * u1.Co, s);
+        UB_TRY(launch_wgrad(a0, nullptr, 0, -2, 1, 9, 3, u1.dy, u1.Co, u1.Co, P->wgrad_ws,
+                            P->wgrad_ws_floats, grads[u1.p_w], s));
+    }
     UB_TRY(launch_fill_zero(grads[u1.p_b], u1.Co, s));  // analytically zero ahead of a BatchNorm
     {
         IgemmEpilogue e;
         memset(&e, 0, sizeof(e));
         e.kind = EPI_STORE; e.out = b.da0; e.ldo = u1.Ci;
         View dyv = make_view(u1.dy, N, u1.Ho(), u1.Wo(), u1.Co);
+        ProfScope ps(P, CLS_DGRAD, fl1, gemm_bytes(po1, u1.Co, u1.Ci, 9, pi1), s);
         UB_TRY(launch_igemm(dyv, nullptr, -2, 0, 1, 9, 3, u1.wd, u1.Ci, e, nullptr, s));
     }
     // ---- first conv unit ----
@@ -489,6 +546,9 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
         FirstConvDesc f;
         f.x = P->x; f.N = N; f.Ci = u0.Ci; f.H = u0.Hin; f.W = u0.Win; f.Co = u0.Co;
         f.w = P->params[u0.p_w]; f.bias = P->params[u0.p_b];
+        const double po = (double)N * u0.Ho() * u0.Wo();
+        ProfScope ps(P, CLS_FIRST, 2.0 * po * u0.Co * 9 * u0.Ci * 3,
+                     2.0 * (4.0 * N * u0.Hin * u0.Win * u0.Ci + 2.0 * po * u0.Co), s);
         return launch_first_conv_bwd(f, u0.scale, u0.shift, u0.mean, u0.rstd, g0, P->scratch,
                                      grads[u0.p_g], grads[u0.p_be], grads[u0.p_w], s);
     }
@@ -497,13 +557,22 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
     d.scale = u0.scale; d.shift = u0.shift; d.mean = u0.mean; d.rstd = u0.rstd;
     d.pool_skip = false; d.g = g0;
     d.partial = P->scratch; d.dgamma = grads[u0.p_g]; d.dbeta = grads[u0.p_be]; d.dy = u0.dy;
-    UB_TRY(launch_bn_bwd(d, s));
-    UB_TRY(launch_wgrad(b.in0, b.two ? &b.in1 : nullptr, 0, -2, 1, 9, 3, u0.dy, u0.Co, u0.Co,
-                        P->wgrad_ws, P->wgrad_ws_floats, grads[u0.p_w], s));
+    const double po0 = (double)N * u0.Ho() * u0.Wo(), pi0 = (double)N * u0.Hin * u0.Win;
+    const double fl0 = 2.0 * po0 * u0.Co * 9.0 * u0.Ci;
+    {
+        ProfScope ps(P, CLS_BN_BWD, 0, po0 * u0.Co * 10.0, s);
+        UB_TRY(launch_bn_bwd(d, s));
+    }
+    {
+        ProfScope ps(P, CLS_WGRAD, fl0, 2.0 * (pi0 * u0.Ci + po0 * u0.Co) + 4.0 * 9 * u0.Ci * u0.Co, s);
+        UB_TRY(launch_wgrad(b.in0, b.two ? &b.in1 : nullptr, 0, -2, 1, 9, 3, u0.dy, u0.Co, u0.Co,
+                            P->wgrad_ws, P->wgrad_ws_floats, grads[u0.p_w], s));
+    }
     IgemmEpilogue e;
     memset(&e, 0, sizeof(e));
     e.kind = EPI_STORE; e.out = b.din; e.ldo = u0.Ci;
     View dyv = make_view(u0.dy, N, u0.Ho(), u0.Wo(), u0.Co);
+    ProfScope ps(P, CLS_DGRAD, fl0, gemm_bytes(po0, u0.Co, u0.Ci, 9, pi0), s);
     return launch_igemm(dyv, nullptr, -2, 0, 1, 9, 3, u0.wd, u0.Ci, e, nullptr, s);
 }
 
@@ -531,6 +600,8 @@ int ub_plan_backward_stage(ub_plan* P, int stage, const float* dlogits, float* c
         if (stage == 0) {
             if (!dlogits) { set_last_error("backward: dlogits is null"); return ub::UB_ERR_ARG; }
             const int np = (int)P->params.size();
+            ProfScope ps(P, CLS_HEAD, 4.0 * N * P->outH * P->outW * P->base * P->NC,
+                         (double)N * P->outH * P->outW * (4.0 * P->base + 4.0 * P->NC), s);
             UB_TRY(launch_head_bwd(dlogits, b.u[1].a, N, P->outH, P->outW, P->base, P->NC,
                                    P->params[np - 2], P->head_da, P->scratch, grads[np - 2],
                                    grads[np - 1], s));
@@ -548,8 +619,13 @@ int ub_plan_backward_stage(ub_plan* P, int stage, const float* dlogits, float* c
         IgemmEpilogue e;
         memset(&e, 0, sizeof(e));
         e.kind = EPI_STORE; e.out = t.dx; e.ldo = t.Ci;
-        UB_TRY(launch_igemm(dup, nullptr, 0, -1, 2, 4, 2, t.wb, t.Ci, e, nullptr, s));
+        const double mt = (double)N * t.Hin * t.Win, flt = 2.0 * mt * 4 * t.Co * t.Ci;
+        {
+            ProfScope ps(P, CLS_CT_DGRAD, flt, gemm_bytes(mt, 4.0 * t.Co, t.Ci, 1, mt), s);
+            UB_TRY(launch_igemm(dup, nullptr, 0, -1, 2, 4, 2, t.wb, t.Ci, e, nullptr, s));
+        }
         const ConvUnit& prev = j == 0 ? P->enc[L - 1].u[1] : P->dec[j - 1].u[1];
+        ProfScope ps(P, CLS_CT_WGRAD, flt, 2.0 * mt * (4.0 * t.Co + t.Ci) + 16.0 * t.Co * t.Ci, s);
         UB_TRY(launch_wgrad(dup, nullptr, 0, -1, 2, 4, 2, prev.a, t.Ci, t.Ci, P->wgrad_ws,
                             P->wgrad_ws_floats, grads[t.p_w], s));
         return launch_fill_zero(grads[t.p_b], t.Co, s);  // removed by the following BatchNorm
@@ -574,6 +650,39 @@ int ub_plan_backward_stage(ub_plan* P, int stage, const float* dlogits, float* c
         up.crop_w = (b.u[1].Wo() - db.u[0].Win) / 2;
     }
     return block_backward(P, b, up, grads, s);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+int64_t ub_launch_count(void) { return (int64_t)ub::launch_count(); }
+
+int ub_plan_profile_enable(ub_plan* P, int on) {
+    if (!P) return ub::UB_ERR_ARG;
+    for (auto& r : P->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    P->prof.clear();
+    P->prof_on = on != 0;
+    return 0;
+}
+int ub_plan_profile_classes(void) { return CLS_COUNT; }
+const char* ub_plan_profile_class_name(int cls) {
+    static const char* names[CLS_COUNT] = {"conv3x3_fprop", "conv3x3_dgrad", "conv3x3_wgrad",
+                                           "convT_fprop", "convT_dgrad", "convT_wgrad",
+                                           "bn_apply_relu_pool", "bn_relu_backward", "first_conv_fp32",
+                                           "head_1x1"};
+    return (cls >= 0 && cls < CLS_COUNT) ? names[cls] : "";
+}
+int ub_plan_profile_collect(ub_plan* P, double* ms, double* flops, double* bytes, int* launches) {
+    if (!P || !ms || !flops || !bytes || !launches) return ub::UB_ERR_ARG;
+    for (int c = 0; c < CLS_COUNT; ++c) { ms[c] = 0; flops[c] = 0; bytes[c] = 0; launches[c] = 0; }
+    for (auto& r : P->prof) {
+        UB_CHECK_CUDA(cudaEventSynchronize(r.e1));
+        float t = 0.f;
+        UB_CHECK_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += 1;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    P->prof.clear();
+    return 0;
 }
 
 }  // extern "C"

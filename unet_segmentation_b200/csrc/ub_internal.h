@@ -21,6 +21,8 @@ enum : int {
 void set_last_error(const char* fmt, ...);
 const char* last_error();
 int num_sms();
+void count_launch(int n = 1);   // every kernel launch of the library is counted (bench.py gpu_launches)
+long long launch_count();
 
 #define UB_CHECK_CUDA(expr)                                                                   \
     do {                                                                                      \
@@ -30,6 +32,11 @@ int num_sms();
                                __LINE__);                                                     \
             return ub::UB_ERR_CUDA;                                                           \
         }                                                                                     \
+    } while (0)
+#define UB_POST_LAUNCH()                 \
+    do {                                 \
+        ub::count_launch(1);             \
+        UB_CHECK_CUDA(cudaGetLastError()); \
     } while (0)
 #define UB_TRY(expr)              \
     do {                          \

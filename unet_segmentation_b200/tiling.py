@@ -1,0 +1,124 @@
+"""Overlap-tile inference (U-Net paper, Fig. 2) for images larger than one forward pass.
+
+The reference repository ships only result pictures of this strategy, not its code (SURVEY F2:
+``predictions_output_overlap_tile/*.png``, ``images/old readme unet.txt:73-87``), so the semantics are
+defined here and pinned by an invariant instead of golden vectors:
+
+  * the image is extended by mirroring (``reflect``) by the network margin (92 px for 5 levels) so
+    that the output covers the whole image;
+  * input tiles have a size S ≡ 12 (mod 16) (572 by default → 388² outputs, no pooling floor loss,
+    SURVEY F8) and origins that are multiples of 16; under these two conditions every max-pool window
+    of a tile coincides with a window of the whole-image forward, so a tile's logits are identical to
+    the corresponding crop of a single huge forward pass (eval-mode BN) — there is nothing to blend,
+    overlapping output pixels are equal and the later tile simply overwrites;
+  * tiles are independent units: they are batched on one GPU and dealt round-robin across ranks
+    (``parallel.shard_indices``) with no inter-GPU reduction.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import parallel
+
+
+def network_margin(levels: int = 5) -> int:
+    """Half of (input - output) for pooling-aligned sizes: 92 for the 5-level reference net
+    (572 -> 388, reference models/unet_model.py:175-187)."""
+    size = 12 + 16 * (1 << levels)          # ≡ 12 (mod 16) and large enough: no floor anywhere
+    s = size
+    for i in range(levels):
+        s -= 4
+        if i < levels - 1:
+            assert s % 2 == 0
+            s //= 2
+    for _ in range(levels - 1):
+        s = 2 * s - 4
+    return (size - s) // 2
+
+
+def plan_tiles(h: int, w: int, tile_in: int = 572, levels: int = 5) -> Tuple[int, int, List[Tuple[int, int]]]:
+    """Returns (tile_out, stride, origins). Origins are output-space top-left corners, multiples
+    of 16, covering [0,h) x [0,w)."""
+    if tile_in % 16 != 12:
+        raise ValueError("tile_in must be ≡ 12 (mod 16) so that no pooling level floors (SURVEY F8)")
+    tile_out = tile_in - 2 * network_margin(levels)
+    if tile_out <= 0:
+        raise ValueError("tile too small for the network margin")
+    stride = (tile_out // 16) * 16
+    ys = list(range(0, max(h - tile_out, 0) + stride, stride)) if h > tile_out else [0]
+    xs = list(range(0, max(w - tile_out, 0) + stride, stride)) if w > tile_out else [0]
+    ys = [y for y in ys if y < h]
+    xs = [x for x in xs if x < w]
+    while ys[-1] + tile_out < h:
+        ys.append(ys[-1] + stride)
+    while xs[-1] + tile_out < w:
+        xs.append(xs[-1] + stride)
+    return tile_out, stride, [(y, x) for y in ys for x in xs]
+
+
+def _reflect_index(i: torch.Tensor, n: int) -> torch.Tensor:
+    """numpy 'reflect' (no edge repeat) extension of arbitrary length."""
+    if n == 1:
+        return torch.zeros_like(i)
+    period = 2 * (n - 1)
+    i = i % period
+    return torch.where(i >= n, period - i, i)
+
+
+def extract_tiles(image: torch.Tensor, origins, tile_in: int, margin: int) -> torch.Tensor:
+    """image (H, W) fp32 -> (T, 1, tile_in, tile_in), mirror-extended around the borders."""
+    h, w = image.shape
+    dev = image.device
+    ar = torch.arange(tile_in, device=dev)
+    tiles = []
+    for (y, x) in origins:
+        iy = _reflect_index(ar + (y - margin), h)
+        ix = _reflect_index(ar + (x - margin), w)
+        tiles.append(image[iy][:, ix])
+    return torch.stack(tiles).unsqueeze(1)
+
+
+@torch.no_grad()
+def overlap_tile_predict(model, image: torch.Tensor, tile_in: int = 572, batch_tiles: int = 8,
+                         rank: int = 0, world: int = 1, group=None, return_logits: bool = False):
+    """Whole-image binary mask (uint8, 255 = foreground) of a 2-D fp32 CUDA image.
+
+    ``model`` is a ``unet_segmentation_b200.UNet`` in eval mode. With ``world > 1`` every rank calls
+    this with the same image and gets the same stitched result.
+    """
+    if image.dim() != 2 or not image.is_cuda:
+        raise ValueError("expected a 2-D CUDA image")
+    if model.training:
+        raise RuntimeError("overlap_tile_predict needs model.eval()")
+    levels = getattr(model, "levels", 5)
+    margin = network_margin(levels)
+    h, w = image.shape
+    tile_out, _, origins = plan_tiles(h, w, tile_in, levels)
+    mine = parallel.shard_indices(len(origins), rank, world)
+    out_masks, out_logits = [], []
+    for b0 in range(0, len(mine), batch_tiles):
+        idx = mine[b0:b0 + batch_tiles]
+        tiles = extract_tiles(image.float(), [origins[i] for i in idx], tile_in, margin)
+        real = tiles.shape[0]
+        if real < batch_tiles and len(mine) > batch_tiles:   # keep one plan shape
+            tiles = torch.cat([tiles, tiles[-1:].expand(batch_tiles - real, -1, -1, -1)])
+        logits, mask = model.predict_mask(tiles.contiguous())
+        out_masks.extend(mask[:real].unbind(0))
+        if return_logits:
+            out_logits.extend(logits[:real].unbind(0))
+    if world > 1:
+        out_masks = parallel.gather_tiles(out_masks, len(origins), rank, world, group)
+        if return_logits:
+            out_logits = parallel.gather_tiles(out_logits, len(origins), rank, world, group)
+    full = torch.zeros(h, w, dtype=torch.uint8, device=image.device)
+    full_logits: Optional[torch.Tensor] = None
+    if return_logits:
+        full_logits = torch.zeros(model.n_classes, h, w, dtype=torch.float32, device=image.device)
+    for k, (y, x) in enumerate(origins):
+        hh, ww = min(tile_out, h - y), min(tile_out, w - x)
+        full[y:y + hh, x:x + ww] = out_masks[k][:hh, :ww]
+        if full_logits is not None:
+            full_logits[:, y:y + hh, x:x + ww] = out_logits[k][:, :hh, :ww]
+    return (full, full_logits) if return_logits else full
