@@ -194,3 +194,41 @@ def test_reference_style_training_loop_runs_and_learns():
     assert all(np.isfinite(losses))
     assert losses[-1] < losses[0]
     assert int(model.inc.double_conv[1].num_batches_tracked) == 4
+
+
+def test_sgd_trajectory_tracks_fp32_oracle():
+    """Six optimizer steps with the reference's SGD(lr=1e-4, momentum=0.99) (scripts/train.py:97):
+    the bf16 path must follow the fp32 oracle's loss curve (also proves the packed bf16 weight
+    caches are refreshed after every optimizer.step())."""
+    from unet_segmentation_b200.loss import WeightedCrossEntropyLoss
+
+    model, sd = make_model(seed=0)
+    model.train()
+    img, t, w = unet_ref.synthetic_batch(2, size=252, seed=21, device="cuda")
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and "running" not in k}
+    full = dict(sd)
+    full.update(params)
+    opt_ref = torch.optim.SGD(list(params.values()), lr=1e-4, momentum=0.99)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.99)
+    crit = WeightedCrossEntropyLoss()
+    ours, ref = [], []
+    for _ in range(6):
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(img), t, w)
+        loss.backward()
+        opt.step()
+        ours.append(float(loss.detach()))
+        opt_ref.zero_grad(set_to_none=True)
+        bufs = {}
+        rl = unet_ref.weighted_cross_entropy(
+            unet_ref.unet_forward(full, img, training=True, buffers_out=bufs), t, w)
+        rl.backward()
+        opt_ref.step()
+        for k, v in bufs.items():
+            full[k] = v
+        ref.append(float(rl.detach()))
+    print("\n[SGD trajectory] ours", [f"{v:.3f}" for v in ours], " oracle", [f"{v:.3f}" for v in ref])
+    assert ref[-1] < ref[0]
+    for a, b in zip(ours, ref):
+        assert abs(a - b) / b < 0.08, (ours, ref)

@@ -43,25 +43,24 @@ __device__ __forceinline__ float bn_relu_bf16(float y, float sc, float sh) {
 // stats[(cta*4 + warp)][2][BN]; CTA b covers channel tile (b % n_tiles).
 // Biased variance normalises, unbiased variance updates running_var (torch semantics).
 // ---------------------------------------------------------------------------------------------
-static __global__ void bn_finalize_kernel(const float* __restrict__ stats, int grid_ctas, int n_tiles,
-                                   int BN, int C, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* running_mean,
-                                   float* running_var, long long* num_batches_tracked,
-                                   float momentum, float eps, float* __restrict__ scale,
-                                   float* __restrict__ shift, float* __restrict__ save_mean,
-                                   float* __restrict__ save_rstd) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
-    if (c >= C) return;
-    const int tile = c / BN, col = c % BN;
-    double s = 0.0, q = 0.0;
-    for (int b = tile; b < grid_ctas; b += n_tiles) {
-        for (int w = 0; w < 4; ++w) {
-            const float* p = stats + ((long long)b * 4 + w) * (2 * BN);
-            s += (double)p[col];
-            q += (double)p[BN + col];
-        }
+// All finalisation kernels use blockDim = (32 channels, 8 slices): the per-CTA partials are summed
+// by 8 threads per channel in double precision and combined through shared memory in a fixed
+// order (deterministic), instead of one thread walking hundreds of partial rows serially.
+__device__ __forceinline__ void finalize_combine(double& s, double& q) {
+    __shared__ double sm[2][8][32];
+    sm[0][threadIdx.y][threadIdx.x] = s;
+    sm[1][threadIdx.y][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        s = 0.0; q = 0.0;
+        for (int k = 0; k < 8; ++k) { s += sm[0][k][threadIdx.x]; q += sm[1][k][threadIdx.x]; }
     }
+}
+__device__ __forceinline__ void bn_finalize_write(int c, double s, double q, double count,
+                                                  const float* gamma, const float* beta,
+                                                  float* running_mean, float* running_var,
+                                                  float momentum, float eps, float* scale,
+                                                  float* shift, float* save_mean, float* save_rstd) {
     const double mean = s / count;
     double var = q / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -77,37 +76,52 @@ static __global__ void bn_finalize_kernel(const float* __restrict__ stats, int g
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
 }
-
-// Generic variant: partials[blocks][2][C] (first-layer statistics, BN backward sums).
-static __global__ void bn_finalize_flat_kernel(const float* __restrict__ part, int blocks, int C,
-                                        double count, const float* __restrict__ gamma,
-                                        const float* __restrict__ beta, float* running_mean,
-                                        float* running_var, long long* num_batches_tracked,
-                                        float momentum, float eps, float* __restrict__ scale,
-                                        float* __restrict__ shift, float* __restrict__ save_mean,
-                                        float* __restrict__ save_rstd) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
-    if (c >= C) return;
+static __global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ stats, int grid_ctas, int n_tiles, int BN, int C,
+                   double count, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* running_mean, float* running_var, long long* num_batches_tracked,
+                   float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
+                   float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    if (c == 0 && threadIdx.y == 0 && num_batches_tracked) *num_batches_tracked += 1;
     double s = 0.0, q = 0.0;
-    for (int b = 0; b < blocks; ++b) {
-        s += (double)part[(long long)b * 2 * C + c];
-        q += (double)part[(long long)b * 2 * C + C + c];
+    if (c < C) {
+        const int tile = c / BN, col = c % BN;
+        const int rows = (grid_ctas - tile + n_tiles - 1) / n_tiles * 4;  // (cta, warp) pairs
+        for (int r = threadIdx.y; r < rows; r += 8) {
+            const int b = tile + (r >> 2) * n_tiles, w = r & 3;
+            const float* p = stats + ((long long)b * 4 + w) * (2 * BN);
+            s += (double)p[col];
+            q += (double)p[BN + col];
+        }
     }
-    const double mean = s / count;
-    double var = q / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = gamma[c] * rstd;
-    scale[c] = sc;
-    shift[c] = beta[c] - (float)mean * sc;
-    save_mean[c] = (float)mean;
-    save_rstd[c] = rstd;
-    if (running_mean) {
-        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    finalize_combine(s, q);
+    if (threadIdx.y == 0 && c < C)
+        bn_finalize_write(c, s, q, count, gamma, beta, running_mean, running_var, momentum, eps,
+                          scale, shift, save_mean, save_rstd);
+}
+
+// Generic variant: partials[blocks][2][C] (first-layer statistics).
+static __global__ void __launch_bounds__(256)
+bn_finalize_flat_kernel(const float* __restrict__ part, int blocks, int C, double count,
+                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                        float* running_mean, float* running_var, long long* num_batches_tracked,
+                        float momentum, float eps, float* __restrict__ scale,
+                        float* __restrict__ shift, float* __restrict__ save_mean,
+                        float* __restrict__ save_rstd) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    if (c == 0 && threadIdx.y == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    double s = 0.0, q = 0.0;
+    if (c < C) {
+        for (int b = threadIdx.y; b < blocks; b += 8) {
+            s += (double)part[(long long)b * 2 * C + c];
+            q += (double)part[(long long)b * 2 * C + C + c];
+        }
     }
+    finalize_combine(s, q);
+    if (threadIdx.y == 0 && c < C)
+        bn_finalize_write(c, s, q, count, gamma, beta, running_mean, running_var, momentum, eps,
+                          scale, shift, save_mean, save_rstd);
 }
 
 // Eval mode: fold conv bias + running statistics into a per-channel affine.
@@ -379,17 +393,22 @@ bn_bwd_kernel(const BnBwdArgs A) {
 }
 
 // dbeta/dgamma = sum over blocks of the partials (fixed order => deterministic).
-static __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+static __global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
     double b = 0.0, g = 0.0;
-    for (int k = 0; k < blocks; ++k) {
-        b += (double)part[(long long)k * 2 * C + c];
-        g += (double)part[(long long)k * 2 * C + C + c];
+    if (c < C) {
+        for (int k = threadIdx.y; k < blocks; k += 8) {
+            b += (double)part[(long long)k * 2 * C + c];
+            g += (double)part[(long long)k * 2 * C + C + c];
+        }
     }
-    dbeta[c] = (float)b;
-    dgamma[c] = (float)g;
+    finalize_combine(b, g);
+    if (threadIdx.y == 0 && c < C) {
+        dbeta[c] = (float)b;
+        dgamma[c] = (float)g;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

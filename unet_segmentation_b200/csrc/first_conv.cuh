@@ -35,17 +35,27 @@ struct FirstConvArgs {
 
 enum : int { FC_STATS = 0, FC_APPLY = 1, FC_BWD_REDUCE = 2, FC_BWD_WGRAD = 3 };
 
-template <int MODE>
+// CI1 = true: single input channel (the reference's DIC-C2DH-HeLa case): the 9x8 weights of the
+// thread's channel group live in registers, no shared-memory traffic in the inner loop.
+template <int MODE, bool CI1>
 static __global__ void __launch_bounds__(256)
 first_conv_kernel(const FirstConvArgs A) {
     extern __shared__ float wsm[];  // [Ci*9][Co] weights, transposed for 8-wide reads
     const int Co = A.Co, CG = Co >> 3, Ci = A.Ci;
-    for (int i = threadIdx.x; i < Co * Ci * 9; i += blockDim.x) {
-        const int co = i / (Ci * 9), r = i % (Ci * 9);
-        wsm[r * Co + co] = A.w[i];
-    }
-    __syncthreads();
     const int cg = threadIdx.x % CG;
+    float wr[9][8];
+    if (CI1) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wr[tap][k] = A.w[(cg * 8 + k) * 9 + tap];
+    } else {
+        for (int i = threadIdx.x; i < Co * Ci * 9; i += blockDim.x) {
+            const int co = i / (Ci * 9), r = i % (Ci * 9);
+            wsm[r * Co + co] = A.w[i];
+        }
+        __syncthreads();
+    }
     const int Ho = A.H - 2, Wo = A.W - 2;
 
     float bi[8], sc[8], sh[8], mu[8], rs[8], kb[8], kg[8];
@@ -82,6 +92,16 @@ first_conv_kernel(const FirstConvArgs A) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) y[k] = bi[k];
         float xsel[9];
+        if (CI1) {
+            const float* xp = A.x + ((long long)n * A.H + hq) * A.W + wq;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const float xv = __ldg(xp + (tap / 3) * A.W + (tap % 3));
+                xsel[tap] = xv;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) y[k] = fmaf(xv, wr[tap][k], y[k]);
+            }
+        } else
         for (int ci = 0; ci < Ci; ++ci) {
             const float* xp = A.x + (((long long)n * Ci + ci) * A.H + hq) * A.W + wq;
 #pragma unroll
@@ -142,6 +162,7 @@ first_conv_kernel(const FirstConvArgs A) {
         }
     } else if (MODE == FC_BWD_WGRAD) {
         __shared__ float red[256 * 9];
+#pragma unroll
         for (int k = 0; k < 8; ++k) {
             __syncthreads();
 #pragma unroll

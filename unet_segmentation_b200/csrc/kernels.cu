@@ -53,7 +53,7 @@ int launch_bn_finalize(const float* stats, const IgemmLaunchInfo& info, int C, d
                        const float* gamma, const float* beta, float* rm, float* rv,
                        long long* nbt, float momentum, float eps, float* scale, float* shift,
                        float* mean, float* rstd, cudaStream_t s) {
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, info.grid, info.n_tiles, info.BN, C,
+    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(stats, info.grid, info.n_tiles, info.BN, C,
                                                        count, gamma, beta, rm, rv, nbt, momentum,
                                                        eps, scale, shift, mean, rstd);
     UB_POST_LAUNCH();
@@ -63,7 +63,7 @@ int launch_bn_finalize_flat(const float* part, int blocks, int C, double count, 
                             const float* beta, float* rm, float* rv, long long* nbt,
                             float momentum, float eps, float* scale, float* shift, float* mean,
                             float* rstd, cudaStream_t s) {
-    bn_finalize_flat_kernel<<<(C + 127) / 128, 128, 0, s>>>(part, blocks, C, count, gamma, beta, rm,
+    bn_finalize_flat_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(part, blocks, C, count, gamma, beta, rm,
                                                             rv, nbt, momentum, eps, scale, shift,
                                                             mean, rstd);
     UB_POST_LAUNCH();
@@ -123,7 +123,7 @@ int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
     if (d.pool_skip) bn_bwd_kernel<true, false><<<blocks, 256, 0, s>>>(A);
     else bn_bwd_kernel<false, false><<<blocks, 256, 0, s>>>(A);
     UB_POST_LAUNCH();
-    bn_bwd_finalize_kernel<<<(d.C + 127) / 128, 128, 0, s>>>(d.partial, blocks, d.C, d.dgamma,
+    bn_bwd_finalize_kernel<<<(d.C + 31) / 32, dim3(32, 8), 0, s>>>(d.partial, blocks, d.C, d.dgamma,
                                                              d.dbeta);
     UB_POST_LAUNCH();
     const int ablocks = ew_blocks(items);
@@ -152,11 +152,16 @@ static int fc_fill(const FirstConvDesc& d, FirstConvArgs& A) {
 }
 template <int MODE>
 static int fc_launch(const FirstConvArgs& A, int blocks, cudaStream_t s) {
+    if (A.Ci == 1) {
+        first_conv_kernel<MODE, true><<<blocks, 256, 0, s>>>(A);
+        UB_POST_LAUNCH();
+        return UB_OK;
+    }
     const size_t smem = (size_t)A.Co * A.Ci * 9 * 4;
     if (smem > 48 * 1024)
-        UB_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<MODE>,
+        UB_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<MODE, false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    first_conv_kernel<MODE><<<blocks, 256, smem, s>>>(A);
+    first_conv_kernel<MODE, false><<<blocks, 256, smem, s>>>(A);
     UB_POST_LAUNCH();
     return UB_OK;
 }
@@ -189,7 +194,7 @@ int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const floa
     const long long items = count * (d.Co / 8);
     const int blocks = red_blocks(items);
     UB_TRY(fc_launch<FC_BWD_REDUCE>(A, blocks, s));
-    bn_bwd_finalize_kernel<<<(d.Co + 127) / 128, 128, 0, s>>>(partial, blocks, d.Co, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(d.Co + 31) / 32, dim3(32, 8), 0, s>>>(partial, blocks, d.Co, dgamma, dbeta);
     UB_POST_LAUNCH();
     A.dgamma = dgamma; A.dbeta = dbeta; A.inv_count = (float)(1.0 / (double)count);
     A.wpartial = partial;
