@@ -140,68 +140,76 @@ static __global__ void bn_fold_eval_kernel(int C, const float* __restrict__ conv
 // ---------------------------------------------------------------------------------------------
 // BN-apply + ReLU (+ fused 2x2/2 floor-mode max-pool).   y -> a (and pooled p)
 // ---------------------------------------------------------------------------------------------
+// Index arithmetic is 32-bit (hosts reject tensors with >= 2^31 16-byte items) and the channel
+// group of a thread is fixed (256 % (C/8) == 0), so the per-channel affine lives in registers and the
+// grid-stride loop needs no division; 4 independent 16-byte loads are in flight per thread.
 template <bool POOL>
 static __global__ void __launch_bounds__(256)
 bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
                      __nv_bfloat16* __restrict__ pooled, int N, int H, int W, int C,
                      const float* __restrict__ scale, const float* __restrict__ shift) {
-    const int CG = C >> 3;
-    if (!POOL) {
-        const long long total = (long long)N * H * W * CG;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-             i += (long long)gridDim.x * blockDim.x) {
-            const int cg = (int)(i % CG);
-            Vec8 x = unpack8(ldg16(y + i * 8));
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + 4));
-            const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8));
-            const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + 4));
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-            Vec8 o;
+    const unsigned CG = (unsigned)C >> 3;
+    const unsigned cg = threadIdx.x % CG;
+    float sc[8], sh[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(fmaf(x.v[k], sc[k], sh[k]), 0.f);
-            *reinterpret_cast<uint4*>(a + i * 8) = pack8(o);
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
+    const unsigned gstride = gridDim.x * 256u / CG;
+    const unsigned first = (blockIdx.x * 256u + threadIdx.x) / CG;
+    if (!POOL) {
+        const unsigned npix = (unsigned)N * H * W;
+        for (unsigned p0 = first; p0 < npix; p0 += 4 * gstride) {
+            uint4 raw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned p = p0 + j * gstride;
+                if (p < npix) raw[j] = ldg16(y + (size_t)p * C + cg * 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned p = p0 + j * gstride;
+                if (p < npix) {
+                    const Vec8 x = unpack8(raw[j]);
+                    Vec8 o;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(fmaf(x.v[k], sc[k], sh[k]), 0.f);
+                    *reinterpret_cast<uint4*>(a + (size_t)p * C + cg * 8) = pack8(o);
+                }
+            }
         }
     } else {
-        const int HW2 = (H + 1) >> 1, WW2 = (W + 1) >> 1;
-        const int Hp = H >> 1, Wp = W >> 1;
-        const long long total = (long long)N * HW2 * WW2 * CG;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-             i += (long long)gridDim.x * blockDim.x) {
-            const int cg = (int)(i % CG);
-            long long t = i / CG;
-            const int wp = (int)(t % WW2); t /= WW2;
-            const int hp = (int)(t % HW2);
-            const int n = (int)(t / HW2);
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + 4));
-            const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8));
-            const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + 4));
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const unsigned HW2 = (H + 1) >> 1, WW2 = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
+        const unsigned nwin = (unsigned)N * HW2 * WW2;
+        for (unsigned wi = first; wi < nwin; wi += gstride) {
+            const unsigned wp = wi % WW2, t = wi / WW2, hp = t % HW2, n = t / HW2;
+            uint4 raw[4];
+            bool inb[4];
+            size_t off[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const unsigned h = hp * 2 + (d >> 1), w = wp * 2 + (d & 1);
+                inb[d] = h < (unsigned)H && w < (unsigned)W;
+                off[d] = ((size_t)(n * H + h) * W + w) * C + cg * 8;
+                if (inb[d]) raw[d] = ldg16(y + off[d]);
+            }
             Vec8 mx;
 #pragma unroll
             for (int k = 0; k < 8; ++k) mx.v[k] = 0.f;  // post-ReLU values are >= 0
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
-                const int h = hp * 2 + (d >> 1), w = wp * 2 + (d & 1);
-                if (h < H && w < W) {
-                    const long long off = (((long long)n * H + h) * W + w) * C + cg * 8;
-                    Vec8 x = unpack8(ldg16(y + off));
+                if (inb[d]) {
+                    const Vec8 x = unpack8(raw[d]);
                     Vec8 o;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         o.v[k] = bn_relu_bf16(x.v[k], sc[k], sh[k]);
                         mx.v[k] = fmaxf(mx.v[k], o.v[k]);
                     }
-                    *reinterpret_cast<uint4*>(a + off) = pack8(o);
+                    *reinterpret_cast<uint4*>(a + off[d]) = pack8(o);
                 }
             }
-            if (hp < Hp && wp < Wp) {
-                const long long off = (((long long)n * Hp + hp) * Wp + wp) * C + cg * 8;
-                *reinterpret_cast<uint4*>(pooled + off) = pack8(mx);
-            }
+            if (hp < Hp && wp < Wp)
+                *reinterpret_cast<uint4*>(pooled + ((size_t)(n * Hp + hp) * Wp + wp) * C + cg * 8) =
+                    pack8(mx);
         }
     }
 }
@@ -210,24 +218,27 @@ bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restr
 static __global__ void __launch_bounds__(256)
 maxpool2_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ pooled, int N,
                 int H, int W, int C) {
-    const int CG = C >> 3, Hp = H >> 1, Wp = W >> 1;
-    const long long total = (long long)N * Hp * Wp * CG;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(i % CG);
-        long long t = i / CG;
-        const int wp = (int)(t % Wp); t /= Wp;
-        const int hp = (int)(t % Hp);
-        const int n = (int)(t / Hp);
-        Vec8 mx;
+    const unsigned CG = (unsigned)C >> 3, Hp = H >> 1, Wp = W >> 1;
+    const unsigned total = (unsigned)N * Hp * Wp * CG;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned cg = i % CG;
+        unsigned t = i / CG;
+        const unsigned wp = t % Wp; t /= Wp;
+        const unsigned hp = t % Hp, n = t / Hp;
+        uint4 raw[4];
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-            const int h = hp * 2 + (d >> 1), w = wp * 2 + (d & 1);
-            Vec8 x = unpack8(ldg16(a + (((long long)n * H + h) * W + w) * C + cg * 8));
-#pragma unroll
-            for (int k = 0; k < 8; ++k) mx.v[k] = d == 0 ? x.v[k] : fmaxf(mx.v[k], x.v[k]);
+            const unsigned h = hp * 2 + (d >> 1), w = wp * 2 + (d & 1);
+            raw[d] = ldg16(a + ((size_t)(n * H + h) * W + w) * C + cg * 8);
         }
-        *reinterpret_cast<uint4*>(pooled + i * 8) = pack8(mx);
+        Vec8 mx = unpack8(raw[0]);
+#pragma unroll
+        for (int d = 1; d < 4; ++d) {
+            const Vec8 x = unpack8(raw[d]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mx.v[k] = fmaxf(mx.v[k], x.v[k]);
+        }
+        *reinterpret_cast<uint4*>(pooled + (size_t)i * 8) = pack8(mx);
     }
 }
 
@@ -262,8 +273,8 @@ struct BnBwdArgs {
 template <bool POOL_SKIP, bool APPLY>
 static __global__ void __launch_bounds__(256)
 bn_bwd_kernel(const BnBwdArgs A) {
-    const int C = A.C, CG = C >> 3, H = A.H, W = A.W;
-    const int cg = threadIdx.x % CG;  // host guarantees 256 % CG == 0 and grid stride % CG == 0
+    const unsigned C = A.C, CG = C >> 3, H = A.H, W = A.W;
+    const unsigned cg = threadIdx.x % CG;  // host guarantees 256 % CG == 0
     float sc[8], sh[8], mu[8], rs[8], kb[8], kg[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -280,95 +291,115 @@ bn_bwd_kernel(const BnBwdArgs A) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) { acc_b[k] = 0.f; acc_g[k] = 0.f; }
 
-    const int HW2 = POOL_SKIP ? (H + 1) >> 1 : H, WW2 = POOL_SKIP ? (W + 1) >> 1 : W;
-    const long long total = (long long)A.N * HW2 * WW2 * CG;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        long long t = i / CG;
-        const int wq = (int)(t % WW2); t /= WW2;
-        const int hq = (int)(t % HW2);
-        const int n = (int)(t / HW2);
+    const unsigned gstride = gridDim.x * 256u / CG;
+    const unsigned first = (blockIdx.x * 256u + threadIdx.x) / CG;
 
-        auto process = [&](int h, int w, const Vec8& yv, const Vec8& gv) {
-            Vec8 o;
+    auto process = [&](size_t pix, const Vec8& yv, const Vec8& gv) {
+        Vec8 o;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float act = fmaf(yv.v[k], sc[k], sh[k]);
-                const float dyh = act > 0.f ? gv.v[k] : 0.f;
-                const float xh = (yv.v[k] - mu[k]) * rs[k];
-                if (APPLY) {
-                    o.v[k] = sc[k] * (dyh - kb[k] - xh * kg[k]);
-                } else {
-                    acc_b[k] += dyh;
-                    acc_g[k] = fmaf(dyh, xh, acc_g[k]);
+        for (int k = 0; k < 8; ++k) {
+            const float act = fmaf(yv.v[k], sc[k], sh[k]);
+            const float dyh = act > 0.f ? gv.v[k] : 0.f;
+            const float xh = (yv.v[k] - mu[k]) * rs[k];
+            if (APPLY) {
+                o.v[k] = sc[k] * (dyh - kb[k] - xh * kg[k]);
+            } else {
+                acc_b[k] += dyh;
+                acc_g[k] = fmaf(dyh, xh, acc_g[k]);
+            }
+        }
+        if (APPLY) *reinterpret_cast<uint4*>(A.dy + pix * C + cg * 8) = pack8(o);
+    };
+
+    if (!POOL_SKIP) {
+        const unsigned npix = (unsigned)A.N * H * W;
+        const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(A.g.ptr);
+        const bool glin = A.g.sW == (long long)C && A.g.sH == (long long)W * C &&
+                          A.g.sN == (long long)H * W * C;
+        for (unsigned p0 = first; p0 < npix; p0 += 4 * gstride) {
+            uint4 yr[4], gr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned p = p0 + j * gstride;
+                if (p < npix) {
+                    yr[j] = ldg16(A.y + (size_t)p * C + cg * 8);
+                    size_t goff;
+                    if (glin) {
+                        goff = (size_t)p * C;
+                    } else {
+                        const unsigned w = p % W, t = p / W, h = t % H, n = t / H;
+                        goff = (size_t)(n * A.g.sN + h * A.g.sH + w * A.g.sW);
+                    }
+                    gr[j] = ldg16(gb + goff + cg * 8);
                 }
             }
-            if (APPLY)
-                *reinterpret_cast<uint4*>(A.dy + (((long long)n * H + h) * W + w) * C + cg * 8) =
-                    pack8(o);
-        };
-
-        if (!POOL_SKIP) {
-            const Vec8 yv = unpack8(ldg16(A.y + (((long long)n * H + hq) * W + wq) * C + cg * 8));
-            const __nv_bfloat16* gptr = reinterpret_cast<const __nv_bfloat16*>(A.g.ptr) +
-                                        n * A.g.sN + hq * A.g.sH + wq * A.g.sW + cg * 8;
-            const Vec8 gv = unpack8(ldg16(gptr));
-            process(hq, wq, yv, gv);
-        } else {
-            Vec8 yv[4], av[4];
-            bool inb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned p = p0 + j * gstride;
+                if (p < npix) process((size_t)p, unpack8(yr[j]), unpack8(gr[j]));
+            }
+        }
+    } else {
+        const unsigned HW2 = (H + 1) >> 1, WW2 = (W + 1) >> 1;
+        const unsigned nwin = (unsigned)A.N * HW2 * WW2;
+        const __nv_bfloat16* gpb = reinterpret_cast<const __nv_bfloat16*>(A.gp.ptr);
+        const __nv_bfloat16* gsb = reinterpret_cast<const __nv_bfloat16*>(A.gs.ptr);
+        for (unsigned wi = first; wi < nwin; wi += gstride) {
+            const unsigned wq = wi % WW2, t = wi / WW2, hq = t % HW2, n = t / HW2;
+            uint4 yr[4], gsr[4], gpr;
+            bool inb[4], ins[4];
+            size_t pix[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const unsigned h = hq * 2 + (d >> 1), w = wq * 2 + (d & 1);
+                inb[d] = h < H && w < W;
+                pix[d] = (size_t)(n * H + h) * W + w;
+                if (inb[d]) yr[d] = ldg16(A.y + pix[d] * C + cg * 8);
+                const int hs = (int)h - A.crop_h, ws = (int)w - A.crop_w;
+                ins[d] = inb[d] && A.has_skip && hs >= 0 && hs < A.gs.H && ws >= 0 && ws < A.gs.W;
+                if (ins[d])
+                    gsr[d] = ldg16(gsb + (size_t)(n * A.gs.sN + hs * A.gs.sH + ws * A.gs.sW) + cg * 8);
+            }
+            const bool full = (hq < (H >> 1)) && (wq < (W >> 1));
+            if (full)
+                gpr = ldg16(gpb + (size_t)(n * A.gp.sN + hq * A.gp.sH + wq * A.gp.sW) + cg * 8);
             Vec8 mx;
 #pragma unroll
             for (int k = 0; k < 8; ++k) mx.v[k] = 0.f;
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
-                const int h = hq * 2 + (d >> 1), w = wq * 2 + (d & 1);
-                inb[d] = h < H && w < W;
                 if (inb[d]) {
-                    yv[d] = unpack8(ldg16(A.y + (((long long)n * H + h) * W + w) * C + cg * 8));
+                    const Vec8 x = unpack8(yr[d]);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        av[d].v[k] = bn_relu_bf16(yv[d].v[k], sc[k], sh[k]);
-                        mx.v[k] = fmaxf(mx.v[k], av[d].v[k]);
-                    }
+                    for (int k = 0; k < 8; ++k)
+                        mx.v[k] = fmaxf(mx.v[k], bn_relu_bf16(x.v[k], sc[k], sh[k]));
                 }
             }
-            const bool full = (hq < (H >> 1)) && (wq < (W >> 1));
             Vec8 gpv;
-            if (full) {
-                const __nv_bfloat16* gptr = reinterpret_cast<const __nv_bfloat16*>(A.gp.ptr) +
-                                            n * A.gp.sN + hq * A.gp.sH + wq * A.gp.sW + cg * 8;
-                gpv = unpack8(ldg16(gptr));
-            }
-            bool taken[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) taken[k] = false;
+            if (full) gpv = unpack8(gpr);
+            unsigned taken = 0u;
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 if (!inb[d]) continue;
-                const int h = hq * 2 + (d >> 1), w = wq * 2 + (d & 1);
+                const Vec8 x = unpack8(yr[d]);
                 Vec8 gv;
+                if (ins[d]) {
+                    gv = unpack8(gsr[d]);
+                } else {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float g = 0.f;
-                    if (full && !taken[k] && av[d].v[k] == mx.v[k]) {
-                        g = gpv.v[k];
-                        taken[k] = true;
-                    }
-                    gv.v[k] = g;
+                    for (int k = 0; k < 8; ++k) gv.v[k] = 0.f;
                 }
-                if (A.has_skip) {
-                    const int hs = h - A.crop_h, ws = w - A.crop_w;
-                    if (hs >= 0 && hs < A.gs.H && ws >= 0 && ws < A.gs.W) {
-                        const __nv_bfloat16* sptr =
-                            reinterpret_cast<const __nv_bfloat16*>(A.gs.ptr) + n * A.gs.sN +
-                            hs * A.gs.sH + ws * A.gs.sW + cg * 8;
-                        const Vec8 sv = unpack8(ldg16(sptr));
+                if (full) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) gv.v[k] += sv.v[k];
+                    for (int k = 0; k < 8; ++k) {
+                        const float av = bn_relu_bf16(x.v[k], sc[k], sh[k]);
+                        if (!((taken >> k) & 1u) && av == mx.v[k]) {
+                            gv.v[k] += gpv.v[k];
+                            taken |= 1u << k;
+                        }
                     }
                 }
-                process(h, w, yv[d], gv);
+                process(pix[d], x, gv);
             }
         }
     }
@@ -382,12 +413,12 @@ bn_bwd_kernel(const BnBwdArgs A) {
             red[threadIdx.x * 16 + 8 + k] = acc_g[k];
         }
         __syncthreads();
-        for (int j = threadIdx.x; j < CG * 16; j += blockDim.x) {
-            const int g2 = j / 16, e = j % 16;
+        for (unsigned j = threadIdx.x; j < CG * 16; j += blockDim.x) {
+            const unsigned g2 = j / 16, e = j % 16;
             float s = 0.f;
-            for (int tt = g2; tt < 256; tt += CG) s += red[tt * 16 + e];
-            const int c = g2 * 8 + (e & 7);
-            A.partial[(long long)blockIdx.x * 2 * C + (e < 8 ? 0 : C) + c] = s;
+            for (unsigned tt = g2; tt < 256; tt += CG) s += red[tt * 16 + e];
+            const unsigned c = g2 * 8 + (e & 7);
+            A.partial[(size_t)blockIdx.x * 2 * C + (e < 8 ? 0 : C) + c] = s;
         }
     }
 }

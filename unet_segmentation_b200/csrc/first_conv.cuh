@@ -81,19 +81,18 @@ first_conv_kernel(const FirstConvArgs A) {
             for (int k = 0; k < 8; ++k) wacc[t][k] = 0.f;
     }
 
-    const long long total = (long long)A.N * Ho * Wo * CG;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        long long t = i / CG;
-        const int wq = (int)(t % Wo); t /= Wo;
-        const int hq = (int)(t % Ho);
-        const int n = (int)(t / Ho);
+    const unsigned npix = (unsigned)A.N * Ho * Wo;
+    const unsigned gstride = gridDim.x * 256u / CG;
+    for (unsigned pq = (blockIdx.x * 256u + threadIdx.x) / CG; pq < npix; pq += gstride) {
+        const size_t i = (size_t)pq * CG + cg;
+        const unsigned wq = pq % (unsigned)Wo, tq = pq / (unsigned)Wo;
+        const unsigned hq = tq % (unsigned)Ho, n = tq / (unsigned)Ho;
         float y[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) y[k] = bi[k];
         float xsel[9];
         if (CI1) {
-            const float* xp = A.x + ((long long)n * A.H + hq) * A.W + wq;
+            const float* xp = A.x + ((size_t)n * A.H + hq) * A.W + wq;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
                 const float xv = __ldg(xp + (tap / 3) * A.W + (tap % 3));
@@ -103,7 +102,7 @@ first_conv_kernel(const FirstConvArgs A) {
             }
         } else
         for (int ci = 0; ci < Ci; ++ci) {
-            const float* xp = A.x + (((long long)n * Ci + ci) * A.H + hq) * A.W + wq;
+            const float* xp = A.x + (((size_t)n * Ci + ci) * A.H + hq) * A.W + wq;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
                 const float xv = __ldg(xp + (tap / 3) * A.W + (tap % 3));
@@ -127,7 +126,7 @@ first_conv_kernel(const FirstConvArgs A) {
             *reinterpret_cast<uint4*>(A.a + i * 8) = pack8(o);
         } else {
             const __nv_bfloat16* gptr = reinterpret_cast<const __nv_bfloat16*>(A.g.ptr) +
-                                        n * A.g.sN + hq * A.g.sH + wq * A.g.sW + cg * 8;
+                                        (size_t)(n * A.g.sN + hq * A.g.sH + wq * A.g.sW) + cg * 8;
             const Vec8 gv = unpack8(ldg16(gptr));
 #pragma unroll
             for (int k = 0; k < 8; ++k) {

@@ -33,10 +33,10 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ a, long long P, long long HW, 
                 }
             }
         }
-        const long long n = p / HW, hw = p % HW;
+        const unsigned n = (unsigned)p / (unsigned)HW, hw = (unsigned)p % (unsigned)HW;
 #pragma unroll
         for (int c = 0; c < HEAD_MAX_CLASSES; ++c)
-            if (c < NC) logits[(n * NC + c) * HW + hw] = acc[c];
+            if (c < NC) logits[((size_t)n * NC + c) * HW + hw] = acc[c];
         if (mask) mask[p] = (NC >= 2 && acc[1] > acc[0]) ? 255 : 0;
     }
 }
@@ -62,11 +62,10 @@ head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restri
             accw[c][k] = 0.f;
         }
     }
-    const long long total = P * CG;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i / CG;
-        const long long n = p / HW, hw = p % HW;
+    const unsigned gstride = gridDim.x * 256u / CG;
+    for (unsigned pu = (blockIdx.x * 256u + threadIdx.x) / CG; pu < (unsigned)P; pu += gstride) {
+        const size_t p = pu;
+        const size_t n = pu / (unsigned)HW, hw = pu % (unsigned)HW;
         const Vec8 x = unpack8(ldg16(a + p * K + cg * 8));
         Vec8 o;
 #pragma unroll

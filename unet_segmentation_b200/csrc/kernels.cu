@@ -81,7 +81,11 @@ int launch_bn_fold_eval(int C, const float* conv_bias, const float* gamma, const
 int launch_bn_apply_relu(const __nv_bfloat16* y, __nv_bfloat16* a, __nv_bfloat16* pooled, int N,
                          int H, int W, int C, const float* scale, const float* shift,
                          cudaStream_t s) {
-    if (C % 8) { set_last_error("bn_apply: C %% 8 != 0"); return UB_ERR_UNSUPPORTED; }
+    UB_TRY(check_cg(C, "bn_apply"));
+    if ((long long)N * H * W * (C / 8) >= 0x7FFFFFFFLL) {
+        set_last_error("bn_apply: tensor too large for 32-bit indexing");
+        return UB_ERR_UNSUPPORTED;
+    }
     if (pooled) {
         const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
         bn_apply_relu_kernel<true><<<ew_blocks(items), 256, 0, s>>>(y, a, pooled, N, H, W, C, scale,
@@ -106,6 +110,10 @@ size_t bn_bwd_partial_floats(int C) { return (size_t)num_sms() * 4 * 2 * C; }
 
 int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
     UB_TRY(check_cg(d.C, "bn_bwd"));
+    if ((long long)d.N * d.H * d.W * (d.C / 8) >= 0x7FFFFFFFLL) {
+        set_last_error("bn_bwd: tensor too large for 32-bit indexing");
+        return UB_ERR_UNSUPPORTED;
+    }
     BnBwdArgs A;
     memset(&A, 0, sizeof(A));
     A.y = d.y; A.N = d.N; A.H = d.H; A.W = d.W; A.C = d.C;
