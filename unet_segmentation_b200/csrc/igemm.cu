@@ -167,11 +167,20 @@ static int wgrad_splits(int rows, int cols, long long mpix) {
     const int m_tiles = (rows + 127) / 128, n_tiles = cols / bn;
     const int units = m_tiles * n_tiles;
     const long long kblocks = (mpix + 63) / 64;
-    long long s = (2LL * num_sms() + units - 1) / units;
     const long long smax = kblocks / 8 > 1 ? kblocks / 8 : 1;
-    if (s > smax) s = smax;
-    if (s < 1) s = 1;
-    return (int)s;
+    // Pick the split count that minimises (number of CTA waves) x (k-blocks per CTA + fixed cost):
+    // avoids e.g. 300 CTAs on 148 SMs (a third, nearly empty, wave).
+    const double fixed = 24.0;  // prologue + fp32 epilogue of one CTA, in k-block units
+    const int sms = num_sms();
+    long long best = 1;
+    double best_cost = 1e30;
+    for (long long s = 1; s <= smax && s <= 256; ++s) {
+        const long long ctas = (long long)units * s;
+        const long long waves = (ctas + sms - 1) / sms;
+        const double cost = (double)waves * ((double)((kblocks + s - 1) / s) + fixed);
+        if (cost < best_cost * 0.999) { best_cost = cost; best = s; }
+    }
+    return (int)best;
 }
 size_t wgrad_ws_floats(int rows, int cols, long long mpix) {
     return (size_t)wgrad_splits(rows, cols, mpix) * (size_t)rows * (size_t)cols;
@@ -222,8 +231,8 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
     } else {
         mA1 = mA0;
     }
-    r = make_tmap_2d(&mB, B, (unsigned long long)cols, (unsigned long long)mpix,
-                     (unsigned long long)ldb * 2, 64);
+    r = make_tmap_chunked(&mB, B, (unsigned long long)cols, (unsigned long long)mpix,
+                          (unsigned long long)ldb * 2, 64, (unsigned)(BN / 64));
     if (r) { set_last_error("wgrad: matrix tensor map failed: %d", r); return UB_ERR_TMAP; }
 
     WgradParams p;

@@ -108,21 +108,23 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             const int n = t / p.Ho;
             const int cw = p.lower + q * p.tstride;
             const int ch = p.lower + pr * p.tstride;
-            int tap = 0, cc = 0;
+            int cc = 0;
+            uint16_t offw = 0, offh = 0;
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
                 const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
                 const uint32_t sb = sa + Cfg::A_BYTES;
-                const uint16_t offw = (uint16_t)(tap % p.tapw);
-                const uint16_t offh = (uint16_t)(tap / p.tapw);
                 if (cc < p.cchunks0)
                     tma_load_im2col(sa, &mapA0, full_bar(stage), cc * 64, cw, ch, n, offw, offh);
                 else
                     tma_load_im2col(sa, &mapA1, full_bar(stage), (cc - p.cchunks0) * 64, cw, ch, n,
                                     offw, offh);
                 tma_load_2d(sb, &mapB, full_bar(stage), kb * 64, n0);
-                if (++cc == cchunks) { cc = 0; ++tap; }
+                if (++cc == cchunks) {
+                    cc = 0;
+                    if (++offw == (uint16_t)p.tapw) { offw = 0; ++offh; }
+                }
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
         }
@@ -341,12 +343,17 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
             a_cc[j] = a_ok[j] ? c % cchunks : 0;
         }
         const uint32_t tx = (a_ok[1] ? 2u : 1u) * 8192u + Cfg::B_BYTES;
+        uint16_t a_offw[2], a_offh[2];
+        for (int j = 0; j < 2; ++j) {
+            a_offw[j] = (uint16_t)(a_tap[j] % p.tapw);
+            a_offh[j] = (uint16_t)(a_tap[j] / p.tapw);
+        }
+        // base pixel (q, pr, n) of the first k-block of this split, then advanced by 64 pixels
+        int m0 = kb_begin * 64;
+        int q = m0 % p.Wo;
+        int pr, n;
+        { const int t = m0 / p.Wo; pr = t % p.Ho; n = t / p.Ho; }
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-            const int m0 = kb * 64;
-            const int q = m0 % p.Wo;
-            const int t = m0 / p.Wo;
-            const int pr = t % p.Ho;
-            const int n = t / p.Ho;
             const int cw = p.lower + q * p.tstride;
             const int ch = p.lower + pr * p.tstride;
             mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -355,18 +362,21 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
             const uint32_t sb = sa + Cfg::A_BYTES;
             for (int j = 0; j < 2; ++j) {
                 if (!a_ok[j]) continue;
-                const uint16_t offw = (uint16_t)(a_tap[j] % p.tapw);
-                const uint16_t offh = (uint16_t)(a_tap[j] / p.tapw);
                 if (a_cc[j] < p.cchunks0)
                     tma_load_im2col(sa + j * 8192, &mapA0, full_bar(stage), a_cc[j] * 64, cw, ch, n,
-                                    offw, offh);
+                                    a_offw[j], a_offh[j]);
                 else
                     tma_load_im2col(sa + j * 8192, &mapA1, full_bar(stage),
-                                    (a_cc[j] - p.cchunks0) * 64, cw, ch, n, offw, offh);
+                                    (a_cc[j] - p.cchunks0) * 64, cw, ch, n, a_offw[j], a_offh[j]);
             }
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(sb + j * 8192, &mapB, full_bar(stage), n0 + j * 64, m0);
+            // B side: one 3-D box (64 ch, 64 pixels, BN/64 chunks) -> [chunk][pixel][64 ch] in smem
+            tma_load_3d(sb, &mapB, full_bar(stage), 0, m0, n_tile * (BN / 64));
+            m0 += 64;
+            q += 64;
+            while (q >= p.Wo) {
+                q -= p.Wo;
+                if (++pr == p.Ho) { pr = 0; ++n; }
+            }
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
     } else if (warp == 1 && lane == 0) {

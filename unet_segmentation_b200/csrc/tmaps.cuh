@@ -63,6 +63,25 @@ inline int make_tmap_2d(CUtensorMap* out, const void* ptr, unsigned long long in
     return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
 
+// [rows][cols] bf16 matrix (row pitch in bytes) seen as (64 channels, rows, cols/64 chunks): one
+// box of (64, box_rows, box_chunks) lands in shared memory as [chunk][row][64 ch] with the
+// 128-byte swizzle, i.e. box_chunks MN-major operand chunks in a single TMA operation.
+inline int make_tmap_chunked(CUtensorMap* out, const void* ptr, unsigned long long cols,
+                             unsigned long long rows, unsigned long long pitch_bytes,
+                             unsigned box_rows, unsigned box_chunks) {
+    TmapApi& api = tmap_api();
+    if (!api.ok) return -1;
+    cuuint64_t dims[3] = {64, rows, cols / 64};
+    cuuint64_t strides[2] = {pitch_bytes, 128};
+    cuuint32_t box[3] = {64, box_rows, box_chunks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = api.tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
 // im2col map over an NHWC bf16 view. Base pixels traverse, in (w,h,n) raster order with step
 // `tstride`, the box [lower, W-1+upper] x [lower, H-1+upper]; a load fetches `pixels` base pixels
 // x 64 channels, each pixel displaced by the per-instruction filter-tap offset.
