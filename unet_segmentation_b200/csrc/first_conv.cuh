@@ -177,6 +177,145 @@ first_conv_kernel(const FirstConvArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// C_in == 1 fast path (the reference's single-channel microscopy images): one thread = PX
+// horizontally adjacent output pixels x 8 channels. The 3 x (PX+2) input patch and the 9x8 weights
+// live in registers, so an item costs 3*(PX+2) cached loads for 72*PX FMAs and PX 16-byte stores /
+// gradient loads are in flight together. The conv bias is folded into the BN constants.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, int PX>
+static __global__ void __launch_bounds__(256)
+first_conv1_kernel(const FirstConvArgs A) {
+    const int Co = A.Co, CG = Co >> 3;
+    const unsigned cg = threadIdx.x % CG;
+    const unsigned Ho = A.H - 2, Wo = A.W - 2, W = A.W;
+    const unsigned GW = (Wo + PX - 1) / PX;  // pixel groups per output row
+    float wr[9][8];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wr[tap][k] = A.w[(cg * 8 + k) * 9 + tap];
+    // y = conv + bias;  act = y*sc + sh = conv*sc + shb;  xhat = (y - mu)*rs = (conv - mub)*rs
+    float bi[8], sc[8], shb[8], mub[8], rs[8], kb[8], kg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = cg * 8 + k;
+        bi[k] = A.bias ? A.bias[c] : 0.f;
+        if (MODE != FC_STATS) { sc[k] = A.scale[c]; shb[k] = fmaf(bi[k], sc[k], A.shift[c]); }
+        if (MODE >= FC_BWD_REDUCE) { mub[k] = A.mean[c] - bi[k]; rs[k] = A.rstd[c]; }
+        if (MODE == FC_BWD_WGRAD) {
+            kb[k] = A.dbeta[c] * A.inv_count;
+            kg[k] = A.dgamma[c] * A.inv_count;
+        }
+    }
+    float acc0[8], acc1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
+    float wacc[9][8];
+    if (MODE == FC_BWD_WGRAD) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wacc[t][k] = 0.f;
+    }
+    const unsigned ngroups = (unsigned)A.N * Ho * GW;
+    const unsigned gstride = gridDim.x * 256u / CG;
+    const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(A.g.ptr);
+    for (unsigned gi = (blockIdx.x * 256u + threadIdx.x) / CG; gi < ngroups; gi += gstride) {
+        const unsigned gw = gi % GW, t = gi / GW, hq = t % Ho, n = t / Ho;
+        const unsigned wq0 = gw * PX;
+        float xp[3][PX + 2];
+        const float* xrow = A.x + ((size_t)n * A.H + hq) * W + wq0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < PX + 2; ++c) xp[r][c] = (wq0 + c < W) ? __ldg(xrow + r * W + c) : 0.f;
+        uint4 graw[PX];
+        if (MODE >= FC_BWD_REDUCE) {
+#pragma unroll
+            for (int j = 0; j < PX; ++j)
+                if (wq0 + j < Wo)
+                    graw[j] = ldg16(gb + (size_t)(n * A.g.sN + hq * A.g.sH + (wq0 + j) * A.g.sW) +
+                                    cg * 8);
+        }
+        const size_t pq0 = ((size_t)n * Ho + hq) * Wo + wq0;
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            if (wq0 + j < Wo) {
+                float y[8];  // raw convolution (bias folded into the constants)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) y[k] = 0.f;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const float xv = xp[tap / 3][j + tap % 3];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) y[k] = fmaf(xv, wr[tap][k], y[k]);
+                }
+                if (MODE == FC_STATS) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float yb = y[k] + bi[k];
+                        acc0[k] += yb;
+                        acc1[k] = fmaf(yb, yb, acc1[k]);
+                    }
+                } else if (MODE == FC_APPLY) {
+                    Vec8 o;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(fmaf(y[k], sc[k], shb[k]), 0.f);
+                    *reinterpret_cast<uint4*>(A.a + (pq0 + j) * Co + cg * 8) = pack8(o);
+                } else {
+                    const Vec8 gv = unpack8(graw[j]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float act = fmaf(y[k], sc[k], shb[k]);
+                        const float dyh = act > 0.f ? gv.v[k] : 0.f;
+                        const float xh = (y[k] - mub[k]) * rs[k];
+                        if (MODE == FC_BWD_REDUCE) {
+                            acc0[k] += dyh;
+                            acc1[k] = fmaf(dyh, xh, acc1[k]);
+                        } else {
+                            const float dy = sc[k] * (dyh - kb[k] - xh * kg[k]);
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap)
+                                wacc[tap][k] = fmaf(dy, xp[tap / 3][j + tap % 3], wacc[tap][k]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (MODE == FC_STATS || MODE == FC_BWD_REDUCE) {
+        __shared__ float red[256 * 16];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            red[threadIdx.x * 16 + k] = acc0[k];
+            red[threadIdx.x * 16 + 8 + k] = acc1[k];
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < CG * 16; j += blockDim.x) {
+            const int g2 = j / 16, e = j % 16;
+            float s = 0.f;
+            for (int tt = g2; tt < 256; tt += CG) s += red[tt * 16 + e];
+            A.partial[(long long)blockIdx.x * 2 * Co + (e < 8 ? 0 : Co) + g2 * 8 + (e & 7)] = s;
+        }
+    } else if (MODE == FC_BWD_WGRAD) {
+        __shared__ float red[256 * 9];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            __syncthreads();
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) red[threadIdx.x * 9 + tap] = wacc[tap][k];
+            __syncthreads();
+            for (int j = threadIdx.x; j < CG * 9; j += blockDim.x) {
+                const int g2 = j / 9, tap = j % 9;
+                float s = 0.f;
+                for (int tt = g2; tt < 256; tt += CG) s += red[tt * 9 + tap];
+                A.wpartial[((long long)blockIdx.x * Co + g2 * 8 + k) * 9 + tap] = s;
+            }
+        }
+    }
+}
+
 // out[co][ci_sel][tap] = sum over blocks of wpartial[b][co][tap]
 static __global__ void first_wgrad_finalize_kernel(const float* __restrict__ wpartial, int blocks, int Co,
                                             int Ci, int ci_sel, float* __restrict__ dw) {

@@ -159,9 +159,16 @@ static int fc_fill(const FirstConvDesc& d, FirstConvArgs& A) {
     return UB_OK;
 }
 template <int MODE>
-static int fc_launch(const FirstConvArgs& A, int blocks, cudaStream_t s) {
+static int fc_launch(const FirstConvArgs& A, int& blocks, cudaStream_t s) {
     if (A.Ci == 1) {
-        first_conv_kernel<MODE, true><<<blocks, 256, 0, s>>>(A);
+        // 4 pixels per thread (2 in the register-heavy fused weight-gradient mode)
+        constexpr int PX = (MODE == FC_BWD_WGRAD) ? 2 : 4;
+        const long long groups = (long long)A.N * (A.H - 2) * ((A.W - 2 + PX - 1) / PX);
+        long long b = (groups * (A.Co / 8) + 255) / 256;
+        if (b > blocks) b = blocks;
+        if (b < 1) b = 1;
+        blocks = (int)b;  // the partial buffers hold one row per launched block
+        first_conv1_kernel<MODE, PX><<<(int)b, 256, 0, s>>>(A);
         UB_POST_LAUNCH();
         return UB_OK;
     }
@@ -179,9 +186,10 @@ int launch_first_conv_stats(const FirstConvDesc& d, float* partial, int* blocks_
     UB_TRY(fc_fill(d, A));
     A.partial = partial;
     const long long items = (long long)d.N * (d.H - 2) * (d.W - 2) * (d.Co / 8);
-    const int blocks = red_blocks(items);
+    int blocks = red_blocks(items);
+    const int rc = fc_launch<FC_STATS>(A, blocks, s);
     *blocks_out = blocks;
-    return fc_launch<FC_STATS>(A, blocks, s);
+    return rc;
 }
 int launch_first_conv_apply(const FirstConvDesc& d, const float* scale, const float* shift,
                             __nv_bfloat16* a, cudaStream_t s) {
@@ -189,7 +197,8 @@ int launch_first_conv_apply(const FirstConvDesc& d, const float* scale, const fl
     UB_TRY(fc_fill(d, A));
     A.scale = scale; A.shift = shift; A.a = a;
     const long long items = (long long)d.N * (d.H - 2) * (d.W - 2) * (d.Co / 8);
-    return fc_launch<FC_APPLY>(A, ew_blocks(items), s);
+    int blocks = ew_blocks(items);
+    return fc_launch<FC_APPLY>(A, blocks, s);
 }
 int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const float* shift,
                           const float* mean, const float* rstd, const View& g, float* partial,
@@ -200,7 +209,7 @@ int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const floa
     A.partial = partial;
     const long long count = (long long)d.N * (d.H - 2) * (d.W - 2);
     const long long items = count * (d.Co / 8);
-    const int blocks = red_blocks(items);
+    int blocks = red_blocks(items);
     UB_TRY(fc_launch<FC_BWD_REDUCE>(A, blocks, s));
     bn_bwd_finalize_kernel<<<(d.Co + 31) / 32, dim3(32, 8), 0, s>>>(partial, blocks, d.Co, dgamma, dbeta);
     UB_POST_LAUNCH();
@@ -208,8 +217,9 @@ int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const floa
     A.wpartial = partial;
     for (int ci = 0; ci < d.Ci; ++ci) {
         A.ci_sel = ci;
-        UB_TRY(fc_launch<FC_BWD_WGRAD>(A, blocks, s));
-        first_wgrad_finalize_kernel<<<(d.Co * 9 + 127) / 128, 128, 0, s>>>(partial, blocks, d.Co,
+        int wblocks = red_blocks(items);
+        UB_TRY(fc_launch<FC_BWD_WGRAD>(A, wblocks, s));
+        first_wgrad_finalize_kernel<<<(d.Co * 9 + 127) / 128, 128, 0, s>>>(partial, wblocks, d.Co,
                                                                            d.Ci, ci, dw);
         UB_POST_LAUNCH();
     }
@@ -224,7 +234,8 @@ int launch_head_fwd(const __nv_bfloat16* a, int N, int H, int W, int K, int NC, 
         return UB_ERR_UNSUPPORTED;
     }
     const long long P = (long long)N * H * W;
-    head_fwd_kernel<<<ew_blocks(P), 256, (size_t)(NC * K + NC) * 4, s>>>(
+    if (P >= 0x7FFFFFF0LL / 8) { set_last_error("head: too many pixels"); return UB_ERR_UNSUPPORTED; }
+    head_fwd_kernel<<<ew_blocks(K == 64 ? P * 8 : P), 256, (size_t)(NC * K + NC) * 4, s>>>(
         a, P, (long long)H * W, K, NC, w, b, logits, mask);
     UB_POST_LAUNCH();
     return UB_OK;
