@@ -43,17 +43,17 @@ __device__ __forceinline__ float bn_relu_bf16(float y, float sc, float sh) {
 // stats[(cta*4 + warp)][2][BN]; CTA b covers channel tile (b % n_tiles).
 // Biased variance normalises, unbiased variance updates running_var (torch semantics).
 // ---------------------------------------------------------------------------------------------
-// All finalisation kernels use blockDim = (32 channels, 8 slices): the per-CTA partials are summed
-// by 8 threads per channel in double precision and combined through shared memory in a fixed
+// All finalisation kernels use blockDim = (32 channels, 16 slices): the per-CTA partials are summed
+// by 16 threads per channel in double precision and combined through shared memory in a fixed
 // order (deterministic), instead of one thread walking hundreds of partial rows serially.
 __device__ __forceinline__ void finalize_combine(double& s, double& q) {
-    __shared__ double sm[2][8][32];
+    __shared__ double sm[2][16][32];
     sm[0][threadIdx.y][threadIdx.x] = s;
     sm[1][threadIdx.y][threadIdx.x] = q;
     __syncthreads();
     if (threadIdx.y == 0) {
         s = 0.0; q = 0.0;
-        for (int k = 0; k < 8; ++k) { s += sm[0][k][threadIdx.x]; q += sm[1][k][threadIdx.x]; }
+        for (int k = 0; k < 16; ++k) { s += sm[0][k][threadIdx.x]; q += sm[1][k][threadIdx.x]; }
     }
 }
 __device__ __forceinline__ void bn_finalize_write(int c, double s, double q, double count,
@@ -76,7 +76,7 @@ __device__ __forceinline__ void bn_finalize_write(int c, double s, double q, dou
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
 }
-static __global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(512)
 bn_finalize_kernel(const float* __restrict__ stats, int grid_ctas, int n_tiles, int BN, int C,
                    double count, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* running_mean, float* running_var, long long* num_batches_tracked,
@@ -88,7 +88,7 @@ bn_finalize_kernel(const float* __restrict__ stats, int grid_ctas, int n_tiles, 
     if (c < C) {
         const int tile = c / BN, col = c % BN;
         const int rows = (grid_ctas - tile + n_tiles - 1) / n_tiles * 4;  // (cta, warp) pairs
-        for (int r = threadIdx.y; r < rows; r += 8) {
+        for (int r = threadIdx.y; r < rows; r += 16) {
             const int b = tile + (r >> 2) * n_tiles, w = r & 3;
             const float* p = stats + ((long long)b * 4 + w) * (2 * BN);
             s += (double)p[col];
@@ -102,7 +102,7 @@ bn_finalize_kernel(const float* __restrict__ stats, int grid_ctas, int n_tiles, 
 }
 
 // Generic variant: partials[blocks][2][C] (first-layer statistics).
-static __global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(512)
 bn_finalize_flat_kernel(const float* __restrict__ part, int blocks, int C, double count,
                         const float* __restrict__ gamma, const float* __restrict__ beta,
                         float* running_mean, float* running_var, long long* num_batches_tracked,
@@ -113,7 +113,7 @@ bn_finalize_flat_kernel(const float* __restrict__ part, int blocks, int C, doubl
     if (c == 0 && threadIdx.y == 0 && num_batches_tracked) *num_batches_tracked += 1;
     double s = 0.0, q = 0.0;
     if (c < C) {
-        for (int b = threadIdx.y; b < blocks; b += 8) {
+        for (int b = threadIdx.y; b < blocks; b += 16) {
             s += (double)part[(long long)b * 2 * C + c];
             q += (double)part[(long long)b * 2 * C + C + c];
         }
@@ -271,7 +271,7 @@ struct BnBwdArgs {
 };
 
 template <bool POOL_SKIP, bool APPLY>
-static __global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256, 2)
 bn_bwd_kernel(const BnBwdArgs A) {
     const unsigned C = A.C, CG = C >> 3, H = A.H, W = A.W;
     const unsigned cg = threadIdx.x % CG;  // host guarantees 256 % CG == 0
@@ -424,13 +424,13 @@ bn_bwd_kernel(const BnBwdArgs A) {
 }
 
 // dbeta/dgamma = sum over blocks of the partials (fixed order => deterministic).
-static __global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(512)
 bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C,
                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int c = blockIdx.x * 32 + threadIdx.x;
     double b = 0.0, g = 0.0;
     if (c < C) {
-        for (int k = threadIdx.y; k < blocks; k += 8) {
+        for (int k = threadIdx.y; k < blocks; k += 16) {
             b += (double)part[(long long)k * 2 * C + c];
             g += (double)part[(long long)k * 2 * C + C + c];
         }

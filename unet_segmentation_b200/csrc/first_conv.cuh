@@ -184,7 +184,7 @@ first_conv_kernel(const FirstConvArgs A) {
 // gradient loads are in flight together. The conv bias is folded into the BN constants.
 // ---------------------------------------------------------------------------------------------
 template <int MODE, int PX>
-static __global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256, (MODE >= FC_BWD_REDUCE) ? 1 : 2)
 first_conv1_kernel(const FirstConvArgs A) {
     const int Co = A.Co, CG = Co >> 3;
     const unsigned cg = threadIdx.x % CG;

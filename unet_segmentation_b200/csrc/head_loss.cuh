@@ -101,17 +101,19 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ a, long long P, long long HW, 
 // Backward of the 1x1 head: da[p][k] = sum_c dl[c][p] * w[c][k] (bf16 out);
 // partial[b][c][k] = sum_p dl[c][p]*a[p][k];  partial_b[b][c] = sum_p dl[c][p].
 // One thread = one pixel x 8 channels, channel group fixed per thread.
+template <int NCT>  // compile-time bound on the class count (register arrays sized by it)
 static __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ a, long long P,
                 long long HW, int K, int NC, const float* __restrict__ w,
                 __nv_bfloat16* __restrict__ da, float* __restrict__ partial) {
+    constexpr int HEAD_MAX_CLASSES = NCT;
     const int CG = K >> 3;
     const int cg = threadIdx.x % CG;
-    float wr[HEAD_MAX_CLASSES][8];
-    float accw[HEAD_MAX_CLASSES][8];
-    float accb[HEAD_MAX_CLASSES];
+    float wr[NCT][8];
+    float accw[NCT][8];
+    float accb[NCT];
 #pragma unroll
-    for (int c = 0; c < HEAD_MAX_CLASSES; ++c) {
+    for (int c = 0; c < NCT; ++c) {
         accb[c] = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -120,26 +122,40 @@ head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restri
         }
     }
     const unsigned gstride = gridDim.x * 256u / CG;
-    for (unsigned pu = (blockIdx.x * 256u + threadIdx.x) / CG; pu < (unsigned)P; pu += gstride) {
-        const size_t p = pu;
-        const size_t n = pu / (unsigned)HW, hw = pu % (unsigned)HW;
-        const Vec8 x = unpack8(ldg16(a + p * K + cg * 8));
-        Vec8 o;
+    for (unsigned p0 = (blockIdx.x * 256u + threadIdx.x) / CG; p0 < (unsigned)P; p0 += 4 * gstride) {
+        uint4 raw[4];
+        float dl[4][NCT];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
+        for (int j = 0; j < 4; ++j) {
+            const unsigned pu = p0 + j * gstride;
+            if (pu < (unsigned)P) {
+                raw[j] = ldg16(a + (size_t)pu * K + cg * 8);
+                const size_t n = pu / (unsigned)HW, hw = pu % (unsigned)HW;
 #pragma unroll
-        for (int c = 0; c < HEAD_MAX_CLASSES; ++c) {
-            if (c < NC) {
-                const float dl = __ldg(dlogits + (n * NC + c) * HW + hw);
-                accb[c] += dl;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    o.v[k] = fmaf(dl, wr[c][k], o.v[k]);
-                    accw[c][k] = fmaf(dl, x.v[k], accw[c][k]);
-                }
+                for (int c = 0; c < NCT; ++c)
+                    dl[j][c] = c < NC ? __ldg(dlogits + (n * NC + c) * HW + hw) : 0.f;
             }
         }
-        *reinterpret_cast<uint4*>(da + p * K + cg * 8) = pack8(o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned pu = p0 + j * gstride;
+            if (pu < (unsigned)P) {
+                const Vec8 x = unpack8(raw[j]);
+                Vec8 o;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
+#pragma unroll
+                for (int c = 0; c < NCT; ++c) {
+                    accb[c] += dl[j][c];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        o.v[k] = fmaf(dl[j][c], wr[c][k], o.v[k]);
+                        accw[c][k] = fmaf(dl[j][c], x.v[k], accw[c][k]);
+                    }
+                }
+                *reinterpret_cast<uint4*>(da + (size_t)pu * K + cg * 8) = pack8(o);
+            }
+        }
     }
     // block reduce: partial[b][c][K] and partial bias at [b][NC*K + c]
     __shared__ float red[256 * 9];

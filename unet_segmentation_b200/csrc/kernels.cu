@@ -53,7 +53,7 @@ int launch_bn_finalize(const float* stats, const IgemmLaunchInfo& info, int C, d
                        const float* gamma, const float* beta, float* rm, float* rv,
                        long long* nbt, float momentum, float eps, float* scale, float* shift,
                        float* mean, float* rstd, cudaStream_t s) {
-    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(stats, info.grid, info.n_tiles, info.BN, C,
+    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 16), 0, s>>>(stats, info.grid, info.n_tiles, info.BN, C,
                                                        count, gamma, beta, rm, rv, nbt, momentum,
                                                        eps, scale, shift, mean, rstd);
     UB_POST_LAUNCH();
@@ -63,7 +63,7 @@ int launch_bn_finalize_flat(const float* part, int blocks, int C, double count, 
                             const float* beta, float* rm, float* rv, long long* nbt,
                             float momentum, float eps, float* scale, float* shift, float* mean,
                             float* rstd, cudaStream_t s) {
-    bn_finalize_flat_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(part, blocks, C, count, gamma, beta, rm,
+    bn_finalize_flat_kernel<<<(C + 31) / 32, dim3(32, 16), 0, s>>>(part, blocks, C, count, gamma, beta, rm,
                                                             rv, nbt, momentum, eps, scale, shift,
                                                             mean, rstd);
     UB_POST_LAUNCH();
@@ -131,7 +131,7 @@ int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
     if (d.pool_skip) bn_bwd_kernel<true, false><<<blocks, 256, 0, s>>>(A);
     else bn_bwd_kernel<false, false><<<blocks, 256, 0, s>>>(A);
     UB_POST_LAUNCH();
-    bn_bwd_finalize_kernel<<<(d.C + 31) / 32, dim3(32, 8), 0, s>>>(d.partial, blocks, d.C, d.dgamma,
+    bn_bwd_finalize_kernel<<<(d.C + 31) / 32, dim3(32, 16), 0, s>>>(d.partial, blocks, d.C, d.dgamma,
                                                              d.dbeta);
     UB_POST_LAUNCH();
     const int ablocks = ew_blocks(items);
@@ -211,7 +211,7 @@ int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const floa
     const long long items = count * (d.Co / 8);
     int blocks = red_blocks(items);
     UB_TRY(fc_launch<FC_BWD_REDUCE>(A, blocks, s));
-    bn_bwd_finalize_kernel<<<(d.Co + 31) / 32, dim3(32, 8), 0, s>>>(partial, blocks, d.Co, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(d.Co + 31) / 32, dim3(32, 16), 0, s>>>(partial, blocks, d.Co, dgamma, dbeta);
     UB_POST_LAUNCH();
     A.dgamma = dgamma; A.dbeta = dbeta; A.inv_count = (float)(1.0 / (double)count);
     A.wpartial = partial;
@@ -251,7 +251,12 @@ int launch_head_bwd(const float* dlogits, const __nv_bfloat16* a, int N, int H, 
     UB_TRY(check_cg(K, "head_bwd"));
     const long long P = (long long)N * H * W;
     const int blocks = red_blocks(P * (K / 8));
-    head_bwd_kernel<<<blocks, 256, 0, s>>>(dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
+    if (NC <= 2)
+        head_bwd_kernel<2><<<blocks, 256, 0, s>>>(dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
+    else if (NC <= 4)
+        head_bwd_kernel<4><<<blocks, 256, 0, s>>>(dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
+    else
+        head_bwd_kernel<8><<<blocks, 256, 0, s>>>(dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
     UB_POST_LAUNCH();
     const int len = NC * K + NC;
     reduce_partials_kernel<<<(len + 127) / 128, 128, 0, s>>>(partial, blocks, len, dw, NC * K, db);
