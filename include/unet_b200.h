@@ -133,10 +133,11 @@ int ub_ccl_label(const uint8_t* mask, int H, int W, int min_size, uint16_t* labe
  * Operator-level entry points (teacher-forced per-layer parity tests). bf16 NHWC
  * views in, the same kernels the plan launches.
  * ---------------------------------------------------------------------------------------------- */
-/* nn.Conv2d(k=3,p=0).weight [Co][Ci][3][3] fp32 -> forward operand wf [Co][9][Ci] bf16 and
- * data-gradient operand wd [Ci][9][Co] bf16 (taps rotated by 180 degrees). wd may be NULL. */
+/* nn.Conv2d(k=3,p=0).weight [Co][Ci][3][3] fp32 -> forward operand wf [9][Co][Ci] bf16 and
+ * data-gradient operand wd [9][Ci][Co] bf16 (tap-major; taps rotated by 180 degrees for wd).
+ * wd may be NULL. */
 int ub_op_pack_conv3x3(const float* w, int Co, int Ci, void* wf, void* wd, void* stream);
-/* nn.ConvTranspose2d(k=2,s=2).weight [Ci][Co][2][2] -> wf [4*Co][Ci], wb [Ci][4*Co] (bf16);
+/* nn.ConvTranspose2d(k=2,s=2).weight [Ci][Co][2][2] -> wf [4*Co][Ci], wb [4][Ci][Co] (bf16);
  * bias [Co] -> bias4 [4*Co]. wb / bias / bias4 may be NULL. */
 int ub_op_pack_convT(const float* w, int Ci, int Co, void* wf, void* wb, const float* bias,
                      float* bias4, void* stream);

@@ -304,3 +304,56 @@ def test_ccl_matches_scipy(ops):
         ref = ref.astype(np.uint16)
         out = ops.ccl_label(torch.from_numpy(m).cuda(), 15).cpu().numpy()
         assert np.array_equal(out, ref), (h, w, p)
+
+
+# ---- wide feature maps: the "row-run" kernel (smem-side im2col) takes over when a 128-pixel tile of
+# ---- one output row is >= 80 % valid (igemm_rr.cuh)
+@pytest.mark.parametrize("n,h,w,ci,co", [
+    (2, 7, 130, 64, 64),        # exactly one full tile per row
+    (1, 9, 254, 64, 128),       # two tiles per row, second partially filled
+    (2, 6, 125, 128, 256),      # 123 valid of 128, two channel chunks, BN = 256
+    (1, 5, 510, 64, 64),        # four tiles per row (inc.b geometry)
+])
+def test_conv3x3_forward_rowrun(ops, n, h, w, ci, co):
+    x = bf(rand(n, ci, h, w))
+    wt = bf(rand(co, ci, 3, 3, scale=(2.0 / (9 * ci)) ** 0.5, seed=1))
+    b = rand(co, seed=2)
+    gamma, beta = rand(co, seed=3) + 1.5, rand(co, seed=4)
+    wf, _ = ops.pack_conv3x3(wt)
+    y, stats, info = ops.conv3x3_forward(ops.nhwc(x), None, wf, b, epilogue=0)
+    _, _, mean, rstd = ops.bn_finalize(stats, info, gamma, beta)
+    ref = F.conv2d(x, wt, b)
+    torch.cuda.synchronize()
+    assert rel_l2(ops.nchw(y), ref) < BF16_TOL
+    assert torch.allclose(mean, ref.mean((0, 2, 3)), rtol=2e-3, atol=2e-4)
+    assert rel_l2(1 / rstd ** 2, ref.var((0, 2, 3), unbiased=False) + 1e-5) < 2e-3
+    # eval epilogue through the same kernel
+    scale, shift = rand(co, seed=5).abs() + 0.5, rand(co, seed=6)
+    y2, _, _ = ops.conv3x3_forward(ops.nhwc(x), None, wf, None, epilogue=2, scale=scale, shift=shift)
+    ref2 = F.relu(F.conv2d(x, wt) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    torch.cuda.synchronize()
+    assert rel_l2(ops.nchw(y2), ref2) < BF16_TOL
+
+
+def test_conv3x3_rowrun_concat_sources(ops):
+    n, hs, ws_, cs, h, w, cu, co = 2, 12, 150, 64, 8, 130, 64, 64
+    skip = bf(rand(n, cs, hs, ws_))
+    up = bf(rand(n, cu, h, w, seed=5))
+    ch, cw = (hs - h) // 2, (ws_ - w) // 2
+    wt = bf(rand(co, cs + cu, 3, 3, scale=0.04, seed=1))
+    wf, _ = ops.pack_conv3x3(wt)
+    y, _, _ = ops.conv3x3_forward(ops.nhwc(skip)[:, ch:ch + h, cw:cw + w, :], ops.nhwc(up), wf, None)
+    ref = F.conv2d(torch.cat([skip[:, :, ch:ch + h, cw:cw + w], up], 1), wt)
+    torch.cuda.synchronize()
+    assert rel_l2(ops.nchw(y), ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", [(1, 6, 126, 64, 64), (2, 5, 252, 64, 128), (1, 4, 123, 128, 256)])
+def test_conv3x3_dgrad_rowrun(ops, n, h, w, ci, co):
+    dy = bf(rand(n, co, h, w))
+    wt = bf(rand(co, ci, 3, 3, scale=0.05, seed=1))
+    _, wd = ops.pack_conv3x3(wt)
+    dx = ops.conv3x3_dgrad(ops.nhwc(dy), wd)
+    ref = torch.nn.grad.conv2d_input((n, ci, h + 2, w + 2), wt, dy)
+    torch.cuda.synchronize()
+    assert rel_l2(ops.nchw(dx), ref) < BF16_TOL

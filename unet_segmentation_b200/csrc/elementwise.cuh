@@ -445,7 +445,8 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C,
 // ---------------------------------------------------------------------------------------------
 // Weight packing (fp32 torch layouts -> bf16 GEMM operands)
 // ---------------------------------------------------------------------------------------------
-// conv [Co][Ci][3][3] -> fprop B [Co][tap][Ci]   and   dgrad B [Ci][tap'][Co], tap' = 8 - tap
+// All GEMM B operands are stored tap-major, [tap][N][C]: K index = (tap, channel).
+// conv [Co][Ci][3][3] -> fprop B [tap][Co][Ci]   and   dgrad B [tap'][Ci][Co], tap' = 8 - tap
 static __global__ void pack_conv3x3_kernel(const float* __restrict__ w, int Co, int Ci,
                                     __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
     const long long total = (long long)Co * Ci * 9;
@@ -453,14 +454,14 @@ static __global__ void pack_conv3x3_kernel(const float* __restrict__ w, int Co, 
          i += (long long)gridDim.x * blockDim.x) {
         // i indexes the fprop layout (coalesced writes)
         const int ci = (int)(i % Ci);
-        const int tap = (int)((i / Ci) % 9);
-        const int co = (int)(i / ((long long)Ci * 9));
+        const int co = (int)((i / Ci) % Co);
+        const int tap = (int)(i / ((long long)Ci * Co));
         const __nv_bfloat16 v = __float2bfloat16_rn(w[((long long)co * Ci + ci) * 9 + tap]);
         wf[i] = v;
-        if (wd) wd[((long long)ci * 9 + (8 - tap)) * Co + co] = v;
+        if (wd) wd[((long long)(8 - tap) * Ci + ci) * Co + co] = v;
     }
 }
-// convT [Ci][Co][2][2] -> fwd B [(q*Co+co)][Ci]   and   bwd-data B [Ci][(q*Co+co)]
+// convT [Ci][Co][2][2] -> fwd B [(q*Co+co)][Ci] (one tap, N = 4*Co)  and  bwd-data B [q][Ci][Co]
 static __global__ void pack_convT2x2_kernel(const float* __restrict__ w, int Ci, int Co,
                                      __nv_bfloat16* __restrict__ wf,
                                      __nv_bfloat16* __restrict__ wb) {
@@ -472,7 +473,7 @@ static __global__ void pack_convT2x2_kernel(const float* __restrict__ w, int Ci,
         const int q = (int)(i / ((long long)Ci * Co));
         const __nv_bfloat16 v = __float2bfloat16_rn(w[((long long)ci * Co + co) * 4 + q]);
         wf[i] = v;
-        if (wb) wb[(long long)ci * 4 * Co + (long long)q * Co + co] = v;
+        if (wb) wb[((long long)q * Ci + ci) * Co + co] = v;
     }
 }
 // bias of the transposed conv replicated over the 4 sub-pixel positions (GEMM column order)

@@ -1,8 +1,10 @@
 // Host-side launchers of the tcgen05 implicit-GEMM kernels (see igemm.cuh).
 #include "igemm.cuh"
+#include "igemm_rr.cuh"
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -60,7 +62,7 @@ static int launch_igemm_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    igemm_kmajor_kernel<BN, EPI><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, p);
+    igemm_kmajor_kernel<BN, EPI><<<grid, 224, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, p);
     UB_POST_LAUNCH();
     return UB_OK;
 }
@@ -89,6 +91,44 @@ static int check_view(const View& v, const char* what) {
         return UB_ERR_ARG;
     }
     return UB_OK;
+}
+
+// ---- row-run variant (igemm_rr.cuh) -----------------------------------------------------------
+template <int BN, int EPI>
+static int launch_rowrun_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                           const RowRunParams& p, int grid, cudaStream_t stream) {
+    using Cfg = RowRunCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_rowrun_kernel<BN, EPI>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    igemm_rowrun_kernel<BN, EPI><<<grid, 224, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, p);
+    UB_POST_LAUNCH();
+    return UB_OK;
+}
+template <int BN>
+static int launch_rowrun_bn(int epi, const CUtensorMap& a0, const CUtensorMap& a1,
+                            const CUtensorMap& b, const RowRunParams& p, int grid,
+                            cudaStream_t stream) {
+    switch (epi) {
+        case EPI_CONV_STATS: return launch_rowrun_t<BN, EPI_CONV_STATS>(a0, a1, b, p, grid, stream);
+        case EPI_STORE: return launch_rowrun_t<BN, EPI_STORE>(a0, a1, b, p, grid, stream);
+        case EPI_AFFINE_RELU: return launch_rowrun_t<BN, EPI_AFFINE_RELU>(a0, a1, b, p, grid, stream);
+    }
+    set_last_error("row-run: unsupported epilogue kind %d", epi);
+    return UB_ERR_ARG;
+}
+// Row-run pays off when a 128-pixel tile of one output row is mostly valid pixels.
+static bool rowrun_eligible(int Wo, int taps, int tstride, int epi_kind) {
+    if (taps != 9 || tstride != 1 || epi_kind == EPI_CONVT) return false;
+    static int disabled = -1;
+    if (disabled < 0) { const char* e = getenv("UB_NO_ROWRUN"); disabled = (e && atoi(e)) ? 1 : 0; }
+    if (disabled) return false;
+    const int tiles = (Wo + 127) / 128;
+    return Wo * 100 >= tiles * 128 * 80;
 }
 
 int launch_igemm(const View& src0, const View* src1, int lower, int upper, int tstride, int taps,
@@ -122,6 +162,54 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
     const long long K = (long long)taps * ctot;
 
     CUtensorMap mA0, mA1, mB;
+    if (rowrun_eligible(Wo, taps, tstride, epi.kind)) {
+        int rr = make_tmap_rows(&mA0, src0, 130, 3);
+        if (!rr && src1) rr = make_tmap_rows(&mA1, *src1, 130, 3);
+        if (!src1) mA1 = mA0;
+        if (!rr) rr = make_tmap_weights(&mB, wB, (unsigned long long)ctot, (unsigned long long)ncols,
+                                        (unsigned long long)taps, (unsigned)BN,
+                                        (unsigned)RowRunCfg<64>::btaps(BN));
+        if (rr) { set_last_error("row-run: tensor map encoding failed: %d", rr); return UB_ERR_TMAP; }
+        RowRunParams q;
+        memset(&q, 0, sizeof(q));
+        q.N = src0.N; q.Ho = Ho; q.Wo = Wo; q.lower = lower;
+        q.cchunks0 = src0.C / 64; q.cchunks1 = src1 ? src1->C / 64 : 0;
+        q.qtiles = (Wo + 127) / 128;
+        q.m_tiles = src0.N * Ho * q.qtiles;
+        q.n_tiles = ncols / BN;
+        q.epi.M = (int)M; q.epi.out = epi.out; q.epi.ldo = epi.ldo; q.epi.bias = epi.bias;
+        q.epi.scale = epi.scale; q.epi.shift = epi.shift; q.epi.stats = epi.stats;
+        static long long* dbg_buf = nullptr;
+        static int dbg_on = -1;
+        if (dbg_on < 0) { const char* e = getenv("UB_RR_PROFILE"); dbg_on = (e && atoi(e)) ? 1 : 0; }
+        if (dbg_on) {
+            if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
+            cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), stream);
+            q.dbg = dbg_buf;
+        }
+        int grid = (num_sms() / q.n_tiles) * q.n_tiles;
+        if (grid <= 0) grid = q.n_tiles;
+        const long long tiles = (long long)q.m_tiles * q.n_tiles;
+        if (grid > tiles) grid = (int)tiles;
+        if (info) { info->grid = grid; info->n_tiles = q.n_tiles; info->BN = BN; info->M = (int)M; }
+        int rc;
+        switch (BN) {
+            case 256: rc = launch_rowrun_bn<256>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
+            case 128: rc = launch_rowrun_bn<128>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
+            default: rc = launch_rowrun_bn<64>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
+        }
+        if (dbg_on && rc == 0) {  // debugging aid only: synchronises
+            long long h[10];
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+            const double g = grid;
+            fprintf(stderr, "[rr BN=%d epi=%d tiles/cta=%.1f] cycles/cta: A-prod wait %.0f of %.0f | "
+                    "B-prod wait %.0f of %.0f | MMA wait A %.0f B %.0f tmem %.0f of %.0f | epi wait %.0f of %.0f\n",
+                    BN, epi.kind, (double)tiles / g, h[0] / g, h[1] / g, h[2] / g, h[3] / g, h[4] / g,
+                    h[5] / g, h[6] / g, h[7] / g, h[8] / g, h[9] / g);
+        }
+        return rc;
+    }
     int r = make_tmap_im2col(&mA0, src0, lower, upper, tstride, 128);
     if (r) { set_last_error("igemm: im2col tensor map (source 0) failed: %d", r); return UB_ERR_TMAP; }
     if (src1) {
@@ -130,9 +218,10 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
     } else {
         mA1 = mA0;
     }
-    r = make_tmap_2d(&mB, wB, (unsigned long long)K, (unsigned long long)ncols,
-                     (unsigned long long)K * 2, (unsigned)BN);
+    r = make_tmap_weights(&mB, wB, (unsigned long long)ctot, (unsigned long long)ncols,
+                          (unsigned long long)taps, (unsigned)BN, 1);
     if (r) { set_last_error("igemm: weight tensor map failed: %d", r); return UB_ERR_TMAP; }
+    (void)K;
 
     IgemmParams p;
     memset(&p, 0, sizeof(p));
@@ -197,7 +286,7 @@ static int launch_wgrad_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    igemm_wgrad_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, p);
+    igemm_wgrad_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, p);
     UB_POST_LAUNCH();
     return UB_OK;
 }

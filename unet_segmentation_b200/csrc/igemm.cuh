@@ -46,8 +46,76 @@ struct IgemmCfg {
     static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
+// Epilogue of one 128 x BN accumulator tile: TMEM -> registers (32 columns at a time), bias /
+// folded-BN affine, bf16 store (row-major, or 2x2 pixel-shuffle scatter for the transposed conv),
+// and the per-channel sum / sum-of-squares of the BatchNorm statistics.
+//   trow: TMEM address of this warp's lane quadrant and accumulator stage; m: GEMM row of the thread.
 template <int BN, int EPI>
-__global__ void __launch_bounds__(192, 1)
+__device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t trow, long long m,
+                                              bool valid, int n0, int lane, float (&ssum)[BN / 32],
+                                              float (&ssq)[BN / 32]) {
+                long long ct_row = 0;
+                if (EPI == EPI_CONVT) {
+                    const int w = (int)(m % p.ct_W);
+                    const long long t = m / p.ct_W;
+                    const int h = (int)(t % p.ct_H);
+                    const long long n = t / p.ct_H;
+                    ct_row = n * p.ct_sN + (long long)(2 * h) * p.ct_sH + (long long)(2 * w) * p.ct_sW;
+                }
+    #pragma unroll
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(trow + (uint32_t)(c * 32), r);
+                    tmem_ld_wait();
+                    const int col0 = n0 + c * 32;
+                    float v[32];
+    #pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    if (EPI == EPI_AFFINE_RELU) {
+    #pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            v[i] = fmaxf(fmaf(v[i], __ldg(p.scale + col0 + i), __ldg(p.shift + col0 + i)),
+                                         0.f);
+                    } else if (p.bias != nullptr) {
+    #pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col0 + i);
+                    }
+                    if (valid) {
+                        __nv_bfloat16* dst;
+                        if (EPI == EPI_CONVT) {
+                            const int qd = col0 / p.ct_cout;
+                            const int co = col0 - qd * p.ct_cout;
+                            dst = p.out + ct_row + (long long)(qd >> 1) * p.ct_sH +
+                                  (long long)(qd & 1) * p.ct_sW + co;
+                        } else {
+                            dst = p.out + m * p.ldo + col0;
+                        }
+                        uint4* d4 = reinterpret_cast<uint4*>(dst);
+    #pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 o;
+                            o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                            d4[j] = o;
+                        }
+                    }
+                    if (EPI == EPI_CONV_STATS) {
+                        float s2[32];
+    #pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            v[i] = valid ? v[i] : 0.f;
+                            s2[i] = v[i] * v[i];
+                        }
+                        ssum[c] += warp_column_sum(v, lane);
+                        ssq[c] += warp_column_sum(s2, lane);
+                    }
+                }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(224, 1)
 igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const IgemmParams p) {
@@ -74,7 +142,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
         tma_prefetch_desc(&mapA1);
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
+            mbar_init(full_bar(s), 2);   // two producer threads (A operand, B operand)
             mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -97,7 +165,10 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
     const int n0 = cta_n * BN;
 
     if (warp == 0 && lane == 0) {
-        // ------------------------------ TMA producer ------------------------------
+        // ------------------------------ TMA producer, A operand (im2col) ------------------------------
+        // Issuing one TMA operation costs a few hundred cycles of the issuing thread, so the two
+        // operands are fed by two threads in different warps; each arms the stage barrier with its own
+        // byte count.
         int stage = 0;
         uint32_t phase = 0;
         for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
@@ -112,19 +183,32 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             uint16_t offw = 0, offh = 0;
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
-                mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                mbar_expect_tx(full_bar(stage), Cfg::A_BYTES);
                 const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-                const uint32_t sb = sa + Cfg::A_BYTES;
                 if (cc < p.cchunks0)
                     tma_load_im2col(sa, &mapA0, full_bar(stage), cc * 64, cw, ch, n, offw, offh);
                 else
                     tma_load_im2col(sa, &mapA1, full_bar(stage), (cc - p.cchunks0) * 64, cw, ch, n,
                                     offw, offh);
-                tma_load_2d(sb, &mapB, full_bar(stage), kb * 64, n0);
                 if (++cc == cchunks) {
                     cc = 0;
                     if (++offw == (uint16_t)p.tapw) { offw = 0; ++offh; }
                 }
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 6 && lane == 0) {
+        // ------------------------------ TMA producer, B operand (weights) ------------------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+            int cc = 0, tap = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_expect_tx(full_bar(stage), Cfg::B_BYTES);
+                tma_load_3d(base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES, &mapB, full_bar(stage),
+                            cc * 64, n0, tap);
+                if (++cc == cchunks) { cc = 0; ++tap; }
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
         }
@@ -156,7 +240,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             umma_commit(tfull_bar(as));
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
-    } else if (warp >= 2) {
+    } else if (warp >= 2 && warp < 6) {
         // ------------------------------ epilogue ------------------------------
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
         const int row_in_tile = quad * 32 + lane;
@@ -173,64 +257,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 
-            long long ct_row = 0;
-            if (EPI == EPI_CONVT) {
-                const int w = (int)(m % p.ct_W);
-                const long long t = m / p.ct_W;
-                const int h = (int)(t % p.ct_H);
-                const long long n = t / p.ct_H;
-                ct_row = n * p.ct_sN + (long long)(2 * h) * p.ct_sH + (long long)(2 * w) * p.ct_sW;
-            }
-#pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(trow + (uint32_t)(c * 32), r);
-                tmem_ld_wait();
-                const int col0 = n0 + c * 32;
-                float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                if (EPI == EPI_AFFINE_RELU) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        v[i] = fmaxf(fmaf(v[i], __ldg(p.scale + col0 + i), __ldg(p.shift + col0 + i)),
-                                     0.f);
-                } else if (p.bias != nullptr) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col0 + i);
-                }
-                if (valid) {
-                    __nv_bfloat16* dst;
-                    if (EPI == EPI_CONVT) {
-                        const int qd = col0 / p.ct_cout;
-                        const int co = col0 - qd * p.ct_cout;
-                        dst = p.out + ct_row + (long long)(qd >> 1) * p.ct_sH +
-                              (long long)(qd & 1) * p.ct_sW + co;
-                    } else {
-                        dst = p.out + m * p.ldo + col0;
-                    }
-                    uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 o;
-                        o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                        o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                        o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                        o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                        d4[j] = o;
-                    }
-                }
-                if (EPI == EPI_CONV_STATS) {
-                    float s2[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        v[i] = valid ? v[i] : 0.f;
-                        s2[i] = v[i] * v[i];
-                    }
-                    ssum[c] += warp_column_sum(v, lane);
-                    ssq[c] += warp_column_sum(s2, lane);
-                }
-            }
+            epilogue_tile<BN, EPI>(p, trow, m, valid, n0, lane, ssum, ssq);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -285,7 +312,7 @@ struct WgradCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(256, 1)
 igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                    const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const WgradParams p) {
@@ -309,8 +336,10 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapA1);
         tma_prefetch_desc(&mapB);
+        // producers arming a stage: the B thread plus one thread per existing 64-row A chunk
+        const uint32_t nprod = ((int)(blockIdx.x / p.n_tiles) * 2 + 1 < p.a_chunks_total) ? 3u : 2u;
         for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
+            mbar_init(full_bar(s), nprod);
             mbar_init(empty_bar(s), 1);
         }
         mbar_init(tfull_bar, 1);
@@ -330,54 +359,57 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
     const int cchunks = p.cchunks0 + p.cchunks1;
     const int n0 = n_tile * BN;
 
-    if (warp == 0 && lane == 0) {
+    // Three producer threads (different warps) feed one stage: the two 64-row im2col chunks of the
+    // A side and the B-side box; each arms the stage barrier with its own byte count.
+    if ((warp == 0 || warp == 6 || warp == 7) && lane == 0) {
+        const int role = warp == 0 ? 0 : (warp == 6 ? 1 : 2);   // 0/1: A chunk j, 2: B
         int stage = 0;
         uint32_t phase = 0;
-        // the (at most) two 64-row chunks of this CTA's M' tile
-        int a_tap[2], a_cc[2];
-        bool a_ok[2];
-        for (int j = 0; j < 2; ++j) {
-            const int c = m_tile * 2 + j;
-            a_ok[j] = c < p.a_chunks_total;
-            a_tap[j] = a_ok[j] ? c / cchunks : 0;
-            a_cc[j] = a_ok[j] ? c % cchunks : 0;
-        }
-        const uint32_t tx = (a_ok[1] ? 2u : 1u) * 8192u + Cfg::B_BYTES;
-        uint16_t a_offw[2], a_offh[2];
-        for (int j = 0; j < 2; ++j) {
-            a_offw[j] = (uint16_t)(a_tap[j] % p.tapw);
-            a_offh[j] = (uint16_t)(a_tap[j] / p.tapw);
+        int a_cc = 0;
+        uint16_t a_offw = 0, a_offh = 0;
+        bool active = true;
+        if (role < 2) {
+            const int c = m_tile * 2 + role;
+            active = c < p.a_chunks_total;
+            if (active) {
+                const int tap = c / cchunks;
+                a_cc = c % cchunks;
+                a_offw = (uint16_t)(tap % p.tapw);
+                a_offh = (uint16_t)(tap / p.tapw);
+            }
         }
         // base pixel (q, pr, n) of the first k-block of this split, then advanced by 64 pixels
         int m0 = kb_begin * 64;
         int q = m0 % p.Wo;
         int pr, n;
         { const int t = m0 / p.Wo; pr = t % p.Ho; n = t / p.Ho; }
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-            const int cw = p.lower + q * p.tstride;
-            const int ch = p.lower + pr * p.tstride;
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), tx);
-            const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-            const uint32_t sb = sa + Cfg::A_BYTES;
-            for (int j = 0; j < 2; ++j) {
-                if (!a_ok[j]) continue;
-                if (a_cc[j] < p.cchunks0)
-                    tma_load_im2col(sa + j * 8192, &mapA0, full_bar(stage), a_cc[j] * 64, cw, ch, n,
-                                    a_offw[j], a_offh[j]);
-                else
-                    tma_load_im2col(sa + j * 8192, &mapA1, full_bar(stage),
-                                    (a_cc[j] - p.cchunks0) * 64, cw, ch, n, a_offw[j], a_offh[j]);
+        if (active) {
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+                if (role < 2) {
+                    const int cw = p.lower + q * p.tstride;
+                    const int ch = p.lower + pr * p.tstride;
+                    mbar_expect_tx(full_bar(stage), 8192u);
+                    if (a_cc < p.cchunks0)
+                        tma_load_im2col(sa + role * 8192, &mapA0, full_bar(stage), a_cc * 64, cw, ch,
+                                        n, a_offw, a_offh);
+                    else
+                        tma_load_im2col(sa + role * 8192, &mapA1, full_bar(stage),
+                                        (a_cc - p.cchunks0) * 64, cw, ch, n, a_offw, a_offh);
+                    q += 64;
+                    while (q >= p.Wo) {
+                        q -= p.Wo;
+                        if (++pr == p.Ho) { pr = 0; ++n; }
+                    }
+                } else {
+                    // B side: one 3-D box (64 ch, 64 pixels, BN/64 chunks) -> [chunk][pixel][64 ch]
+                    mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::B_BYTES);
+                    tma_load_3d(sa + Cfg::A_BYTES, &mapB, full_bar(stage), 0, m0, n_tile * (BN / 64));
+                    m0 += 64;
+                }
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
-            // B side: one 3-D box (64 ch, 64 pixels, BN/64 chunks) -> [chunk][pixel][64 ch] in smem
-            tma_load_3d(sb, &mapB, full_bar(stage), 0, m0, n_tile * (BN / 64));
-            m0 += 64;
-            q += 64;
-            while (q >= p.Wo) {
-                q -= p.Wo;
-                if (++pr == p.Ho) { pr = 0; ++n; }
-            }
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
     } else if (warp == 1 && lane == 0) {
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
@@ -398,7 +430,7 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar);
-    } else if (warp >= 2) {
+    } else if (warp >= 2 && warp < 6) {
         const int quad = warp & 3;
         const int row = m_tile * 128 + quad * 32 + lane;
         const bool valid = row < p.a_chunks_total * 64;

@@ -1,0 +1,265 @@
+// "Row-run" implicit-GEMM 3x3 convolution (forward and data gradient) for wide feature maps.
+//
+// The im2col TMA path (igemm.cuh) re-reads every input pixel nine times, once per filter tap, and is
+// bound by the ~55 B/cycle an SM can ingest from L2. Here a tile is 128 consecutive output pixels of
+// ONE output row: for each 64-channel chunk the three input rows it needs (130 pixels each) are
+// loaded ONCE with tiled-mode TMA into 128-byte-swizzled shared memory, and the nine taps are
+// addressed as shifted windows of those rows: the UMMA shared-memory descriptor of tap (r, s) starts
+// at row-buffer r + s*128 bytes. (Measured on B200: the 128B swizzle is a function of the absolute
+// shared-memory address, so a descriptor start shifted by whole 128-byte rows, with base_offset 0,
+// reads exactly the rows TMA wrote — scripts_dev/shift_probe.py.) A-operand ingest drops 2.9x.
+//
+// Pipelines: A ring (SA stages of 3 row buffers) fed by warp 0, B ring (SB stages of one
+// (tap, chunk) weight tile) fed by warp 6, MMA issue by warp 1, epilogue warps 2-5 on a
+// double-buffered TMEM accumulator — same epilogues as igemm_kmajor_kernel.
+#pragma once
+#include "igemm.cuh"
+
+namespace ub {
+
+struct RowRunParams {
+    int N, Ho, Wo;        // output extents; the tile (n, p, qt) covers q in [128*qt, 128*qt + 128)
+    int lower;            // input coordinate of tap (0,0) relative to the output pixel (0 / -2)
+    int cchunks0, cchunks1;
+    int qtiles;           // ceil(Wo / 128)
+    int m_tiles, n_tiles; // m_tiles = N * Ho * qtiles
+    IgemmParams epi;      // epilogue fields (out, ldo, bias, scale, shift, stats); M = N*Ho*Wo
+    long long* dbg;       // optional role profile: [role][0] = cycles waiting, [role][1] = total
+};
+
+// mbarrier wait that optionally accounts the cycles spent waiting (role profiling, UB_RR_PROFILE=1)
+__device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bool prof,
+                                               long long& waited) {
+    if (!prof) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    waited += clock64() - t0;
+}
+
+// One TMA operation costs the issuing thread a few hundred cycles whatever its size, and one
+// barrier wait + tcgen05 fence costs the MMA thread ~230 cycles, so operations are made as large as
+// possible: ONE box (64 ch, 130 px, 3 rows) per A stage, and BTAPS filter taps of weights per B stage
+// (a whole filter row for BN <= 128), i.e. 12 MMAs per B wait and 36 per A wait.
+template <int BN>
+struct RowRunCfg {
+    static constexpr int btaps(int bn) { return bn <= 128 ? 3 : 1; }
+    static constexpr int BTAPS = btaps(BN);
+    static constexpr int ROW_BYTES = 130 * 128;            // input rows are packed back to back
+    static constexpr int A_TX = 3 * ROW_BYTES;             // bytes one A stage receives (49920)
+    static constexpr int A_STAGE = 49 * 1024;              // 1024-aligned stage pitch
+    static constexpr int B_TILE = BN * 128;                // one tap: [BN][64] K-major
+    static constexpr int B_STAGE = BTAPS * B_TILE;
+    static constexpr int SA = (BN == 64) ? 3 : 2;
+    static constexpr int SB = (BN == 64) ? 3 : (BN == 128 ? 2 : 3);
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = SA * A_STAGE + SB * B_STAGE + BAR_BYTES + 1024;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c,
+                                            int w, int h, int n) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+        : "memory");
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(224, 1)
+igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
+                    const __grid_constant__ CUtensorMap mapA1,
+                    const __grid_constant__ CUtensorMap mapB, const RowRunParams p) {
+    using Cfg = RowRunCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - raw);
+    const uint32_t b_base = base + Cfg::SA * Cfg::A_STAGE;
+    const uint32_t bar_base = b_base + Cfg::SB * Cfg::B_STAGE;
+    auto fullA = [&](int s) { return bar_base + 8u * s; };
+    auto emptyA = [&](int s) { return bar_base + 8u * (Cfg::SA + s); };
+    auto fullB = [&](int s) { return bar_base + 8u * (2 * Cfg::SA + s); };
+    auto emptyB = [&](int s) { return bar_base + 8u * (2 * Cfg::SA + Cfg::SB + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::SA + 2 * Cfg::SB + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::SA + 2 * Cfg::SB + 2 + s); };
+    constexpr int kSlot = 2 * Cfg::SA + 2 * Cfg::SB + 4;
+    const uint32_t tmem_slot = bar_base + 8u * kSlot;
+    volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(
+        gbase + Cfg::SA * Cfg::A_STAGE + Cfg::SB * Cfg::B_STAGE + 8 * kSlot);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA0);
+        tma_prefetch_desc(&mapA1);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < Cfg::SA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+        for (int s = 0; s < Cfg::SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_g;
+
+    const int cchunks = p.cchunks0 + p.cchunks1;
+    const int cta_n = blockIdx.x % p.n_tiles;
+    const int m_first = blockIdx.x / p.n_tiles;
+    const int m_step = gridDim.x / p.n_tiles;
+    const int n0 = cta_n * BN;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- A producer: 3 input rows x 130 pixels x 64 channels per chunk ----------
+        int stage = 0;
+        uint32_t phase = 0;
+        const bool prof = p.dbg != nullptr;
+        long long waited = 0;
+        const long long tstart = clock64();
+        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+            const int qt = mt % p.qtiles;
+            const int t = mt / p.qtiles;
+            const int pr = t % p.Ho;
+            const int n = t / p.Ho;
+            const int w0 = qt * 128 + p.lower;
+            const int h0 = pr + p.lower;
+            for (int cc = 0; cc < cchunks; ++cc) {
+                mbar_wait_prof(emptyA(stage), phase ^ 1u, prof, waited);
+                mbar_expect_tx(fullA(stage), Cfg::A_TX);
+                const uint32_t sa = base + stage * Cfg::A_STAGE;
+                const CUtensorMap* mp = cc < p.cchunks0 ? &mapA0 : &mapA1;
+                const int c = (cc < p.cchunks0 ? cc : cc - p.cchunks0) * 64;
+                tma_load_4d(sa, mp, fullA(stage), c, w0, h0, n);   // box (64, 130, 3, 1)
+                if (++stage == Cfg::SA) { stage = 0; phase ^= 1u; }
+            }
+        }
+        if (prof) {
+            atomicAdd((unsigned long long*)&p.dbg[0], (unsigned long long)waited);
+            atomicAdd((unsigned long long*)&p.dbg[1], (unsigned long long)(clock64() - tstart));
+        }
+    } else if (warp == 6 && lane == 0) {
+        // ---------------- B producer: one (tap, chunk) weight tile per stage ----------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        const bool prof = p.dbg != nullptr;
+        long long waited = 0;
+        const long long tstart = clock64();
+        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+            for (int cc = 0; cc < cchunks; ++cc) {
+#pragma unroll 1
+                for (int tap = 0; tap < 9; tap += Cfg::BTAPS) {
+                    mbar_wait_prof(emptyB(stage), phase ^ 1u, prof, waited);
+                    mbar_expect_tx(fullB(stage), Cfg::B_STAGE);
+                    tma_load_3d(b_base + stage * Cfg::B_STAGE, &mapB, fullB(stage), cc * 64, n0, tap);
+                    if (++stage == Cfg::SB) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        if (prof) {
+            atomicAdd((unsigned long long*)&p.dbg[2], (unsigned long long)waited);
+            atomicAdd((unsigned long long*)&p.dbg[3], (unsigned long long)(clock64() - tstart));
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer -----------------------------------------------------------------
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+        int sa_i = 0, sb_i = 0;
+        uint32_t pa = 0, pb = 0;
+        int as = 0;
+        uint32_t aphase = 0;
+        const bool prof = p.dbg != nullptr;
+        long long wA = 0, wB = 0, wT = 0;
+        const long long tstart = clock64();
+        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+            mbar_wait_prof(tempty_bar(as), aphase ^ 1u, prof, wT);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+            uint32_t acc = 0;
+            for (int cc = 0; cc < cchunks; ++cc) {
+                mbar_wait_prof(fullA(sa_i), pa, prof, wA);
+                const uint32_t sa = base + sa_i * Cfg::A_STAGE;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; tap += Cfg::BTAPS) {
+                    mbar_wait_prof(fullB(sb_i), pb, prof, wB);
+                    tc_fence_after();
+#pragma unroll
+                    for (int j = 0; j < Cfg::BTAPS; ++j) {
+                        const int r = (tap + j) / 3, sft = (tap + j) % 3;
+                        // tap (r, sft) = window of input row r shifted by sft pixels (128 B each)
+                        const uint64_t da =
+                            make_smem_desc(sa + r * Cfg::ROW_BYTES + sft * 128, 0, 1024);
+                        const uint64_t db =
+                            make_smem_desc(b_base + sb_i * Cfg::B_STAGE + j * Cfg::B_TILE, 0, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(emptyB(sb_i));
+                    if (++sb_i == Cfg::SB) { sb_i = 0; pb ^= 1u; }
+                }
+                umma_commit(emptyA(sa_i));
+                if (++sa_i == Cfg::SA) { sa_i = 0; pa ^= 1u; }
+            }
+            umma_commit(tfull_bar(as));
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+        if (prof) {
+            atomicAdd((unsigned long long*)&p.dbg[4], (unsigned long long)wA);
+            atomicAdd((unsigned long long*)&p.dbg[5], (unsigned long long)wB);
+            atomicAdd((unsigned long long*)&p.dbg[6], (unsigned long long)wT);
+            atomicAdd((unsigned long long*)&p.dbg[7], (unsigned long long)(clock64() - tstart));
+        }
+    } else if (warp >= 2 && warp < 6) {
+        // ---------------- epilogue ----------------------------------------------------------------------
+        const int quad = warp & 3;
+        const int row_in_tile = quad * 32 + lane;
+        int as = 0;
+        uint32_t aphase = 0;
+        float ssum[BN / 32], ssq[BN / 32];
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+        const bool prof = p.dbg != nullptr;
+        long long wE = 0;
+        const long long tstart = clock64();
+        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+            const int qt = mt % p.qtiles;
+            const int t = mt / p.qtiles;      // = n * Ho + p
+            const int q = qt * 128 + row_in_tile;
+            const bool valid = q < p.Wo;
+            const long long m = (long long)t * p.Wo + q;
+            mbar_wait_prof(tfull_bar(as), aphase, prof, wE);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+            epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, ssum, ssq);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+        if (prof && warp == 2 && lane == 0) {
+            atomicAdd((unsigned long long*)&p.dbg[8], (unsigned long long)wE);
+            atomicAdd((unsigned long long*)&p.dbg[9], (unsigned long long)(clock64() - tstart));
+        }
+        if (EPI == EPI_CONV_STATS) {
+            float* dst = p.epi.stats + ((long long)blockIdx.x * 4 + quad) * (2 * BN);
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                dst[c * 32 + lane] = ssum[c];
+                dst[BN + c * 32 + lane] = ssq[c];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace ub

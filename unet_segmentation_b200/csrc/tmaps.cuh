@@ -63,6 +63,24 @@ inline int make_tmap_2d(CUtensorMap* out, const void* ptr, unsigned long long in
     return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
 
+// Tap-major packed weights [taps][n][c] (bf16): box = (64 channels, box_n rows, box_taps taps) lands
+// in shared memory as box_taps consecutive K-major [box_n][64] tiles.
+inline int make_tmap_weights(CUtensorMap* out, const void* ptr, unsigned long long c,
+                             unsigned long long n, unsigned long long taps, unsigned box_n,
+                             unsigned box_taps) {
+    TmapApi& api = tmap_api();
+    if (!api.ok) return -1;
+    cuuint64_t dims[3] = {c, n, taps};
+    cuuint64_t strides[2] = {c * 2, n * c * 2};
+    cuuint32_t box[3] = {64, box_n, box_taps};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = api.tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
 // [rows][cols] bf16 matrix (row pitch in bytes) seen as (64 channels, rows, cols/64 chunks): one
 // box of (64, box_rows, box_chunks) lands in shared memory as [chunk][row][64 ch] with the
 // 128-byte swizzle, i.e. box_chunks MN-major operand chunks in a single TMA operation.
@@ -76,6 +94,22 @@ inline int make_tmap_chunked(CUtensorMap* out, const void* ptr, unsigned long lo
     cuuint32_t box[3] = {64, box_rows, box_chunks};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = api.tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+// Tiled 4-D map over an NHWC bf16 view, box = (64 channels, box_w pixels, box_h rows). Out-of-range
+// coordinates (negative or past the edge) are zero filled: that is the padding of the data gradient.
+inline int make_tmap_rows(CUtensorMap* out, const View& v, unsigned box_w, unsigned box_h = 1) {
+    TmapApi& api = tmap_api();
+    if (!api.ok) return -1;
+    cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+    cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
+    cuuint32_t box[4] = {64, box_w, box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = api.tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims,
                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

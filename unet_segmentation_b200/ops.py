@@ -51,8 +51,8 @@ def pack_conv3x3(w: torch.Tensor, with_dgrad: bool = True):
     lib = _lib.load()
     co, ci = w.shape[:2]
     w = w.contiguous().float()
-    wf = torch.empty(co, 9, ci, dtype=torch.bfloat16, device=w.device)
-    wd = torch.empty(ci, 9, co, dtype=torch.bfloat16, device=w.device) if with_dgrad else None
+    wf = torch.empty(9, co, ci, dtype=torch.bfloat16, device=w.device)       # [tap][Co][Ci]
+    wd = torch.empty(9, ci, co, dtype=torch.bfloat16, device=w.device) if with_dgrad else None
     check(lib.ub_op_pack_conv3x3(_p(w), co, ci, _p(wf), _p(wd), _stream()), "pack_conv3x3")
     return wf, wd
 
@@ -62,7 +62,7 @@ def pack_convT(w: torch.Tensor, bias: torch.Tensor | None = None):
     ci, co = w.shape[:2]
     w = w.contiguous().float()
     wf = torch.empty(4 * co, ci, dtype=torch.bfloat16, device=w.device)
-    wb = torch.empty(ci, 4 * co, dtype=torch.bfloat16, device=w.device)
+    wb = torch.empty(4, ci, co, dtype=torch.bfloat16, device=w.device)       # [q][Ci][Co]
     b4 = torch.empty(4 * co, dtype=torch.float32, device=w.device) if bias is not None else None
     check(lib.ub_op_pack_convT(_p(w), ci, co, _p(wf), _p(wb), _p(bias), _p(b4), _stream()),
           "pack_convT")
@@ -73,7 +73,7 @@ def conv3x3_forward(src0, src1, wf, bias, epilogue=1, scale=None, shift=None):
     """Returns (y, stats, info). epilogue 0 = +bias & BN statistics, 1 = +bias, 2 = affine+ReLU."""
     lib = _lib.load()
     n, h, w, _ = src0.shape
-    co = wf.shape[0]
+    co = wf.shape[1]
     y = torch.empty(n, h - 2, w - 2, co, dtype=torch.bfloat16, device=src0.device)
     stats = None
     info = (C.c_int * 4)()
@@ -123,7 +123,7 @@ def bn_relu_backward(y, scale, shift, mean, rstd, g=None, gp=None, gs=None, crop
 def conv3x3_dgrad(dy, wd):
     lib = _lib.load()
     n, h, w, _ = dy.shape
-    ci = wd.shape[0]
+    ci = wd.shape[1]
     dx = torch.empty(n, h + 2, w + 2, ci, dtype=torch.bfloat16, device=dy.device)
     check(lib.ub_op_conv3x3_dgrad(_vp(dy), _p(wd), ci, _p(dx), _stream()), "conv3x3_dgrad")
     return dx
@@ -154,7 +154,7 @@ def convT_forward(x, wf, bias4, dst):
 def convT_dgrad(dup, wb):
     lib = _lib.load()
     n, h2, w2, _ = dup.shape
-    ci = wb.shape[0]
+    ci = wb.shape[1]
     dx = torch.empty(n, h2 // 2, w2 // 2, ci, dtype=torch.bfloat16, device=dup.device)
     check(lib.ub_op_convT_dgrad(_vp(dup), _p(wb), ci, _p(dx), _stream()), "convT_dgrad")
     return dx
