@@ -3,7 +3,7 @@
 #include "../unet_segmentation_b200/csrc/common.cuh"
 using namespace ub;
 
-template <int BN, int MMAS, bool FENCE, bool COMMIT, bool WAITBAR>
+template <int BN, int MMAS, bool FENCE, bool COMMIT, bool WAITBAR, int SHIFT = 0>
 __global__ void __launch_bounds__(128, 1) k(int iters, long long* out) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(128, 1) k(int iters, long long* out) {
         for (int it = 0; it < iters; ++it) {
             if (WAITBAR) { mbar_arrive(bar2); mbar_wait(bar2, ph); ph ^= 1u; }   // already-complete wait
             if (FENCE) tc_fence_after();
-            const uint64_t da = make_smem_desc(base + (it & 3) * 16384, 0, 1024);
+            const uint64_t da = make_smem_desc(base + (it & 1) * 16384 + SHIFT, 0, 1024);
             const uint64_t db = make_smem_desc(base + 65536 + (it & 1) * 32768, 0, 1024);
 #pragma unroll
             for (int j = 0; j < MMAS; ++j)
@@ -39,11 +39,11 @@ __global__ void __launch_bounds__(128, 1) k(int iters, long long* out) {
     if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<256>(tmem); }
 }
 
-template <int BN, int MMAS, bool FENCE, bool COMMIT, bool WAITBAR>
+template <int BN, int MMAS, bool FENCE, bool COMMIT, bool WAITBAR, int SHIFT = 0>
 void run(const char* name, long long* d) {
     const int smem = 65536 + 65536 + 2048, iters = 2000;
-    cudaFuncSetAttribute(k<BN, MMAS, FENCE, COMMIT, WAITBAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    for (int r = 0; r < 2; ++r) k<BN, MMAS, FENCE, COMMIT, WAITBAR><<<1, 128, smem>>>(iters, d);
+    cudaFuncSetAttribute(k<BN, MMAS, FENCE, COMMIT, WAITBAR, SHIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int r = 0; r < 2; ++r) k<BN, MMAS, FENCE, COMMIT, WAITBAR, SHIFT><<<1, 128, smem>>>(iters, d);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
     printf("%-44s BN=%3d: issue %6.1f cyc/iter, total %6.1f cyc/iter (exec floor %4d) %s\n", name, BN, h[0] / (double)iters,
@@ -52,6 +52,12 @@ void run(const char* name, long long* d) {
 
 int main() {
     long long* d; cudaMalloc(&d, 64);
+    run<64, 4, false, false, false, 128>("4 MMA, A start +128 B", d);
+    run<64, 4, false, false, false, 256>("4 MMA, A start +256 B", d);
+    run<64, 4, false, false, false, 512>("4 MMA, A start +512 B", d);
+    run<128, 4, false, false, false, 0>("4 MMA aligned", d);
+    run<128, 4, false, false, false, 128>("4 MMA, A start +128 B", d);
+    run<256, 4, false, false, false, 128>("4 MMA, A start +128 B", d);
     run<64, 4, false, false, false>("4 MMA", d);
     run<64, 4, false, true, false>("4 MMA + commit", d);
     run<64, 4, true, true, false>("fence + 4 MMA + commit", d);

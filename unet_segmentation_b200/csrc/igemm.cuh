@@ -164,10 +164,13 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
     const int m_step = gridDim.x / p.n_tiles;
     const int n0 = cta_n * BN;
 
-    if (warp == 0 && lane == 0) {
+    // Role code is executed by WHOLE warps with warp-uniform control flow; only the instruction that
+    // must be issued once (TMA, MMA, commit, expect_tx) sits under elect_one(). In a single-lane
+    // divergent branch the compiler has to wrap every TMA/MMA issue in an elect + R2UR.BROADCAST
+    // waterfall loop to obtain uniform-register operands, which costs hundreds of cycles per issue.
+    if (warp == 0) {
         // ------------------------------ TMA producer, A operand (im2col) ------------------------------
-        // Issuing one TMA operation costs a few hundred cycles of the issuing thread, so the two
-        // operands are fed by two threads in different warps; each arms the stage barrier with its own
+        // The two operands are fed by two different warps; each arms the stage barrier with its own
         // byte count.
         int stage = 0;
         uint32_t phase = 0;
@@ -183,13 +186,16 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             uint16_t offw = 0, offh = 0;
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
-                mbar_expect_tx(full_bar(stage), Cfg::A_BYTES);
                 const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-                if (cc < p.cchunks0)
-                    tma_load_im2col(sa, &mapA0, full_bar(stage), cc * 64, cw, ch, n, offw, offh);
-                else
-                    tma_load_im2col(sa, &mapA1, full_bar(stage), (cc - p.cchunks0) * 64, cw, ch, n,
-                                    offw, offh);
+                if (elect_one()) {
+                    mbar_expect_tx(full_bar(stage), Cfg::A_BYTES);
+                    if (cc < p.cchunks0)
+                        tma_load_im2col(sa, &mapA0, full_bar(stage), cc * 64, cw, ch, n, offw, offh);
+                    else
+                        tma_load_im2col(sa, &mapA1, full_bar(stage), (cc - p.cchunks0) * 64, cw, ch,
+                                        n, offw, offh);
+                }
+                __syncwarp();
                 if (++cc == cchunks) {
                     cc = 0;
                     if (++offw == (uint16_t)p.tapw) { offw = 0; ++offh; }
@@ -197,7 +203,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 6 && lane == 0) {
+    } else if (warp == 6) {
         // ------------------------------ TMA producer, B operand (weights) ------------------------------
         int stage = 0;
         uint32_t phase = 0;
@@ -205,14 +211,17 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             int cc = 0, tap = 0;
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
-                mbar_expect_tx(full_bar(stage), Cfg::B_BYTES);
-                tma_load_3d(base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES, &mapB, full_bar(stage),
-                            cc * 64, n0, tap);
+                if (elect_one()) {
+                    mbar_expect_tx(full_bar(stage), Cfg::B_BYTES);
+                    tma_load_3d(base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES, &mapB,
+                                full_bar(stage), cc * 64, n0, tap);
+                }
+                __syncwarp();
                 if (++cc == cchunks) { cc = 0; ++tap; }
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
         int stage = 0;
@@ -230,14 +239,18 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
                 const uint32_t sb = sa + Cfg::A_BYTES;
                 const uint64_t da = make_smem_desc(sa, 0, 1024);
                 const uint64_t db = make_smem_desc(sb, 0, 1024);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)  // 16 bf16 = 32 B along K => +2 in 16-byte units
-                    umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                              (uint32_t)((kb | k) != 0));
-                umma_commit(empty_bar(stage));
+                    for (int k = 0; k < 4; ++k)  // 16 bf16 = 32 B along K => +2 in 16-byte units
+                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                  (uint32_t)((kb | k) != 0));
+                    umma_commit(empty_bar(stage));
+                }
+                __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(tfull_bar(as));
+            if (elect_one()) umma_commit(tfull_bar(as));
+            __syncwarp();
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
     } else if (warp >= 2 && warp < 6) {
@@ -361,7 +374,7 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
 
     // Three producer threads (different warps) feed one stage: the two 64-row im2col chunks of the
     // A side and the B-side box; each arms the stage barrier with its own byte count.
-    if ((warp == 0 || warp == 6 || warp == 7) && lane == 0) {
+    if (warp == 0 || warp == 6 || warp == 7) {
         const int role = warp == 0 ? 0 : (warp == 6 ? 1 : 2);   // 0/1: A chunk j, 2: B
         int stage = 0;
         uint32_t phase = 0;
@@ -390,13 +403,16 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                 if (role < 2) {
                     const int cw = p.lower + q * p.tstride;
                     const int ch = p.lower + pr * p.tstride;
-                    mbar_expect_tx(full_bar(stage), 8192u);
-                    if (a_cc < p.cchunks0)
-                        tma_load_im2col(sa + role * 8192, &mapA0, full_bar(stage), a_cc * 64, cw, ch,
-                                        n, a_offw, a_offh);
-                    else
-                        tma_load_im2col(sa + role * 8192, &mapA1, full_bar(stage),
-                                        (a_cc - p.cchunks0) * 64, cw, ch, n, a_offw, a_offh);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(stage), 8192u);
+                        if (a_cc < p.cchunks0)
+                            tma_load_im2col(sa + role * 8192, &mapA0, full_bar(stage), a_cc * 64, cw,
+                                            ch, n, a_offw, a_offh);
+                        else
+                            tma_load_im2col(sa + role * 8192, &mapA1, full_bar(stage),
+                                            (a_cc - p.cchunks0) * 64, cw, ch, n, a_offw, a_offh);
+                    }
+                    __syncwarp();
                     q += 64;
                     while (q >= p.Wo) {
                         q -= p.Wo;
@@ -404,14 +420,18 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                     }
                 } else {
                     // B side: one 3-D box (64 ch, 64 pixels, BN/64 chunks) -> [chunk][pixel][64 ch]
-                    mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::B_BYTES);
-                    tma_load_3d(sa + Cfg::A_BYTES, &mapB, full_bar(stage), 0, m0, n_tile * (BN / 64));
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::B_BYTES);
+                        tma_load_3d(sa + Cfg::A_BYTES, &mapB, full_bar(stage), 0, m0,
+                                    n_tile * (BN / 64));
+                    }
+                    __syncwarp();
                     m0 += 64;
                 }
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
         int stage = 0;
         uint32_t phase = 0;
@@ -420,16 +440,20 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
             tc_fence_after();
             const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
             const uint32_t sb = sa + Cfg::A_BYTES;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // 16 pixels = 16 rows of 128 B
-                const uint64_t da = make_smem_desc(sa + k * 2048, 8192, 1024);
-                const uint64_t db = make_smem_desc(sb + k * 2048, 8192, 1024);
-                umma_bf16(tmem_base, da, db, idesc, (uint32_t)((kb != kb_begin) || (k != 0)));
+                for (int k = 0; k < 4; ++k) {  // 16 pixels = 16 rows of 128 B
+                    const uint64_t da = make_smem_desc(sa + k * 2048, 8192, 1024);
+                    const uint64_t db = make_smem_desc(sb + k * 2048, 8192, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (uint32_t)((kb != kb_begin) || (k != 0)));
+                }
+                umma_commit(empty_bar(stage));
             }
-            umma_commit(empty_bar(stage));
+            __syncwarp();
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar);
+        if (elect_one()) umma_commit(tfull_bar);
+        __syncwarp();
     } else if (warp >= 2 && warp < 6) {
         const int quad = warp & 3;
         const int row = m_tile * 128 + quad * 32 + lane;

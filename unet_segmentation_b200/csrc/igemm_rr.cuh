@@ -112,7 +112,8 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
     const int m_step = gridDim.x / p.n_tiles;
     const int n0 = cta_n * BN;
 
-    if (warp == 0 && lane == 0) {
+    // (whole warps run the role loops; see the note on elect_one() in igemm_kmajor_kernel)
+    if (warp == 0) {
         // ---------------- A producer: 3 input rows x 130 pixels x 64 channels per chunk ----------
         int stage = 0;
         uint32_t phase = 0;
@@ -128,19 +129,23 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             const int h0 = pr + p.lower;
             for (int cc = 0; cc < cchunks; ++cc) {
                 mbar_wait_prof(emptyA(stage), phase ^ 1u, prof, waited);
-                mbar_expect_tx(fullA(stage), Cfg::A_TX);
                 const uint32_t sa = base + stage * Cfg::A_STAGE;
-                const CUtensorMap* mp = cc < p.cchunks0 ? &mapA0 : &mapA1;
-                const int c = (cc < p.cchunks0 ? cc : cc - p.cchunks0) * 64;
-                tma_load_4d(sa, mp, fullA(stage), c, w0, h0, n);   // box (64, 130, 3, 1)
+                if (elect_one()) {
+                    mbar_expect_tx(fullA(stage), Cfg::A_TX);
+                    if (cc < p.cchunks0)   // box (64, 130, 3, 1)
+                        tma_load_4d(sa, &mapA0, fullA(stage), cc * 64, w0, h0, n);
+                    else
+                        tma_load_4d(sa, &mapA1, fullA(stage), (cc - p.cchunks0) * 64, w0, h0, n);
+                }
+                __syncwarp();
                 if (++stage == Cfg::SA) { stage = 0; phase ^= 1u; }
             }
         }
-        if (prof) {
+        if (prof && lane == 0) {
             atomicAdd((unsigned long long*)&p.dbg[0], (unsigned long long)waited);
             atomicAdd((unsigned long long*)&p.dbg[1], (unsigned long long)(clock64() - tstart));
         }
-    } else if (warp == 6 && lane == 0) {
+    } else if (warp == 6) {
         // ---------------- B producer: one (tap, chunk) weight tile per stage ----------------------
         int stage = 0;
         uint32_t phase = 0;
@@ -152,17 +157,21 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
 #pragma unroll 1
                 for (int tap = 0; tap < 9; tap += Cfg::BTAPS) {
                     mbar_wait_prof(emptyB(stage), phase ^ 1u, prof, waited);
-                    mbar_expect_tx(fullB(stage), Cfg::B_STAGE);
-                    tma_load_3d(b_base + stage * Cfg::B_STAGE, &mapB, fullB(stage), cc * 64, n0, tap);
+                    if (elect_one()) {
+                        mbar_expect_tx(fullB(stage), Cfg::B_STAGE);
+                        tma_load_3d(b_base + stage * Cfg::B_STAGE, &mapB, fullB(stage), cc * 64, n0,
+                                    tap);
+                    }
+                    __syncwarp();
                     if (++stage == Cfg::SB) { stage = 0; phase ^= 1u; }
                 }
             }
         }
-        if (prof) {
+        if (prof && lane == 0) {
             atomicAdd((unsigned long long*)&p.dbg[2], (unsigned long long)waited);
             atomicAdd((unsigned long long*)&p.dbg[3], (unsigned long long)(clock64() - tstart));
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ---------------- MMA issuer -----------------------------------------------------------------
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
         int sa_i = 0, sb_i = 0;
@@ -184,6 +193,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                 for (int tap = 0; tap < 9; tap += Cfg::BTAPS) {
                     mbar_wait_prof(fullB(sb_i), pb, prof, wB);
                     tc_fence_after();
+                    if (elect_one()) {
 #pragma unroll
                     for (int j = 0; j < Cfg::BTAPS; ++j) {
                         const int r = (tap + j) / 3, sft = (tap + j) % 3;
@@ -199,15 +209,18 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                         }
                     }
                     umma_commit(emptyB(sb_i));
+                    if (tap + Cfg::BTAPS >= 9) umma_commit(emptyA(sa_i));
+                    if (tap + Cfg::BTAPS >= 9 && cc == cchunks - 1) umma_commit(tfull_bar(as));
+                    }
+                    __syncwarp();
+                    acc = 1;
                     if (++sb_i == Cfg::SB) { sb_i = 0; pb ^= 1u; }
                 }
-                umma_commit(emptyA(sa_i));
                 if (++sa_i == Cfg::SA) { sa_i = 0; pa ^= 1u; }
             }
-            umma_commit(tfull_bar(as));
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
-        if (prof) {
+        if (prof && lane == 0) {
             atomicAdd((unsigned long long*)&p.dbg[4], (unsigned long long)wA);
             atomicAdd((unsigned long long*)&p.dbg[5], (unsigned long long)wB);
             atomicAdd((unsigned long long*)&p.dbg[6], (unsigned long long)wT);
