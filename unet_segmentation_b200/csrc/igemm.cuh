@@ -196,9 +196,11 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
                                         n, offw, offh);
                 }
                 __syncwarp();
-                if (++cc == cchunks) {
-                    cc = 0;
-                    if (++offw == (uint16_t)p.tapw) { offw = 0; ++offh; }
+                // K order = (channel chunk, tap): the same summation order as the row-run kernel, so
+                // a layer gives bit-identical results whichever kernel its width selects.
+                if (++offw == (uint16_t)p.tapw) {
+                    offw = 0;
+                    if (++offh == (uint16_t)(p.taps / p.tapw)) { offh = 0; ++cc; }
                 }
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
@@ -217,7 +219,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
                                 full_bar(stage), cc * 64, n0, tap);
                 }
                 __syncwarp();
-                if (++cc == cchunks) { cc = 0; ++tap; }
+                if (++tap == p.taps) { tap = 0; ++cc; }
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
         }
