@@ -71,7 +71,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -342,6 +342,40 @@ def main():
                         "peak_source": f"{peaks['_source']} HBM copy",
                         "share_of_step": d["ms_per_step"] / ms_per_step}
 
+    # ---------------- overlap-tile inference (BASELINE metric ii), tiles sharded over ranks ----------
+    infer = None
+    if not args.no_infer:
+        from unet_segmentation_b200 import tiling
+
+        model.eval()
+        gen = torch.Generator().manual_seed(7)
+        for mod in model.modules():      # non-trivial running statistics, identical on every rank
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.copy_((torch.randn(mod.num_features, generator=gen) * 0.1).to(dev))
+                mod.running_var.copy_((0.5 + torch.rand(mod.num_features, generator=gen)).to(dev))
+        infer = {}
+        for size in (1024, 8192):
+            gi = torch.Generator().manual_seed(99)
+            frame = 0.4 + 0.2 * torch.rand(512, 512, generator=gi)
+            img = frame.repeat(size // 512, size // 512).to(dev)   # mosaic of 512^2 frames
+            n_tiles = len(tiling.plan_tiles(size, size, 572)[2])
+            if n_tiles < world:
+                continue
+            bt = 8 if n_tiles // world >= 8 else max(1, n_tiles // world)
+            tiling.overlap_tile_predict(model, img, batch_tiles=bt, rank=rank, world=world)  # warm-up
+            barrier()
+            reps = 2
+            e0.record()
+            for _ in range(reps):
+                mask = tiling.overlap_tile_predict(model, img, batch_tiles=bt, rank=rank, world=world)
+            e1.record()
+            barrier()
+            ms_i = max_over_ranks(e0.elapsed_time(e1)) / reps
+            infer[f"{size}x{size}"] = {"mpix_per_s": size * size / (ms_i * 1e-3) / 1e6, "ms": ms_i,
+                                       "tiles": n_tiles, "tile_in": 572, "tile_out": 388,
+                                       "batch_tiles": bt, "fg_fraction": float((mask > 0).float().mean())}
+        model.train()
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -373,6 +407,7 @@ def main():
             "step_tflops": world * N * FLOP_PER_IMG_STEP / (ms_per_step * 1e-3) / 1e12,
             "step_frac_of_bf16_sustained": N * FLOP_PER_IMG_STEP / (ms_per_step * 1e-3) / 1e12 / sus,
             "kernel_breakdown": breakdown,
+            "infer_overlap_tile": infer,
             "final_loss": final_loss,
             "allreduce": ({"collectives_per_step": reducer.n_collectives /
                            (args.steps * 2 + warmup + 2 + prof_steps),

@@ -169,19 +169,21 @@ int ub_op_bn_finalize(const float* stats, const int* info, int C, const float* g
                       const float* beta, float* running_mean, float* running_var,
                       int64_t* num_batches_tracked, float momentum, float eps, float* scale,
                       float* shift, float* mean, float* rstd, void* stream);
-/* a = relu(y*scale + shift); pooled (optional) = 2x2/2 floor-mode max-pool of a. */
-int ub_op_bn_apply_relu(const void* y, void* a, void* pooled, int N, int H, int W, int C,
-                        const float* scale, const float* shift, void* stream);
+/* a = relu(y*scale + shift); pooled (optional) = 2x2/2 floor-mode max-pool of a; argmax (optional,
+ * uint8 [N][H/2][W/2][C]) = position 0..3 of the first maximum of each window (torch tie rule). */
+int ub_op_bn_apply_relu(const void* y, void* a, void* pooled, uint8_t* argmax, int N, int H, int W,
+                        int C, const float* scale, const float* shift, void* stream);
 int64_t ub_op_bn_bwd_workspace_floats(int C);
 /* BN+ReLU backward. Upstream gradient of a: `g` (direct), or — when g == NULL — gathered from the
  * pooled-tensor gradient gp (2x2 max-pool backward, first arg-max) plus the skip-connection
- * gradient gs placed at (crop_h, crop_w) (gs may be NULL). Outputs dgamma, dbeta (fp32) and
+ * gradient gs placed at (crop_h, crop_w) (gs may be NULL). argmax (optional) = the array saved by
+ * ub_op_bn_apply_relu; without it the arg-max is recomputed from y. Outputs dgamma, dbeta (fp32) and
  * dy (bf16 [N][H][W][C], gradient of the conv output). */
 int ub_op_bn_relu_backward(const void* y, int N, int H, int W, int C, const float* scale,
                            const float* shift, const float* mean, const float* rstd,
                            const ub_view* g, const ub_view* gp, const ub_view* gs, int crop_h,
-                           int crop_w, float* workspace, float* dgamma, float* dbeta, void* dy,
-                           void* stream);
+                           int crop_w, const uint8_t* argmax, float* workspace, float* dgamma,
+                           float* dbeta, void* dy, void* stream);
 
 /* First convolution (fp32, C_in = n_channels): training forward = statistics + finalize + apply. */
 int64_t ub_op_first_conv_workspace_floats(int Co);

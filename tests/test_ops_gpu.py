@@ -69,7 +69,7 @@ def test_conv3x3_forward_stats_and_bn(ops):
     wf, _ = ops.pack_conv3x3(wt)
     y, stats, info = ops.conv3x3_forward(ops.nhwc(x), None, wf, b, epilogue=0)
     scale, shift, mean, rstd = ops.bn_finalize(stats, info, gamma, beta, rm, rv, nbt)
-    a, p = ops.bn_apply_relu(y, scale, shift, pool=True)
+    a, p, _ = ops.bn_apply_relu(y, scale, shift, pool=True)
     ref_y = F.conv2d(x, wt, b)
     bn = torch.nn.BatchNorm2d(co).cuda().train()
     with torch.no_grad():
@@ -207,6 +207,16 @@ def test_bn_relu_backward_pool_skip(ops, h, w):
     dcat_nhwc = ops.nhwc(dcat)
     dy, dgamma, dbeta = ops.bn_relu_backward(ops.nhwc(y), scale, shift, mean, rstd, g=None,
                                              gp=ops.nhwc(gp), gs=dcat_nhwc[..., :c], crop=(ch, cw))
+    # same through the per-pixel kernel that uses the arg-max saved by the forward pass
+    _, _, amax = ops.bn_apply_relu(ops.nhwc(y), scale, shift, pool=True)
+    dy2, dgamma2, dbeta2 = ops.bn_relu_backward(ops.nhwc(y), scale, shift, mean, rstd, g=None,
+                                                gp=ops.nhwc(gp), gs=dcat_nhwc[..., :c],
+                                                crop=(ch, cw), argmax=amax)
+    torch.cuda.synchronize()
+    # (the two kernels reduce in different orders, so dy may differ in the last bf16 bit)
+    assert rel_l2(dy2.float(), dy.float()) < 2e-3
+    assert rel_l2(dgamma2, dgamma) < 1e-4 and rel_l2(dbeta2, dbeta) < 1e-4
+    dy_pix, dgamma_pix, dbeta_pix = dy2, dgamma2, dbeta2
 
     def g_fn(a):
         # forward rounding of a to bf16 decides the arg-max, as in the kernel
@@ -219,6 +229,8 @@ def test_bn_relu_backward_pool_skip(ops, h, w):
     torch.cuda.synchronize()
     assert rel_l2(dgamma, rg) < F32_TOL and rel_l2(dbeta, rb) < F32_TOL
     assert rel_l2(ops.nchw(dy), ry) < BF16_TOL
+    assert rel_l2(dgamma_pix, rg) < F32_TOL and rel_l2(dbeta_pix, rb) < F32_TOL
+    assert rel_l2(ops.nchw(dy_pix), ry) < BF16_TOL
 
 
 @pytest.mark.parametrize("ci", [1, 3])

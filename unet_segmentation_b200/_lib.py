@@ -72,10 +72,10 @@ _SIGNATURES = {
     "ub_op_convT_wgrad": (c_int, [_VP, _P, c_int, _P, c_int64, _P, _P]),
     "ub_op_bn_finalize": (c_int, [_P, C.POINTER(c_int), c_int, _P, _P, _P, _P, _P, c_float, c_float,
                                   _P, _P, _P, _P, _P]),
-    "ub_op_bn_apply_relu": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ub_op_bn_apply_relu": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "ub_op_bn_bwd_workspace_floats": (c_int64, [c_int]),
     "ub_op_bn_relu_backward": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _VP, _VP,
-                                       _VP, c_int, c_int, _P, _P, _P, _P, _P]),
+                                       _VP, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "ub_op_first_conv_workspace_floats": (c_int64, [c_int]),
     "ub_op_first_conv_forward": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P,
                                          _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),

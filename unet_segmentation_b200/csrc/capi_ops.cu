@@ -140,17 +140,17 @@ int ub_op_bn_finalize(const float* stats, const int* info, int C, const float* g
     return launch_bn_finalize(stats, li, C, (double)li.M, gamma, beta, rm, rv, (long long*)nbt,
                               momentum, eps, scale, shift, mean, rstd, S(stream));
 }
-int ub_op_bn_apply_relu(const void* y, void* a, void* pooled, int N, int H, int W, int C,
-                        const float* scale, const float* shift, void* stream) {
+int ub_op_bn_apply_relu(const void* y, void* a, void* pooled, uint8_t* argmax, int N, int H, int W,
+                        int C, const float* scale, const float* shift, void* stream) {
     return launch_bn_apply_relu((const __nv_bfloat16*)y, (__nv_bfloat16*)a, (__nv_bfloat16*)pooled,
-                                N, H, W, C, scale, shift, S(stream));
+                                argmax, N, H, W, C, scale, shift, S(stream));
 }
 int64_t ub_op_bn_bwd_workspace_floats(int C) { return (int64_t)bn_bwd_partial_floats(C); }
 int ub_op_bn_relu_backward(const void* y, int N, int H, int W, int C, const float* scale,
                            const float* shift, const float* mean, const float* rstd,
                            const ub_view* g, const ub_view* gp, const ub_view* gs, int crop_h,
-                           int crop_w, float* workspace, float* dgamma, float* dbeta, void* dy,
-                           void* stream) {
+                           int crop_w, const uint8_t* argmax, float* workspace, float* dgamma,
+                           float* dbeta, void* dy, void* stream) {
     UB_REQUIRE(y && workspace && dgamma && dbeta && dy, "bn_relu_backward: null pointer");
     UB_REQUIRE(g || gp, "bn_relu_backward: need g or gp");
     BnBwdDesc d;
@@ -162,6 +162,7 @@ int ub_op_bn_relu_backward(const void* y, int N, int H, int W, int C, const floa
     if (gp) d.gp = to_view(gp);
     if (gs) { d.gs = to_view(gs); d.has_skip = true; }
     d.crop_h = crop_h; d.crop_w = crop_w;
+    d.amax = argmax;
     d.partial = workspace; d.dgamma = dgamma; d.dbeta = dbeta; d.dy = (__nv_bfloat16*)dy;
     return launch_bn_bwd(d, S(stream));
 }

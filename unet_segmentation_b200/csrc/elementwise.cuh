@@ -146,8 +146,9 @@ static __global__ void bn_fold_eval_kernel(int C, const float* __restrict__ conv
 template <bool POOL>
 static __global__ void __launch_bounds__(256)
 bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
-                     __nv_bfloat16* __restrict__ pooled, int N, int H, int W, int C,
-                     const float* __restrict__ scale, const float* __restrict__ shift) {
+                     __nv_bfloat16* __restrict__ pooled, unsigned char* __restrict__ amax, int N,
+                     int H, int W, int C, const float* __restrict__ scale,
+                     const float* __restrict__ shift) {
     const unsigned CG = (unsigned)C >> 3;
     const unsigned cg = threadIdx.x % CG;
     float sc[8], sh[8];
@@ -192,8 +193,9 @@ bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restr
                 if (inb[d]) raw[d] = ldg16(y + off[d]);
             }
             Vec8 mx;
+            unsigned am[8];   // first arg-max of the window in row-major order (torch tie rule)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) mx.v[k] = 0.f;  // post-ReLU values are >= 0
+            for (int k = 0; k < 8; ++k) { mx.v[k] = -1.f; am[k] = 0u; }  // post-ReLU values are >= 0
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 if (inb[d]) {
@@ -202,14 +204,21 @@ bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restr
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         o.v[k] = bn_relu_bf16(x.v[k], sc[k], sh[k]);
-                        mx.v[k] = fmaxf(mx.v[k], o.v[k]);
+                        if (o.v[k] > mx.v[k]) { mx.v[k] = o.v[k]; am[k] = (unsigned)d; }
                     }
                     *reinterpret_cast<uint4*>(a + off[d]) = pack8(o);
                 }
             }
-            if (hp < Hp && wp < Wp)
-                *reinterpret_cast<uint4*>(pooled + ((size_t)(n * Hp + hp) * Wp + wp) * C + cg * 8) =
-                    pack8(mx);
+            if (hp < Hp && wp < Wp) {
+                const size_t po = ((size_t)(n * Hp + hp) * Wp + wp) * C + cg * 8;
+                *reinterpret_cast<uint4*>(pooled + po) = pack8(mx);
+                if (amax) {
+                    uint2 pk;
+                    pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+                    pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+                    *reinterpret_cast<uint2*>(amax + po) = pk;
+                }
+            }
         }
     }
 }
@@ -263,6 +272,7 @@ struct BnBwdArgs {
     View gs;                 // POOL_SKIP: grad of cropped skip [N,th,tw,C] (may be a slice)
     int crop_h, crop_w;
     int has_skip;
+    const unsigned char* amax;  // POOL_SKIP: arg-max (0..3) per pooled element, saved by the forward
     float* partial;          // reduce: [gridDim.x][2][C]
     const float* dgamma;     // apply
     const float* dbeta;
@@ -270,7 +280,9 @@ struct BnBwdArgs {
     __nv_bfloat16* dy;       // apply: [N,H,W,C]
 };
 
-template <bool POOL_SKIP, bool APPLY>
+// PIX (POOL_SKIP only): the forward saved the pool arg-max, so the kernel runs per pixel like the
+// DIRECT path instead of recomputing whole 2x2 windows.
+template <bool POOL_SKIP, bool APPLY, bool PIX = false>
 static __global__ void __launch_bounds__(256, 2)
 bn_bwd_kernel(const BnBwdArgs A) {
     const unsigned C = A.C, CG = C >> 3, H = A.H, W = A.W;
@@ -311,7 +323,61 @@ bn_bwd_kernel(const BnBwdArgs A) {
         if (APPLY) *reinterpret_cast<uint4*>(A.dy + pix * C + cg * 8) = pack8(o);
     };
 
-    if (!POOL_SKIP) {
+    if (POOL_SKIP && PIX) {
+        const unsigned npix = (unsigned)A.N * H * W;
+        const unsigned Hp = H >> 1, Wp = W >> 1;
+        const __nv_bfloat16* gpb = reinterpret_cast<const __nv_bfloat16*>(A.gp.ptr);
+        const __nv_bfloat16* gsb = reinterpret_cast<const __nv_bfloat16*>(A.gs.ptr);
+        for (unsigned p0 = first; p0 < npix; p0 += 4 * gstride) {
+            uint4 yr[4], gpr[4], gsr[4];
+            uint2 amr[4];
+            bool full[4], ins[4];
+            unsigned dsel[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned p = p0 + j * gstride;
+                full[j] = false; ins[j] = false;
+                if (p < npix) {
+                    yr[j] = ldg16(A.y + (size_t)p * C + cg * 8);
+                    const unsigned w = p % W, t = p / W, h = t % H, n = t / H;
+                    const unsigned hq = h >> 1, wq = w >> 1;
+                    dsel[j] = ((h & 1u) << 1) | (w & 1u);
+                    full[j] = hq < Hp && wq < Wp;
+                    if (full[j]) {
+                        gpr[j] = ldg16(gpb + (size_t)(n * A.gp.sN + hq * A.gp.sH + wq * A.gp.sW) + cg * 8);
+                        amr[j] = __ldg(reinterpret_cast<const uint2*>(
+                            A.amax + ((size_t)(n * Hp + hq) * Wp + wq) * C + cg * 8));
+                    }
+                    const int hs = (int)h - A.crop_h, ws = (int)w - A.crop_w;
+                    ins[j] = A.has_skip && hs >= 0 && hs < A.gs.H && ws >= 0 && ws < A.gs.W;
+                    if (ins[j])
+                        gsr[j] = ldg16(gsb + (size_t)(n * A.gs.sN + hs * A.gs.sH + ws * A.gs.sW) + cg * 8);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned p = p0 + j * gstride;
+                if (p < npix) {
+                    Vec8 gv;
+                    if (ins[j]) {
+                        gv = unpack8(gsr[j]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) gv.v[k] = 0.f;
+                    }
+                    if (full[j]) {
+                        const Vec8 gpv = unpack8(gpr[j]);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const unsigned a8 = ((k < 4 ? amr[j].x : amr[j].y) >> (8 * (k & 3))) & 0xFFu;
+                            if (a8 == dsel[j]) gv.v[k] += gpv.v[k];
+                        }
+                    }
+                    process((size_t)p, unpack8(yr[j]), gv);
+                }
+            }
+        }
+    } else if (!POOL_SKIP) {
         const unsigned npix = (unsigned)A.N * H * W;
         const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(A.g.ptr);
         const bool glin = A.g.sW == (long long)C && A.g.sH == (long long)W * C &&

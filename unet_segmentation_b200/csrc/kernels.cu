@@ -78,9 +78,9 @@ int launch_bn_fold_eval(int C, const float* conv_bias, const float* gamma, const
     return UB_OK;
 }
 
-int launch_bn_apply_relu(const __nv_bfloat16* y, __nv_bfloat16* a, __nv_bfloat16* pooled, int N,
-                         int H, int W, int C, const float* scale, const float* shift,
-                         cudaStream_t s) {
+int launch_bn_apply_relu(const __nv_bfloat16* y, __nv_bfloat16* a, __nv_bfloat16* pooled,
+                         unsigned char* amax, int N, int H, int W, int C, const float* scale,
+                         const float* shift, cudaStream_t s) {
     UB_TRY(check_cg(C, "bn_apply"));
     if ((long long)N * H * W * (C / 8) >= 0x7FFFFFFFLL) {
         set_last_error("bn_apply: tensor too large for 32-bit indexing");
@@ -88,12 +88,12 @@ int launch_bn_apply_relu(const __nv_bfloat16* y, __nv_bfloat16* a, __nv_bfloat16
     }
     if (pooled) {
         const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-        bn_apply_relu_kernel<true><<<ew_blocks(items), 256, 0, s>>>(y, a, pooled, N, H, W, C, scale,
-                                                                    shift);
+        bn_apply_relu_kernel<true><<<ew_blocks(items), 256, 0, s>>>(y, a, pooled, amax, N, H, W, C,
+                                                                    scale, shift);
     } else {
         const long long items = (long long)N * H * W * (C / 8);
-        bn_apply_relu_kernel<false><<<ew_blocks(items), 256, 0, s>>>(y, a, nullptr, N, H, W, C,
-                                                                     scale, shift);
+        bn_apply_relu_kernel<false><<<ew_blocks(items), 256, 0, s>>>(y, a, nullptr, nullptr, N, H, W,
+                                                                     C, scale, shift);
     }
     UB_POST_LAUNCH();
     return UB_OK;
@@ -120,22 +120,26 @@ int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
     A.scale = d.scale; A.shift = d.shift; A.mean = d.mean; A.rstd = d.rstd;
     A.g = d.g; A.gp = d.gp; A.gs = d.gs; A.crop_h = d.crop_h; A.crop_w = d.crop_w;
     A.has_skip = d.has_skip ? 1 : 0;
+    A.amax = d.amax;
     A.partial = d.partial;
     A.dgamma = d.dgamma; A.dbeta = d.dbeta; A.dy = d.dy;
     const long long count = (long long)d.N * d.H * d.W;
     A.inv_count = (float)(1.0 / (double)count);
-    const long long items = d.pool_skip
+    const bool pix = d.pool_skip && d.amax != nullptr;
+    const long long items = (d.pool_skip && !pix)
                                 ? (long long)d.N * ((d.H + 1) / 2) * ((d.W + 1) / 2) * (d.C / 8)
                                 : count * (d.C / 8);
     const int blocks = red_blocks(items);
-    if (d.pool_skip) bn_bwd_kernel<true, false><<<blocks, 256, 0, s>>>(A);
+    if (pix) bn_bwd_kernel<true, false, true><<<blocks, 256, 0, s>>>(A);
+    else if (d.pool_skip) bn_bwd_kernel<true, false><<<blocks, 256, 0, s>>>(A);
     else bn_bwd_kernel<false, false><<<blocks, 256, 0, s>>>(A);
     UB_POST_LAUNCH();
     bn_bwd_finalize_kernel<<<(d.C + 31) / 32, dim3(32, 16), 0, s>>>(d.partial, blocks, d.C, d.dgamma,
                                                              d.dbeta);
     UB_POST_LAUNCH();
     const int ablocks = ew_blocks(items);
-    if (d.pool_skip) bn_bwd_kernel<true, true><<<ablocks, 256, 0, s>>>(A);
+    if (pix) bn_bwd_kernel<true, true, true><<<ablocks, 256, 0, s>>>(A);
+    else if (d.pool_skip) bn_bwd_kernel<true, true><<<ablocks, 256, 0, s>>>(A);
     else bn_bwd_kernel<false, true><<<ablocks, 256, 0, s>>>(A);
     UB_POST_LAUNCH();
     return UB_OK;

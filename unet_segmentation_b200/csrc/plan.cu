@@ -30,6 +30,7 @@ struct Block {
     bool two = false;
     bool pool = false;
     bf16* pooled = nullptr;  // [N, Ho/2, Wo/2, Co]
+    unsigned char* amax = nullptr;  // pool arg-max per pooled element (training)
     bf16* da0 = nullptr;     // gradient of u[0].a
     bf16* din = nullptr;     // gradient of the block input [N, Hin, Win, Ci] (contiguous)
 };
@@ -250,6 +251,8 @@ int ub_plan_create(ub_plan** out, int N, int n_channels, int H, int W, int base,
         if (b.pool) {
             const int ph = b.u[1].Ho() / 2, pw = b.u[1].Wo() / 2;
             if (int r = P->alloc(&b.pooled, (size_t)N * ph * pw * b.u[1].Co)) return fail(r);
+            if (P->training)
+                if (int r = P->alloc(&b.amax, (size_t)N * ph * pw * b.u[1].Co)) return fail(r);
         }
         if (P->training) {
             if (int r = P->alloc(&b.da0, (size_t)N * b.u[0].Ho() * b.u[0].Wo() * b.u[0].Co))
@@ -383,7 +386,7 @@ int ub_plan_pack_weights(ub_plan* P, void* stream) {
 
 // ------------------------------------------------------------------------------------------------
 static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const View* in1,
-                             bf16* pooled, cudaStream_t s) {
+                             bf16* pooled, unsigned char* amax, cudaStream_t s) {
     const int N = P->N;
     const double pix_out = (double)N * u.Ho() * u.Wo(), pix_in = (double)N * u.Hin * u.Win;
     if (u.first) {
@@ -422,7 +425,8 @@ static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const Vie
         UB_TRY(launch_bn_finalize(P->scratch, u.info, u.Co, (double)u.info.M, P->params[u.p_g],
                                   P->params[u.p_be], P->rm[u.bn], P->rv[u.bn], P->nbt[u.bn],
                                   P->momentum, P->eps, u.scale, u.shift, u.mean, u.rstd, s));
-        return launch_bn_apply_relu(u.y, u.a, pooled, N, u.Ho(), u.Wo(), u.Co, u.scale, u.shift, s);
+        return launch_bn_apply_relu(u.y, u.a, pooled, amax, N, u.Ho(), u.Wo(), u.Co, u.scale,
+                                    u.shift, s);
     }
     UB_TRY(launch_bn_fold_eval(u.Co, P->params[u.p_b], P->params[u.p_g], P->params[u.p_be],
                                P->rm[u.bn], P->rv[u.bn], P->eps, u.scale, u.shift, s));
@@ -439,9 +443,10 @@ static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const Vie
 }
 
 static int block_forward(ub_plan* P, Block& b, cudaStream_t s) {
-    UB_TRY(conv_unit_forward(P, b.u[0], b.in0, b.two ? &b.in1 : nullptr, nullptr, s));
+    UB_TRY(conv_unit_forward(P, b.u[0], b.in0, b.two ? &b.in1 : nullptr, nullptr, nullptr, s));
     View mid = make_view(b.u[0].a, P->N, b.u[0].Ho(), b.u[0].Wo(), b.u[0].Co);
-    return conv_unit_forward(P, b.u[1], mid, nullptr, b.pool ? b.pooled : nullptr, s);
+    return conv_unit_forward(P, b.u[1], mid, nullptr, b.pool ? b.pooled : nullptr,
+                             b.pool ? b.amax : nullptr, s);
 }
 
 int ub_plan_forward(ub_plan* P, const float* x, float* logits, uint8_t* mask, void* stream) {
@@ -503,6 +508,7 @@ struct Upstream {
     View g{}, gp{}, gs{};
     int crop_h = 0, crop_w = 0;
     bool has_skip = false;
+    const unsigned char* amax = nullptr;
 };
 
 static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const* grads,
@@ -517,6 +523,7 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
     d.scale = u1.scale; d.shift = u1.shift; d.mean = u1.mean; d.rstd = u1.rstd;
     d.pool_skip = up.pool_skip; d.g = up.g; d.gp = up.gp; d.gs = up.gs;
     d.crop_h = up.crop_h; d.crop_w = up.crop_w; d.has_skip = up.has_skip;
+    d.amax = up.amax;
     d.partial = P->scratch; d.dgamma = grads[u1.p_g]; d.dbeta = grads[u1.p_be]; d.dy = u1.dy;
     const double po1 = (double)N * u1.Ho() * u1.Wo(), pi1 = (double)N * u1.Hin * u1.Win;
     const double fl1 = 2.0 * po1 * u1.Co * 9.0 * u1.Ci;
@@ -646,6 +653,7 @@ int ub_plan_backward_stage(ub_plan* P, int stage, const float* dlogits, float* c
         gs.C = b.u[1].Co;  // first channel range of d(concat) = gradient of the cropped skip
         up.gs = gs;
         up.has_skip = true;
+        up.amax = b.amax;
         up.crop_h = (b.u[1].Ho() - db.u[0].Hin) / 2;
         up.crop_w = (b.u[1].Wo() - db.u[0].Win) / 2;
     }

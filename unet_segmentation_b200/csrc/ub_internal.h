@@ -88,9 +88,9 @@ int launch_bn_finalize_flat(const float* part, int blocks, int C, double count, 
 int launch_bn_fold_eval(int C, const float* conv_bias, const float* gamma, const float* beta,
                         const float* rm, const float* rv, float eps, float* scale, float* shift,
                         cudaStream_t s);
-int launch_bn_apply_relu(const __nv_bfloat16* y, __nv_bfloat16* a, __nv_bfloat16* pooled, int N,
-                         int H, int W, int C, const float* scale, const float* shift,
-                         cudaStream_t s);
+int launch_bn_apply_relu(const __nv_bfloat16* y, __nv_bfloat16* a, __nv_bfloat16* pooled,
+                         unsigned char* amax, int N, int H, int W, int C, const float* scale,
+                         const float* shift, cudaStream_t s);
 int launch_maxpool2(const __nv_bfloat16* a, __nv_bfloat16* pooled, int N, int H, int W, int C,
                     cudaStream_t s);
 struct BnBwdDesc {
@@ -103,6 +103,7 @@ struct BnBwdDesc {
     View gs;       // skip grad
     int crop_h, crop_w;
     bool has_skip;
+    const unsigned char* amax;  // pool arg-max saved by launch_bn_apply_relu (may be null)
     float* partial;        // workspace, >= bn_bwd_partial_floats(C)
     float* dgamma;         // out [C]
     float* dbeta;          // out [C]

@@ -102,12 +102,14 @@ def bn_apply_relu(y, scale, shift, pool=False):
     n, h, w, c = y.shape
     a = torch.empty_like(y)
     p = torch.empty(n, h // 2, w // 2, c, dtype=y.dtype, device=y.device) if pool else None
-    check(lib.ub_op_bn_apply_relu(_p(y), _p(a), _p(p), n, h, w, c, _p(scale), _p(shift), _stream()),
-          "bn_apply_relu")
-    return a, p
+    am = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device=y.device) if pool else None
+    check(lib.ub_op_bn_apply_relu(_p(y), _p(a), _p(p), _p(am), n, h, w, c, _p(scale), _p(shift),
+                                  _stream()), "bn_apply_relu")
+    return (a, p, am) if pool else (a, p)
 
 
-def bn_relu_backward(y, scale, shift, mean, rstd, g=None, gp=None, gs=None, crop=(0, 0)):
+def bn_relu_backward(y, scale, shift, mean, rstd, g=None, gp=None, gs=None, crop=(0, 0),
+                     argmax=None):
     lib = _lib.load()
     n, h, w, c = y.shape
     ws = torch.empty(int(lib.ub_op_bn_bwd_workspace_floats(c)), dtype=torch.float32, device=y.device)
@@ -115,8 +117,8 @@ def bn_relu_backward(y, scale, shift, mean, rstd, g=None, gp=None, gs=None, crop
     dbeta = torch.empty_like(dgamma)
     dy = torch.empty_like(y)
     check(lib.ub_op_bn_relu_backward(_p(y), n, h, w, c, _p(scale), _p(shift), _p(mean), _p(rstd),
-                                     _vp(g), _vp(gp), _vp(gs), crop[0], crop[1], _p(ws), _p(dgamma),
-                                     _p(dbeta), _p(dy), _stream()), "bn_relu_backward")
+                                     _vp(g), _vp(gp), _vp(gs), crop[0], crop[1], _p(argmax), _p(ws),
+                                     _p(dgamma), _p(dbeta), _p(dy), _stream()), "bn_relu_backward")
     return dy, dgamma, dbeta
 
 
