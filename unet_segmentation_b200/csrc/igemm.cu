@@ -255,7 +255,8 @@ static int wgrad_splits(int rows, int cols, long long mpix) {
     if (!bn) return 1;
     const int m_tiles = (rows + 127) / 128, n_tiles = cols / bn;
     const int units = m_tiles * n_tiles;
-    const long long kblocks = (mpix + 63) / 64;
+    const int kpix = bn == 256 ? 64 : 128;
+    const long long kblocks = (mpix + kpix - 1) / kpix;
     const long long smax = kblocks / 8 > 1 ? kblocks / 8 : 1;
     // Pick the split count that minimises (number of CTA waves) x (k-blocks per CTA + fixed cost):
     // avoids e.g. 300 CTAs on 148 SMs (a third, nearly empty, wave).
@@ -312,16 +313,17 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
         return UB_ERR_ARG;
     }
     CUtensorMap mA0, mA1, mB;
-    int r = make_tmap_im2col(&mA0, src0, lower, upper, tstride, 64);
+    const int kpix = BN == 256 ? 64 : 128;
+    int r = make_tmap_im2col(&mA0, src0, lower, upper, tstride, (unsigned)kpix);
     if (r) { set_last_error("wgrad: im2col tensor map failed: %d", r); return UB_ERR_TMAP; }
     if (src1) {
-        r = make_tmap_im2col(&mA1, *src1, lower, upper, tstride, 64);
+        r = make_tmap_im2col(&mA1, *src1, lower, upper, tstride, (unsigned)kpix);
         if (r) { set_last_error("wgrad: im2col tensor map (source 1) failed: %d", r); return UB_ERR_TMAP; }
     } else {
         mA1 = mA0;
     }
     r = make_tmap_chunked(&mB, B, (unsigned long long)cols, (unsigned long long)mpix,
-                          (unsigned long long)ldb * 2, 64, (unsigned)(BN / 64));
+                          (unsigned long long)ldb * 2, (unsigned)kpix, (unsigned)(BN / 64));
     if (r) { set_last_error("wgrad: matrix tensor map failed: %d", r); return UB_ERR_TMAP; }
 
     WgradParams p;
@@ -331,7 +333,7 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
     p.cchunks0 = src0.C / 64; p.cchunks1 = src1 ? src1->C / 64 : 0;
     p.a_chunks_total = rows / 64;
     p.n_tiles = cols / BN; p.splits = splits;
-    p.kblocks_total = (int)((mpix + 63) / 64);
+    p.kblocks_total = (int)((mpix + kpix - 1) / kpix);
     p.ws = ws; p.ldw = cols; p.split_stride = (long long)rows * cols;
     const int m_tiles = (rows + 127) / 128;
     dim3 grid(m_tiles * p.n_tiles, splits);

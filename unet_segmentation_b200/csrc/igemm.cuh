@@ -309,7 +309,7 @@ struct WgradParams {
     int cchunks0, cchunks1;
     int a_chunks_total;  // taps * (cchunks0 + cchunks1)
     int n_tiles, splits;
-    int kblocks_total;   // ceil(Mpix / 64)
+    int kblocks_total;   // ceil(Mpix / KPIX)
     float* ws;           // [splits][a_chunks_total*64][ldw]
     long long ldw;
     long long split_stride;
@@ -317,10 +317,15 @@ struct WgradParams {
 
 template <int BN>
 struct WgradCfg {
-    static constexpr int A_BYTES = 2 * 8192;
-    static constexpr int B_BYTES = (BN / 64) * 8192;
+    // Pixels (GEMM K) per pipeline stage. One barrier wait + tcgen05 fence costs the MMA thread
+    // ~230 cycles, so narrow tiles (BN <= 128, 48-64 cycles per MMA) take 128 pixels = 8 MMAs per
+    // stage; BN = 256 is already execution-bound with 64.
+    static constexpr int KPIX = (BN == 256) ? 64 : 128;
+    static constexpr int CHUNK_BYTES = KPIX * 128;   // one [KPIX pixels][64 channels] MN-major chunk
+    static constexpr int A_BYTES = 2 * CHUNK_BYTES;
+    static constexpr int B_BYTES = (BN / 64) * CHUNK_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
     static constexpr uint32_t TMEM_COLS = BN;
@@ -394,7 +399,7 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
             }
         }
         // base pixel (q, pr, n) of the first k-block of this split, then advanced by 64 pixels
-        int m0 = kb_begin * 64;
+        int m0 = kb_begin * Cfg::KPIX;
         int q = m0 % p.Wo;
         int pr, n;
         { const int t = m0 / p.Wo; pr = t % p.Ho; n = t / p.Ho; }
@@ -406,29 +411,29 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                     const int cw = p.lower + q * p.tstride;
                     const int ch = p.lower + pr * p.tstride;
                     if (elect_one()) {
-                        mbar_expect_tx(full_bar(stage), 8192u);
+                        mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::CHUNK_BYTES);
                         if (a_cc < p.cchunks0)
-                            tma_load_im2col(sa + role * 8192, &mapA0, full_bar(stage), a_cc * 64, cw,
+                            tma_load_im2col(sa + role * Cfg::CHUNK_BYTES, &mapA0, full_bar(stage), a_cc * 64, cw,
                                             ch, n, a_offw, a_offh);
                         else
-                            tma_load_im2col(sa + role * 8192, &mapA1, full_bar(stage),
+                            tma_load_im2col(sa + role * Cfg::CHUNK_BYTES, &mapA1, full_bar(stage),
                                             (a_cc - p.cchunks0) * 64, cw, ch, n, a_offw, a_offh);
                     }
                     __syncwarp();
-                    q += 64;
+                    q += Cfg::KPIX;
                     while (q >= p.Wo) {
                         q -= p.Wo;
                         if (++pr == p.Ho) { pr = 0; ++n; }
                     }
                 } else {
-                    // B side: one 3-D box (64 ch, 64 pixels, BN/64 chunks) -> [chunk][pixel][64 ch]
+                    // B side: one 3-D box (64 ch, KPIX pixels, BN/64 chunks) -> [chunk][pixel][64 ch]
                     if (elect_one()) {
                         mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::B_BYTES);
                         tma_load_3d(sa + Cfg::A_BYTES, &mapB, full_bar(stage), 0, m0,
                                     n_tile * (BN / 64));
                     }
                     __syncwarp();
-                    m0 += 64;
+                    m0 += Cfg::KPIX;
                 }
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
@@ -444,9 +449,9 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
             const uint32_t sb = sa + Cfg::A_BYTES;
             if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // 16 pixels = 16 rows of 128 B
-                    const uint64_t da = make_smem_desc(sa + k * 2048, 8192, 1024);
-                    const uint64_t db = make_smem_desc(sb + k * 2048, 8192, 1024);
+                for (int k = 0; k < Cfg::KPIX / 16; ++k) {  // 16 pixels = 16 rows of 128 B
+                    const uint64_t da = make_smem_desc(sa + k * 2048, Cfg::CHUNK_BYTES, 1024);
+                    const uint64_t db = make_smem_desc(sb + k * 2048, Cfg::CHUNK_BYTES, 1024);
                     umma_bf16(tmem_base, da, db, idesc, (uint32_t)((kb != kb_begin) || (k != 0)));
                 }
                 umma_commit(empty_bar(stage));
