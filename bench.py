@@ -173,6 +173,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-infer", action="store_true")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused = unet_segmentation_b200.optim.FusedSGD, torch = torch.optim.SGD")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -211,7 +213,12 @@ def main():
     parallel.broadcast_parameters(model)
     reducer = parallel.StageGradAllReducer(model) if world > 1 else None
     criterion = WeightedCrossEntropyLoss()
-    opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.99)   # scripts/train.py:97
+    if args.optimizer == "fused":     # same update rule as scripts/train.py:97, one fused kernel
+        from unet_segmentation_b200.optim import FusedSGD
+
+        opt = FusedSGD(model, lr=1e-4, momentum=0.99)
+    else:
+        opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.99)   # scripts/train.py:97
 
     # synthetic data, seed = 1234 + rank; full-size mask / weight map as the dataset
     # hands them over (scripts/train.py:108-112), cropped on the device like train.py:118-126
@@ -282,19 +289,41 @@ def main():
     value = world * N * args.steps / (ms_total * 1e-3)
 
     # ---------------- end-to-end with host buffers (e2e) ----------------
-    def e2e_step():
-        img = img_h.to(dev, non_blocking=True)
-        mask = mask_h.to(dev, non_blocking=True)
-        wmap = wmap_h.to(dev, non_blocking=True)
-        loss = step(img, mask, wmap)
-        loss_h.copy_(loss.detach(), non_blocking=True)
+    # Every step's inputs come from pinned host memory and the loss goes back to the host. The
+    # copies of step i+1 are issued on a side stream while step i computes (double buffering, what a
+    # DataLoader with pin_memory + a prefetcher does); nothing is reused across steps.
+    copy_stream = torch.cuda.Stream(device=dev)
+    dbuf = [(torch.empty_like(img_d), torch.empty_like(mask_d), torch.empty_like(wmap_d))
+            for _ in range(2)]
+    free_ev = [None, None]      # compute finished with buffer set k
 
-    for _ in range(2):
-        e2e_step()
+    def h2d(i):
+        k = i & 1
+        with torch.cuda.stream(copy_stream):
+            if free_ev[k] is not None:
+                copy_stream.wait_event(free_ev[k])
+            for dst, src in zip(dbuf[k], (img_h, mask_h, wmap_h)):
+                dst.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return k, ev
+
+    def e2e_loop(n_steps):
+        nxt = h2d(0)
+        for i in range(n_steps):
+            k, ev = nxt
+            torch.cuda.current_stream().wait_event(ev)
+            if i + 1 < n_steps:
+                nxt = h2d(i + 1)
+            loss = step(*dbuf[k])
+            free_ev[k] = torch.cuda.Event()
+            free_ev[k].record(torch.cuda.current_stream())
+            loss_h.copy_(loss.detach(), non_blocking=True)
+
+    e2e_loop(2)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_loop(args.steps)
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -395,7 +424,9 @@ def main():
                                    f"{SIZE}x{SIZE} + weight maps (BASELINE configs[1]"
                                    f"{'/[2]' if world > 1 else ''})",
                        "global_batch": world * N, "parallelism": f"dp{world}",
-                       "optimizer": "SGD(lr=1e-4, momentum=0.99) torch foreach, inside the step",
+                       "optimizer": ("SGD(lr=1e-4, momentum=0.99), FusedSGD (update + bf16 operand "
+                                     "refresh in one kernel), inside the step" if args.optimizer == "fused"
+                                     else "SGD(lr=1e-4, momentum=0.99) torch foreach, inside the step"),
                        "bn": "per-rank batch statistics", "l2": "per-step working set 11 GB >> 126 MB L2",
                        "first_conv": "fp32 CUDA-core (SURVEY F4)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,

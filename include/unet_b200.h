@@ -95,6 +95,15 @@ int ub_plan_stage_params(const ub_plan* plan, int stage, int* first_param, int* 
 int ub_plan_backward_stage(ub_plan* plan, int stage, const float* dlogits, float* const* grads,
                            void* stream);
 
+/* Fused optimizer step: torch.optim.SGD semantics (scripts/train.py:97,131 use
+ * lr 1e-4, momentum 0.99) applied to the bound fp32 parameters in place, with the plan's packed bf16
+ * operands refreshed in the same pass (no ub_plan_pack_weights needed afterwards for THIS plan).
+ * grads / momentum_bufs: ub_plan_num_params() device pointers in parameter order; momentum_bufs may
+ * be NULL when momentum == 0; first_step != 0 initialises the buffers with the gradient. */
+int ub_plan_sgd_step(ub_plan* plan, const float* const* grads, float* const* momentum_bufs, float lr,
+                     float momentum, float dampening, float weight_decay, int nesterov,
+                     int first_step, void* stream);
+
 /* Measurement support (bench.py): total number of kernels the library has launched so far, and
  * optional in-step timing: while enabled, every kernel group the plan launches is bracketed by two
  * CUDA events on the launching stream; collect() synchronises them and returns, per kernel class

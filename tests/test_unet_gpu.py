@@ -232,3 +232,48 @@ def test_sgd_trajectory_tracks_fp32_oracle():
     assert ref[-1] < ref[0]
     for a, b in zip(ours, ref):
         assert abs(a - b) / b < 0.08, (ours, ref)
+
+
+def test_fused_sgd_matches_torch_sgd():
+    """FusedSGD (one multi-tensor kernel: SGD update + bf16 operand refresh) against
+    torch.optim.SGD with the same hyper-parameters, including momentum, weight decay and Nesterov."""
+    from unet_segmentation_b200.loss import WeightedCrossEntropyLoss
+    from unet_segmentation_b200.optim import FusedSGD
+
+    img, t, w = unet_ref.synthetic_batch(2, size=252, seed=31, device="cuda")
+    crit = WeightedCrossEntropyLoss()
+    for kw in (dict(lr=1e-3, momentum=0.9, weight_decay=1e-4),
+               dict(lr=1e-3, momentum=0.9, nesterov=True),
+               dict(lr=1e-2)):
+        m1, _ = make_model(seed=0)
+        m2, _ = make_model(seed=0)
+        m1.train(); m2.train()
+        o1 = torch.optim.SGD(m1.parameters(), **kw)
+        o2 = FusedSGD(m2, **kw)
+        for it in range(3):
+            for m, o in ((m1, o1), (m2, o2)):
+                o.zero_grad(set_to_none=True)
+                crit(m(img), t, w).backward()
+                o.step()
+            torch.cuda.synchronize()
+            # step 1 starts from identical weights and identical (deterministic) gradients: the two
+            # optimizers may differ only by fp32 rounding (FMA contraction). Later steps amplify that
+            # through bf16 rounding / ReLU-mask flips (SURVEY F3), so the bar is loose there.
+            tol = 2e-6 if it == 0 else 0.15
+            for (n1, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+                assert rel_l2(p2, p1) < tol, (kw, it, n1, rel_l2(p2, p1))
+            if kw.get("momentum"):
+                b1 = o1.state[m1.outc.conv.weight]["momentum_buffer"]
+                b2 = o2.state[m2.outc.conv.weight]["momentum_buffer"]
+                assert rel_l2(b2, b1) < (1e-6 if it == 0 else 0.15)
+        # the operand caches written by the fused kernel == a fresh re-pack of the same weights
+        m3, _ = make_model(seed=0)
+        m3.load_state_dict(m2.state_dict())
+        m3.train()
+        with torch.no_grad():
+            m2.eval(); m3.eval()
+            assert torch.equal(m2(img), m3(img))          # eval plan re-packed lazily (epoch bump)
+        m2.train(); m3.train()
+        l2 = m2(img); l3 = m3(img)
+        torch.cuda.synchronize()
+        assert torch.equal(l2, l3), kw                      # training plan uses the fused-written caches

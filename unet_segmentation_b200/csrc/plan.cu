@@ -6,6 +6,7 @@
 
 #include "../../include/unet_b200.h"
 #include "igemm.cuh"
+#include "sgd.cuh"
 #include "ub_internal.h"
 
 using namespace ub;
@@ -660,6 +661,72 @@ int ub_plan_backward_stage(ub_plan* P, int stage, const float* dlogits, float* c
     return block_backward(P, b, up, grads, s);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused SGD step over all parameters + refresh of the packed bf16 operands (sgd.cuh).
+int ub_plan_sgd_step(ub_plan* P, const float* const* grads, float* const* momentum_bufs, float lr,
+                     float momentum, float dampening, float weight_decay, int nesterov,
+                     int first_step, void* stream) {
+    if (!P || !grads) { set_last_error("sgd_step: null pointer"); return ub::UB_ERR_ARG; }
+    const int np = (int)P->params.size();
+    if (momentum != 0.f && !momentum_bufs) {
+        set_last_error("sgd_step: momentum buffers required");
+        return ub::UB_ERR_ARG;
+    }
+    for (int i = 0; i < np; ++i)
+        if (!P->params[i] || !grads[i] || (momentum != 0.f && !momentum_bufs[i])) {
+            set_last_error("sgd_step: parameter, gradient or momentum buffer %d is null", i);
+            return ub::UB_ERR_ARG;
+        }
+    std::vector<SgdTensor> all(np);
+    auto base = [&](int i) -> SgdTensor& {
+        SgdTensor& t = all[i];
+        memset(&t, 0, sizeof(t));
+        t.p = const_cast<float*>(P->params[i]);
+        t.g = grads[i];
+        t.buf = momentum != 0.f ? momentum_bufs[i] : nullptr;
+        t.kind = SGD_PLAIN;
+        t.n = (int)P->param_numel[i];
+        return t;
+    };
+    for (int i = 0; i < np; ++i) base(i);
+    auto conv_units = [&](Block& b) {
+        for (int k = 0; k < 2; ++k) {
+            ConvUnit& u = b.u[k];
+            if (u.first) continue;
+            SgdTensor& t = all[u.p_w];
+            t.kind = SGD_CONV3; t.d0 = u.Co; t.d1 = u.Ci; t.T = 9; t.outA = u.wf; t.outB = u.wd;
+        }
+    };
+    for (auto& b : P->enc) conv_units(b);
+    for (auto& b : P->dec) conv_units(b);
+    for (auto& u : P->ups) {
+        SgdTensor& t = all[u.p_w];
+        t.kind = SGD_CONVT; t.d0 = u.Ci; t.d1 = u.Co; t.T = 4; t.outA = u.wb; t.outB = u.wf;
+        SgdTensor& tb = all[u.p_b];
+        tb.kind = SGD_CONVT_BIAS; tb.d0 = u.Co; tb.bias4 = u.bias4;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int i0 = 0; i0 < np; i0 += SGD_MAX_TENSORS) {
+        SgdBatch B;
+        memset(&B, 0, sizeof(B));
+        B.count = np - i0 < SGD_MAX_TENSORS ? np - i0 : SGD_MAX_TENSORS;
+        B.lr = lr; B.momentum = momentum; B.dampening = dampening; B.weight_decay = weight_decay;
+        B.nesterov = nesterov; B.first_step = first_step;
+        int blocks = 0;
+        for (int j = 0; j < B.count; ++j) {
+            B.t[j] = all[i0 + j];
+            B.t[j].block_begin = blocks;
+            const SgdTensor& t = B.t[j];
+            blocks += (t.kind == SGD_CONV3 || t.kind == SGD_CONVT) ? (t.d0 / 32) * (t.d1 / 32)
+                                                                     : (t.n + 2047) / 2048;
+        }
+        sgd_fused_kernel<<<blocks, 256, 0, s>>>(B);
+        UB_POST_LAUNCH();
+    }
+    P->packed = true;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 int64_t ub_launch_count(void) { return (int64_t)ub::launch_count(); }

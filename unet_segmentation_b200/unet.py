@@ -123,7 +123,20 @@ class _Plan:
     def device_bytes(self) -> int:
         return int(self.lib.ub_plan_device_bytes(self.handle))
 
-    def bind(self, params, bn_modules):
+    def bind_pointers_only(self, params, bn_modules):
+        """(Re)bind parameter / buffer pointers without touching the packed operand caches."""
+        ptrs = tuple(p.data_ptr() for p in params)
+        if ptrs != self.bound_ptrs:
+            arr = (C.c_void_p * len(ptrs))(*ptrs)
+            check(self.lib.ub_plan_bind_params(self.handle, arr, len(ptrs)), "ub_plan_bind_params")
+            self.bound_ptrs = ptrs
+            self.packed_versions = None
+
+    def mark_packed(self, params, epoch):
+        """The fused optimizer refreshed this plan's operand caches itself."""
+        self.packed_versions = (tuple(p._version for p in params), epoch)
+
+    def bind(self, params, bn_modules, epoch=0):
         ptrs = tuple(p.data_ptr() for p in params)
         if ptrs != self.bound_ptrs:
             arr = (C.c_void_p * len(ptrs))(*ptrs)
@@ -140,7 +153,7 @@ class _Plan:
             check(self.lib.ub_plan_bind_bn_buffers(self.handle, rm, rv, nb, k),
                   "ub_plan_bind_bn_buffers")
             self.bound_buf_ptrs = bptrs
-        versions = tuple(p._version for p in params)
+        versions = (tuple(p._version for p in params), epoch)
         if versions != self.packed_versions:
             check(self.lib.ub_plan_pack_weights(self.handle, _stream()), "ub_plan_pack_weights")
             self.packed_versions = versions
@@ -239,6 +252,7 @@ class UNet(nn.Module):
                 setattr(self, f"up{j}", Up(cp, cp // 2, cp // 2, bilinear))
             self.outc = OutConv(c[0], n_classes)
         self._plans: dict = {}
+        self._weights_epoch = 0     # bumped by FusedSGD: raw in-place updates bypass torch versions
         self._stage_hook: Optional[Callable] = None
         self._backward_done_hook: Optional[Callable] = None
 
@@ -289,8 +303,13 @@ class UNet(nn.Module):
             plan = _Plan(n, c, h, w, self.base_channels, self.levels, self.n_classes, training,
                          x.device)
             self._plans[key] = plan
-        plan.bind(self._ordered_params(), self._ordered_bns())
+        plan.bind(self._ordered_params(), self._ordered_bns(), self._weights_epoch)
+        if training:
+            self._last_train_key = key
         return plan
+
+    def _latest_training_plan(self):
+        return self._plans.get(getattr(self, "_last_train_key", None))
 
     def _check_input(self, x):
         if not isinstance(x, torch.Tensor) or x.dim() != 4:
