@@ -194,7 +194,9 @@ int ub_op_bn_relu_backward(const void* y, int N, int H, int W, int C, const floa
                            int crop_w, const uint8_t* argmax, float* workspace, float* dgamma,
                            float* dbeta, void* dy, void* stream);
 
-/* First convolution (fp32, C_in = n_channels): training forward = statistics + finalize + apply. */
+/* First convolution (fp32, C_in = n_channels): training forward = statistics + finalize + apply.
+ * The backward takes the forward activation `a` (bf16 [N][H-2][W-2][Co]): for a single-channel
+ * input the ReLU mask is read from it and dW / dgamma follow from patch moments in one pass. */
 int64_t ub_op_first_conv_workspace_floats(int Co);
 int ub_op_first_conv_forward(const float* x, int N, int Ci, int H, int W, const float* w,
                              const float* bias, int Co, const float* gamma, const float* beta,
@@ -205,8 +207,8 @@ int ub_op_first_conv_forward(const float* x, int N, int Ci, int H, int W, const 
 int ub_op_first_conv_backward(const float* x, int N, int Ci, int H, int W, const float* w,
                               const float* bias, int Co, const float* scale, const float* shift,
                               const float* mean, const float* rstd, const ub_view* g,
-                              float* workspace, float* dgamma, float* dbeta, float* dw,
-                              void* stream);
+                              const void* a, float* workspace, float* dgamma, float* dbeta,
+                              float* dw, void* stream);
 
 /* 1x1 head: a[N][H][W][K] bf16 -> logits NCHW fp32 (+ optional 2-class mask). */
 int ub_op_head_forward(const void* a, int N, int H, int W, int K, int n_classes, const float* w,

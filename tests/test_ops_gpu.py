@@ -250,7 +250,7 @@ def test_first_conv(ops, ci):
     ref_a = F.relu(F.batch_norm(F.conv2d(x, wr, b), bn_rm, bn_rv, gr, br, True, 0.1, 1e-5))
     g = bf(rand(n, co, h - 2, w - 2, seed=5))
     ref_a.backward(g)
-    dw, dgamma, dbeta = ops.first_conv_backward(x, wt, b, st, ops.nhwc(g))
+    dw, dgamma, dbeta = ops.first_conv_backward(x, wt, b, st, ops.nhwc(g), a)
     torch.cuda.synchronize()
     assert rel_l2(ops.nchw(a), ref_a) < BF16_TOL
     # near-zero channel means: compare against the scale of the data, not of the mean itself

@@ -175,23 +175,21 @@ int ub_op_first_conv_forward(const float* x, int N, int Ci, int H, int W, const 
                              void* a, void* stream) {
     FirstConvDesc d;
     d.x = x; d.N = N; d.Ci = Ci; d.H = H; d.W = W; d.Co = Co; d.w = w; d.bias = bias;
-    int blocks = 0;
-    UB_TRY(launch_first_conv_stats(d, workspace, &blocks, S(stream)));
-    const double count = (double)N * (H - 2) * (W - 2);
-    UB_TRY(launch_bn_finalize_flat(workspace, blocks, Co, count, gamma, beta, rm, rv,
-                                   (long long*)nbt, momentum, eps, scale, shift, mean, rstd,
-                                   S(stream)));
+    UB_TRY(launch_first_conv_train_stats(d, workspace, gamma, beta, rm, rv, (long long*)nbt,
+                                         momentum, eps, scale, shift, mean, rstd, nullptr,
+                                         S(stream)));
     return launch_first_conv_apply(d, scale, shift, (__nv_bfloat16*)a, S(stream));
 }
 int ub_op_first_conv_backward(const float* x, int N, int Ci, int H, int W, const float* w,
                               const float* bias, int Co, const float* scale, const float* shift,
                               const float* mean, const float* rstd, const ub_view* g,
-                              float* workspace, float* dgamma, float* dbeta, float* dw,
-                              void* stream) {
+                              const void* a, float* workspace, float* dgamma, float* dbeta,
+                              float* dw, void* stream) {
     FirstConvDesc d;
     d.x = x; d.N = N; d.Ci = Ci; d.H = H; d.W = W; d.Co = Co; d.w = w; d.bias = bias;
-    return launch_first_conv_bwd(d, scale, shift, mean, rstd, to_view(g), workspace, dgamma, dbeta,
-                                 dw, S(stream));
+    return launch_first_conv_bwd(d, scale, shift, mean, rstd, to_view(g),
+                                 (const __nv_bfloat16*)a, nullptr, workspace, dgamma, dbeta, dw,
+                                 S(stream));
 }
 
 int ub_op_head_forward(const void* a, int N, int H, int W, int K, int n_classes, const float* w,

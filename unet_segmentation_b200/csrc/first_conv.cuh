@@ -178,49 +178,174 @@ first_conv_kernel(const FirstConvArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// C_in == 1 fast path (the reference's single-channel microscopy images): one thread = PX
-// horizontally adjacent output pixels x 8 channels. The 3 x (PX+2) input patch and the 9x8 weights
-// live in registers, so an item costs 3*(PX+2) cached loads for 72*PX FMAs and PX 16-byte stores /
-// gradient loads are in flight together. The conv bias is folded into the BN constants.
+// C_in == 1 path (the reference's single-channel microscopy images).
+//
+// The convolution is linear in the 3x3 input patch p(pix) (9 values), y_c = w_c . p + b_c, so the
+// per-channel sums the training step needs follow EXACTLY from a few patch moments instead of
+// 64-channel passes over the image:
+//   forward  BN statistics:  sum y_c, sum y_c^2  <-  S1[t] = sum p_t,  S2[t,t'] = sum p_t p_t'
+//   backward (one pass over the upstream gradient g and the stored activation a):
+//       m_c = g_c * [a_c > 0],   dbeta_c = sum m_c,   G[c][t] = sum m_c p_t
+//       dgamma_c = rstd_c * (w_c . G[c] + (b'_c - mean_c) dbeta_c)
+//       dW[c][t] = scale_c * (G[c][t] - dbeta_c/n * S1[t] - dgamma_c/n * sum xhat_c p_t)
+//       sum xhat_c p_t = rstd_c * (sum_t' w_ct' S2[t',t] + (b'_c - mean_c) S1[t])
+// All moments are taken of the CENTRED patch p - c0 (c0 = mean of the centre tap; b' = b + c0 sum w):
+// sum dy = 0, so centring changes nothing algebraically and removes the cancellation a
+// low-contrast image (mean 0.47, std 0.04) would otherwise cause. Finalisation runs in double.
 // ---------------------------------------------------------------------------------------------
-template <int MODE, int PX>
-static __global__ void __launch_bounds__(256, (MODE >= FC_BWD_REDUCE) ? 1 : 2)
-first_conv1_kernel(const FirstConvArgs A) {
+constexpr int FC_COV_TERMS = 54;     // 9 first moments + 45 second moments (upper triangle)
+constexpr int FC_COV_DOUBLES = 56;   // [0] = c0, [1] = pixel count, [2..10] = S1, [11..55] = S2
+__host__ __device__ __forceinline__ int fc_tri(int a, int b) {  // a <= b < 9
+    return a * 9 - (a * (a - 1)) / 2 + (b - a);
+}
+__device__ __forceinline__ double shfl_xor_f64(double v, int off) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xffffffffu, lo, off);
+    hi = __shfl_xor_sync(0xffffffffu, hi, off);
+    return __hiloint2double(hi, lo);
+}
+
+// Patch moments about the provisional centre x[0] (exactly re-centred by the finalisation kernel).
+// One thread = PX horizontally adjacent output pixels; partial[gridDim.x][54] doubles.
+template <int PX>
+static __global__ void __launch_bounds__(256)
+fc1_cov_kernel(const float* __restrict__ x, int N, int H, int W, double* __restrict__ partial) {
+    const unsigned Ho = H - 2, Wo = W - 2;
+    const unsigned GW = (Wo + PX - 1) / PX;
+    const unsigned ngroups = (unsigned)N * Ho * GW;
+    const float cg = __ldg(x);
+    float s1[9], s2[45];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s1[t] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 45; ++t) s2[t] = 0.f;
+    for (unsigned gi = blockIdx.x * 256u + threadIdx.x; gi < ngroups; gi += gridDim.x * 256u) {
+        const unsigned gw = gi % GW, t = gi / GW, hq = t % Ho, n = t / Ho;
+        const unsigned wq0 = gw * PX;
+        const float* xrow = x + ((size_t)n * H + hq) * W + wq0;
+        float xp[3][PX + 2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < PX + 2; ++c)
+                xp[r][c] = (wq0 + c < (unsigned)W) ? __ldg(xrow + r * W + c) - cg : 0.f;
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            if (wq0 + j < Wo) {
+                float v[9];
+#pragma unroll
+                for (int tp = 0; tp < 9; ++tp) v[tp] = xp[tp / 3][j + tp % 3];
+#pragma unroll
+                for (int a = 0; a < 9; ++a) {
+                    s1[a] += v[a];
+#pragma unroll
+                    for (int b = a; b < 9; ++b) s2[fc_tri(a, b)] = fmaf(v[a], v[b], s2[fc_tri(a, b)]);
+                }
+            }
+        }
+    }
+    __shared__ double red[8][FC_COV_TERMS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < FC_COV_TERMS; ++i) {
+        double v = (double)(i < 9 ? s1[i] : s2[i - 9]);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += shfl_xor_f64(v, off);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < FC_COV_TERMS) {
+        double v = 0.0;
+        for (int w8 = 0; w8 < 8; ++w8) v += red[w8][threadIdx.x];
+        partial[(size_t)blockIdx.x * FC_COV_TERMS + threadIdx.x] = v;
+    }
+}
+
+// Reduces the moment partials, re-centres them about c0, stores them in cov[] for the backward
+// pass and (gamma != null) finalises the BatchNorm statistics of every output channel.
+static __global__ void __launch_bounds__(1024)
+fc1_cov_finalize_kernel(const double* __restrict__ partial, int blocks, const float* __restrict__ x,
+                        double count, double* __restrict__ cov, int Co, const float* __restrict__ w,
+                        const float* __restrict__ bias, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float* running_mean, float* running_var,
+                        long long* num_batches_tracked, float momentum, float eps,
+                        float* __restrict__ scale, float* __restrict__ shift,
+                        float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+    __shared__ double sg[FC_COV_TERMS];
+    __shared__ double sc[FC_COV_DOUBLES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < FC_COV_TERMS; i += 32) {
+        double v = 0.0;
+        for (int b = lane; b < blocks; b += 32) v += partial[(size_t)b * FC_COV_TERMS + i];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += shfl_xor_f64(v, off);
+        if (lane == 0) sg[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < FC_COV_DOUBLES) {
+        const int i = threadIdx.x;
+        const double d = sg[4] / count;          // c0 - provisional centre
+        double v;
+        if (i == 0) v = (double)__ldg(x) + d;
+        else if (i == 1) v = count;
+        else if (i < 11) v = sg[i - 2] - count * d;
+        else {
+            int a = 0, k = i - 11;
+            while (k >= 9 - a) { k -= 9 - a; ++a; }
+            const int b = a + k;
+            v = sg[9 + fc_tri(a, b)] - d * sg[a] - d * sg[b] + count * d * d;
+        }
+        sc[i] = v;
+        if (cov) cov[i] = v;
+    }
+    __syncthreads();
+    if (gamma == nullptr) return;
+    if (threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    for (int c = threadIdx.x; c < Co; c += blockDim.x) {
+        double wv[9], wsum = 0.0;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) { wv[t] = (double)w[c * 9 + t]; wsum += wv[t]; }
+        const double bp = (bias ? (double)bias[c] : 0.0) + sc[0] * wsum;
+        double m1 = 0.0, e2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+            m1 += wv[a] * sc[2 + a];
+#pragma unroll
+            for (int b = 0; b < 9; ++b)
+                e2 += wv[a] * wv[b] * sc[11 + (a <= b ? fc_tri(a, b) : fc_tri(b, a))];
+        }
+        m1 /= count; e2 /= count;
+        double var = e2 - m1 * m1;
+        if (var < 0.0) var = 0.0;
+        const double mean = bp + m1;
+        bn_finalize_write(c, mean * count, (var + mean * mean) * count, count, gamma, beta,
+                          running_mean, running_var, momentum, eps, scale, shift, save_mean,
+                          save_rstd);
+    }
+}
+
+// BN-apply + ReLU of the recomputed convolution: one thread = PX adjacent pixels x 8 channels, the
+// 3 x (PX+2) input patch and the 9x8 weights live in registers; the conv bias is folded into shift.
+template <int PX>
+static __global__ void __launch_bounds__(256, 2)
+fc1_apply_kernel(const FirstConvArgs A) {
     const int Co = A.Co, CG = Co >> 3;
     const unsigned cg = threadIdx.x % CG;
     const unsigned Ho = A.H - 2, Wo = A.W - 2, W = A.W;
-    const unsigned GW = (Wo + PX - 1) / PX;  // pixel groups per output row
-    float wr[9][8];
+    const unsigned GW = (Wo + PX - 1) / PX;
+    float wr[9][8], sc[8], shb[8];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
         for (int k = 0; k < 8; ++k) wr[tap][k] = A.w[(cg * 8 + k) * 9 + tap];
-    // y = conv + bias;  act = y*sc + sh = conv*sc + shb;  xhat = (y - mu)*rs = (conv - mub)*rs
-    float bi[8], sc[8], shb[8], mub[8], rs[8], kb[8], kg[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int c = cg * 8 + k;
-        bi[k] = A.bias ? A.bias[c] : 0.f;
-        if (MODE != FC_STATS) { sc[k] = A.scale[c]; shb[k] = fmaf(bi[k], sc[k], A.shift[c]); }
-        if (MODE >= FC_BWD_REDUCE) { mub[k] = A.mean[c] - bi[k]; rs[k] = A.rstd[c]; }
-        if (MODE == FC_BWD_WGRAD) {
-            kb[k] = A.dbeta[c] * A.inv_count;
-            kg[k] = A.dgamma[c] * A.inv_count;
-        }
-    }
-    float acc0[8], acc1[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
-    float wacc[9][8];
-    if (MODE == FC_BWD_WGRAD) {
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) wacc[t][k] = 0.f;
+        sc[k] = A.scale[c];
+        shb[k] = fmaf(A.bias ? A.bias[c] : 0.f, sc[k], A.shift[c]);
     }
     const unsigned ngroups = (unsigned)A.N * Ho * GW;
     const unsigned gstride = gridDim.x * 256u / CG;
-    const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(A.g.ptr);
     for (unsigned gi = (blockIdx.x * 256u + threadIdx.x) / CG; gi < ngroups; gi += gstride) {
         const unsigned gw = gi % GW, t = gi / GW, hq = t % Ho, n = t / Ho;
         const unsigned wq0 = gw * PX;
@@ -230,19 +355,11 @@ first_conv1_kernel(const FirstConvArgs A) {
         for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int c = 0; c < PX + 2; ++c) xp[r][c] = (wq0 + c < W) ? __ldg(xrow + r * W + c) : 0.f;
-        uint4 graw[PX];
-        if (MODE >= FC_BWD_REDUCE) {
-#pragma unroll
-            for (int j = 0; j < PX; ++j)
-                if (wq0 + j < Wo)
-                    graw[j] = ldg16(gb + (size_t)(n * A.g.sN + hq * A.g.sH + (wq0 + j) * A.g.sW) +
-                                    cg * 8);
-        }
         const size_t pq0 = ((size_t)n * Ho + hq) * Wo + wq0;
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
             if (wq0 + j < Wo) {
-                float y[8];  // raw convolution (bias folded into the constants)
+                float y[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) y[k] = 0.f;
 #pragma unroll
@@ -251,69 +368,124 @@ first_conv1_kernel(const FirstConvArgs A) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) y[k] = fmaf(xv, wr[tap][k], y[k]);
                 }
-                if (MODE == FC_STATS) {
+                Vec8 o;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float yb = y[k] + bi[k];
-                        acc0[k] += yb;
-                        acc1[k] = fmaf(yb, yb, acc1[k]);
-                    }
-                } else if (MODE == FC_APPLY) {
-                    Vec8 o;
+                for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(fmaf(y[k], sc[k], shb[k]), 0.f);
+                *reinterpret_cast<uint4*>(A.a + (pq0 + j) * Co + cg * 8) = pack8(o);
+            }
+        }
+    }
+}
+
+// Backward, single pass: m = g * [a > 0]; per-block partial[b][Co][10] = (G[c][0..8], dbeta_c).
+template <int PX>
+static __global__ void __launch_bounds__(256, 2)
+fc1_bwd_kernel(const FirstConvArgs A, const double* __restrict__ cov) {
+    const int Co = A.Co, CG = Co >> 3;
+    const unsigned cg = threadIdx.x % CG;
+    const unsigned Ho = A.H - 2, Wo = A.W - 2, W = A.W;
+    const unsigned GW = (Wo + PX - 1) / PX;
+    const float c0 = (float)cov[0];
+    float G[9][8], db[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(fmaf(y[k], sc[k], shb[k]), 0.f);
-                    *reinterpret_cast<uint4*>(A.a + (pq0 + j) * Co + cg * 8) = pack8(o);
-                } else {
-                    const Vec8 gv = unpack8(graw[j]);
+    for (int k = 0; k < 8; ++k) {
+        db[k] = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float act = fmaf(y[k], sc[k], shb[k]);
-                        const float dyh = act > 0.f ? gv.v[k] : 0.f;
-                        const float xh = (y[k] - mub[k]) * rs[k];
-                        if (MODE == FC_BWD_REDUCE) {
-                            acc0[k] += dyh;
-                            acc1[k] = fmaf(dyh, xh, acc1[k]);
-                        } else {
-                            const float dy = sc[k] * (dyh - kb[k] - xh * kg[k]);
+        for (int t = 0; t < 9; ++t) G[t][k] = 0.f;
+    }
+    const unsigned ngroups = (unsigned)A.N * Ho * GW;
+    const unsigned gstride = gridDim.x * 256u / CG;
+    const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(A.g.ptr);
+    for (unsigned gi = (blockIdx.x * 256u + threadIdx.x) / CG; gi < ngroups; gi += gstride) {
+        const unsigned gw = gi % GW, t = gi / GW, hq = t % Ho, n = t / Ho;
+        const unsigned wq0 = gw * PX;
+        const size_t pq0 = ((size_t)n * Ho + hq) * Wo + wq0;
+        uint4 graw[PX], araw[PX];
 #pragma unroll
-                            for (int tap = 0; tap < 9; ++tap)
-                                wacc[tap][k] = fmaf(dy, xp[tap / 3][j + tap % 3], wacc[tap][k]);
-                        }
-                    }
+        for (int j = 0; j < PX; ++j) {
+            if (wq0 + j < Wo) {
+                graw[j] = ldg16(gb + (size_t)(n * A.g.sN + hq * A.g.sH + (wq0 + j) * A.g.sW) + cg * 8);
+                araw[j] = ldg16(A.a + (pq0 + j) * Co + cg * 8);
+            }
+        }
+        float xp[3][PX + 2];
+        const float* xrow = A.x + ((size_t)n * A.H + hq) * W + wq0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < PX + 2; ++c)
+                xp[r][c] = (wq0 + c < W) ? __ldg(xrow + r * W + c) - c0 : 0.f;
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            if (wq0 + j < Wo) {
+                const Vec8 gv = unpack8(graw[j]);
+                const Vec8 av = unpack8(araw[j]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float m = av.v[k] > 0.f ? gv.v[k] : 0.f;
+                    db[k] += m;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap)
+                        G[tap][k] = fmaf(m, xp[tap / 3][j + tap % 3], G[tap][k]);
                 }
             }
         }
     }
-    if (MODE == FC_STATS || MODE == FC_BWD_REDUCE) {
-        __shared__ float red[256 * 16];
+    __shared__ float red[256 * 10];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            red[threadIdx.x * 16 + k] = acc0[k];
-            red[threadIdx.x * 16 + 8 + k] = acc1[k];
-        }
+    for (int k = 0; k < 8; ++k) {
         __syncthreads();
-        for (int j = threadIdx.x; j < CG * 16; j += blockDim.x) {
-            const int g2 = j / 16, e = j % 16;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) red[threadIdx.x * 10 + tap] = G[tap][k];
+        red[threadIdx.x * 10 + 9] = db[k];
+        __syncthreads();
+        for (int j = threadIdx.x; j < CG * 10; j += blockDim.x) {
+            const int g2 = j / 10, e = j % 10;
             float s = 0.f;
-            for (int tt = g2; tt < 256; tt += CG) s += red[tt * 16 + e];
-            A.partial[(long long)blockIdx.x * 2 * Co + (e < 8 ? 0 : Co) + g2 * 8 + (e & 7)] = s;
-        }
-    } else if (MODE == FC_BWD_WGRAD) {
-        __shared__ float red[256 * 9];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            __syncthreads();
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) red[threadIdx.x * 9 + tap] = wacc[tap][k];
-            __syncthreads();
-            for (int j = threadIdx.x; j < CG * 9; j += blockDim.x) {
-                const int g2 = j / 9, tap = j % 9;
-                float s = 0.f;
-                for (int tt = g2; tt < 256; tt += CG) s += red[tt * 9 + tap];
-                A.wpartial[((long long)blockIdx.x * Co + g2 * 8 + k) * 9 + tap] = s;
-            }
+            for (int tt = g2; tt < 256; tt += CG) s += red[tt * 10 + e];
+            A.partial[((size_t)blockIdx.x * Co + g2 * 8 + k) * 10 + e] = s;
         }
     }
+}
+
+// One block per output channel (320 threads = 10 warps, warp e reduces term e over the blocks).
+static __global__ void __launch_bounds__(320)
+fc1_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int Co,
+                        const double* __restrict__ cov, const float* __restrict__ w,
+                        const float* __restrict__ bias, const float* __restrict__ scale,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta,
+                        float* __restrict__ dw) {
+    const int c = blockIdx.x, e = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ double v[10];
+    double s = 0.0;
+    for (int b = lane; b < blocks; b += 32) s += (double)partial[((size_t)b * Co + c) * 10 + e];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += shfl_xor_f64(s, off);
+    if (lane == 0) v[e] = s;
+    __syncthreads();
+    if (threadIdx.x >= 9) return;
+    const int t = threadIdx.x;
+    const double n = cov[1];
+    double wv[9], wsum = 0.0, wG = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        wv[k] = (double)w[c * 9 + k];
+        wsum += wv[k];
+        wG += wv[k] * v[k];
+    }
+    const double bp = (bias ? (double)bias[c] : 0.0) + cov[0] * wsum;
+    const double off = bp - (double)mean[c];
+    const double rs = (double)rstd[c];
+    const double db = v[9];
+    const double dg = rs * (wG + off * db);
+    double x2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) x2 += wv[k] * cov[11 + (k <= t ? fc_tri(k, t) : fc_tri(t, k))];
+    const double s1t = cov[2 + t];
+    const double xhp = rs * (x2 + off * s1t);
+    dw[c * 9 + t] = (float)((double)scale[c] * (v[t] - db / n * s1t - dg / n * xhp));
+    if (t == 0) { dgamma[c] = (float)dg; dbeta[c] = (float)db; }
 }
 
 // out[co][ci_sel][tap] = sum over blocks of wpartial[b][co][tap]

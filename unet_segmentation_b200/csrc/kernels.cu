@@ -148,8 +148,11 @@ int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 size_t first_conv_partial_floats(int Co) {
     const size_t a = (size_t)num_sms() * 4 * 2 * Co;
-    const size_t b = (size_t)num_sms() * 4 * Co * 9;
-    return a > b ? a : b;
+    const size_t b = (size_t)num_sms() * 4 * Co * 10;
+    const size_t c = (size_t)num_sms() * 2 * FC_COV_TERMS * 2;
+    size_t m = a > b ? a : b;
+    if (c > m) m = c;
+    return m + 128;   // + room for the re-computed patch moments (op-level backward)
 }
 static int fc_fill(const FirstConvDesc& d, FirstConvArgs& A) {
     UB_TRY(check_cg(d.Co, "first conv"));
@@ -162,20 +165,9 @@ static int fc_fill(const FirstConvDesc& d, FirstConvArgs& A) {
     A.x = d.x; A.N = d.N; A.Ci = d.Ci; A.H = d.H; A.W = d.W; A.Co = d.Co; A.w = d.w; A.bias = d.bias;
     return UB_OK;
 }
+// generic n_channels > 1 path: direct fp32 kernel, weights in shared memory
 template <int MODE>
-static int fc_launch(const FirstConvArgs& A, int& blocks, cudaStream_t s) {
-    if (A.Ci == 1) {
-        // 4 pixels per thread (2 in the register-heavy fused weight-gradient mode)
-        constexpr int PX = (MODE == FC_BWD_WGRAD) ? 2 : 4;
-        const long long groups = (long long)A.N * (A.H - 2) * ((A.W - 2 + PX - 1) / PX);
-        long long b = (groups * (A.Co / 8) + 255) / 256;
-        if (b > blocks) b = blocks;
-        if (b < 1) b = 1;
-        blocks = (int)b;  // the partial buffers hold one row per launched block
-        first_conv1_kernel<MODE, PX><<<(int)b, 256, 0, s>>>(A);
-        UB_POST_LAUNCH();
-        return UB_OK;
-    }
+static int fc_launch(const FirstConvArgs& A, int blocks, cudaStream_t s) {
     const size_t smem = (size_t)A.Co * A.Ci * 9 * 4;
     if (smem > 48 * 1024)
         UB_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<MODE, false>,
@@ -184,47 +176,107 @@ static int fc_launch(const FirstConvArgs& A, int& blocks, cudaStream_t s) {
     UB_POST_LAUNCH();
     return UB_OK;
 }
-int launch_first_conv_stats(const FirstConvDesc& d, float* partial, int* blocks_out,
-                            cudaStream_t s) {
+constexpr int FC1_PX = 4;
+// single-channel patch moments -> cov[] (+ BatchNorm statistics when gamma != null)
+static int fc1_moments(const FirstConvDesc& d, float* ws, double* cov, const float* gamma,
+                       const float* beta, float* rm, float* rv, long long* nbt, float momentum,
+                       float eps, float* scale, float* shift, float* mean, float* rstd,
+                       cudaStream_t s) {
+    const long long groups = (long long)d.N * (d.H - 2) * ((d.W - 2 + FC1_PX - 1) / FC1_PX);
+    long long b = (groups + 255) / 256;
+    if (b > num_sms() * 2) b = num_sms() * 2;
+    double* partial = reinterpret_cast<double*>(ws);
+    fc1_cov_kernel<FC1_PX><<<(int)b, 256, 0, s>>>(d.x, d.N, d.H, d.W, partial);
+    UB_POST_LAUNCH();
+    const double count = (double)d.N * (d.H - 2) * (d.W - 2);
+    fc1_cov_finalize_kernel<<<1, 1024, 0, s>>>(partial, (int)b, d.x, count, cov, d.Co, d.w, d.bias,
+                                               gamma, beta, rm, rv, nbt, momentum, eps, scale,
+                                               shift, mean, rstd);
+    UB_POST_LAUNCH();
+    return UB_OK;
+}
+int launch_first_conv_train_stats(const FirstConvDesc& d, float* ws, const float* gamma,
+                                  const float* beta, float* rm, float* rv, long long* nbt,
+                                  float momentum, float eps, float* scale, float* shift,
+                                  float* mean, float* rstd, double* cov, cudaStream_t s) {
     FirstConvArgs A;
     UB_TRY(fc_fill(d, A));
-    A.partial = partial;
+    if ((reinterpret_cast<uintptr_t>(ws) & 7) != 0) {
+        set_last_error("first conv: workspace must be 8-byte aligned");
+        return UB_ERR_ARG;
+    }
+    if (d.Ci == 1)
+        return fc1_moments(d, ws, cov, gamma, beta, rm, rv, nbt, momentum, eps, scale, shift, mean,
+                           rstd, s);
+    A.partial = ws;
     const long long items = (long long)d.N * (d.H - 2) * (d.W - 2) * (d.Co / 8);
-    int blocks = red_blocks(items);
-    const int rc = fc_launch<FC_STATS>(A, blocks, s);
-    *blocks_out = blocks;
-    return rc;
+    const int blocks = red_blocks(items);
+    UB_TRY(fc_launch<FC_STATS>(A, blocks, s));
+    return launch_bn_finalize_flat(ws, blocks, d.Co, (double)d.N * (d.H - 2) * (d.W - 2), gamma,
+                                   beta, rm, rv, nbt, momentum, eps, scale, shift, mean, rstd, s);
 }
 int launch_first_conv_apply(const FirstConvDesc& d, const float* scale, const float* shift,
                             __nv_bfloat16* a, cudaStream_t s) {
     FirstConvArgs A;
     UB_TRY(fc_fill(d, A));
     A.scale = scale; A.shift = shift; A.a = a;
+    if (d.Ci == 1) {
+        const long long groups = (long long)d.N * (d.H - 2) * ((d.W - 2 + FC1_PX - 1) / FC1_PX);
+        fc1_apply_kernel<FC1_PX><<<ew_blocks(groups * (d.Co / 8)), 256, 0, s>>>(A);
+        UB_POST_LAUNCH();
+        return UB_OK;
+    }
     const long long items = (long long)d.N * (d.H - 2) * (d.W - 2) * (d.Co / 8);
-    int blocks = ew_blocks(items);
-    return fc_launch<FC_APPLY>(A, blocks, s);
+    return fc_launch<FC_APPLY>(A, ew_blocks(items), s);
 }
 int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const float* shift,
-                          const float* mean, const float* rstd, const View& g, float* partial,
-                          float* dgamma, float* dbeta, float* dw, cudaStream_t s) {
+                          const float* mean, const float* rstd, const View& g,
+                          const __nv_bfloat16* a, const double* cov, float* ws, float* dgamma,
+                          float* dbeta, float* dw, cudaStream_t s) {
     FirstConvArgs A;
     UB_TRY(fc_fill(d, A));
     A.scale = scale; A.shift = shift; A.mean = mean; A.rstd = rstd; A.g = g;
-    A.partial = partial;
     const long long count = (long long)d.N * (d.H - 2) * (d.W - 2);
     const long long items = count * (d.Co / 8);
+    if (d.Ci == 1) {
+        if (!a) { set_last_error("first conv backward: the forward activation is required"); return UB_ERR_ARG; }
+        if ((reinterpret_cast<uintptr_t>(ws) & 7) != 0) {
+            set_last_error("first conv: workspace must be 8-byte aligned");
+            return UB_ERR_ARG;
+        }
+        float* partial = ws + 128;
+        if (!cov) {   // op-level call without plan state: recompute the patch moments
+            double* c = reinterpret_cast<double*>(ws);
+            UB_TRY(fc1_moments(d, partial, c, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f,
+                               nullptr, nullptr, nullptr, nullptr, s));
+            cov = c;
+        }
+        A.a = const_cast<__nv_bfloat16*>(a);
+        A.partial = partial;
+        constexpr int PX = 2;
+        const long long groups = (long long)d.N * (d.H - 2) * ((d.W - 2 + PX - 1) / PX);
+        long long b = (groups * (d.Co / 8) + 255) / 256;
+        if (b > num_sms() * 2) b = num_sms() * 2;
+        fc1_bwd_kernel<PX><<<(int)b, 256, 0, s>>>(A, cov);
+        UB_POST_LAUNCH();
+        fc1_bwd_finalize_kernel<<<d.Co, 320, 0, s>>>(partial, (int)b, d.Co, cov, d.w, d.bias, scale,
+                                                     mean, rstd, dgamma, dbeta, dw);
+        UB_POST_LAUNCH();
+        return UB_OK;
+    }
+    A.partial = ws;
     int blocks = red_blocks(items);
     UB_TRY(fc_launch<FC_BWD_REDUCE>(A, blocks, s));
-    bn_bwd_finalize_kernel<<<(d.Co + 31) / 32, dim3(32, 16), 0, s>>>(partial, blocks, d.Co, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(d.Co + 31) / 32, dim3(32, 16), 0, s>>>(ws, blocks, d.Co, dgamma, dbeta);
     UB_POST_LAUNCH();
     A.dgamma = dgamma; A.dbeta = dbeta; A.inv_count = (float)(1.0 / (double)count);
-    A.wpartial = partial;
+    A.wpartial = ws;
     for (int ci = 0; ci < d.Ci; ++ci) {
         A.ci_sel = ci;
-        int wblocks = red_blocks(items);
+        const int wblocks = red_blocks(items);
         UB_TRY(fc_launch<FC_BWD_WGRAD>(A, wblocks, s));
-        first_wgrad_finalize_kernel<<<(d.Co * 9 + 127) / 128, 128, 0, s>>>(partial, wblocks, d.Co,
-                                                                           d.Ci, ci, dw);
+        first_wgrad_finalize_kernel<<<(d.Co * 9 + 127) / 128, 128, 0, s>>>(ws, wblocks, d.Co, d.Ci,
+                                                                           ci, dw);
         UB_POST_LAUNCH();
     }
     return UB_OK;

@@ -60,6 +60,7 @@ struct ub_plan {
     std::vector<void*> allocs;
     size_t bytes = 0;
     float* scratch = nullptr;   // stats / reduction partials
+    double* fc_cov = nullptr;   // patch moments of the single-channel first conv (forward -> backward)
     float* wgrad_ws = nullptr;
     size_t wgrad_ws_floats = 0;
     bf16* head_da = nullptr;
@@ -309,6 +310,7 @@ int ub_plan_create(ub_plan** out, int N, int n_channels, int H, int W, int base,
     }
     upd(scratch, head_bwd_partial_floats(base, n_classes));
     if (int r = P->alloc(&P->scratch, scratch)) return fail(r);
+    if (int r = P->alloc(&P->fc_cov, (size_t)FIRST_CONV_COV_DOUBLES)) return fail(r);
     if (P->training) {
         P->wgrad_ws_floats = wws;
         if (int r = P->alloc(&P->wgrad_ws, wws)) return fail(r);
@@ -398,12 +400,10 @@ static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const Vie
         d.w = P->params[u.p_w];
         if (P->training) {
             d.bias = P->params[u.p_b];
-            int blocks = 0;
-            UB_TRY(launch_first_conv_stats(d, P->scratch, &blocks, s));
-            UB_TRY(launch_bn_finalize_flat(P->scratch, blocks, u.Co, (double)N * u.Ho() * u.Wo(),
-                                           P->params[u.p_g], P->params[u.p_be], P->rm[u.bn],
-                                           P->rv[u.bn], P->nbt[u.bn], P->momentum, P->eps, u.scale,
-                                           u.shift, u.mean, u.rstd, s));
+            UB_TRY(launch_first_conv_train_stats(d, P->scratch, P->params[u.p_g], P->params[u.p_be],
+                                                 P->rm[u.bn], P->rv[u.bn], P->nbt[u.bn],
+                                                 P->momentum, P->eps, u.scale, u.shift, u.mean,
+                                                 u.rstd, P->fc_cov, s));
         } else {
             d.bias = nullptr;
             UB_TRY(launch_bn_fold_eval(u.Co, P->params[u.p_b], P->params[u.p_g], P->params[u.p_be],
@@ -555,10 +555,10 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
         f.x = P->x; f.N = N; f.Ci = u0.Ci; f.H = u0.Hin; f.W = u0.Win; f.Co = u0.Co;
         f.w = P->params[u0.p_w]; f.bias = P->params[u0.p_b];
         const double po = (double)N * u0.Ho() * u0.Wo();
-        ProfScope ps(P, CLS_FIRST, 2.0 * po * u0.Co * 9 * u0.Ci * 3,
-                     2.0 * (4.0 * N * u0.Hin * u0.Win * u0.Ci + 2.0 * po * u0.Co), s);
-        return launch_first_conv_bwd(f, u0.scale, u0.shift, u0.mean, u0.rstd, g0, P->scratch,
-                                     grads[u0.p_g], grads[u0.p_be], grads[u0.p_w], s);
+        ProfScope ps(P, CLS_FIRST, 2.0 * po * u0.Co * 9 * u0.Ci,
+                     4.0 * N * u0.Hin * u0.Win * u0.Ci + 4.0 * po * u0.Co, s);
+        return launch_first_conv_bwd(f, u0.scale, u0.shift, u0.mean, u0.rstd, g0, u0.a, P->fc_cov,
+                                     P->scratch, grads[u0.p_g], grads[u0.p_be], grads[u0.p_w], s);
     }
     memset(&d, 0, sizeof(d));
     d.y = u0.y; d.N = N; d.H = u0.Ho(); d.W = u0.Wo(); d.C = u0.Co;

@@ -119,12 +119,21 @@ struct FirstConvDesc {
     const float* bias;
 };
 size_t first_conv_partial_floats(int Co);
-int launch_first_conv_stats(const FirstConvDesc& d, float* partial, int* blocks, cudaStream_t s);
+constexpr int FIRST_CONV_COV_DOUBLES = 56;  // patch moments kept between forward and backward (Ci = 1)
+// Train-mode BatchNorm statistics of the first conv (+ running-stat update). `cov` (may be null)
+// receives the patch moments of a single-channel input for launch_first_conv_bwd.
+int launch_first_conv_train_stats(const FirstConvDesc& d, float* ws, const float* gamma,
+                                  const float* beta, float* rm, float* rv, long long* nbt,
+                                  float momentum, float eps, float* scale, float* shift,
+                                  float* mean, float* rstd, double* cov, cudaStream_t s);
 int launch_first_conv_apply(const FirstConvDesc& d, const float* scale, const float* shift,
                             __nv_bfloat16* a, cudaStream_t s);
+// `a` = the forward activation (needed for Ci = 1: ReLU mask), `cov` = moments saved by the forward
+// (null: recomputed into the workspace).
 int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const float* shift,
-                          const float* mean, const float* rstd, const View& g, float* partial,
-                          float* dgamma, float* dbeta, float* dw, cudaStream_t s);
+                          const float* mean, const float* rstd, const View& g,
+                          const __nv_bfloat16* a, const double* cov, float* ws, float* dgamma,
+                          float* dbeta, float* dw, cudaStream_t s);
 
 int launch_head_fwd(const __nv_bfloat16* a, int N, int H, int W, int K, int NC, const float* w,
                     const float* b, float* logits, unsigned char* mask, cudaStream_t s);

@@ -189,7 +189,7 @@ def first_conv_forward(x, w, bias, gamma, beta, running_mean=None, running_var=N
     return a, st
 
 
-def first_conv_backward(x, w, bias, st, g):
+def first_conv_backward(x, w, bias, st, g, a):
     lib = _lib.load()
     n, ci, h, wd_ = x.shape
     co = w.shape[0]
@@ -199,7 +199,7 @@ def first_conv_backward(x, w, bias, st, g):
     dbeta = torch.empty_like(dgamma)
     dw = torch.empty(co, ci, 3, 3, dtype=torch.float32, device=x.device)
     check(lib.ub_op_first_conv_backward(_p(x), n, ci, h, wd_, _p(w), _p(bias), co,
-                                        *[_p(s) for s in st], _vp(g), _p(ws), _p(dgamma),
+                                        *[_p(s) for s in st], _vp(g), _p(a), _p(ws), _p(dgamma),
                                         _p(dbeta), _p(dw), _stream()), "first_conv_backward")
     return dw, dgamma, dbeta
 
