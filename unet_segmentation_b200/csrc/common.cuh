@@ -175,6 +175,126 @@ __device__ __forceinline__ void tmem_ld_wait() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): two CTAs of a 2-CTA cluster (one TPC) execute ONE 256-row MMA. Each CTA
+// stages its own 128 rows of A and HALF of the B tile, so the B operand crosses L2->SM and the
+// shared-memory read port once per pair instead of once per CTA. The MMA is issued by the leader
+// (cluster rank 0); TMA loads of both CTAs complete on the leader's stage barrier; tcgen05.commit
+// multicasts its arrival to the barrier at the same offset in both CTAs.
+// All helpers are templated on CG (1 = single CTA, 2 = pair) so one kernel body serves both.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\t"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier given by a shared::cluster address (possibly in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+                 : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_3d_cg(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                               int c0, int c1, int c2) {
+    if (CG == 1) {
+        tma_load_3d(dst, m, bar, c0, c1, c2);
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+            ".cta_group::2 [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+            : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_4d_cg(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                               int c, int w, int h, int n) {
+    if (CG == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+            : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+            ".cta_group::2 [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+            : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_im2col_cg(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                                   int c, int w, int h, int n, uint16_t offw,
+                                                   uint16_t offh) {
+    if (CG == 1) {
+        tma_load_im2col(dst, m, bar, c, w, h, n, offw, offh);
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+            ".cta_group::2 [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n),
+            "h"(offw), "h"(offh)
+            : "memory");
+    }
+}
+template <uint32_t kCols, int CG>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t smem_dst) {
+    if (CG == 1) {
+        tmem_alloc<kCols>(smem_dst);
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+                     "n"(kCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <uint32_t kCols, int CG>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr) {
+    if (CG == 1) {
+        tmem_dealloc<kCols>(taddr);
+    } else {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols)
+                     : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void umma_bf16_cg(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                             uint32_t idesc, uint32_t accumulate) {
+    if (CG == 1) {
+        umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// CG == 2: the arrival is multicast to the barrier at this offset in BOTH CTAs of the pair.
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint32_t bar) {
+    if (CG == 1) {
+        umma_commit(bar);
+    } else {
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+            " [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+            : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // UMMA descriptors (bit layout: cute/arch/mma_sm100_desc.hpp of CUTLASS, restated)
 // ---------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle.

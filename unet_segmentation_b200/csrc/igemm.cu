@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <utility>
 
 #include "elementwise.cuh"
 #include "tmaps.cuh"
@@ -51,31 +52,59 @@ size_t igemm_stats_floats(int ncols) {
     return (size_t)num_sms() * 4 * 2 * bn;
 }
 
-template <int BN, int EPI>
+// Launch with an optional 2-CTA cluster (cta_group::2 pairs).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_clustered(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                    cudaStream_t stream, int cluster, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = cluster > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+// cta_group::2 pairs: on unless UB_PAIR=0
+static bool pairs_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("UB_PAIR"); on = (e && !atoi(e)) ? 0 : 1; }
+    return on != 0;
+}
+
+// Pairs pay off for BN >= 128 (a 2-CTA MMA with N = 64 issues slower than two 1-CTA MMAs, measured)
+// with at least 16 k-blocks per tile (short-K tiles are epilogue-bound) and two waves of tiles.
+static int pick_cg(int BN, int kblocks, long long tiles) {
+    return (pairs_enabled() && BN >= 128 && kblocks >= 16 && tiles >= 2LL * num_sms()) ? 2 : 1;
+}
+
+template <int BN, int EPI, int CG>
 static int launch_igemm_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                           const IgemmParams& p, int grid, cudaStream_t stream) {
-    using Cfg = IgemmCfg<BN>;
+    using Cfg = IgemmCfg<BN, CG>;
     static bool attr_set = false;
     if (!attr_set) {
-        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel<BN, EPI>,
+        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel<BN, EPI, CG>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    igemm_kmajor_kernel<BN, EPI><<<grid, 224, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, p);
+    UB_CHECK_CUDA(launch_clustered(igemm_kmajor_kernel<BN, EPI, CG>, dim3(grid), dim3(224),
+                                   Cfg::SMEM_BYTES, stream, CG, a0, a1, b, p));
     UB_POST_LAUNCH();
     return UB_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_igemm_bn(int epi, const CUtensorMap& a0, const CUtensorMap& a1,
                            const CUtensorMap& b, const IgemmParams& p, int grid,
                            cudaStream_t stream) {
     switch (epi) {
-        case EPI_CONV_STATS: return launch_igemm_t<BN, EPI_CONV_STATS>(a0, a1, b, p, grid, stream);
-        case EPI_STORE: return launch_igemm_t<BN, EPI_STORE>(a0, a1, b, p, grid, stream);
-        case EPI_AFFINE_RELU: return launch_igemm_t<BN, EPI_AFFINE_RELU>(a0, a1, b, p, grid, stream);
-        case EPI_CONVT: return launch_igemm_t<BN, EPI_CONVT>(a0, a1, b, p, grid, stream);
+        case EPI_CONV_STATS: return launch_igemm_t<BN, EPI_CONV_STATS, CG>(a0, a1, b, p, grid, stream);
+        case EPI_STORE: return launch_igemm_t<BN, EPI_STORE, CG>(a0, a1, b, p, grid, stream);
+        case EPI_AFFINE_RELU: return launch_igemm_t<BN, EPI_AFFINE_RELU, CG>(a0, a1, b, p, grid, stream);
+        case EPI_CONVT: return launch_igemm_t<BN, EPI_CONVT, CG>(a0, a1, b, p, grid, stream);
     }
     set_last_error("unknown epilogue kind %d", epi);
     return UB_ERR_ARG;
@@ -94,29 +123,30 @@ static int check_view(const View& v, const char* what) {
 }
 
 // ---- row-run variant (igemm_rr.cuh) -----------------------------------------------------------
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 static int launch_rowrun_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const RowRunParams& p, int grid, cudaStream_t stream) {
-    using Cfg = RowRunCfg<BN>;
+    using Cfg = RowRunCfg<BN, CG>;
     static bool attr_set = false;
     if (!attr_set) {
-        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_rowrun_kernel<BN, EPI>,
+        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_rowrun_kernel<BN, EPI, CG>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    igemm_rowrun_kernel<BN, EPI><<<grid, 224, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, p);
+    UB_CHECK_CUDA(launch_clustered(igemm_rowrun_kernel<BN, EPI, CG>, dim3(grid), dim3(224),
+                                   Cfg::SMEM_BYTES, stream, CG, a0, a1, b, p));
     UB_POST_LAUNCH();
     return UB_OK;
 }
-template <int BN>
+template <int BN, int CG>
 static int launch_rowrun_bn(int epi, const CUtensorMap& a0, const CUtensorMap& a1,
                             const CUtensorMap& b, const RowRunParams& p, int grid,
                             cudaStream_t stream) {
     switch (epi) {
-        case EPI_CONV_STATS: return launch_rowrun_t<BN, EPI_CONV_STATS>(a0, a1, b, p, grid, stream);
-        case EPI_STORE: return launch_rowrun_t<BN, EPI_STORE>(a0, a1, b, p, grid, stream);
-        case EPI_AFFINE_RELU: return launch_rowrun_t<BN, EPI_AFFINE_RELU>(a0, a1, b, p, grid, stream);
+        case EPI_CONV_STATS: return launch_rowrun_t<BN, EPI_CONV_STATS, CG>(a0, a1, b, p, grid, stream);
+        case EPI_STORE: return launch_rowrun_t<BN, EPI_STORE, CG>(a0, a1, b, p, grid, stream);
+        case EPI_AFFINE_RELU: return launch_rowrun_t<BN, EPI_AFFINE_RELU, CG>(a0, a1, b, p, grid, stream);
     }
     set_last_error("row-run: unsupported epilogue kind %d", epi);
     return UB_ERR_ARG;
@@ -163,13 +193,6 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
 
     CUtensorMap mA0, mA1, mB;
     if (rowrun_eligible(Wo, taps, tstride, epi.kind)) {
-        int rr = make_tmap_rows(&mA0, src0, 130, 3);
-        if (!rr && src1) rr = make_tmap_rows(&mA1, *src1, 130, 3);
-        if (!src1) mA1 = mA0;
-        if (!rr) rr = make_tmap_weights(&mB, wB, (unsigned long long)ctot, (unsigned long long)ncols,
-                                        (unsigned long long)taps, (unsigned)BN,
-                                        (unsigned)RowRunCfg<64>::btaps(BN));
-        if (rr) { set_last_error("row-run: tensor map encoding failed: %d", rr); return UB_ERR_TMAP; }
         RowRunParams q;
         memset(&q, 0, sizeof(q));
         q.N = src0.N; q.Ho = Ho; q.Wo = Wo; q.lower = lower;
@@ -177,6 +200,14 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
         q.qtiles = (Wo + 127) / 128;
         q.m_tiles = src0.N * Ho * q.qtiles;
         q.n_tiles = ncols / BN;
+        const int CG = pick_cg(BN, 9 * (q.cchunks0 + q.cchunks1), (long long)q.m_tiles * q.n_tiles);
+        int rr = make_tmap_rows(&mA0, src0, 130, 3);
+        if (!rr && src1) rr = make_tmap_rows(&mA1, *src1, 130, 3);
+        if (!src1) mA1 = mA0;
+        if (!rr) rr = make_tmap_weights(&mB, wB, (unsigned long long)ctot, (unsigned long long)ncols,
+                                        (unsigned long long)taps, (unsigned)(BN / CG),
+                                        (unsigned)RowRunCfg<64>::btaps(BN, CG));
+        if (rr) { set_last_error("row-run: tensor map encoding failed: %d", rr); return UB_ERR_TMAP; }
         q.epi.M = (int)M; q.epi.out = epi.out; q.epi.ldo = epi.ldo; q.epi.bias = epi.bias;
         q.epi.scale = epi.scale; q.epi.shift = epi.shift; q.epi.stats = epi.stats;
         static long long* dbg_buf = nullptr;
@@ -187,16 +218,25 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
             cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), stream);
             q.dbg = dbg_buf;
         }
-        int grid = (num_sms() / q.n_tiles) * q.n_tiles;
-        if (grid <= 0) grid = q.n_tiles;
-        const long long tiles = (long long)q.m_tiles * q.n_tiles;
-        if (grid > tiles) grid = (int)tiles;
+        int units = (num_sms() / CG / q.n_tiles) * q.n_tiles;
+        if (units <= 0) units = q.n_tiles;
+        const long long tiles = (long long)((q.m_tiles + CG - 1) / CG) * q.n_tiles;
+        if (units > tiles) units = (int)tiles;
+        const int grid = units * CG;
         if (info) { info->grid = grid; info->n_tiles = q.n_tiles; info->BN = BN; info->M = (int)M; }
         int rc;
-        switch (BN) {
-            case 256: rc = launch_rowrun_bn<256>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
-            case 128: rc = launch_rowrun_bn<128>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
-            default: rc = launch_rowrun_bn<64>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
+        if (CG == 2) {
+            switch (BN) {
+                case 256: rc = launch_rowrun_bn<256, 2>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
+                case 128: rc = launch_rowrun_bn<128, 2>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
+                default: rc = launch_rowrun_bn<64, 2>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
+            }
+        } else {
+            switch (BN) {
+                case 256: rc = launch_rowrun_bn<256, 1>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
+                case 128: rc = launch_rowrun_bn<128, 1>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
+                default: rc = launch_rowrun_bn<64, 1>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
+            }
         }
         if (dbg_on && rc == 0) {  // debugging aid only: synchronises
             long long h[10];
@@ -218,11 +258,6 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
     } else {
         mA1 = mA0;
     }
-    r = make_tmap_weights(&mB, wB, (unsigned long long)ctot, (unsigned long long)ncols,
-                          (unsigned long long)taps, (unsigned)BN, 1);
-    if (r) { set_last_error("igemm: weight tensor map failed: %d", r); return UB_ERR_TMAP; }
-    (void)K;
-
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     p.M = (int)M; p.Wo = Wo; p.Ho = Ho; p.lower = lower; p.tstride = tstride;
@@ -230,6 +265,12 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
     p.cchunks0 = src0.C / 64; p.cchunks1 = src1 ? src1->C / 64 : 0;
     p.m_tiles = (int)((M + 127) / 128);
     p.n_tiles = ncols / BN;
+    // CTA pairs (256 x BN tiles) whenever there are at least two full waves of pair tiles
+    const int CG = pick_cg(BN, taps * (p.cchunks0 + p.cchunks1), (long long)p.m_tiles * p.n_tiles);
+    r = make_tmap_weights(&mB, wB, (unsigned long long)ctot, (unsigned long long)ncols,
+                          (unsigned long long)taps, (unsigned)(BN / CG), 1);
+    if (r) { set_last_error("igemm: weight tensor map failed: %d", r); return UB_ERR_TMAP; }
+    (void)K;
     p.out = epi.out; p.ldo = epi.ldo; p.bias = epi.bias; p.scale = epi.scale; p.shift = epi.shift;
     p.stats = epi.stats;
     if (epi.kind == EPI_CONVT) {
@@ -237,23 +278,36 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
         p.ct_cout = ncols / 4; p.ct_H = src0.H; p.ct_W = src0.W;
         p.ct_sN = epi.ct_dst.sN; p.ct_sH = epi.ct_dst.sH; p.ct_sW = epi.ct_dst.sW;
     }
-    int grid = (num_sms() / p.n_tiles) * p.n_tiles;
-    if (grid <= 0) grid = p.n_tiles;
-    const long long tiles = (long long)p.m_tiles * p.n_tiles;
-    if (grid > tiles) grid = (int)tiles;
+    int units = (num_sms() / CG / p.n_tiles) * p.n_tiles;
+    if (units <= 0) units = p.n_tiles;
+    const long long tiles = (long long)((p.m_tiles + CG - 1) / CG) * p.n_tiles;
+    if (units > tiles) units = (int)tiles;
+    const int grid = units * CG;
     if (info) { info->grid = grid; info->n_tiles = p.n_tiles; info->BN = BN; info->M = (int)M; }
+    if (CG == 2) {
+        switch (BN) {
+            case 256: return launch_igemm_bn<256, 2>(epi.kind, mA0, mA1, mB, p, grid, stream);
+            case 128: return launch_igemm_bn<128, 2>(epi.kind, mA0, mA1, mB, p, grid, stream);
+            default: return launch_igemm_bn<64, 2>(epi.kind, mA0, mA1, mB, p, grid, stream);
+        }
+    }
     switch (BN) {
-        case 256: return launch_igemm_bn<256>(epi.kind, mA0, mA1, mB, p, grid, stream);
-        case 128: return launch_igemm_bn<128>(epi.kind, mA0, mA1, mB, p, grid, stream);
-        default: return launch_igemm_bn<64>(epi.kind, mA0, mA1, mB, p, grid, stream);
+        case 256: return launch_igemm_bn<256, 1>(epi.kind, mA0, mA1, mB, p, grid, stream);
+        case 128: return launch_igemm_bn<128, 1>(epi.kind, mA0, mA1, mB, p, grid, stream);
+        default: return launch_igemm_bn<64, 1>(epi.kind, mA0, mA1, mB, p, grid, stream);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
+static int wgrad_cg(int cols) {
+    const int bn = pick_bn(cols);
+    return (pairs_enabled() && bn >= 128) ? 2 : 1;
+}
 static int wgrad_splits(int rows, int cols, long long mpix) {
     const int bn = pick_bn(cols);
     if (!bn) return 1;
-    const int m_tiles = (rows + 127) / 128, n_tiles = cols / bn;
+    const int cg = wgrad_cg(cols);
+    const int m_tiles = (rows + 128 * cg - 1) / (128 * cg), n_tiles = cols / bn;
     const int units = m_tiles * n_tiles;
     const int kpix = bn == 256 ? 64 : 128;
     const long long kblocks = (mpix + kpix - 1) / kpix;
@@ -261,33 +315,35 @@ static int wgrad_splits(int rows, int cols, long long mpix) {
     // Pick the split count that minimises (number of CTA waves) x (k-blocks per CTA + fixed cost):
     // avoids e.g. 300 CTAs on 148 SMs (a third, nearly empty, wave).
     const double fixed = 24.0;  // prologue + fp32 epilogue of one CTA, in k-block units
-    const int sms = num_sms();
+    const int slots = num_sms() / cg;   // CTAs (or CTA pairs) resident at once
     long long best = 1;
     double best_cost = 1e30;
     for (long long s = 1; s <= smax && s <= 256; ++s) {
         const long long ctas = (long long)units * s;
-        const long long waves = (ctas + sms - 1) / sms;
+        const long long waves = (ctas + slots - 1) / slots;
         const double cost = (double)waves * ((double)((kblocks + s - 1) / s) + fixed);
         if (cost < best_cost * 0.999) { best_cost = cost; best = s; }
     }
     return (int)best;
 }
 size_t wgrad_ws_floats(int rows, int cols, long long mpix) {
+    // sized for either tiling (UB_PAIR may differ between the size query and the launch only in tests)
     return (size_t)wgrad_splits(rows, cols, mpix) * (size_t)rows * (size_t)cols;
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_wgrad_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                           const WgradParams& p, dim3 grid, cudaStream_t stream) {
-    using Cfg = WgradCfg<BN>;
+    using Cfg = WgradCfg<BN, CG>;
     static bool attr_set = false;
     if (!attr_set) {
-        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<BN>,
+        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<BN, CG>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    igemm_wgrad_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(a0, a1, b, p);
+    UB_CHECK_CUDA(launch_clustered(igemm_wgrad_kernel<BN, CG>, grid, dim3(256), Cfg::SMEM_BYTES,
+                                   stream, CG, a0, a1, b, p));
     UB_POST_LAUNCH();
     return UB_OK;
 }
@@ -307,6 +363,7 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
     const long long mpix = (long long)src0.N * Ho * Wo;
     const int ctot = src0.C + (src1 ? src1->C : 0);
     const int rows = taps * ctot;
+    const int CG = wgrad_cg(cols);
     const int splits = wgrad_splits(rows, cols, mpix);
     if ((size_t)splits * rows * cols > ws_floats) {
         set_last_error("wgrad: workspace too small");
@@ -323,7 +380,7 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
         mA1 = mA0;
     }
     r = make_tmap_chunked(&mB, B, (unsigned long long)cols, (unsigned long long)mpix,
-                          (unsigned long long)ldb * 2, (unsigned)kpix, (unsigned)(BN / 64));
+                          (unsigned long long)ldb * 2, (unsigned)kpix, (unsigned)(BN / 64 / CG));
     if (r) { set_last_error("wgrad: matrix tensor map failed: %d", r); return UB_ERR_TMAP; }
 
     WgradParams p;
@@ -335,13 +392,18 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
     p.n_tiles = cols / BN; p.splits = splits;
     p.kblocks_total = (int)((mpix + kpix - 1) / kpix);
     p.ws = ws; p.ldw = cols; p.split_stride = (long long)rows * cols;
-    const int m_tiles = (rows + 127) / 128;
-    dim3 grid(m_tiles * p.n_tiles, splits);
+    const int m_tiles = (rows + 128 * CG - 1) / (128 * CG);
+    dim3 grid(m_tiles * p.n_tiles * CG, splits);
     int rc;
-    switch (BN) {
-        case 256: rc = launch_wgrad_t<256>(mA0, mA1, mB, p, grid, stream); break;
-        case 128: rc = launch_wgrad_t<128>(mA0, mA1, mB, p, grid, stream); break;
-        default: rc = launch_wgrad_t<64>(mA0, mA1, mB, p, grid, stream); break;
+    if (CG == 2) {
+        if (BN == 256) rc = launch_wgrad_t<256, 2>(mA0, mA1, mB, p, grid, stream);
+        else rc = launch_wgrad_t<128, 2>(mA0, mA1, mB, p, grid, stream);
+    } else {
+        switch (BN) {
+            case 256: rc = launch_wgrad_t<256, 1>(mA0, mA1, mB, p, grid, stream); break;
+            case 128: rc = launch_wgrad_t<128, 1>(mA0, mA1, mB, p, grid, stream); break;
+            default: rc = launch_wgrad_t<64, 1>(mA0, mA1, mB, p, grid, stream); break;
+        }
     }
     UB_TRY(rc);
     const long long total = (long long)rows * cols;

@@ -35,12 +35,16 @@ struct IgemmParams {
     long long ct_sN, ct_sH, ct_sW;  // element strides of the destination [N,2H,2W,*] view
 };
 
-template <int BN>
+// CG = CTAs per MMA (1, or 2 = cta_group::2 pair computing a 256 x BN tile; each CTA stages its own
+// 128 rows of A and BN/2 rows of B).
+template <int BN, int CG = 1>
 struct IgemmCfg {
     static constexpr int A_BYTES = 128 * 128;
-    static constexpr int B_BYTES = BN * 128;
+    static constexpr int B_ROWS = BN / CG;
+    static constexpr int B_BYTES = B_ROWS * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int STAGES = (CG == 2) ? (BN == 256 ? 6 : 8)
+                                            : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -114,12 +118,12 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                 }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(224, 1)
 igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const IgemmParams p) {
-    using Cfg = IgemmCfg<BN>;
+    using Cfg = IgemmCfg<BN, CG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -136,32 +140,37 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // pair geometry: `unit` = CTA (CG 1) or CTA pair (CG 2); rank 0 issues the MMAs
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int unit = blockIdx.x / CG;
+    const int nunits = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapA1);
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(full_bar(s), 2);   // two producer threads (A operand, B operand)
+            mbar_init(full_bar(s), 2);   // the leader's two producer threads (A operand, B operand)
             mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);
+            mbar_init(tempty_bar(s), 4 * CG);   // epilogue warps of every CTA of the unit
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (warp == 1) tmem_alloc_cg<Cfg::TMEM_COLS, CG>(tmem_slot);
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_g;
 
     const int cchunks = p.cchunks0 + p.cchunks1;
     const int kblocks = p.taps * cchunks;
-    const int cta_n = blockIdx.x % p.n_tiles;
-    const int m_first = blockIdx.x / p.n_tiles;
-    const int m_step = gridDim.x / p.n_tiles;
+    const int cta_n = unit % p.n_tiles;
+    const int m_first = unit / p.n_tiles;
+    const int m_step = nunits / p.n_tiles;
+    const int m_units = (p.m_tiles + CG - 1) / CG;
     const int n0 = cta_n * BN;
 
     // Role code is executed by WHOLE warps with warp-uniform control flow; only the instruction that
@@ -170,11 +179,13 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
     // waterfall loop to obtain uniform-register operands, which costs hundreds of cycles per issue.
     if (warp == 0) {
         // ------------------------------ TMA producer, A operand (im2col) ------------------------------
-        // The two operands are fed by two different warps; each arms the stage barrier with its own
-        // byte count.
+        // The two operands are fed by two different warps; each arms the leader's stage barrier with
+        // the bytes of the whole unit (in a pair the peer's loads complete on the leader's barrier).
         int stage = 0;
         uint32_t phase = 0;
-        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+        for (int mu = m_first; mu < m_units; mu += m_step) {
+            int mt = mu * CG + (int)rank;
+            if (mt >= p.m_tiles) mt = p.m_tiles - 1;   // odd tail: reload a valid tile, rows masked
             const int m0 = mt * 128;
             const int q = m0 % p.Wo;
             const int t = m0 / p.Wo;
@@ -187,13 +198,14 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+                const uint32_t fb = (CG == 2) ? mapa_rank(full_bar(stage), 0) : full_bar(stage);
                 if (elect_one()) {
-                    mbar_expect_tx(full_bar(stage), Cfg::A_BYTES);
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), CG * Cfg::A_BYTES);
                     if (cc < p.cchunks0)
-                        tma_load_im2col(sa, &mapA0, full_bar(stage), cc * 64, cw, ch, n, offw, offh);
+                        tma_load_im2col_cg<CG>(sa, &mapA0, fb, cc * 64, cw, ch, n, offw, offh);
                     else
-                        tma_load_im2col(sa, &mapA1, full_bar(stage), (cc - p.cchunks0) * 64, cw, ch,
-                                        n, offw, offh);
+                        tma_load_im2col_cg<CG>(sa, &mapA1, fb, (cc - p.cchunks0) * 64, cw, ch, n,
+                                               offw, offh);
                 }
                 __syncwarp();
                 // K order = (channel chunk, tap): the same summation order as the row-run kernel, so
@@ -209,28 +221,30 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
         // ------------------------------ TMA producer, B operand (weights) ------------------------------
         int stage = 0;
         uint32_t phase = 0;
-        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+        const int nrow0 = n0 + (int)rank * Cfg::B_ROWS;
+        for (int mu = m_first; mu < m_units; mu += m_step) {
             int cc = 0, tap = 0;
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t fb = (CG == 2) ? mapa_rank(full_bar(stage), 0) : full_bar(stage);
                 if (elect_one()) {
-                    mbar_expect_tx(full_bar(stage), Cfg::B_BYTES);
-                    tma_load_3d(base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES, &mapB,
-                                full_bar(stage), cc * 64, n0, tap);
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), CG * Cfg::B_BYTES);
+                    tma_load_3d_cg<CG>(base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES, &mapB, fb,
+                                       cc * 64, nrow0, tap);
                 }
                 __syncwarp();
                 if (++tap == p.taps) { tap = 0; ++cc; }
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------ MMA issuer ------------------------------
-        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    } else if (warp == 1 && rank == 0) {
+        // ------------------------------ MMA issuer (leader CTA) ------------------------------
+        constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN, 0, 0);
         int stage = 0;
         uint32_t phase = 0;
         int as = 0;
         uint32_t aphase = 0;
-        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+        for (int mu = m_first; mu < m_units; mu += m_step) {
             mbar_wait(tempty_bar(as), aphase ^ 1u);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
@@ -244,14 +258,14 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)  // 16 bf16 = 32 B along K => +2 in 16-byte units
-                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                  (uint32_t)((kb | k) != 0));
-                    umma_commit(empty_bar(stage));
+                        umma_bf16_cg<CG>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                         (uint32_t)((kb | k) != 0));
+                    umma_commit_cg<CG>(empty_bar(stage));
                 }
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
-            if (elect_one()) umma_commit(tfull_bar(as));
+            if (elect_one()) umma_commit_cg<CG>(tfull_bar(as));
             __syncwarp();
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
@@ -265,8 +279,8 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
 
-        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
-            const long long m = (long long)mt * 128 + row_in_tile;
+        for (int mu = m_first; mu < m_units; mu += m_step) {
+            const long long m = (long long)(mu * CG + (int)rank) * 128 + row_in_tile;
             const bool valid = m < p.M;
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
@@ -275,11 +289,16 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             epilogue_tile<BN, EPI>(p, trow, m, valid, n0, lane, ssum, ssq);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(mapa_rank(tempty_bar(as), 0));
+                else mbar_arrive(tempty_bar(as));
+            }
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
         if (EPI == EPI_CONV_STATS) {
-            float* dst = p.stats + ((long long)blockIdx.x * 4 + quad) * (2 * BN);
+            // partial row of "virtual CTA" rank*nunits + unit: nunits % n_tiles == 0, so the channel
+            // tile of a row is still (row index % n_tiles) for bn_finalize_kernel
+            float* dst = p.stats + ((long long)((int)rank * nunits + unit) * 4 + quad) * (2 * BN);
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c) {
                 dst[c * 32 + lane] = ssum[c];
@@ -289,10 +308,10 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        tmem_dealloc_cg<Cfg::TMEM_COLS, CG>(tmem_base);
     }
 }
 
@@ -315,28 +334,31 @@ struct WgradParams {
     long long split_stride;
 };
 
-template <int BN>
+template <int BN, int CG = 1>
 struct WgradCfg {
     // Pixels (GEMM K) per pipeline stage. One barrier wait + tcgen05 fence costs the MMA thread
     // ~230 cycles, so narrow tiles (BN <= 128, 48-64 cycles per MMA) take 128 pixels = 8 MMAs per
     // stage; BN = 256 is already execution-bound with 64.
     static constexpr int KPIX = (BN == 256) ? 64 : 128;
     static constexpr int CHUNK_BYTES = KPIX * 128;   // one [KPIX pixels][64 channels] MN-major chunk
-    static constexpr int A_BYTES = 2 * CHUNK_BYTES;
-    static constexpr int B_BYTES = (BN / 64) * CHUNK_BYTES;
+    static constexpr int A_BYTES = 2 * CHUNK_BYTES;  // per CTA: two 64-row chunks = 128 GEMM rows
+    static constexpr int B_CHUNKS = BN / 64 / CG;    // per CTA: BN / CG columns of dY
+    static constexpr int B_BYTES = B_CHUNKS * CHUNK_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+    static constexpr int STAGES = (CG == 2) ? (BN == 256 ? 6 : 4)
+                                            : ((BN == 256) ? 4 : (BN == 128 ? 3 : 4));
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
     static constexpr uint32_t TMEM_COLS = BN;
+    static_assert(CG == 1 || BN >= 128, "a CTA pair splits dY by 64-channel chunks");
 };
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(256, 1)
 igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                    const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const WgradParams p) {
-    using Cfg = WgradCfg<BN>;
+    using Cfg = WgradCfg<BN, CG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -351,13 +373,19 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int unit = blockIdx.x / CG;              // (m tile of 128*CG rows, n tile)
+    const int m_tile = unit / p.n_tiles;
+    const int n_tile = unit % p.n_tiles;
+    // 64-row A chunks of this CTA: c = (m_tile*CG + rank)*2 + {0, 1}; the leader's come first
+    const int chunk0 = (m_tile * CG + (int)rank) * 2;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapA1);
         tma_prefetch_desc(&mapB);
-        // producers arming a stage: the B thread plus one thread per existing 64-row A chunk
-        const uint32_t nprod = ((int)(blockIdx.x / p.n_tiles) * 2 + 1 < p.a_chunks_total) ? 3u : 2u;
+        // threads arming a stage (leader CTA): the B thread plus one per existing 64-row A chunk
+        const uint32_t nprod = (chunk0 + 1 < p.a_chunks_total) ? 3u : 2u;
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(full_bar(s), nprod);
             mbar_init(empty_bar(s), 1);
@@ -365,14 +393,12 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
         mbar_init(tfull_bar, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (warp == 1) tmem_alloc_cg<Cfg::TMEM_COLS, CG>(tmem_slot);
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_g;
 
-    const int m_tile = blockIdx.x / p.n_tiles;
-    const int n_tile = blockIdx.x % p.n_tiles;
     const int split = blockIdx.y;
     const int kb_begin = (int)((long long)p.kblocks_total * split / p.splits);
     const int kb_end = (int)((long long)p.kblocks_total * (split + 1) / p.splits);
@@ -380,7 +406,8 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
     const int n0 = n_tile * BN;
 
     // Three producer threads (different warps) feed one stage: the two 64-row im2col chunks of the
-    // A side and the B-side box; each arms the stage barrier with its own byte count.
+    // A side and the B-side box. In a pair every load completes on the LEADER's stage barrier, which
+    // the leader's producers arm with the bytes of both CTAs.
     if (warp == 0 || warp == 6 || warp == 7) {
         const int role = warp == 0 ? 0 : (warp == 6 ? 1 : 2);   // 0/1: A chunk j, 2: B
         int stage = 0;
@@ -388,9 +415,13 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
         int a_cc = 0;
         uint16_t a_offw = 0, a_offh = 0;
         bool active = true;
+        uint32_t tx = Cfg::B_BYTES * CG;
         if (role < 2) {
-            const int c = m_tile * 2 + role;
+            const int c = chunk0 + role;
             active = c < p.a_chunks_total;
+            // the peer's chunk of the same role (two chunks further) may lie past the end
+            tx = (CG == 2 && c + 2 < p.a_chunks_total) ? 2u * Cfg::CHUNK_BYTES
+                                                        : (uint32_t)Cfg::CHUNK_BYTES;
             if (active) {
                 const int tap = c / cchunks;
                 a_cc = c % cchunks;
@@ -398,7 +429,7 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                 a_offh = (uint16_t)(tap / p.tapw);
             }
         }
-        // base pixel (q, pr, n) of the first k-block of this split, then advanced by 64 pixels
+        // base pixel (q, pr, n) of the first k-block of this split, then advanced by KPIX pixels
         int m0 = kb_begin * Cfg::KPIX;
         int q = m0 % p.Wo;
         int pr, n;
@@ -407,17 +438,18 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
             for (int kb = kb_begin; kb < kb_end; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+                const uint32_t fb = (CG == 2) ? mapa_rank(full_bar(stage), 0) : full_bar(stage);
                 if (role < 2) {
                     const int cw = p.lower + q * p.tstride;
                     const int ch = p.lower + pr * p.tstride;
                     if (elect_one()) {
-                        mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::CHUNK_BYTES);
+                        if (rank == 0) mbar_expect_tx(full_bar(stage), tx);
                         if (a_cc < p.cchunks0)
-                            tma_load_im2col(sa + role * Cfg::CHUNK_BYTES, &mapA0, full_bar(stage), a_cc * 64, cw,
-                                            ch, n, a_offw, a_offh);
+                            tma_load_im2col_cg<CG>(sa + role * Cfg::CHUNK_BYTES, &mapA0, fb, a_cc * 64,
+                                                   cw, ch, n, a_offw, a_offh);
                         else
-                            tma_load_im2col(sa + role * Cfg::CHUNK_BYTES, &mapA1, full_bar(stage),
-                                            (a_cc - p.cchunks0) * 64, cw, ch, n, a_offw, a_offh);
+                            tma_load_im2col_cg<CG>(sa + role * Cfg::CHUNK_BYTES, &mapA1, fb,
+                                                   (a_cc - p.cchunks0) * 64, cw, ch, n, a_offw, a_offh);
                     }
                     __syncwarp();
                     q += Cfg::KPIX;
@@ -426,11 +458,11 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                         if (++pr == p.Ho) { pr = 0; ++n; }
                     }
                 } else {
-                    // B side: one 3-D box (64 ch, KPIX pixels, BN/64 chunks) -> [chunk][pixel][64 ch]
+                    // B side: one 3-D box (64 ch, KPIX pixels, B_CHUNKS chunks) -> [chunk][pixel][64 ch]
                     if (elect_one()) {
-                        mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::B_BYTES);
-                        tma_load_3d(sa + Cfg::A_BYTES, &mapB, full_bar(stage), 0, m0,
-                                    n_tile * (BN / 64));
+                        if (rank == 0) mbar_expect_tx(full_bar(stage), tx);
+                        tma_load_3d_cg<CG>(sa + Cfg::A_BYTES, &mapB, fb, 0, m0,
+                                           n_tile * (BN / 64) + (int)rank * Cfg::B_CHUNKS);
                     }
                     __syncwarp();
                     m0 += Cfg::KPIX;
@@ -438,8 +470,8 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+    } else if (warp == 1 && rank == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN, 1, 1);
         int stage = 0;
         uint32_t phase = 0;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -452,18 +484,18 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                 for (int k = 0; k < Cfg::KPIX / 16; ++k) {  // 16 pixels = 16 rows of 128 B
                     const uint64_t da = make_smem_desc(sa + k * 2048, Cfg::CHUNK_BYTES, 1024);
                     const uint64_t db = make_smem_desc(sb + k * 2048, Cfg::CHUNK_BYTES, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (uint32_t)((kb != kb_begin) || (k != 0)));
+                    umma_bf16_cg<CG>(tmem_base, da, db, idesc, (uint32_t)((kb != kb_begin) || (k != 0)));
                 }
-                umma_commit(empty_bar(stage));
+                umma_commit_cg<CG>(empty_bar(stage));
             }
             __syncwarp();
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (elect_one()) umma_commit(tfull_bar);
+        if (elect_one()) umma_commit_cg<CG>(tfull_bar);
         __syncwarp();
     } else if (warp >= 2 && warp < 6) {
         const int quad = warp & 3;
-        const int row = m_tile * 128 + quad * 32 + lane;
+        const int row = (m_tile * CG + (int)rank) * 128 + quad * 32 + lane;
         const bool valid = row < p.a_chunks_total * 64;
         float* dst = p.ws + (long long)split * p.split_stride + (long long)row * p.ldw + n0;
         if (kb_end > kb_begin) {
@@ -490,10 +522,10 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        tmem_dealloc_cg<Cfg::TMEM_COLS, CG>(tmem_base);
     }
 }
 

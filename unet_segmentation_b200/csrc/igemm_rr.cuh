@@ -40,37 +40,29 @@ __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bo
 // barrier wait + tcgen05 fence costs the MMA thread ~230 cycles, so operations are made as large as
 // possible: ONE box (64 ch, 130 px, 3 rows) per A stage, and BTAPS filter taps of weights per B stage
 // (a whole filter row for BN <= 128), i.e. 12 MMAs per B wait and 36 per A wait.
-template <int BN>
+template <int BN, int CG = 1>
 struct RowRunCfg {
-    static constexpr int btaps(int bn) { return bn <= 128 ? 3 : 1; }
-    static constexpr int BTAPS = btaps(BN);
+    static constexpr int btaps(int bn, int cg) { return (bn <= 128 || cg == 2) ? 3 : 1; }
+    static constexpr int BTAPS = btaps(BN, CG);
     static constexpr int ROW_BYTES = 130 * 128;            // input rows are packed back to back
     static constexpr int A_TX = 3 * ROW_BYTES;             // bytes one A stage receives (49920)
     static constexpr int A_STAGE = 49 * 1024;              // 1024-aligned stage pitch
-    static constexpr int B_TILE = BN * 128;                // one tap: [BN][64] K-major
+    static constexpr int B_ROWS = BN / CG;                 // weight rows staged by one CTA
+    static constexpr int B_TILE = B_ROWS * 128;            // one tap: [B_ROWS][64] K-major
     static constexpr int B_STAGE = BTAPS * B_TILE;
-    static constexpr int SA = (BN == 64) ? 3 : 2;
-    static constexpr int SB = (BN == 64) ? 3 : (BN == 128 ? 2 : 3);
+    static constexpr int SA = (CG == 2) ? (BN == 256 ? 2 : 3) : ((BN == 64) ? 3 : 2);
+    static constexpr int SB = (CG == 2) ? (BN == 64 ? 4 : 2) : ((BN == 64) ? 3 : (BN == 128 ? 2 : 3));
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = SA * A_STAGE + SB * B_STAGE + BAR_BYTES + 1024;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c,
-                                            int w, int h, int n) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
-        : "memory");
-}
-
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(224, 1)
 igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const RowRunParams p) {
-    using Cfg = RowRunCfg<BN>;
+    using Cfg = RowRunCfg<BN, CG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -90,6 +82,10 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // CTA pair geometry (see common.cuh): unit = CTA or CTA pair, rank 0 issues the MMAs
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int unit = blockIdx.x / CG;
+    const int nunits = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0);
@@ -97,19 +93,20 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < Cfg::SA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
         for (int s = 0; s < Cfg::SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * CG); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (warp == 1) tmem_alloc_cg<Cfg::TMEM_COLS, CG>(tmem_slot);
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_g;
 
     const int cchunks = p.cchunks0 + p.cchunks1;
-    const int cta_n = blockIdx.x % p.n_tiles;
-    const int m_first = blockIdx.x / p.n_tiles;
-    const int m_step = gridDim.x / p.n_tiles;
+    const int cta_n = unit % p.n_tiles;
+    const int m_first = unit / p.n_tiles;
+    const int m_step = nunits / p.n_tiles;
+    const int m_units = (p.m_tiles + CG - 1) / CG;
     const int n0 = cta_n * BN;
 
     // (whole warps run the role loops; see the note on elect_one() in igemm_kmajor_kernel)
@@ -120,7 +117,9 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         const bool prof = p.dbg != nullptr;
         long long waited = 0;
         const long long tstart = clock64();
-        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+        for (int mu = m_first; mu < m_units; mu += m_step) {
+            int mt = mu * CG + (int)rank;
+            if (mt >= p.m_tiles) mt = p.m_tiles - 1;   // odd tail: reload a valid tile, rows masked
             const int qt = mt % p.qtiles;
             const int t = mt / p.qtiles;
             const int pr = t % p.Ho;
@@ -130,12 +129,13 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             for (int cc = 0; cc < cchunks; ++cc) {
                 mbar_wait_prof(emptyA(stage), phase ^ 1u, prof, waited);
                 const uint32_t sa = base + stage * Cfg::A_STAGE;
+                const uint32_t fb = (CG == 2) ? mapa_rank(fullA(stage), 0) : fullA(stage);
                 if (elect_one()) {
-                    mbar_expect_tx(fullA(stage), Cfg::A_TX);
+                    if (rank == 0) mbar_expect_tx(fullA(stage), CG * Cfg::A_TX);
                     if (cc < p.cchunks0)   // box (64, 130, 3, 1)
-                        tma_load_4d(sa, &mapA0, fullA(stage), cc * 64, w0, h0, n);
+                        tma_load_4d_cg<CG>(sa, &mapA0, fb, cc * 64, w0, h0, n);
                     else
-                        tma_load_4d(sa, &mapA1, fullA(stage), (cc - p.cchunks0) * 64, w0, h0, n);
+                        tma_load_4d_cg<CG>(sa, &mapA1, fb, (cc - p.cchunks0) * 64, w0, h0, n);
                 }
                 __syncwarp();
                 if (++stage == Cfg::SA) { stage = 0; phase ^= 1u; }
@@ -146,21 +146,23 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             atomicAdd((unsigned long long*)&p.dbg[1], (unsigned long long)(clock64() - tstart));
         }
     } else if (warp == 6) {
-        // ---------------- B producer: one (tap, chunk) weight tile per stage ----------------------
+        // ---------------- B producer: BTAPS (tap, chunk) weight tiles per stage --------------------
         int stage = 0;
         uint32_t phase = 0;
         const bool prof = p.dbg != nullptr;
         long long waited = 0;
         const long long tstart = clock64();
-        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+        const int nrow0 = n0 + (int)rank * Cfg::B_ROWS;
+        for (int mu = m_first; mu < m_units; mu += m_step) {
             for (int cc = 0; cc < cchunks; ++cc) {
 #pragma unroll 1
                 for (int tap = 0; tap < 9; tap += Cfg::BTAPS) {
                     mbar_wait_prof(emptyB(stage), phase ^ 1u, prof, waited);
+                    const uint32_t fb = (CG == 2) ? mapa_rank(fullB(stage), 0) : fullB(stage);
                     if (elect_one()) {
-                        mbar_expect_tx(fullB(stage), Cfg::B_STAGE);
-                        tma_load_3d(b_base + stage * Cfg::B_STAGE, &mapB, fullB(stage), cc * 64, n0,
-                                    tap);
+                        if (rank == 0) mbar_expect_tx(fullB(stage), CG * Cfg::B_STAGE);
+                        tma_load_3d_cg<CG>(b_base + stage * Cfg::B_STAGE, &mapB, fb, cc * 64, nrow0,
+                                           tap);
                     }
                     __syncwarp();
                     if (++stage == Cfg::SB) { stage = 0; phase ^= 1u; }
@@ -171,9 +173,9 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             atomicAdd((unsigned long long*)&p.dbg[2], (unsigned long long)waited);
             atomicAdd((unsigned long long*)&p.dbg[3], (unsigned long long)(clock64() - tstart));
         }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer -----------------------------------------------------------------
-        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    } else if (warp == 1 && rank == 0) {
+        // ---------------- MMA issuer (leader CTA) ---------------------------------------------------
+        constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN, 0, 0);
         int sa_i = 0, sb_i = 0;
         uint32_t pa = 0, pb = 0;
         int as = 0;
@@ -181,7 +183,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         const bool prof = p.dbg != nullptr;
         long long wA = 0, wB = 0, wT = 0;
         const long long tstart = clock64();
-        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+        for (int mu = m_first; mu < m_units; mu += m_step) {
             mbar_wait_prof(tempty_bar(as), aphase ^ 1u, prof, wT);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
@@ -204,13 +206,14 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                             make_smem_desc(b_base + sb_i * Cfg::B_STAGE + j * Cfg::B_TILE, 0, 1024);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
+                            umma_bf16_cg<CG>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k),
+                                             idesc, acc);
                             acc = 1;
                         }
                     }
-                    umma_commit(emptyB(sb_i));
-                    if (tap + Cfg::BTAPS >= 9) umma_commit(emptyA(sa_i));
-                    if (tap + Cfg::BTAPS >= 9 && cc == cchunks - 1) umma_commit(tfull_bar(as));
+                    umma_commit_cg<CG>(emptyB(sb_i));
+                    if (tap + Cfg::BTAPS >= 9) umma_commit_cg<CG>(emptyA(sa_i));
+                    if (tap + Cfg::BTAPS >= 9 && cc == cchunks - 1) umma_commit_cg<CG>(tfull_bar(as));
                     }
                     __syncwarp();
                     acc = 1;
@@ -238,11 +241,12 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         const bool prof = p.dbg != nullptr;
         long long wE = 0;
         const long long tstart = clock64();
-        for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+        for (int mu = m_first; mu < m_units; mu += m_step) {
+            const int mt = mu * CG + (int)rank;
             const int qt = mt % p.qtiles;
             const int t = mt / p.qtiles;      // = n * Ho + p
             const int q = qt * 128 + row_in_tile;
-            const bool valid = q < p.Wo;
+            const bool valid = q < p.Wo && mt < p.m_tiles;
             const long long m = (long long)t * p.Wo + q;
             mbar_wait_prof(tfull_bar(as), aphase, prof, wE);
             tc_fence_after();
@@ -250,7 +254,10 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, ssum, ssq);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(mapa_rank(tempty_bar(as), 0));
+                else mbar_arrive(tempty_bar(as));
+            }
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
         if (prof && warp == 2 && lane == 0) {
@@ -258,7 +265,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             atomicAdd((unsigned long long*)&p.dbg[9], (unsigned long long)(clock64() - tstart));
         }
         if (EPI == EPI_CONV_STATS) {
-            float* dst = p.epi.stats + ((long long)blockIdx.x * 4 + quad) * (2 * BN);
+            float* dst = p.epi.stats + ((long long)((int)rank * nunits + unit) * 4 + quad) * (2 * BN);
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c) {
                 dst[c * 32 + lane] = ssum[c];
@@ -268,10 +275,10 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        tmem_dealloc_cg<Cfg::TMEM_COLS, CG>(tmem_base);
     }
 }
 
