@@ -387,21 +387,25 @@ def main():
             gi = torch.Generator().manual_seed(99)
             frame = 0.4 + 0.2 * torch.rand(512, 512, generator=gi)
             img = frame.repeat(size // 512, size // 512).to(dev)   # mosaic of 512^2 frames
-            n_tiles = len(tiling.plan_tiles(size, size, 572)[2])
+            tile_in = tiling.choose_tile(size, size, world)    # least executed work per rank
+            tile_out, _, origins = tiling.plan_tiles(size, size, tile_in)
+            n_tiles = len(origins)
             if n_tiles < world:
                 continue
-            bt = 8 if n_tiles // world >= 8 else max(1, n_tiles // world)
-            tiling.overlap_tile_predict(model, img, batch_tiles=bt, rank=rank, world=world)  # warm-up
+            bt = min(8, max(1, n_tiles // world))
+            tiling.overlap_tile_predict(model, img, tile_in=tile_in, batch_tiles=bt, rank=rank,
+                                        world=world)  # warm-up
             barrier()
-            reps = 2
+            reps = 3
             e0.record()
             for _ in range(reps):
-                mask = tiling.overlap_tile_predict(model, img, batch_tiles=bt, rank=rank, world=world)
+                mask = tiling.overlap_tile_predict(model, img, tile_in=tile_in, batch_tiles=bt,
+                                                   rank=rank, world=world)
             e1.record()
             barrier()
             ms_i = max_over_ranks(e0.elapsed_time(e1)) / reps
             infer[f"{size}x{size}"] = {"mpix_per_s": size * size / (ms_i * 1e-3) / 1e6, "ms": ms_i,
-                                       "tiles": n_tiles, "tile_in": 572, "tile_out": 388,
+                                       "tiles": n_tiles, "tile_in": tile_in, "tile_out": tile_out,
                                        "batch_tiles": bt, "fg_fraction": float((mask > 0).float().mean())}
         model.train()
 

@@ -68,25 +68,43 @@ def _reflect_index(i: torch.Tensor, n: int) -> torch.Tensor:
 
 
 def extract_tiles(image: torch.Tensor, origins, tile_in: int, margin: int) -> torch.Tensor:
-    """image (H, W) fp32 -> (T, 1, tile_in, tile_in), mirror-extended around the borders."""
+    """image (H, W) fp32 -> (T, 1, tile_in, tile_in), mirror-extended around the borders (one
+    gather for the whole batch of tiles)."""
     h, w = image.shape
     dev = image.device
     ar = torch.arange(tile_in, device=dev)
-    tiles = []
-    for (y, x) in origins:
-        iy = _reflect_index(ar + (y - margin), h)
-        ix = _reflect_index(ar + (x - margin), w)
-        tiles.append(image[iy][:, ix])
-    return torch.stack(tiles).unsqueeze(1)
+    oy = torch.tensor([y - margin for (y, _) in origins], device=dev)
+    ox = torch.tensor([x - margin for (_, x) in origins], device=dev)
+    iy = _reflect_index(ar[None, :] + oy[:, None], h)      # (T, S)
+    ix = _reflect_index(ar[None, :] + ox[:, None], w)
+    return image[iy[:, :, None], ix[:, None, :]].unsqueeze(1)
+
+
+def choose_tile(h: int, w: int, world: int = 1, levels: int = 5, max_tile_in: int = 1468,
+                min_tile_in: int = 380) -> int:
+    """Input tile size (≡ 12 mod 16) that minimises the executed work of overlap-tile inference:
+    (tiles per rank, rounded up) x tile_in^2, i.e. it trades the halo overhead of small tiles
+    (572 -> 388: 2.04 MFLOP per output pixel vs 1.47 without halo) against the coverage waste of
+    tiles that do not divide the image and against rank imbalance."""
+    best, best_cost = 572, None
+    for tile_in in range(min_tile_in + (12 - min_tile_in) % 16, max_tile_in + 1, 16):
+        n = len(plan_tiles(h, w, tile_in, levels)[2])
+        per_rank = -(-n // world)
+        cost = per_rank * tile_in * tile_in
+        if best_cost is None or cost < best_cost:
+            best, best_cost = tile_in, cost
+    return best
 
 
 @torch.no_grad()
-def overlap_tile_predict(model, image: torch.Tensor, tile_in: int = 572, batch_tiles: int = 8,
-                         rank: int = 0, world: int = 1, group=None, return_logits: bool = False):
+def overlap_tile_predict(model, image: torch.Tensor, tile_in: Optional[int] = 572,
+                         batch_tiles: int = 8, rank: int = 0, world: int = 1, group=None,
+                         return_logits: bool = False):
     """Whole-image binary mask (uint8, 255 = foreground) of a 2-D fp32 CUDA image.
 
     ``model`` is a ``unet_segmentation_b200.UNet`` in eval mode. With ``world > 1`` every rank calls
-    this with the same image and gets the same stitched result.
+    this with the same image and gets the same stitched result. ``tile_in=None`` picks the tile
+    size with ``choose_tile``.
     """
     if image.dim() != 2 or not image.is_cuda:
         raise ValueError("expected a 2-D CUDA image")
@@ -95,6 +113,8 @@ def overlap_tile_predict(model, image: torch.Tensor, tile_in: int = 572, batch_t
     levels = getattr(model, "levels", 5)
     margin = network_margin(levels)
     h, w = image.shape
+    if tile_in is None:
+        tile_in = choose_tile(h, w, world, levels)
     tile_out, _, origins = plan_tiles(h, w, tile_in, levels)
     mine = parallel.shard_indices(len(origins), rank, world)
     out_masks, out_logits = [], []
