@@ -88,11 +88,22 @@ bn_finalize_kernel(const float* __restrict__ stats, int grid_ctas, int n_tiles, 
     if (c < C) {
         const int tile = c / BN, col = c % BN;
         const int rows = (grid_ctas - tile + n_tiles - 1) / n_tiles * 4;  // (cta, warp) pairs
-        for (int r = threadIdx.y; r < rows; r += 16) {
-            const int b = tile + (r >> 2) * n_tiles, w = r & 3;
-            const float* p = stats + ((long long)b * 4 + w) * (2 * BN);
-            s += (double)p[col];
-            q += (double)p[BN + col];
+        // 4 independent row loads in flight (a dependent load -> add chain costs ~0.35 us per row)
+        for (int r0 = threadIdx.y; r0 < rows; r0 += 64) {
+            float ps[4], pq[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = r0 + 16 * j;
+                ps[j] = 0.f; pq[j] = 0.f;
+                if (r < rows) {
+                    const int b = tile + (r >> 2) * n_tiles, w = r & 3;
+                    const float* p = stats + ((long long)b * 4 + w) * (2 * BN);
+                    ps[j] = p[col];
+                    pq[j] = p[BN + col];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s += (double)ps[j]; q += (double)pq[j]; }
         }
     }
     finalize_combine(s, q);
@@ -113,9 +124,16 @@ bn_finalize_flat_kernel(const float* __restrict__ part, int blocks, int C, doubl
     if (c == 0 && threadIdx.y == 0 && num_batches_tracked) *num_batches_tracked += 1;
     double s = 0.0, q = 0.0;
     if (c < C) {
-        for (int b = threadIdx.y; b < blocks; b += 16) {
-            s += (double)part[(long long)b * 2 * C + c];
-            q += (double)part[(long long)b * 2 * C + C + c];
+        for (int b0 = threadIdx.y; b0 < blocks; b0 += 64) {
+            float ps[4], pq[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = b0 + 16 * j;
+                ps[j] = b < blocks ? part[(long long)b * 2 * C + c] : 0.f;
+                pq[j] = b < blocks ? part[(long long)b * 2 * C + C + c] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s += (double)ps[j]; q += (double)pq[j]; }
         }
     }
     finalize_combine(s, q);
@@ -496,9 +514,16 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C,
     const int c = blockIdx.x * 32 + threadIdx.x;
     double b = 0.0, g = 0.0;
     if (c < C) {
-        for (int k = threadIdx.y; k < blocks; k += 16) {
-            b += (double)part[(long long)k * 2 * C + c];
-            g += (double)part[(long long)k * 2 * C + C + c];
+        for (int k0 = threadIdx.y; k0 < blocks; k0 += 64) {
+            float pb[4], pg[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + 16 * j;
+                pb[j] = k < blocks ? part[(long long)k * 2 * C + c] : 0.f;
+                pg[j] = k < blocks ? part[(long long)k * 2 * C + C + c] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { b += (double)pb[j]; g += (double)pg[j]; }
         }
     }
     finalize_combine(b, g);

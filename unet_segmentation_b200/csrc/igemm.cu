@@ -76,7 +76,9 @@ static bool pairs_enabled() {
 // Pairs pay off for BN >= 128 (a 2-CTA MMA with N = 64 issues slower than two 1-CTA MMAs, measured)
 // with at least 16 k-blocks per tile (short-K tiles are epilogue-bound) and two waves of tiles.
 static int pick_cg(int BN, int kblocks, long long tiles) {
-    return (pairs_enabled() && BN >= 128 && kblocks >= 16 && tiles >= 2LL * num_sms()) ? 2 : 1;
+    static int minkb = -1;
+    if (minkb < 0) { const char* e = getenv("UB_PAIR_MINKB"); minkb = e ? atoi(e) : 16; }
+    return (pairs_enabled() && BN >= 128 && kblocks >= minkb && tiles >= 2LL * num_sms()) ? 2 : 1;
 }
 
 template <int BN, int EPI, int CG>
@@ -90,7 +92,7 @@ static int launch_igemm_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    UB_CHECK_CUDA(launch_clustered(igemm_kmajor_kernel<BN, EPI, CG>, dim3(grid), dim3(224),
+    UB_CHECK_CUDA(launch_clustered(igemm_kmajor_kernel<BN, EPI, CG>, dim3(grid), dim3(IGEMM_THREADS),
                                    Cfg::SMEM_BYTES, stream, CG, a0, a1, b, p));
     UB_POST_LAUNCH();
     return UB_OK;
@@ -134,7 +136,7 @@ static int launch_rowrun_t(const CUtensorMap& a0, const CUtensorMap& a1, const C
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    UB_CHECK_CUDA(launch_clustered(igemm_rowrun_kernel<BN, EPI, CG>, dim3(grid), dim3(224),
+    UB_CHECK_CUDA(launch_clustered(igemm_rowrun_kernel<BN, EPI, CG>, dim3(grid), dim3(IGEMM_THREADS),
                                    Cfg::SMEM_BYTES, stream, CG, a0, a1, b, p));
     UB_POST_LAUNCH();
     return UB_OK;

@@ -50,14 +50,32 @@ struct IgemmCfg {
     static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
+// Warp roles (352 threads): 0 = A producer, 1 = MMA issuer + TMEM allocator, 6 = B producer,
+// 2-5 and 7-10 = epilogue (lane quadrant = warp & 3; warps 7-10 take the upper half of the columns).
+// BN = 64 keeps four epilogue warps (one 32-column chunk pair each): its tiles are MMA-issue bound
+// and a second epilogue warp on the MMA warp's scheduler costs more than it saves (measured).
+constexpr int IGEMM_THREADS = 352;
+template <int BN> struct EpiCfg {
+    static constexpr int HALVES = (BN == 64) ? 1 : 2;      // column halves = epilogue warps / 4
+    static constexpr int NCH = BN / 32 / HALVES;           // 32-column chunks per warp
+};
+template <int BN>
+__device__ __forceinline__ bool is_epilogue_warp(int warp) {
+    return warp >= 2 && warp != 6 && (EpiCfg<BN>::HALVES == 2 || warp < 6);
+}
+
 // Epilogue of one 128 x BN accumulator tile: TMEM -> registers (32 columns at a time), bias /
 // folded-BN affine, bf16 store (row-major, or 2x2 pixel-shuffle scatter for the transposed conv),
 // and the per-channel sum / sum-of-squares of the BatchNorm statistics.
 //   trow: TMEM address of this warp's lane quadrant and accumulator stage; m: GEMM row of the thread.
+//   Eight epilogue warps share a tile: the warp of column half `chalf` handles chunks
+//   [chalf*NCH, chalf*NCH + NCH) of its lane quadrant, so the BatchNorm-statistics
+//   epilogue of short-K tiles keeps up with the MMAs.
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t trow, long long m,
-                                              bool valid, int n0, int lane, float (&ssum)[BN / 32],
-                                              float (&ssq)[BN / 32]) {
+                                              bool valid, int n0, int lane, int chalf,
+                                              float (&ssum)[EpiCfg<BN>::NCH],
+                                              float (&ssq)[EpiCfg<BN>::NCH]) {
                 long long ct_row = 0;
                 if (EPI == EPI_CONVT) {
                     const int w = (int)(m % p.ct_W);
@@ -67,7 +85,8 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                     ct_row = n * p.ct_sN + (long long)(2 * h) * p.ct_sH + (long long)(2 * w) * p.ct_sW;
                 }
     #pragma unroll
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int cl = 0; cl < EpiCfg<BN>::NCH; ++cl) {
+                    const int c = chalf * EpiCfg<BN>::NCH + cl;
                     uint32_t r[32];
                     tmem_ld_32x32(trow + (uint32_t)(c * 32), r);
                     tmem_ld_wait();
@@ -112,14 +131,14 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                             v[i] = valid ? v[i] : 0.f;
                             s2[i] = v[i] * v[i];
                         }
-                        ssum[c] += warp_column_sum(v, lane);
-                        ssq[c] += warp_column_sum(s2, lane);
+                        ssum[cl] += warp_column_sum(v, lane);
+                        ssq[cl] += warp_column_sum(s2, lane);
                     }
                 }
 }
 
 template <int BN, int EPI, int CG>
-__global__ void __launch_bounds__(224, 1)
+__global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const IgemmParams p) {
@@ -155,7 +174,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4 * CG);   // epilogue warps of every CTA of the unit
+            mbar_init(tempty_bar(s), 4 * EpiCfg<BN>::HALVES * CG);   // epilogue warps of the unit
         }
         fence_mbar_init();
     }
@@ -269,15 +288,17 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             __syncwarp();
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
-    } else if (warp >= 2 && warp < 6) {
+    } else if (is_epilogue_warp<BN>(warp)) {
         // ------------------------------ epilogue ------------------------------
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        const int chalf = warp > 6 ? 1 : 0;
         const int row_in_tile = quad * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
-        float ssum[BN / 32], ssq[BN / 32];
+        constexpr int NCH = EpiCfg<BN>::NCH;
+        float ssum[NCH], ssq[NCH];
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+        for (int c = 0; c < NCH; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
 
         for (int mu = m_first; mu < m_units; mu += m_step) {
             const long long m = (long long)(mu * CG + (int)rank) * 128 + row_in_tile;
@@ -286,7 +307,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 
-            epilogue_tile<BN, EPI>(p, trow, m, valid, n0, lane, ssum, ssq);
+            epilogue_tile<BN, EPI>(p, trow, m, valid, n0, lane, chalf, ssum, ssq);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -298,9 +319,10 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
         if (EPI == EPI_CONV_STATS) {
             // partial row of "virtual CTA" rank*nunits + unit: nunits % n_tiles == 0, so the channel
             // tile of a row is still (row index % n_tiles) for bn_finalize_kernel
-            float* dst = p.stats + ((long long)((int)rank * nunits + unit) * 4 + quad) * (2 * BN);
+            float* dst = p.stats + ((long long)((int)rank * nunits + unit) * 4 + quad) * (2 * BN) +
+                         chalf * (NCH * 32);
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 dst[c * 32 + lane] = ssum[c];
                 dst[BN + c * 32 + lane] = ssq[c];
             }

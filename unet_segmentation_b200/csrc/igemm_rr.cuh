@@ -58,7 +58,7 @@ struct RowRunCfg {
 };
 
 template <int BN, int EPI, int CG>
-__global__ void __launch_bounds__(224, 1)
+__global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const RowRunParams p) {
@@ -93,7 +93,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < Cfg::SA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
         for (int s = 0; s < Cfg::SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * CG); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * EpiCfg<BN>::HALVES * CG); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_cg<Cfg::TMEM_COLS, CG>(tmem_slot);
@@ -229,15 +229,17 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             atomicAdd((unsigned long long*)&p.dbg[6], (unsigned long long)wT);
             atomicAdd((unsigned long long*)&p.dbg[7], (unsigned long long)(clock64() - tstart));
         }
-    } else if (warp >= 2 && warp < 6) {
-        // ---------------- epilogue ----------------------------------------------------------------------
+    } else if (is_epilogue_warp<BN>(warp)) {
+        // ---------------- epilogue (lane quadrant x column half) --------------------------------------
         const int quad = warp & 3;
+        const int chalf = warp > 6 ? 1 : 0;
         const int row_in_tile = quad * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
-        float ssum[BN / 32], ssq[BN / 32];
+        constexpr int NCH = EpiCfg<BN>::NCH;
+        float ssum[NCH], ssq[NCH];
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+        for (int c = 0; c < NCH; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
         const bool prof = p.dbg != nullptr;
         long long wE = 0;
         const long long tstart = clock64();
@@ -251,7 +253,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             mbar_wait_prof(tfull_bar(as), aphase, prof, wE);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-            epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, ssum, ssq);
+            epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, chalf, ssum, ssq);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -265,9 +267,10 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             atomicAdd((unsigned long long*)&p.dbg[9], (unsigned long long)(clock64() - tstart));
         }
         if (EPI == EPI_CONV_STATS) {
-            float* dst = p.epi.stats + ((long long)((int)rank * nunits + unit) * 4 + quad) * (2 * BN);
+            float* dst = p.epi.stats + ((long long)((int)rank * nunits + unit) * 4 + quad) * (2 * BN) +
+                         chalf * (NCH * 32);
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 dst[c * 32 + lane] = ssum[c];
                 dst[BN + c * 32 + lane] = ssq[c];
             }
