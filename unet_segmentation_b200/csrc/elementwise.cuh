@@ -346,6 +346,10 @@ bn_bwd_kernel(const BnBwdArgs A) {
         const unsigned Hp = H >> 1, Wp = W >> 1;
         const __nv_bfloat16* gpb = reinterpret_cast<const __nv_bfloat16*>(A.gp.ptr);
         const __nv_bfloat16* gsb = reinterpret_cast<const __nv_bfloat16*>(A.gs.ptr);
+        // (w, h, n) of the thread's current pixel is advanced incrementally by the grid stride:
+        // no integer division in the loop (it made this kernel issue-bound, 2.7 TB/s).
+        const unsigned dW = gstride % W, dH = (gstride / W) % H, dN = (gstride / W) / H;
+        unsigned w = first % W, h = (first / W) % H, n = (first / W) / H;
         for (unsigned p0 = first; p0 < npix; p0 += 4 * gstride) {
             uint4 yr[4], gpr[4], gsr[4];
             uint2 amr[4];
@@ -357,7 +361,6 @@ bn_bwd_kernel(const BnBwdArgs A) {
                 full[j] = false; ins[j] = false;
                 if (p < npix) {
                     yr[j] = ldg16(A.y + (size_t)p * C + cg * 8);
-                    const unsigned w = p % W, t = p / W, h = t % H, n = t / H;
                     const unsigned hq = h >> 1, wq = w >> 1;
                     dsel[j] = ((h & 1u) << 1) | (w & 1u);
                     full[j] = hq < Hp && wq < Wp;
@@ -371,6 +374,14 @@ bn_bwd_kernel(const BnBwdArgs A) {
                     if (ins[j])
                         gsr[j] = ldg16(gsb + (size_t)(n * A.gs.sN + hs * A.gs.sH + ws * A.gs.sW) + cg * 8);
                 }
+                // advance to pixel p + gstride
+                w += dW;
+                const unsigned cw = w >= W ? 1u : 0u;
+                w -= cw ? W : 0u;
+                h += dH + cw;
+                const unsigned chh = h >= H ? 1u : 0u;
+                h -= chh ? H : 0u;
+                n += dN + chh;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

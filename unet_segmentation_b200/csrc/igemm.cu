@@ -125,30 +125,32 @@ static int check_view(const View& v, const char* what) {
 }
 
 // ---- row-run variant (igemm_rr.cuh) -----------------------------------------------------------
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, bool WRES>
 static int launch_rowrun_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const RowRunParams& p, int grid, cudaStream_t stream) {
-    using Cfg = RowRunCfg<BN, CG>;
+    using Cfg = RowRunCfg<BN, CG, WRES>;
     static bool attr_set = false;
     if (!attr_set) {
-        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_rowrun_kernel<BN, EPI, CG>,
+        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_rowrun_kernel<BN, EPI, CG, WRES>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    UB_CHECK_CUDA(launch_clustered(igemm_rowrun_kernel<BN, EPI, CG>, dim3(grid), dim3(IGEMM_THREADS),
-                                   Cfg::SMEM_BYTES, stream, CG, a0, a1, b, p));
+    UB_CHECK_CUDA(launch_clustered(igemm_rowrun_kernel<BN, EPI, CG, WRES>, dim3(grid),
+                                   dim3(IGEMM_THREADS), Cfg::SMEM_BYTES, stream, CG, a0, a1, b, p));
     UB_POST_LAUNCH();
     return UB_OK;
 }
-template <int BN, int CG>
+template <int BN, int CG, bool WRES = false>
 static int launch_rowrun_bn(int epi, const CUtensorMap& a0, const CUtensorMap& a1,
                             const CUtensorMap& b, const RowRunParams& p, int grid,
                             cudaStream_t stream) {
     switch (epi) {
-        case EPI_CONV_STATS: return launch_rowrun_t<BN, EPI_CONV_STATS, CG>(a0, a1, b, p, grid, stream);
-        case EPI_STORE: return launch_rowrun_t<BN, EPI_STORE, CG>(a0, a1, b, p, grid, stream);
-        case EPI_AFFINE_RELU: return launch_rowrun_t<BN, EPI_AFFINE_RELU, CG>(a0, a1, b, p, grid, stream);
+        case EPI_CONV_STATS:
+            return launch_rowrun_t<BN, EPI_CONV_STATS, CG, WRES>(a0, a1, b, p, grid, stream);
+        case EPI_STORE: return launch_rowrun_t<BN, EPI_STORE, CG, WRES>(a0, a1, b, p, grid, stream);
+        case EPI_AFFINE_RELU:
+            return launch_rowrun_t<BN, EPI_AFFINE_RELU, CG, WRES>(a0, a1, b, p, grid, stream);
     }
     set_last_error("row-run: unsupported epilogue kind %d", epi);
     return UB_ERR_ARG;
@@ -203,6 +205,10 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
         q.m_tiles = src0.N * Ho * q.qtiles;
         q.n_tiles = ncols / BN;
         const int CG = pick_cg(BN, 9 * (q.cchunks0 + q.cchunks1), (long long)q.m_tiles * q.n_tiles);
+        // Cin = Cout = 64: weights resident in shared memory (UB_WRES=0 disables)
+        static int wres_on = -1;
+        if (wres_on < 0) { const char* e = getenv("UB_WRES"); wres_on = (e && !atoi(e)) ? 0 : 1; }
+        const bool wres = wres_on && BN == 64 && CG == 1 && q.cchunks0 + q.cchunks1 == 1 && q.n_tiles == 1;
         int rr = make_tmap_rows(&mA0, src0, 130, 3);
         if (!rr && src1) rr = make_tmap_rows(&mA1, *src1, 130, 3);
         if (!src1) mA1 = mA0;
@@ -237,7 +243,10 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
             switch (BN) {
                 case 256: rc = launch_rowrun_bn<256, 1>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
                 case 128: rc = launch_rowrun_bn<128, 1>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
-                default: rc = launch_rowrun_bn<64, 1>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
+                default:
+                    if (wres) rc = launch_rowrun_bn<64, 1, true>(epi.kind, mA0, mA1, mB, q, grid, stream);
+                    else rc = launch_rowrun_bn<64, 1>(epi.kind, mA0, mA1, mB, q, grid, stream);
+                    break;
             }
         }
         if (dbg_on && rc == 0) {  // debugging aid only: synchronises

@@ -40,7 +40,11 @@ __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bo
 // barrier wait + tcgen05 fence costs the MMA thread ~230 cycles, so operations are made as large as
 // possible: ONE box (64 ch, 130 px, 3 rows) per A stage, and BTAPS filter taps of weights per B stage
 // (a whole filter row for BN <= 128), i.e. 12 MMAs per B wait and 36 per A wait.
-template <int BN, int CG = 1>
+// WRES (BN = 64, one 64-channel chunk, i.e. Cin = Cout = 64): the nine weight taps (72 KB) stay
+// resident in shared memory for the whole kernel instead of being re-staged for every tile — these
+// tiles are bound by shared-memory bandwidth (TMA writes + MMA operand reads), and the weights were
+// 21 % of it.
+template <int BN, int CG = 1, bool WRES = false>
 struct RowRunCfg {
     static constexpr int btaps(int bn, int cg) { return (bn <= 128 || cg == 2) ? 3 : 1; }
     static constexpr int BTAPS = btaps(BN, CG);
@@ -51,24 +55,27 @@ struct RowRunCfg {
     static constexpr int B_TILE = B_ROWS * 128;            // one tap: [B_ROWS][64] K-major
     static constexpr int B_STAGE = BTAPS * B_TILE;
     static constexpr int SA = (CG == 2) ? (BN == 256 ? 2 : 3) : ((BN == 64) ? 3 : 2);
-    static constexpr int SB = (CG == 2) ? (BN == 64 ? 4 : 2) : ((BN == 64) ? 3 : (BN == 128 ? 2 : 3));
+    static constexpr int SB = WRES ? 1
+                                   : ((CG == 2) ? (BN == 64 ? 4 : 2) : ((BN == 64) ? 3 : (BN == 128 ? 2 : 3)));
+    static constexpr int B_AREA = WRES ? 9 * B_TILE : SB * B_STAGE;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = SA * A_STAGE + SB * B_STAGE + BAR_BYTES + 1024;
+    static constexpr int SMEM_BYTES = SA * A_STAGE + B_AREA + BAR_BYTES + 1024;
+    static_assert(!WRES || (BN == 64 && CG == 1), "resident weights: BN = 64, single CTA");
     static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, bool WRES>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const RowRunParams p) {
-    using Cfg = RowRunCfg<BN, CG>;
+    using Cfg = RowRunCfg<BN, CG, WRES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - raw);
     const uint32_t b_base = base + Cfg::SA * Cfg::A_STAGE;
-    const uint32_t bar_base = b_base + Cfg::SB * Cfg::B_STAGE;
+    const uint32_t bar_base = b_base + Cfg::B_AREA;
     auto fullA = [&](int s) { return bar_base + 8u * s; };
     auto emptyA = [&](int s) { return bar_base + 8u * (Cfg::SA + s); };
     auto fullB = [&](int s) { return bar_base + 8u * (2 * Cfg::SA + s); };
@@ -78,7 +85,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
     constexpr int kSlot = 2 * Cfg::SA + 2 * Cfg::SB + 4;
     const uint32_t tmem_slot = bar_base + 8u * kSlot;
     volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(
-        gbase + Cfg::SA * Cfg::A_STAGE + Cfg::SB * Cfg::B_STAGE + 8 * kSlot);
+        gbase + Cfg::SA * Cfg::A_STAGE + Cfg::B_AREA + 8 * kSlot);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -153,6 +160,15 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         long long waited = 0;
         const long long tstart = clock64();
         const int nrow0 = n0 + (int)rank * Cfg::B_ROWS;
+        if (WRES) {   // all nine taps once: three boxes of (64 ch, 64 rows, 3 taps)
+            if (elect_one()) {
+                mbar_expect_tx(fullB(0), 9 * Cfg::B_TILE);
+#pragma unroll
+                for (int tap = 0; tap < 9; tap += 3)
+                    tma_load_3d(b_base + tap * Cfg::B_TILE, &mapB, fullB(0), 0, nrow0, tap);
+            }
+            __syncwarp();
+        } else
         for (int mu = m_first; mu < m_units; mu += m_step) {
             for (int cc = 0; cc < cchunks; ++cc) {
 #pragma unroll 1
@@ -183,11 +199,35 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         const bool prof = p.dbg != nullptr;
         long long wA = 0, wB = 0, wT = 0;
         const long long tstart = clock64();
+        if (WRES) mbar_wait_prof(fullB(0), 0, prof, wB);
         for (int mu = m_first; mu < m_units; mu += m_step) {
             mbar_wait_prof(tempty_bar(as), aphase ^ 1u, prof, wT);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
             uint32_t acc = 0;
+            if (WRES) {
+                // one chunk, resident weights: all 36 MMAs of the tile behind a single wait
+                mbar_wait_prof(fullA(sa_i), pa, prof, wA);
+                tc_fence_after();
+                const uint32_t sa = base + sa_i * Cfg::A_STAGE;
+                if (elect_one()) {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint64_t da = make_smem_desc(
+                            sa + (tap / 3) * Cfg::ROW_BYTES + (tap % 3) * 128, 0, 1024);
+                        const uint64_t db = make_smem_desc(b_base + tap * Cfg::B_TILE, 0, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(emptyA(sa_i));
+                    umma_commit(tfull_bar(as));
+                }
+                __syncwarp();
+                if (++sa_i == Cfg::SA) { sa_i = 0; pa ^= 1u; }
+            } else
             for (int cc = 0; cc < cchunks; ++cc) {
                 mbar_wait_prof(fullA(sa_i), pa, prof, wA);
                 const uint32_t sa = base + sa_i * Cfg::A_STAGE;
