@@ -182,6 +182,12 @@ int ub_op_bn_finalize(const float* stats, const int* info, int C, const float* g
  * uint8 [N][H/2][W/2][C]) = position 0..3 of the first maximum of each window (torch tie rule). */
 int ub_op_bn_apply_relu(const void* y, void* a, void* pooled, uint8_t* argmax, int N, int H, int W,
                         int C, const float* scale, const float* shift, void* stream);
+/* BN-apply + ReLU of the last conv unit with the 1x1 output convolution fused (reference
+ * models/unet_model.py:56-63,145): writes a (bf16 NHWC) and logits (fp32 NCHW [N][n_classes][H][W]).
+ * C in {64, 128, 256}, n_classes <= 8. */
+int ub_op_bn_apply_relu_head(const void* y, void* a, int N, int H, int W, int C, const float* scale,
+                             const float* shift, int n_classes, const float* head_w,
+                             const float* head_b, float* logits, void* stream);
 int64_t ub_op_bn_bwd_workspace_floats(int C);
 /* BN+ReLU backward. Upstream gradient of a: `g` (direct), or — when g == NULL — gathered from the
  * pooled-tensor gradient gp (2x2 max-pool backward, first arg-max) plus the skip-connection

@@ -369,3 +369,24 @@ def test_conv3x3_dgrad_rowrun(ops, n, h, w, ci, co):
     ref = torch.nn.grad.conv2d_input((n, ci, h + 2, w + 2), wt, dy)
     torch.cuda.synchronize()
     assert rel_l2(ops.nchw(dx), ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("n,h,w,c,nc", [(2, 17, 13, 64, 2), (1, 40, 33, 64, 3), (2, 9, 21, 128, 2),
+                                        (1, 324, 324, 64, 2)])
+def test_bn_apply_relu_fused_head(ops, n, h, w, c, nc):
+    """Last conv unit: BN-apply + ReLU with the 1x1 OutConv fused (reference
+    models/unet_model.py:56-63,145) == separate BN-apply kernel followed by the head kernel."""
+    y = bf(rand(n, c, h, w))
+    scale, shift = rand(c, seed=1) * 0.3 + 1.0, rand(c, seed=2) * 0.2
+    wt, b = rand(nc, c, scale=0.2, seed=3), rand(nc, seed=4)
+    a, logits = ops.bn_apply_relu_head(ops.nhwc(y), scale, shift, wt, b)
+    a2, _ = ops.bn_apply_relu(ops.nhwc(y), scale, shift)
+    logits2, _ = ops.head_forward(a2, wt, b)
+    ref_a = bf(F.relu(y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)))
+    ref = F.conv2d(ref_a, wt.view(nc, c, 1, 1), b)
+    torch.cuda.synchronize()
+    assert torch.equal(a, a2)
+    assert rel_l2(logits, logits2) < 1e-6
+    assert rel_l2(logits, ref) < 1e-4
+    if c == 64:
+        assert torch.equal(logits, logits2)      # same summation tree as the stand-alone head

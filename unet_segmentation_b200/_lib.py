@@ -75,6 +75,8 @@ _SIGNATURES = {
     "ub_op_bn_finalize": (c_int, [_P, C.POINTER(c_int), c_int, _P, _P, _P, _P, _P, c_float, c_float,
                                   _P, _P, _P, _P, _P]),
     "ub_op_bn_apply_relu": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ub_op_bn_apply_relu_head": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P,
+                                         _P, _P]),
     "ub_op_bn_bwd_workspace_floats": (c_int64, [c_int]),
     "ub_op_bn_relu_backward": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _VP, _VP,
                                        _VP, c_int, c_int, _P, _P, _P, _P, _P, _P]),

@@ -145,6 +145,13 @@ int ub_op_bn_apply_relu(const void* y, void* a, void* pooled, uint8_t* argmax, i
     return launch_bn_apply_relu((const __nv_bfloat16*)y, (__nv_bfloat16*)a, (__nv_bfloat16*)pooled,
                                 argmax, N, H, W, C, scale, shift, S(stream));
 }
+int ub_op_bn_apply_relu_head(const void* y, void* a, int N, int H, int W, int C, const float* scale,
+                             const float* shift, int n_classes, const float* head_w,
+                             const float* head_b, float* logits, void* stream) {
+    UB_REQUIRE(y && a && scale && shift && head_w && logits, "bn_apply_relu_head: null pointer");
+    return launch_bn_apply_relu_head((const __nv_bfloat16*)y, (__nv_bfloat16*)a, N, H, W, C, scale,
+                                     shift, n_classes, head_w, head_b, logits, S(stream));
+}
 int64_t ub_op_bn_bwd_workspace_floats(int C) { return (int64_t)bn_bwd_partial_floats(C); }
 int ub_op_bn_relu_backward(const void* y, int N, int H, int W, int C, const float* scale,
                            const float* shift, const float* mean, const float* rstd,

@@ -241,6 +241,72 @@ bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restr
     }
 }
 
+// BN-apply + ReLU of the LAST conv unit fused with the 1x1 output convolution (reference OutConv,
+// models/unet_model.py:56-63, :145): the logits are dotted from the activation values while they
+// are still in registers (as rounded to bf16, i.e. exactly what is stored), so the separate head
+// kernel does not re-read the 128 B/pixel activation. The C/8 lanes that share a pixel combine
+// their partial dot products with xor-shuffles; lane 0 of the group writes the NCHW fp32 logits.
+template <int NCT>
+static __global__ void __launch_bounds__(256)
+bn_apply_relu_head_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
+                          unsigned npix, unsigned HW, int C, const float* __restrict__ scale,
+                          const float* __restrict__ shift, int NC, const float* __restrict__ hw_,
+                          const float* __restrict__ hb, float* __restrict__ logits) {
+    const unsigned CG = (unsigned)C >> 3;   // 8 or 16 or 32: a pixel's lanes are one aligned group
+    const unsigned cg = threadIdx.x % CG;
+    float sc[8], sh[8], wr[NCT][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
+#pragma unroll
+    for (int c = 0; c < NCT; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wr[c][k] = c < NC ? hw_[c * C + cg * 8 + k] : 0.f;
+    const unsigned gstride = gridDim.x * 256u / CG;
+    const unsigned first = (blockIdx.x * 256u + threadIdx.x) / CG;
+    const unsigned iters = (npix + 4u * gstride - 1u) / (4u * gstride);   // uniform: shuffles inside
+    for (unsigned it = 0; it < iters; ++it) {
+        const unsigned p0 = first + it * 4u * gstride;
+        uint4 raw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned p = p0 + j * gstride;
+            if (p < npix) raw[j] = ldg16(y + (size_t)p * C + cg * 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned p = p0 + j * gstride;
+            const bool ok = p < npix;
+            float acc[NCT];
+#pragma unroll
+            for (int c = 0; c < NCT; ++c) acc[c] = 0.f;
+            if (ok) {
+                const Vec8 x = unpack8(raw[j]);
+                Vec8 o;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o.v[k] = bn_relu_bf16(x.v[k], sc[k], sh[k]);
+                *reinterpret_cast<uint4*>(a + (size_t)p * C + cg * 8) = pack8(o);
+#pragma unroll
+                for (int c = 0; c < NCT; ++c)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[c] = fmaf(o.v[k], wr[c][k], acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < NCT; ++c) {
+                if (c < NC) {   // NC is uniform
+                    for (unsigned off = 1; off < CG; off <<= 1)
+                        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+                }
+            }
+            if (ok && cg == 0) {
+                const unsigned n = p / HW, hw = p % HW;
+#pragma unroll
+                for (int c = 0; c < NCT; ++c)
+                    if (c < NC) logits[((size_t)n * NC + c) * HW + hw] = acc[c] + (hb ? hb[c] : 0.f);
+            }
+        }
+    }
+}
+
 // Stand-alone 2x2 max-pool (eval path, where BN+ReLU is folded into the conv epilogue).
 static __global__ void __launch_bounds__(256)
 maxpool2_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ pooled, int N,

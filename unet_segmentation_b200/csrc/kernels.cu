@@ -98,6 +98,33 @@ int launch_bn_apply_relu(const __nv_bfloat16* y, __nv_bfloat16* a, __nv_bfloat16
     UB_POST_LAUNCH();
     return UB_OK;
 }
+// BN-apply + ReLU of the last unit with the 1x1 head fused (training forward).
+bool bn_apply_head_supported(int C, int NC) {
+    return C % 8 == 0 && (C == 64 || C == 128 || C == 256) && NC >= 1 && NC <= HEAD_MAX_CLASSES;
+}
+int launch_bn_apply_relu_head(const __nv_bfloat16* y, __nv_bfloat16* a, int N, int H, int W, int C,
+                              const float* scale, const float* shift, int NC, const float* hw,
+                              const float* hb, float* logits, cudaStream_t s) {
+    if (!bn_apply_head_supported(C, NC)) {
+        set_last_error("bn_apply+head: C=%d / n_classes=%d unsupported", C, NC);
+        return UB_ERR_UNSUPPORTED;
+    }
+    const long long items = (long long)N * H * W * (C / 8);
+    if (items >= 0x7FFFFFFFLL) {
+        set_last_error("bn_apply+head: tensor too large for 32-bit indexing");
+        return UB_ERR_UNSUPPORTED;
+    }
+    const unsigned npix = (unsigned)((long long)N * H * W), HW = (unsigned)(H * W);
+    const int blocks = ew_blocks(items);
+    if (NC <= 2)
+        bn_apply_relu_head_kernel<2><<<blocks, 256, 0, s>>>(y, a, npix, HW, C, scale, shift, NC, hw, hb, logits);
+    else if (NC <= 4)
+        bn_apply_relu_head_kernel<4><<<blocks, 256, 0, s>>>(y, a, npix, HW, C, scale, shift, NC, hw, hb, logits);
+    else
+        bn_apply_relu_head_kernel<8><<<blocks, 256, 0, s>>>(y, a, npix, HW, C, scale, shift, NC, hw, hb, logits);
+    UB_POST_LAUNCH();
+    return UB_OK;
+}
 int launch_maxpool2(const __nv_bfloat16* a, __nv_bfloat16* pooled, int N, int H, int W, int C,
                     cudaStream_t s) {
     const long long items = (long long)N * (H / 2) * (W / 2) * (C / 8);
@@ -315,7 +342,7 @@ int launch_head_bwd(const float* dlogits, const __nv_bfloat16* a, int N, int H, 
         head_bwd_kernel<8><<<blocks, 256, 0, s>>>(dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
     UB_POST_LAUNCH();
     const int len = NC * K + NC;
-    reduce_partials_kernel<<<(len + 127) / 128, 128, 0, s>>>(partial, blocks, len, dw, NC * K, db);
+    reduce_partials_kernel<<<(len + 31) / 32, dim3(32, 16), 0, s>>>(partial, blocks, len, dw, NC * K, db);
     UB_POST_LAUNCH();
     return UB_OK;
 }

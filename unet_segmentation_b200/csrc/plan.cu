@@ -60,6 +60,7 @@ struct ub_plan {
     std::vector<void*> allocs;
     size_t bytes = 0;
     float* scratch = nullptr;   // stats / reduction partials
+    float* fused_logits = nullptr;  // training forward: logits written by the last BN-apply (fused head)
     double* fc_cov = nullptr;   // patch moments of the single-channel first conv (forward -> backward)
     float* wgrad_ws = nullptr;
     size_t wgrad_ws_floats = 0;
@@ -426,6 +427,12 @@ static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const Vie
         UB_TRY(launch_bn_finalize(P->scratch, u.info, u.Co, (double)u.info.M, P->params[u.p_g],
                                   P->params[u.p_be], P->rm[u.bn], P->rv[u.bn], P->nbt[u.bn],
                                   P->momentum, P->eps, u.scale, u.shift, u.mean, u.rstd, s));
+        if (P->fused_logits && &u == &P->dec[P->L - 2].u[1]) {   // last unit: 1x1 head fused in
+            const int np = (int)P->params.size();
+            return launch_bn_apply_relu_head(u.y, u.a, N, u.Ho(), u.Wo(), u.Co, u.scale, u.shift,
+                                             P->NC, P->params[np - 2], P->params[np - 1],
+                                             P->fused_logits, s);
+        }
         return launch_bn_apply_relu(u.y, u.a, pooled, amax, N, u.Ho(), u.Wo(), u.Co, u.scale,
                                     u.shift, s);
     }
@@ -458,6 +465,7 @@ int ub_plan_forward(ub_plan* P, const float* x, float* logits, uint8_t* mask, vo
     cudaStream_t s = (cudaStream_t)stream;
     P->x = x;
     const int L = P->L;
+    P->fused_logits = (P->training && bn_apply_head_supported(P->base, P->NC)) ? logits : nullptr;
     for (int i = 0; i < L; ++i) UB_TRY(block_forward(P, P->enc[i], s));
     for (int j = 0; j < L - 1; ++j) {
         UpT& t = P->ups[j];
@@ -475,6 +483,7 @@ int ub_plan_forward(ub_plan* P, const float* x, float* logits, uint8_t* mask, vo
         }
         UB_TRY(block_forward(P, P->dec[j], s));
     }
+    if (P->fused_logits) return 0;
     const ConvUnit& last = P->dec[L - 2].u[1];
     const int np = (int)P->params.size();
     ProfScope ps(P, CLS_HEAD, 2.0 * P->N * P->outH * P->outW * P->base * P->NC,

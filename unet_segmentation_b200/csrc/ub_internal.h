@@ -91,6 +91,10 @@ int launch_bn_fold_eval(int C, const float* conv_bias, const float* gamma, const
 int launch_bn_apply_relu(const __nv_bfloat16* y, __nv_bfloat16* a, __nv_bfloat16* pooled,
                          unsigned char* amax, int N, int H, int W, int C, const float* scale,
                          const float* shift, cudaStream_t s);
+bool bn_apply_head_supported(int C, int NC);
+int launch_bn_apply_relu_head(const __nv_bfloat16* y, __nv_bfloat16* a, int N, int H, int W, int C,
+                              const float* scale, const float* shift, int NC, const float* hw,
+                              const float* hb, float* logits, cudaStream_t s);
 int launch_maxpool2(const __nv_bfloat16* a, __nv_bfloat16* pooled, int N, int H, int W, int C,
                     cudaStream_t s);
 struct BnBwdDesc {

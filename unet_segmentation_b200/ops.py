@@ -108,6 +108,19 @@ def bn_apply_relu(y, scale, shift, pool=False):
     return (a, p, am) if pool else (a, p)
 
 
+def bn_apply_relu_head(y, scale, shift, head_w, head_b):
+    """BN-apply + ReLU with the 1x1 head fused: returns (a bf16 NHWC, logits fp32 NCHW)."""
+    lib = _lib.load()
+    n, h, w, c = y.shape
+    nc = head_w.shape[0]
+    a = torch.empty_like(y)
+    logits = torch.empty(n, nc, h, w, dtype=torch.float32, device=y.device)
+    check(lib.ub_op_bn_apply_relu_head(_p(y), _p(a), n, h, w, c, _p(scale), _p(shift), nc,
+                                       _p(head_w.contiguous()), _p(head_b), _p(logits), _stream()),
+          "bn_apply_relu_head")
+    return a, logits
+
+
 def bn_relu_backward(y, scale, shift, mean, rstd, g=None, gp=None, gs=None, crop=(0, 0),
                      argmax=None):
     lib = _lib.load()
