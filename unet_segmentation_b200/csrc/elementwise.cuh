@@ -40,20 +40,23 @@ __device__ __forceinline__ float bn_relu_bf16(float y, float sc, float sh) {
 
 // ---------------------------------------------------------------------------------------------
 // BN statistics finalisation (train mode). Partials come from the conv epilogue:
-// stats[(cta*4 + warp)][2][BN]; CTA b covers channel tile (b % n_tiles).
+// stats[cta][2][BN] (one row per CTA, its epilogue warps pre-combined); CTA b covers channel tile
+// (b % n_tiles).
 // Biased variance normalises, unbiased variance updates running_var (torch semantics).
 // ---------------------------------------------------------------------------------------------
-// All finalisation kernels use blockDim = (32 channels, 16 slices): the per-CTA partials are summed
-// by 16 threads per channel in double precision and combined through shared memory in a fixed
-// order (deterministic), instead of one thread walking hundreds of partial rows serially.
+// All finalisation kernels use blockDim = (32 channels, 32 slices): the per-CTA partials are summed
+// by 32 threads per channel in double precision and combined through shared memory in a fixed
+// order (deterministic), instead of one thread walking hundreds of partial rows serially (each
+// dependent load -> add step costs ~0.35 us, so the rows per thread are what these kernels cost).
+constexpr int FIN_SLICES = 32;
 __device__ __forceinline__ void finalize_combine(double& s, double& q) {
-    __shared__ double sm[2][16][32];
+    __shared__ double sm[2][FIN_SLICES][32];
     sm[0][threadIdx.y][threadIdx.x] = s;
     sm[1][threadIdx.y][threadIdx.x] = q;
     __syncthreads();
     if (threadIdx.y == 0) {
         s = 0.0; q = 0.0;
-        for (int k = 0; k < 16; ++k) { s += sm[0][k][threadIdx.x]; q += sm[1][k][threadIdx.x]; }
+        for (int k = 0; k < FIN_SLICES; ++k) { s += sm[0][k][threadIdx.x]; q += sm[1][k][threadIdx.x]; }
     }
 }
 __device__ __forceinline__ void bn_finalize_write(int c, double s, double q, double count,
@@ -76,7 +79,7 @@ __device__ __forceinline__ void bn_finalize_write(int c, double s, double q, dou
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
 }
-static __global__ void __launch_bounds__(512)
+static __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ stats, int grid_ctas, int n_tiles, int BN, int C,
                    double count, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* running_mean, float* running_var, long long* num_batches_tracked,
@@ -87,23 +90,11 @@ bn_finalize_kernel(const float* __restrict__ stats, int grid_ctas, int n_tiles, 
     double s = 0.0, q = 0.0;
     if (c < C) {
         const int tile = c / BN, col = c % BN;
-        const int rows = (grid_ctas - tile + n_tiles - 1) / n_tiles * 4;  // (cta, warp) pairs
-        // 4 independent row loads in flight (a dependent load -> add chain costs ~0.35 us per row)
-        for (int r0 = threadIdx.y; r0 < rows; r0 += 64) {
-            float ps[4], pq[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = r0 + 16 * j;
-                ps[j] = 0.f; pq[j] = 0.f;
-                if (r < rows) {
-                    const int b = tile + (r >> 2) * n_tiles, w = r & 3;
-                    const float* p = stats + ((long long)b * 4 + w) * (2 * BN);
-                    ps[j] = p[col];
-                    pq[j] = p[BN + col];
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { s += (double)ps[j]; q += (double)pq[j]; }
+        const int rows = (grid_ctas - tile + n_tiles - 1) / n_tiles;  // CTAs of this channel tile
+        for (int r = threadIdx.y; r < rows; r += FIN_SLICES) {
+            const float* p = stats + (long long)(tile + r * n_tiles) * (2 * BN);
+            s += (double)p[col];
+            q += (double)p[BN + col];
         }
     }
     finalize_combine(s, q);
@@ -113,7 +104,7 @@ bn_finalize_kernel(const float* __restrict__ stats, int grid_ctas, int n_tiles, 
 }
 
 // Generic variant: partials[blocks][2][C] (first-layer statistics).
-static __global__ void __launch_bounds__(512)
+static __global__ void __launch_bounds__(1024)
 bn_finalize_flat_kernel(const float* __restrict__ part, int blocks, int C, double count,
                         const float* __restrict__ gamma, const float* __restrict__ beta,
                         float* running_mean, float* running_var, long long* num_batches_tracked,
@@ -124,16 +115,9 @@ bn_finalize_flat_kernel(const float* __restrict__ part, int blocks, int C, doubl
     if (c == 0 && threadIdx.y == 0 && num_batches_tracked) *num_batches_tracked += 1;
     double s = 0.0, q = 0.0;
     if (c < C) {
-        for (int b0 = threadIdx.y; b0 < blocks; b0 += 64) {
-            float ps[4], pq[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = b0 + 16 * j;
-                ps[j] = b < blocks ? part[(long long)b * 2 * C + c] : 0.f;
-                pq[j] = b < blocks ? part[(long long)b * 2 * C + C + c] : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { s += (double)ps[j]; q += (double)pq[j]; }
+        for (int b = threadIdx.y; b < blocks; b += FIN_SLICES) {
+            s += (double)part[(long long)b * 2 * C + c];
+            q += (double)part[(long long)b * 2 * C + C + c];
         }
     }
     finalize_combine(s, q);
@@ -585,22 +569,15 @@ bn_bwd_kernel(const BnBwdArgs A) {
 }
 
 // dbeta/dgamma = sum over blocks of the partials (fixed order => deterministic).
-static __global__ void __launch_bounds__(512)
+static __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C,
                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int c = blockIdx.x * 32 + threadIdx.x;
     double b = 0.0, g = 0.0;
     if (c < C) {
-        for (int k0 = threadIdx.y; k0 < blocks; k0 += 64) {
-            float pb[4], pg[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = k0 + 16 * j;
-                pb[j] = k < blocks ? part[(long long)k * 2 * C + c] : 0.f;
-                pg[j] = k < blocks ? part[(long long)k * 2 * C + C + c] : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { b += (double)pb[j]; g += (double)pg[j]; }
+        for (int k = threadIdx.y; k < blocks; k += FIN_SLICES) {
+            b += (double)part[(long long)k * 2 * C + c];
+            g += (double)part[(long long)k * 2 * C + C + c];
         }
     }
     finalize_combine(b, g);
@@ -650,21 +627,37 @@ static __global__ void tile_bias4_kernel(const float* __restrict__ b, int Co, fl
     if (i < 4 * Co) out[i] = b[i % Co];
 }
 
-// Split-K reduction of weight-gradient partial tiles + permutation into the torch layout:
+// Split-K reduction of weight-gradient partial tiles + permutation into the torch layout
+// (cols % 32 == 0, RC % 8 == 0):
 //   ws[split][row = tap*RC + rc][col]  ->  out[(col*RC + rc)*T + tap]
 //   conv3x3: RC = Ci, col = co, T = 9;   convT2x2: RC = Co, col = ci, T = 4
-static __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits,
-                                    long long split_stride, int rows, int cols, int RC, int T,
-                                    float* __restrict__ out) {
-    const long long total = (long long)rows * cols;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int col = (int)(i % cols);
-        const int row = (int)(i / cols);
-        float s = 0.f;
-        for (int k = 0; k < splits; ++k) s += ws[(long long)k * split_stride + i];
-        const int tap = row / RC, rc = row % RC;
-        out[((long long)col * RC + rc) * T + tap] = s;
+// One block = 32 columns x 8 `rc` values x all T taps; blockDim = (32, 8). Thread (tx, ty) sums, over
+// the splits, the T values of (col0+tx, rc0+ty) — reads are coalesced along the columns and the T
+// chains are independent — then the block transposes through shared memory so that the torch-layout
+// rows out[col][rc0..rc0+8)[0..T) (8*T contiguous floats per column) are written with full sectors.
+template <int T>
+static __global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long split_stride, int cols,
+                    int RC, float* __restrict__ out) {
+    __shared__ float sm[32][8 * T + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int col0 = blockIdx.x * 32, rc0 = blockIdx.y * 8;
+    float acc[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t] = 0.f;
+    const float* base = ws + (long long)(rc0 + ty) * cols + col0 + tx;
+    for (int k = 0; k < splits; ++k) {
+        const float* p = base + (long long)k * split_stride;
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[t] += __ldg(p + (long long)t * RC * cols);
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) sm[tx][ty * T + t] = acc[t];
+    __syncthreads();
+    const int tid = ty * 32 + tx;
+    for (int i = tid; i < 32 * 8 * T; i += 256) {
+        const int c = i / (8 * T), r = i % (8 * T);
+        out[((long long)(col0 + c) * RC + rc0) * T + r] = sm[c][r];
     }
 }
 

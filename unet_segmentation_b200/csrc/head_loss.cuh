@@ -184,25 +184,15 @@ head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restri
     }
 }
 
-// out[j] = sum_b partial[b][j]  (fixed order). blockDim = (32 elements, 16 slices): 16 threads per
-// output element with 4 independent loads in flight each, combined through shared memory.
-static __global__ void __launch_bounds__(512)
+// out[j] = sum_b partial[b][j]  (fixed order). blockDim = (32 elements, 32 slices), see
+// finalize_combine.
+static __global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const float* __restrict__ partial, int blocks, int len,
                        float* __restrict__ out0, int len0, float* __restrict__ out1) {
     const int j = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0, unused = 0.0;
-    if (j < len) {
-        for (int b0 = threadIdx.y; b0 < blocks; b0 += 64) {
-            float v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int b = b0 + 16 * q;
-                v[q] = b < blocks ? partial[(long long)b * len + j] : 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) s += (double)v[q];
-        }
-    }
+    if (j < len)
+        for (int b = threadIdx.y; b < blocks; b += FIN_SLICES) s += (double)partial[(long long)b * len + j];
     finalize_combine(s, unused);
     if (threadIdx.y != 0 || j >= len) return;
     if (j < len0) out0[j] = (float)s;

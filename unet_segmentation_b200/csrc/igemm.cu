@@ -49,7 +49,7 @@ static int pick_bn(int ncols) {
 size_t igemm_stats_floats(int ncols) {
     int bn = pick_bn(ncols);
     if (!bn) return 0;
-    return (size_t)num_sms() * 4 * 2 * bn;
+    return (size_t)num_sms() * 2 * bn;   // one [2][BN] row per CTA
 }
 
 // Launch with an optional 2-CTA cluster (cta_group::2 pairs).
@@ -417,11 +417,15 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
         }
     }
     UB_TRY(rc);
-    const long long total = (long long)rows * cols;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, splits, p.split_stride, rows, cols, ctot,
-                                                    taps, out);
+    const dim3 rgrid(cols / 32, ctot / 8);
+    if (taps == 9)
+        wgrad_reduce_kernel<9><<<rgrid, dim3(32, 8), 0, stream>>>(ws, splits, p.split_stride, cols, ctot, out);
+    else if (taps == 4)
+        wgrad_reduce_kernel<4><<<rgrid, dim3(32, 8), 0, stream>>>(ws, splits, p.split_stride, cols, ctot, out);
+    else {
+        set_last_error("wgrad: unsupported tap count %d", taps);
+        return UB_ERR_UNSUPPORTED;
+    }
     UB_POST_LAUNCH();
     return UB_OK;
 }

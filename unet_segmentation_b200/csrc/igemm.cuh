@@ -29,7 +29,7 @@ struct IgemmParams {
     const float* bias;   // per GEMM column, may be null
     const float* scale;  // EPI_AFFINE_RELU: y = relu(acc*scale + shift)
     const float* shift;
-    float* stats;        // EPI_CONV_STATS: [gridDim.x*4][2][BN] per-warp partial (sum, sumsq)
+    float* stats;        // EPI_CONV_STATS: [gridDim.x][2][BN] per-CTA partial (sum, sumsq)
     // EPI_CONVT: GEMM column = q*ct_cout + co, q = dy*2+dx; row = (n,h,w) of the input
     int ct_cout, ct_H, ct_W;
     long long ct_sN, ct_sH, ct_sW;  // element strides of the destination [N,2H,2W,*] view
@@ -46,7 +46,8 @@ struct IgemmCfg {
     static constexpr int STAGES = (CG == 2) ? (BN == 256 ? 6 : 8)
                                             : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+    static constexpr int STAT_BYTES = 4 * 2 * BN * 4;   // BN-statistics rows of the 4 lane quadrants
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + 1024;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
@@ -62,6 +63,28 @@ template <int BN> struct EpiCfg {
 template <int BN>
 __device__ __forceinline__ bool is_epilogue_warp(int warp) {
     return warp >= 2 && warp != 6 && (EpiCfg<BN>::HALVES == 2 || warp < 6);
+}
+
+// End of a CONV_STATS kernel: the epilogue warps of a CTA combine their per-quadrant column sums in
+// shared memory (fixed order) and write ONE partial row [2][BN] per CTA, so the finalisation kernel
+// walks 4x fewer rows. `red` = [4 quadrants][2][BN] floats of shared memory.
+template <int BN>
+__device__ __forceinline__ void write_cta_stats(float* red, float* dst_row, int warp, int lane,
+                                                int quad, int chalf,
+                                                const float (&ssum)[EpiCfg<BN>::NCH],
+                                                const float (&ssq)[EpiCfg<BN>::NCH]) {
+    constexpr int NCH = EpiCfg<BN>::NCH;
+    constexpr int NT = 128 * EpiCfg<BN>::HALVES;   // epilogue threads
+    float* mine = red + quad * (2 * BN) + chalf * (NCH * 32);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        mine[c * 32 + lane] = ssum[c];
+        mine[BN + c * 32 + lane] = ssq[c];
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory");   // epilogue warps only
+    const int e = (warp < 6 ? warp - 2 : warp - 3) * 32 + lane;   // 0 .. NT-1
+    for (int i = e; i < 2 * BN; i += NT)
+        dst_row[i] = ((red[i] + red[2 * BN + i]) + red[4 * BN + i]) + red[6 * BN + i];
 }
 
 // Epilogue of one 128 x BN accumulator tile: TMEM -> registers (32 columns at a time), bias /
@@ -319,13 +342,9 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
         if (EPI == EPI_CONV_STATS) {
             // partial row of "virtual CTA" rank*nunits + unit: nunits % n_tiles == 0, so the channel
             // tile of a row is still (row index % n_tiles) for bn_finalize_kernel
-            float* dst = p.stats + ((long long)((int)rank * nunits + unit) * 4 + quad) * (2 * BN) +
-                         chalf * (NCH * 32);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                dst[c * 32 + lane] = ssum[c];
-                dst[BN + c * 32 + lane] = ssq[c];
-            }
+            float* red = reinterpret_cast<float*>(gbase + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+            write_cta_stats<BN>(red, p.stats + (long long)((int)rank * nunits + unit) * (2 * BN), warp,
+                                lane, quad, chalf, ssum, ssq);
         }
     }
 

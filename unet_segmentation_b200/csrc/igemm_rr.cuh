@@ -59,7 +59,8 @@ struct RowRunCfg {
                                    : ((CG == 2) ? (BN == 64 ? 4 : 2) : ((BN == 64) ? 3 : (BN == 128 ? 2 : 3)));
     static constexpr int B_AREA = WRES ? 9 * B_TILE : SB * B_STAGE;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = SA * A_STAGE + B_AREA + BAR_BYTES + 1024;
+    static constexpr int STAT_BYTES = 4 * 2 * BN * 4;   // BN-statistics rows of the 4 lane quadrants
+    static constexpr int SMEM_BYTES = SA * A_STAGE + B_AREA + BAR_BYTES + STAT_BYTES + 1024;
     static_assert(!WRES || (BN == 64 && CG == 1), "resident weights: BN = 64, single CTA");
     static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
@@ -307,13 +308,10 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             atomicAdd((unsigned long long*)&p.dbg[9], (unsigned long long)(clock64() - tstart));
         }
         if (EPI == EPI_CONV_STATS) {
-            float* dst = p.epi.stats + ((long long)((int)rank * nunits + unit) * 4 + quad) * (2 * BN) +
-                         chalf * (NCH * 32);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                dst[c * 32 + lane] = ssum[c];
-                dst[BN + c * 32 + lane] = ssq[c];
-            }
+            float* red = reinterpret_cast<float*>(gbase + Cfg::SA * Cfg::A_STAGE + Cfg::B_AREA +
+                                                  Cfg::BAR_BYTES);
+            write_cta_stats<BN>(red, p.epi.stats + (long long)((int)rank * nunits + unit) * (2 * BN),
+                                warp, lane, quad, chalf, ssum, ssq);
         }
     }
 

@@ -17,9 +17,9 @@ static inline int ew_blocks(long long items, int per_sm = 8) {
     return (int)b;
 }
 // Grid for the "fixed channel group per thread" kernels: 4 CTAs per SM.
-static inline int red_blocks(long long items) {
+static inline int red_blocks(long long items, int per_sm = 4) {
     long long b = (items + 255) / 256;
-    const long long cap = (long long)num_sms() * 4;
+    const long long cap = (long long)num_sms() * per_sm;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (int)b;
@@ -53,7 +53,7 @@ int launch_bn_finalize(const float* stats, const IgemmLaunchInfo& info, int C, d
                        const float* gamma, const float* beta, float* rm, float* rv,
                        long long* nbt, float momentum, float eps, float* scale, float* shift,
                        float* mean, float* rstd, cudaStream_t s) {
-    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 16), 0, s>>>(stats, info.grid, info.n_tiles, info.BN, C,
+    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_SLICES), 0, s>>>(stats, info.grid, info.n_tiles, info.BN, C,
                                                        count, gamma, beta, rm, rv, nbt, momentum,
                                                        eps, scale, shift, mean, rstd);
     UB_POST_LAUNCH();
@@ -63,7 +63,7 @@ int launch_bn_finalize_flat(const float* part, int blocks, int C, double count, 
                             const float* beta, float* rm, float* rv, long long* nbt,
                             float momentum, float eps, float* scale, float* shift, float* mean,
                             float* rstd, cudaStream_t s) {
-    bn_finalize_flat_kernel<<<(C + 31) / 32, dim3(32, 16), 0, s>>>(part, blocks, C, count, gamma, beta, rm,
+    bn_finalize_flat_kernel<<<(C + 31) / 32, dim3(32, FIN_SLICES), 0, s>>>(part, blocks, C, count, gamma, beta, rm,
                                                             rv, nbt, momentum, eps, scale, shift,
                                                             mean, rstd);
     UB_POST_LAUNCH();
@@ -156,12 +156,12 @@ int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
     const long long items = (d.pool_skip && !pix)
                                 ? (long long)d.N * ((d.H + 1) / 2) * ((d.W + 1) / 2) * (d.C / 8)
                                 : count * (d.C / 8);
-    const int blocks = red_blocks(items);
+    const int blocks = red_blocks(items, 2);   // = resident CTAs (launch bounds 256 x 2): one wave
     if (pix) bn_bwd_kernel<true, false, true><<<blocks, 256, 0, s>>>(A);
     else if (d.pool_skip) bn_bwd_kernel<true, false><<<blocks, 256, 0, s>>>(A);
     else bn_bwd_kernel<false, false><<<blocks, 256, 0, s>>>(A);
     UB_POST_LAUNCH();
-    bn_bwd_finalize_kernel<<<(d.C + 31) / 32, dim3(32, 16), 0, s>>>(d.partial, blocks, d.C, d.dgamma,
+    bn_bwd_finalize_kernel<<<(d.C + 31) / 32, dim3(32, FIN_SLICES), 0, s>>>(d.partial, blocks, d.C, d.dgamma,
                                                              d.dbeta);
     UB_POST_LAUNCH();
     const int ablocks = ew_blocks(items);
@@ -294,7 +294,7 @@ int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const floa
     A.partial = ws;
     int blocks = red_blocks(items);
     UB_TRY(fc_launch<FC_BWD_REDUCE>(A, blocks, s));
-    bn_bwd_finalize_kernel<<<(d.Co + 31) / 32, dim3(32, 16), 0, s>>>(ws, blocks, d.Co, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(d.Co + 31) / 32, dim3(32, FIN_SLICES), 0, s>>>(ws, blocks, d.Co, dgamma, dbeta);
     UB_POST_LAUNCH();
     A.dgamma = dgamma; A.dbeta = dbeta; A.inv_count = (float)(1.0 / (double)count);
     A.wpartial = ws;
@@ -342,7 +342,7 @@ int launch_head_bwd(const float* dlogits, const __nv_bfloat16* a, int N, int H, 
         head_bwd_kernel<8><<<blocks, 256, 0, s>>>(dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
     UB_POST_LAUNCH();
     const int len = NC * K + NC;
-    reduce_partials_kernel<<<(len + 31) / 32, dim3(32, 16), 0, s>>>(partial, blocks, len, dw, NC * K, db);
+    reduce_partials_kernel<<<(len + 31) / 32, dim3(32, FIN_SLICES), 0, s>>>(partial, blocks, len, dw, NC * K, db);
     UB_POST_LAUNCH();
     return UB_OK;
 }
