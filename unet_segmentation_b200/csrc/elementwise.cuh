@@ -638,9 +638,16 @@ static __global__ void tile_bias4_kernel(const float* __restrict__ b, int Co, fl
 template <int T>
 static __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long split_stride, int cols,
-                    int RC, float* __restrict__ out) {
+                    int RC, float* __restrict__ out, float* zero0, int nzero0, float* zero1,
+                    int nzero1) {
     __shared__ float sm[32][8 * T + 1];
     const int tx = threadIdx.x, ty = threadIdx.y;
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        // bias gradients that are analytically zero in training mode (a bias ahead of a BatchNorm is
+        // removed by the mean subtraction) are cleared here instead of by extra launches
+        for (int i = ty * 32 + tx; i < nzero0; i += 256) zero0[i] = 0.f;
+        for (int i = ty * 32 + tx; i < nzero1; i += 256) zero1[i] = 0.f;
+    }
     const int col0 = blockIdx.x * 32, rc0 = blockIdx.y * 8;
     float acc[T];
 #pragma unroll

@@ -324,6 +324,38 @@ fc1_cov_finalize_kernel(const double* __restrict__ partial, int blocks, const fl
     }
 }
 
+// 3 x (PX+2) input patch of PX adjacent output pixels starting at column wq0 (a multiple of PX):
+// vector loads when the row pitch keeps the patch 8/16-byte aligned and inside the row, otherwise
+// guarded scalar loads. `sub` is subtracted from every valid value (patch centring).
+template <int PX>
+__device__ __forceinline__ void fc1_load_patch(const float* __restrict__ xrow, unsigned W,
+                                               unsigned wq0, float sub, float (&xp)[3][PX + 2]) {
+    const bool vec = (W % 4u == 0u) && (wq0 + PX + 2 <= W) &&
+                     ((reinterpret_cast<uintptr_t>(xrow) & (PX == 4 ? 15u : 7u)) == 0u);
+    if (vec) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (PX == 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(xrow + r * W));
+                const float2 b = __ldg(reinterpret_cast<const float2*>(xrow + r * W + 4));
+                xp[r][0] = a.x - sub; xp[r][1] = a.y - sub; xp[r][2] = a.z - sub; xp[r][3] = a.w - sub;
+                xp[r][PX] = b.x - sub; xp[r][PX + 1] = b.y - sub;
+            } else {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(xrow + r * W));
+                const float2 b = __ldg(reinterpret_cast<const float2*>(xrow + r * W + 2));
+                xp[r][0] = a.x - sub; xp[r][1] = a.y - sub;
+                xp[r][PX] = b.x - sub; xp[r][PX + 1] = b.y - sub;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < PX + 2; ++c)
+                xp[r][c] = (wq0 + c < W) ? __ldg(xrow + r * W + c) - sub : 0.f;
+    }
+}
+
 // BN-apply + ReLU of the recomputed convolution: one thread = PX adjacent pixels x 8 channels, the
 // 3 x (PX+2) input patch and the 9x8 weights live in registers; the conv bias is folded into shift.
 template <int PX>
@@ -350,11 +382,7 @@ fc1_apply_kernel(const FirstConvArgs A) {
         const unsigned gw = gi % GW, t = gi / GW, hq = t % Ho, n = t / Ho;
         const unsigned wq0 = gw * PX;
         float xp[3][PX + 2];
-        const float* xrow = A.x + ((size_t)n * A.H + hq) * W + wq0;
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < PX + 2; ++c) xp[r][c] = (wq0 + c < W) ? __ldg(xrow + r * W + c) : 0.f;
+        fc1_load_patch<PX>(A.x + ((size_t)n * A.H + hq) * W + wq0, W, wq0, 0.f, xp);
         const size_t pq0 = ((size_t)n * Ho + hq) * Wo + wq0;
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
@@ -409,12 +437,7 @@ fc1_bwd_kernel(const FirstConvArgs A, const double* __restrict__ cov) {
             }
         }
         float xp[3][PX + 2];
-        const float* xrow = A.x + ((size_t)n * A.H + hq) * W + wq0;
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < PX + 2; ++c)
-                xp[r][c] = (wq0 + c < W) ? __ldg(xrow + r * W + c) - c0 : 0.f;
+        fc1_load_patch<PX>(A.x + ((size_t)n * A.H + hq) * W + wq0, W, wq0, c0, xp);
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
             if (wq0 + j < Wo) {

@@ -361,7 +361,8 @@ static int launch_wgrad_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
 
 int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int tstride, int taps,
                  int tapw, const __nv_bfloat16* B, long long ldb, int cols, float* ws,
-                 size_t ws_floats, float* out, cudaStream_t stream) {
+                 size_t ws_floats, float* out, cudaStream_t stream, float* zero0, int nzero0,
+                 float* zero1, int nzero1) {
     UB_TRY(check_view(src0, "wgrad source 0"));
     if (src1) UB_TRY(check_view(*src1, "wgrad source 1"));
     const int BN = pick_bn(cols);
@@ -419,9 +420,11 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
     UB_TRY(rc);
     const dim3 rgrid(cols / 32, ctot / 8);
     if (taps == 9)
-        wgrad_reduce_kernel<9><<<rgrid, dim3(32, 8), 0, stream>>>(ws, splits, p.split_stride, cols, ctot, out);
+        wgrad_reduce_kernel<9><<<rgrid, dim3(32, 8), 0, stream>>>(ws, splits, p.split_stride, cols, ctot, out,
+                                                                  zero0, nzero0, zero1, nzero1);
     else if (taps == 4)
-        wgrad_reduce_kernel<4><<<rgrid, dim3(32, 8), 0, stream>>>(ws, splits, p.split_stride, cols, ctot, out);
+        wgrad_reduce_kernel<4><<<rgrid, dim3(32, 8), 0, stream>>>(ws, splits, p.split_stride, cols, ctot, out,
+                                                                  zero0, nzero0, zero1, nzero1);
     else {
         set_last_error("wgrad: unsupported tap count %d", taps);
         return UB_ERR_UNSUPPORTED;

@@ -544,10 +544,11 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
     View a0 = make_view(u0.a, N, u0.Ho(), u0.Wo(), u0.Co);
     {
         ProfScope ps(P, CLS_WGRAD, fl1, 2.0 * (pi1 * u1.Ci + po1 * u1.Co) + 4.0 * 9 * u1.Ci * u1.Co, s);
+        // both conv biases of the block sit ahead of a BatchNorm: analytically zero gradients
         UB_TRY(launch_wgrad(a0, nullptr, 0, -2, 1, 9, 3, u1.dy, u1.Co, u1.Co, P->wgrad_ws,
-                            P->wgrad_ws_floats, grads[u1.p_w], s));
+                            P->wgrad_ws_floats, grads[u1.p_w], s, grads[u1.p_b], u1.Co,
+                            grads[u0.p_b], u0.Co));
     }
-    UB_TRY(launch_fill_zero(grads[u1.p_b], u1.Co, s));  // analytically zero ahead of a BatchNorm
     {
         IgemmEpilogue e;
         memset(&e, 0, sizeof(e));
@@ -558,7 +559,6 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
     }
     // ---- first conv unit ----
     View g0 = make_view(b.da0, N, u0.Ho(), u0.Wo(), u0.Co);
-    UB_TRY(launch_fill_zero(grads[u0.p_b], u0.Co, s));
     if (u0.first) {
         FirstConvDesc f;
         f.x = P->x; f.N = N; f.Ci = u0.Ci; f.H = u0.Hin; f.W = u0.Win; f.Co = u0.Co;
@@ -643,9 +643,9 @@ int ub_plan_backward_stage(ub_plan* P, int stage, const float* dlogits, float* c
         }
         const ConvUnit& prev = j == 0 ? P->enc[L - 1].u[1] : P->dec[j - 1].u[1];
         ProfScope ps(P, CLS_CT_WGRAD, flt, 2.0 * mt * (4.0 * t.Co + t.Ci) + 16.0 * t.Co * t.Ci, s);
-        UB_TRY(launch_wgrad(dup, nullptr, 0, -1, 2, 4, 2, prev.a, t.Ci, t.Ci, P->wgrad_ws,
-                            P->wgrad_ws_floats, grads[t.p_w], s));
-        return launch_fill_zero(grads[t.p_b], t.Co, s);  // removed by the following BatchNorm
+        // the transposed-conv bias is removed by the following BatchNorm: zero gradient
+        return launch_wgrad(dup, nullptr, 0, -1, 2, 4, 2, prev.a, t.Ci, t.Ci, P->wgrad_ws,
+                            P->wgrad_ws_floats, grads[t.p_w], s, grads[t.p_b], t.Co);
     }
     const int i = 2 * L - 2 - stage;
     Block& b = P->enc[i];

@@ -67,9 +67,12 @@ size_t igemm_stats_floats(int ncols);  // upper bound of the stats partial buffe
 
 // Weight gradient. A side: im2col'd activations (rows = taps * (C0+C1)); B side: [Mpix][cols]
 // matrix with row pitch ldb. Result (fp32, torch layout, see wgrad_reduce_kernel) in `out`.
+// zero0 / zero1 (optional): float ranges cleared by the reduction kernel (analytically-zero bias
+// gradients of the same backward stage).
 int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int tstride, int taps,
                  int tapw, const __nv_bfloat16* B, long long ldb, int cols, float* ws,
-                 size_t ws_floats, float* out, cudaStream_t stream);
+                 size_t ws_floats, float* out, cudaStream_t stream, float* zero0 = nullptr,
+                 int nzero0 = 0, float* zero1 = nullptr, int nzero1 = 0);
 size_t wgrad_ws_floats(int rows, int cols, long long mpix);
 
 // ---- kernels.cu ------------------------------------------------------------------------------
