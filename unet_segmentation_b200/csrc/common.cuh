@@ -45,6 +45,28 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL), opt-in (UB_PDL=1; measured slower on the full step, see
+// pdl_enabled()). With it every kernel of the library is launched with the
+// programmatic-stream-serialization attribute (ub_launch, ub_internal.h) and
+//   * signals `launch_dependents` first thing, so the NEXT kernel's CTAs are scheduled while this
+//     grid drains (their launch latency and prologue overlap our tail), and
+//   * executes `griddepcontrol.wait` BEFORE its first global-memory access (read or write): the
+//     wait returns when the preceding grid has completed and its writes are visible. Completion
+//     order is therefore still the stream order, transitively.
+// Both instructions are no-ops when a kernel is launched without the attribute.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_entry() {
+    pdl_trigger();
+    pdl_wait();
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

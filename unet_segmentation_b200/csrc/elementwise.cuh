@@ -85,6 +85,7 @@ bn_finalize_kernel(const float* __restrict__ stats, int grid_ctas, int n_tiles, 
                    float* running_mean, float* running_var, long long* num_batches_tracked,
                    float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
                    float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+    pdl_entry();
     const int c = blockIdx.x * 32 + threadIdx.x;
     if (c == 0 && threadIdx.y == 0 && num_batches_tracked) *num_batches_tracked += 1;
     double s = 0.0, q = 0.0;
@@ -111,6 +112,7 @@ bn_finalize_flat_kernel(const float* __restrict__ part, int blocks, int C, doubl
                         float momentum, float eps, float* __restrict__ scale,
                         float* __restrict__ shift, float* __restrict__ save_mean,
                         float* __restrict__ save_rstd) {
+    pdl_entry();
     const int c = blockIdx.x * 32 + threadIdx.x;
     if (c == 0 && threadIdx.y == 0 && num_batches_tracked) *num_batches_tracked += 1;
     double s = 0.0, q = 0.0;
@@ -132,6 +134,7 @@ static __global__ void bn_fold_eval_kernel(int C, const float* __restrict__ conv
                                     const float* __restrict__ rm, const float* __restrict__ rv,
                                     float eps, float* __restrict__ scale,
                                     float* __restrict__ shift) {
+    pdl_entry();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float sc = gamma[c] / sqrtf(rv[c] + eps);
@@ -151,6 +154,7 @@ bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restr
                      __nv_bfloat16* __restrict__ pooled, unsigned char* __restrict__ amax, int N,
                      int H, int W, int C, const float* __restrict__ scale,
                      const float* __restrict__ shift) {
+    pdl_entry();
     const unsigned CG = (unsigned)C >> 3;
     const unsigned cg = threadIdx.x % CG;
     float sc[8], sh[8];
@@ -236,6 +240,7 @@ bn_apply_relu_head_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __
                           unsigned npix, unsigned HW, int C, const float* __restrict__ scale,
                           const float* __restrict__ shift, int NC, const float* __restrict__ hw_,
                           const float* __restrict__ hb, float* __restrict__ logits) {
+    pdl_entry();
     const unsigned CG = (unsigned)C >> 3;   // 8 or 16 or 32: a pixel's lanes are one aligned group
     const unsigned cg = threadIdx.x % CG;
     float sc[8], sh[8], wr[NCT][8];
@@ -295,6 +300,7 @@ bn_apply_relu_head_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __
 static __global__ void __launch_bounds__(256)
 maxpool2_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ pooled, int N,
                 int H, int W, int C) {
+    pdl_entry();
     const unsigned CG = (unsigned)C >> 3, Hp = H >> 1, Wp = W >> 1;
     const unsigned total = (unsigned)N * Hp * Wp * CG;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -353,6 +359,7 @@ struct BnBwdArgs {
 template <bool POOL_SKIP, bool APPLY, bool PIX = false>
 static __global__ void __launch_bounds__(256, 2)
 bn_bwd_kernel(const BnBwdArgs A) {
+    pdl_entry();
     const unsigned C = A.C, CG = C >> 3, H = A.H, W = A.W;
     const unsigned cg = threadIdx.x % CG;  // host guarantees 256 % CG == 0
     float sc[8], sh[8], mu[8], rs[8], kb[8], kg[8];
@@ -572,6 +579,7 @@ bn_bwd_kernel(const BnBwdArgs A) {
 static __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C,
                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    pdl_entry();
     const int c = blockIdx.x * 32 + threadIdx.x;
     double b = 0.0, g = 0.0;
     if (c < C) {
@@ -594,6 +602,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C,
 // conv [Co][Ci][3][3] -> fprop B [tap][Co][Ci]   and   dgrad B [tap'][Ci][Co], tap' = 8 - tap
 static __global__ void pack_conv3x3_kernel(const float* __restrict__ w, int Co, int Ci,
                                     __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+    pdl_entry();
     const long long total = (long long)Co * Ci * 9;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -610,6 +619,7 @@ static __global__ void pack_conv3x3_kernel(const float* __restrict__ w, int Co, 
 static __global__ void pack_convT2x2_kernel(const float* __restrict__ w, int Ci, int Co,
                                      __nv_bfloat16* __restrict__ wf,
                                      __nv_bfloat16* __restrict__ wb) {
+    pdl_entry();
     const long long total = (long long)Ci * Co * 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -623,6 +633,7 @@ static __global__ void pack_convT2x2_kernel(const float* __restrict__ w, int Ci,
 }
 // bias of the transposed conv replicated over the 4 sub-pixel positions (GEMM column order)
 static __global__ void tile_bias4_kernel(const float* __restrict__ b, int Co, float* __restrict__ out) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 4 * Co) out[i] = b[i % Co];
 }
@@ -640,6 +651,7 @@ static __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long split_stride, int cols,
                     int RC, float* __restrict__ out, float* zero0, int nzero0, float* zero1,
                     int nzero1) {
+    pdl_entry();
     __shared__ float sm[32][8 * T + 1];
     const int tx = threadIdx.x, ty = threadIdx.y;
     if (blockIdx.x == 0 && blockIdx.y == 0) {
@@ -669,6 +681,7 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long split_st
 }
 
 static __global__ void fill_zero_kernel(float* p, long long n) {
+    pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x)
         p[i] = 0.f;

@@ -40,6 +40,7 @@ enum : int { FC_STATS = 0, FC_APPLY = 1, FC_BWD_REDUCE = 2, FC_BWD_WGRAD = 3 };
 template <int MODE, bool CI1>
 static __global__ void __launch_bounds__(256)
 first_conv_kernel(const FirstConvArgs A) {
+    pdl_entry();
     extern __shared__ float wsm[];  // [Ci*9][Co] weights, transposed for 8-wide reads
     const int Co = A.Co, CG = Co >> 3, Ci = A.Ci;
     const int cg = threadIdx.x % CG;
@@ -210,6 +211,7 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int off) {
 template <int PX>
 static __global__ void __launch_bounds__(256)
 fc1_cov_kernel(const float* __restrict__ x, int N, int H, int W, double* __restrict__ partial) {
+    pdl_entry();
     const unsigned Ho = H - 2, Wo = W - 2;
     const unsigned GW = (Wo + PX - 1) / PX;
     const unsigned ngroups = (unsigned)N * Ho * GW;
@@ -271,6 +273,7 @@ fc1_cov_finalize_kernel(const double* __restrict__ partial, int blocks, const fl
                         long long* num_batches_tracked, float momentum, float eps,
                         float* __restrict__ scale, float* __restrict__ shift,
                         float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+    pdl_entry();
     __shared__ double sg[FC_COV_TERMS];
     __shared__ double sc[FC_COV_DOUBLES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -361,6 +364,7 @@ __device__ __forceinline__ void fc1_load_patch(const float* __restrict__ xrow, u
 template <int PX>
 static __global__ void __launch_bounds__(256, 2)
 fc1_apply_kernel(const FirstConvArgs A) {
+    pdl_entry();
     const int Co = A.Co, CG = Co >> 3;
     const unsigned cg = threadIdx.x % CG;
     const unsigned Ho = A.H - 2, Wo = A.W - 2, W = A.W;
@@ -409,6 +413,7 @@ fc1_apply_kernel(const FirstConvArgs A) {
 template <int PX>
 static __global__ void __launch_bounds__(256, 2)
 fc1_bwd_kernel(const FirstConvArgs A, const double* __restrict__ cov) {
+    pdl_entry();
     const int Co = A.Co, CG = Co >> 3;
     const unsigned cg = threadIdx.x % CG;
     const unsigned Ho = A.H - 2, Wo = A.W - 2, W = A.W;
@@ -479,6 +484,7 @@ fc1_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int Co,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         float* __restrict__ dgamma, float* __restrict__ dbeta,
                         float* __restrict__ dw) {
+    pdl_entry();
     const int c = blockIdx.x, e = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ double v[10];
     double s = 0.0;
@@ -514,6 +520,7 @@ fc1_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int Co,
 // out[co][ci_sel][tap] = sum over blocks of wpartial[b][co][tap]
 static __global__ void first_wgrad_finalize_kernel(const float* __restrict__ wpartial, int blocks, int Co,
                                             int Ci, int ci_sel, float* __restrict__ dw) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Co * 9) return;
     double s = 0.0;

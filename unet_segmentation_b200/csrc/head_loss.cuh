@@ -14,6 +14,7 @@ static __global__ void __launch_bounds__(256)
 head_fwd_kernel(const __nv_bfloat16* __restrict__ a, long long P, long long HW, int K, int NC,
                 const float* __restrict__ w, const float* __restrict__ b,
                 float* __restrict__ logits, unsigned char* __restrict__ mask) {
+    pdl_entry();
     if (K == 64) {
         // Fast path (the reference's 64-channel head): 8 threads per pixel, one coalesced 16-byte
         // load each, partial dot products combined with three shuffle steps.
@@ -106,6 +107,7 @@ static __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ a, long long P,
                 long long HW, int K, int NC, const float* __restrict__ w,
                 __nv_bfloat16* __restrict__ da, float* __restrict__ partial) {
+    pdl_entry();
     constexpr int HEAD_MAX_CLASSES = NCT;
     const int CG = K >> 3;
     const int cg = threadIdx.x % CG;
@@ -189,6 +191,7 @@ head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restri
 static __global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const float* __restrict__ partial, int blocks, int len,
                        float* __restrict__ out0, int len0, float* __restrict__ out1) {
+    pdl_entry();
     const int j = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0, unused = 0.0;
     if (j < len)
@@ -218,6 +221,7 @@ struct WceArgs {
 
 static __global__ void __launch_bounds__(256)
 wce_fwd_bwd_kernel(const WceArgs A) {
+    pdl_entry();
     const long long HW = (long long)A.H * A.W;
     const long long P = (long long)A.N * HW;
     const float inv_count = 1.f / (float)P;
@@ -284,6 +288,7 @@ wce_fwd_bwd_kernel(const WceArgs A) {
 
 static __global__ void wce_finalize_kernel(const float* __restrict__ partial, int blocks, double count,
                                     float* __restrict__ loss) {
+    pdl_entry();
     __shared__ double sm[256];
     double s = 0.0;
     for (int i = threadIdx.x; i < blocks; i += blockDim.x) s += (double)partial[i];
@@ -299,6 +304,7 @@ static __global__ void wce_finalize_kernel(const float* __restrict__ partial, in
 // out = in * (*scalar)   (loss backward: grad_output is a device scalar)
 static __global__ void scale_by_scalar_kernel(const float* __restrict__ in, const float* __restrict__ s,
                                        float* __restrict__ out, long long n) {
+    pdl_entry();
     const float k = *s;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x)

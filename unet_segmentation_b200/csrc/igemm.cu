@@ -52,19 +52,13 @@ size_t igemm_stats_floats(int ncols) {
     return (size_t)num_sms() * 2 * bn;   // one [2][BN] row per CTA
 }
 
-// Launch with an optional 2-CTA cluster (cta_group::2 pairs).
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_clustered(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                                    cudaStream_t stream, int cluster, Args&&... args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = cluster > 1 ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+bool pdl_enabled() {
+    static int on = -1;
+    // Off by default: with every edge of the step programmatic, early-resident CTAs of the next
+    // kernel take registers / thread slots from the HBM-bound kernels and the step got 1 % SLOWER
+    // (15.55 -> 15.75 ms, same box). UB_PDL=1 enables it for experiments.
+    if (on < 0) { const char* e = getenv("UB_PDL"); on = (e && atoi(e)) ? 1 : 0; }
+    return on != 0;
 }
 // cta_group::2 pairs: on unless UB_PAIR=0
 static bool pairs_enabled() {
@@ -92,7 +86,7 @@ static int launch_igemm_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    UB_CHECK_CUDA(launch_clustered(igemm_kmajor_kernel<BN, EPI, CG>, dim3(grid), dim3(IGEMM_THREADS),
+    UB_CHECK_CUDA(ub_launch(igemm_kmajor_kernel<BN, EPI, CG>, dim3(grid), dim3(IGEMM_THREADS),
                                    Cfg::SMEM_BYTES, stream, CG, a0, a1, b, p));
     UB_POST_LAUNCH();
     return UB_OK;
@@ -136,7 +130,7 @@ static int launch_rowrun_t(const CUtensorMap& a0, const CUtensorMap& a1, const C
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    UB_CHECK_CUDA(launch_clustered(igemm_rowrun_kernel<BN, EPI, CG, WRES>, dim3(grid),
+    UB_CHECK_CUDA(ub_launch(igemm_rowrun_kernel<BN, EPI, CG, WRES>, dim3(grid),
                                    dim3(IGEMM_THREADS), Cfg::SMEM_BYTES, stream, CG, a0, a1, b, p));
     UB_POST_LAUNCH();
     return UB_OK;
@@ -353,7 +347,7 @@ static int launch_wgrad_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    UB_CHECK_CUDA(launch_clustered(igemm_wgrad_kernel<BN, CG>, grid, dim3(256), Cfg::SMEM_BYTES,
+    UB_CHECK_CUDA(ub_launch(igemm_wgrad_kernel<BN, CG>, grid, dim3(256), Cfg::SMEM_BYTES,
                                    stream, CG, a0, a1, b, p));
     UB_POST_LAUNCH();
     return UB_OK;
@@ -420,11 +414,9 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
     UB_TRY(rc);
     const dim3 rgrid(cols / 32, ctot / 8);
     if (taps == 9)
-        wgrad_reduce_kernel<9><<<rgrid, dim3(32, 8), 0, stream>>>(ws, splits, p.split_stride, cols, ctot, out,
-                                                                  zero0, nzero0, zero1, nzero1);
+        UB_LAUNCH_NC((wgrad_reduce_kernel<9>), rgrid, dim3(32, 8), 0, stream, ws, splits, p.split_stride, cols, ctot, out, zero0, nzero0, zero1, nzero1);
     else if (taps == 4)
-        wgrad_reduce_kernel<4><<<rgrid, dim3(32, 8), 0, stream>>>(ws, splits, p.split_stride, cols, ctot, out,
-                                                                  zero0, nzero0, zero1, nzero1);
+        UB_LAUNCH_NC((wgrad_reduce_kernel<4>), rgrid, dim3(32, 8), 0, stream, ws, splits, p.split_stride, cols, ctot, out, zero0, nzero0, zero1, nzero1);
     else {
         set_last_error("wgrad: unsupported tap count %d", taps);
         return UB_ERR_UNSUPPORTED;

@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const IgemmParams p) {
+    pdl_trigger();   // let the next kernel's CTAs be scheduled while this grid drains
     using Cfg = IgemmCfg<BN, CG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -206,6 +207,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_g;
+    pdl_wait();   // prologue done; from here on global memory of the preceding kernels is read
 
     const int cchunks = p.cchunks0 + p.cchunks1;
     const int kblocks = p.taps * cchunks;
@@ -399,6 +401,7 @@ __global__ void __launch_bounds__(256, 1)
 igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                    const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const WgradParams p) {
+    pdl_trigger();   // let the next kernel's CTAs be scheduled while this grid drains
     using Cfg = WgradCfg<BN, CG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -439,6 +442,7 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_g;
+    pdl_wait();   // prologue done; from here on global memory of the preceding kernels is read
 
     const int split = blockIdx.y;
     const int kb_begin = (int)((long long)p.kblocks_total * split / p.splits);

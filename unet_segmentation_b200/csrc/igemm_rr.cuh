@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const RowRunParams p) {
+    pdl_trigger();   // let the next kernel's CTAs be scheduled while this grid drains
     using Cfg = RowRunCfg<BN, CG, WRES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -109,6 +110,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_g;
+    pdl_wait();   // prologue done; from here on global memory of the preceding kernels is read
 
     const int cchunks = p.cchunks0 + p.cchunks1;
     const int cta_n = unit % p.n_tiles;

@@ -34,16 +34,16 @@ static int check_cg(int C, const char* what) {
 
 int launch_pack_conv3x3(const float* w, int Co, int Ci, __nv_bfloat16* wf, __nv_bfloat16* wd,
                         cudaStream_t s) {
-    pack_conv3x3_kernel<<<ew_blocks((long long)Co * Ci * 9), 256, 0, s>>>(w, Co, Ci, wf, wd);
+    UB_LAUNCH_NC(pack_conv3x3_kernel, ew_blocks((long long)Co * Ci * 9), 256, 0, s, w, Co, Ci, wf, wd);
     UB_POST_LAUNCH();
     return UB_OK;
 }
 int launch_pack_convT(const float* w, int Ci, int Co, __nv_bfloat16* wf, __nv_bfloat16* wb,
                       const float* bias, float* bias4, cudaStream_t s) {
-    pack_convT2x2_kernel<<<ew_blocks((long long)Co * Ci * 4), 256, 0, s>>>(w, Ci, Co, wf, wb);
+    UB_LAUNCH_NC(pack_convT2x2_kernel, ew_blocks((long long)Co * Ci * 4), 256, 0, s, w, Ci, Co, wf, wb);
     UB_POST_LAUNCH();
     if (bias && bias4) {
-        tile_bias4_kernel<<<(4 * Co + 255) / 256, 256, 0, s>>>(bias, Co, bias4);
+        UB_LAUNCH_NC(tile_bias4_kernel, (4 * Co + 255) / 256, 256, 0, s, bias, Co, bias4);
         UB_POST_LAUNCH();
     }
     return UB_OK;
@@ -53,9 +53,7 @@ int launch_bn_finalize(const float* stats, const IgemmLaunchInfo& info, int C, d
                        const float* gamma, const float* beta, float* rm, float* rv,
                        long long* nbt, float momentum, float eps, float* scale, float* shift,
                        float* mean, float* rstd, cudaStream_t s) {
-    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_SLICES), 0, s>>>(stats, info.grid, info.n_tiles, info.BN, C,
-                                                       count, gamma, beta, rm, rv, nbt, momentum,
-                                                       eps, scale, shift, mean, rstd);
+    UB_LAUNCH_NC(bn_finalize_kernel, (C + 31) / 32, dim3(32, FIN_SLICES), 0, s, stats, info.grid, info.n_tiles, info.BN, C, count, gamma, beta, rm, rv, nbt, momentum, eps, scale, shift, mean, rstd);
     UB_POST_LAUNCH();
     return UB_OK;
 }
@@ -63,17 +61,14 @@ int launch_bn_finalize_flat(const float* part, int blocks, int C, double count, 
                             const float* beta, float* rm, float* rv, long long* nbt,
                             float momentum, float eps, float* scale, float* shift, float* mean,
                             float* rstd, cudaStream_t s) {
-    bn_finalize_flat_kernel<<<(C + 31) / 32, dim3(32, FIN_SLICES), 0, s>>>(part, blocks, C, count, gamma, beta, rm,
-                                                            rv, nbt, momentum, eps, scale, shift,
-                                                            mean, rstd);
+    UB_LAUNCH_NC(bn_finalize_flat_kernel, (C + 31) / 32, dim3(32, FIN_SLICES), 0, s, part, blocks, C, count, gamma, beta, rm, rv, nbt, momentum, eps, scale, shift, mean, rstd);
     UB_POST_LAUNCH();
     return UB_OK;
 }
 int launch_bn_fold_eval(int C, const float* conv_bias, const float* gamma, const float* beta,
                         const float* rm, const float* rv, float eps, float* scale, float* shift,
                         cudaStream_t s) {
-    bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, conv_bias, gamma, beta, rm, rv, eps,
-                                                        scale, shift);
+    UB_LAUNCH_NC(bn_fold_eval_kernel, (C + 127) / 128, 128, 0, s, C, conv_bias, gamma, beta, rm, rv, eps, scale, shift);
     UB_POST_LAUNCH();
     return UB_OK;
 }
@@ -88,12 +83,10 @@ int launch_bn_apply_relu(const __nv_bfloat16* y, __nv_bfloat16* a, __nv_bfloat16
     }
     if (pooled) {
         const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-        bn_apply_relu_kernel<true><<<ew_blocks(items), 256, 0, s>>>(y, a, pooled, amax, N, H, W, C,
-                                                                    scale, shift);
+        UB_LAUNCH_NC((bn_apply_relu_kernel<true>), ew_blocks(items), 256, 0, s, y, a, pooled, amax, N, H, W, C, scale, shift);
     } else {
         const long long items = (long long)N * H * W * (C / 8);
-        bn_apply_relu_kernel<false><<<ew_blocks(items), 256, 0, s>>>(y, a, nullptr, nullptr, N, H, W,
-                                                                     C, scale, shift);
+        UB_LAUNCH_NC((bn_apply_relu_kernel<false>), ew_blocks(items), 256, 0, s, y, a, nullptr, nullptr, N, H, W, C, scale, shift);
     }
     UB_POST_LAUNCH();
     return UB_OK;
@@ -117,18 +110,18 @@ int launch_bn_apply_relu_head(const __nv_bfloat16* y, __nv_bfloat16* a, int N, i
     const unsigned npix = (unsigned)((long long)N * H * W), HW = (unsigned)(H * W);
     const int blocks = ew_blocks(items);
     if (NC <= 2)
-        bn_apply_relu_head_kernel<2><<<blocks, 256, 0, s>>>(y, a, npix, HW, C, scale, shift, NC, hw, hb, logits);
+        UB_LAUNCH_NC((bn_apply_relu_head_kernel<2>), blocks, 256, 0, s, y, a, npix, HW, C, scale, shift, NC, hw, hb, logits);
     else if (NC <= 4)
-        bn_apply_relu_head_kernel<4><<<blocks, 256, 0, s>>>(y, a, npix, HW, C, scale, shift, NC, hw, hb, logits);
+        UB_LAUNCH_NC((bn_apply_relu_head_kernel<4>), blocks, 256, 0, s, y, a, npix, HW, C, scale, shift, NC, hw, hb, logits);
     else
-        bn_apply_relu_head_kernel<8><<<blocks, 256, 0, s>>>(y, a, npix, HW, C, scale, shift, NC, hw, hb, logits);
+        UB_LAUNCH_NC((bn_apply_relu_head_kernel<8>), blocks, 256, 0, s, y, a, npix, HW, C, scale, shift, NC, hw, hb, logits);
     UB_POST_LAUNCH();
     return UB_OK;
 }
 int launch_maxpool2(const __nv_bfloat16* a, __nv_bfloat16* pooled, int N, int H, int W, int C,
                     cudaStream_t s) {
     const long long items = (long long)N * (H / 2) * (W / 2) * (C / 8);
-    maxpool2_kernel<<<ew_blocks(items), 256, 0, s>>>(a, pooled, N, H, W, C);
+    UB_LAUNCH_NC(maxpool2_kernel, ew_blocks(items), 256, 0, s, a, pooled, N, H, W, C);
     UB_POST_LAUNCH();
     return UB_OK;
 }
@@ -157,17 +150,16 @@ int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
                                 ? (long long)d.N * ((d.H + 1) / 2) * ((d.W + 1) / 2) * (d.C / 8)
                                 : count * (d.C / 8);
     const int blocks = red_blocks(items, 2);   // = resident CTAs (launch bounds 256 x 2): one wave
-    if (pix) bn_bwd_kernel<true, false, true><<<blocks, 256, 0, s>>>(A);
-    else if (d.pool_skip) bn_bwd_kernel<true, false><<<blocks, 256, 0, s>>>(A);
-    else bn_bwd_kernel<false, false><<<blocks, 256, 0, s>>>(A);
+    if (pix) UB_LAUNCH_NC((bn_bwd_kernel<true, false, true>), blocks, 256, 0, s, A);
+    else if (d.pool_skip) UB_LAUNCH_NC((bn_bwd_kernel<true, false>), blocks, 256, 0, s, A);
+    else UB_LAUNCH_NC((bn_bwd_kernel<false, false>), blocks, 256, 0, s, A);
     UB_POST_LAUNCH();
-    bn_bwd_finalize_kernel<<<(d.C + 31) / 32, dim3(32, FIN_SLICES), 0, s>>>(d.partial, blocks, d.C, d.dgamma,
-                                                             d.dbeta);
+    UB_LAUNCH_NC(bn_bwd_finalize_kernel, (d.C + 31) / 32, dim3(32, FIN_SLICES), 0, s, d.partial, blocks, d.C, d.dgamma, d.dbeta);
     UB_POST_LAUNCH();
     const int ablocks = ew_blocks(items);
-    if (pix) bn_bwd_kernel<true, true, true><<<ablocks, 256, 0, s>>>(A);
-    else if (d.pool_skip) bn_bwd_kernel<true, true><<<ablocks, 256, 0, s>>>(A);
-    else bn_bwd_kernel<false, true><<<ablocks, 256, 0, s>>>(A);
+    if (pix) UB_LAUNCH_NC((bn_bwd_kernel<true, true, true>), ablocks, 256, 0, s, A);
+    else if (d.pool_skip) UB_LAUNCH_NC((bn_bwd_kernel<true, true>), ablocks, 256, 0, s, A);
+    else UB_LAUNCH_NC((bn_bwd_kernel<false, true>), ablocks, 256, 0, s, A);
     UB_POST_LAUNCH();
     return UB_OK;
 }
@@ -199,7 +191,7 @@ static int fc_launch(const FirstConvArgs& A, int blocks, cudaStream_t s) {
     if (smem > 48 * 1024)
         UB_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<MODE, false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    first_conv_kernel<MODE, false><<<blocks, 256, smem, s>>>(A);
+    UB_LAUNCH_NC((first_conv_kernel<MODE, false>), blocks, 256, smem, s, A);
     UB_POST_LAUNCH();
     return UB_OK;
 }
@@ -213,12 +205,10 @@ static int fc1_moments(const FirstConvDesc& d, float* ws, double* cov, const flo
     long long b = (groups + 255) / 256;
     if (b > num_sms() * 2) b = num_sms() * 2;
     double* partial = reinterpret_cast<double*>(ws);
-    fc1_cov_kernel<FC1_PX><<<(int)b, 256, 0, s>>>(d.x, d.N, d.H, d.W, partial);
+    UB_LAUNCH_NC((fc1_cov_kernel<FC1_PX>), (int)b, 256, 0, s, d.x, d.N, d.H, d.W, partial);
     UB_POST_LAUNCH();
     const double count = (double)d.N * (d.H - 2) * (d.W - 2);
-    fc1_cov_finalize_kernel<<<1, 1024, 0, s>>>(partial, (int)b, d.x, count, cov, d.Co, d.w, d.bias,
-                                               gamma, beta, rm, rv, nbt, momentum, eps, scale,
-                                               shift, mean, rstd);
+    UB_LAUNCH_NC(fc1_cov_finalize_kernel, 1, 1024, 0, s, partial, (int)b, d.x, count, cov, d.Co, d.w, d.bias, gamma, beta, rm, rv, nbt, momentum, eps, scale, shift, mean, rstd);
     UB_POST_LAUNCH();
     return UB_OK;
 }
@@ -249,7 +239,7 @@ int launch_first_conv_apply(const FirstConvDesc& d, const float* scale, const fl
     A.scale = scale; A.shift = shift; A.a = a;
     if (d.Ci == 1) {
         const long long groups = (long long)d.N * (d.H - 2) * ((d.W - 2 + FC1_PX - 1) / FC1_PX);
-        fc1_apply_kernel<FC1_PX><<<ew_blocks(groups * (d.Co / 8)), 256, 0, s>>>(A);
+        UB_LAUNCH_NC((fc1_apply_kernel<FC1_PX>), ew_blocks(groups * (d.Co / 8)), 256, 0, s, A);
         UB_POST_LAUNCH();
         return UB_OK;
     }
@@ -284,17 +274,16 @@ int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const floa
         const long long groups = (long long)d.N * (d.H - 2) * ((d.W - 2 + PX - 1) / PX);
         long long b = (groups * (d.Co / 8) + 255) / 256;
         if (b > num_sms() * 2) b = num_sms() * 2;
-        fc1_bwd_kernel<PX><<<(int)b, 256, 0, s>>>(A, cov);
+        UB_LAUNCH_NC((fc1_bwd_kernel<PX>), (int)b, 256, 0, s, A, cov);
         UB_POST_LAUNCH();
-        fc1_bwd_finalize_kernel<<<d.Co, 320, 0, s>>>(partial, (int)b, d.Co, cov, d.w, d.bias, scale,
-                                                     mean, rstd, dgamma, dbeta, dw);
+        UB_LAUNCH_NC(fc1_bwd_finalize_kernel, d.Co, 320, 0, s, partial, (int)b, d.Co, cov, d.w, d.bias, scale, mean, rstd, dgamma, dbeta, dw);
         UB_POST_LAUNCH();
         return UB_OK;
     }
     A.partial = ws;
     int blocks = red_blocks(items);
     UB_TRY(fc_launch<FC_BWD_REDUCE>(A, blocks, s));
-    bn_bwd_finalize_kernel<<<(d.Co + 31) / 32, dim3(32, FIN_SLICES), 0, s>>>(ws, blocks, d.Co, dgamma, dbeta);
+    UB_LAUNCH_NC(bn_bwd_finalize_kernel, (d.Co + 31) / 32, dim3(32, FIN_SLICES), 0, s, ws, blocks, d.Co, dgamma, dbeta);
     UB_POST_LAUNCH();
     A.dgamma = dgamma; A.dbeta = dbeta; A.inv_count = (float)(1.0 / (double)count);
     A.wpartial = ws;
@@ -302,8 +291,7 @@ int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const floa
         A.ci_sel = ci;
         const int wblocks = red_blocks(items);
         UB_TRY(fc_launch<FC_BWD_WGRAD>(A, wblocks, s));
-        first_wgrad_finalize_kernel<<<(d.Co * 9 + 127) / 128, 128, 0, s>>>(ws, wblocks, d.Co, d.Ci,
-                                                                           ci, dw);
+        UB_LAUNCH_NC(first_wgrad_finalize_kernel, (d.Co * 9 + 127) / 128, 128, 0, s, ws, wblocks, d.Co, d.Ci, ci, dw);
         UB_POST_LAUNCH();
     }
     return UB_OK;
@@ -318,8 +306,7 @@ int launch_head_fwd(const __nv_bfloat16* a, int N, int H, int W, int K, int NC, 
     }
     const long long P = (long long)N * H * W;
     if (P >= 0x7FFFFFF0LL / 8) { set_last_error("head: too many pixels"); return UB_ERR_UNSUPPORTED; }
-    head_fwd_kernel<<<ew_blocks(K == 64 ? P * 8 : P), 256, (size_t)(NC * K + NC) * 4, s>>>(
-        a, P, (long long)H * W, K, NC, w, b, logits, mask);
+    UB_LAUNCH_NC(head_fwd_kernel, ew_blocks(K == 64 ? P * 8 : P), 256, (size_t)(NC * K + NC) * 4, s, a, P, (long long)H * W, K, NC, w, b, logits, mask);
     UB_POST_LAUNCH();
     return UB_OK;
 }
@@ -335,14 +322,14 @@ int launch_head_bwd(const float* dlogits, const __nv_bfloat16* a, int N, int H, 
     const long long P = (long long)N * H * W;
     const int blocks = red_blocks(P * (K / 8));
     if (NC <= 2)
-        head_bwd_kernel<2><<<blocks, 256, 0, s>>>(dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
+        UB_LAUNCH_NC((head_bwd_kernel<2>), blocks, 256, 0, s, dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
     else if (NC <= 4)
-        head_bwd_kernel<4><<<blocks, 256, 0, s>>>(dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
+        UB_LAUNCH_NC((head_bwd_kernel<4>), blocks, 256, 0, s, dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
     else
-        head_bwd_kernel<8><<<blocks, 256, 0, s>>>(dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
+        UB_LAUNCH_NC((head_bwd_kernel<8>), blocks, 256, 0, s, dlogits, a, P, (long long)H * W, K, NC, w, da, partial);
     UB_POST_LAUNCH();
     const int len = NC * K + NC;
-    reduce_partials_kernel<<<(len + 31) / 32, dim3(32, FIN_SLICES), 0, s>>>(partial, blocks, len, dw, NC * K, db);
+    UB_LAUNCH_NC(reduce_partials_kernel, (len + 31) / 32, dim3(32, FIN_SLICES), 0, s, partial, blocks, len, dw, NC * K, db);
     UB_POST_LAUNCH();
     return UB_OK;
 }
@@ -359,21 +346,21 @@ int launch_wce(const WceDesc& d, float* loss, float* dz, float* partial, int* er
     const long long P = (long long)d.N * d.H * d.W;
     if (P <= 0 || d.C < 1) { set_last_error("wce: empty input"); return UB_ERR_ARG; }
     const int blocks = ew_blocks(P);
-    wce_fwd_bwd_kernel<<<blocks, 256, 0, s>>>(A);
+    UB_LAUNCH_NC(wce_fwd_bwd_kernel, blocks, 256, 0, s, A);
     UB_POST_LAUNCH();
-    wce_finalize_kernel<<<1, 256, 0, s>>>(partial, blocks, (double)P, loss);
+    UB_LAUNCH_NC(wce_finalize_kernel, 1, 256, 0, s, partial, blocks, (double)P, loss);
     UB_POST_LAUNCH();
     return UB_OK;
 }
 int launch_scale_by_scalar(const float* in, const float* scalar, float* out, long long n,
                            cudaStream_t s) {
-    scale_by_scalar_kernel<<<ew_blocks(n), 256, 0, s>>>(in, scalar, out, n);
+    UB_LAUNCH_NC(scale_by_scalar_kernel, ew_blocks(n), 256, 0, s, in, scalar, out, n);
     UB_POST_LAUNCH();
     return UB_OK;
 }
 int launch_fill_zero(float* p, long long n, cudaStream_t s) {
     if (n <= 0) return UB_OK;
-    fill_zero_kernel<<<ew_blocks(n), 256, 0, s>>>(p, n);
+    UB_LAUNCH_NC(fill_zero_kernel, ew_blocks(n), 256, 0, s, p, n);
     UB_POST_LAUNCH();
     return UB_OK;
 }

@@ -730,7 +730,7 @@ int ub_plan_sgd_step(ub_plan* P, const float* const* grads, float* const* moment
             blocks += (t.kind == SGD_CONV3 || t.kind == SGD_CONVT) ? (t.d0 / 32) * (t.d1 / 32)
                                                                      : (t.n + 2047) / 2048;
         }
-        sgd_fused_kernel<<<blocks, 256, 0, s>>>(B);
+        UB_LAUNCH_NC(sgd_fused_kernel, blocks, 256, 0, s, B);
         UB_POST_LAUNCH();
     }
     P->packed = true;

@@ -46,6 +46,7 @@ __device__ __forceinline__ float sgd_update(float p, float g, float* buf_io, con
 // packed layouts are written in 64-byte runs), or 2048 elements of a plain tensor.
 static __global__ void __launch_bounds__(256)
 sgd_fused_kernel(const __grid_constant__ SgdBatch B) {
+    pdl_entry();
     __shared__ __nv_bfloat16 tile[9 * 32 * 33];
     int ti = 0;
     for (int i = 1; i < B.count; ++i)

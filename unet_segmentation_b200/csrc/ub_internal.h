@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -43,6 +44,35 @@ long long launch_count();
         int _r = (expr);          \
         if (_r != 0) return _r;   \
     } while (0)
+
+// Kernel launch with programmatic dependent launch (see common.cuh: pdl_*) and an optional
+// 2-CTA cluster (cta_group::2 pairs). UB_PDL=0 launches with plain stream serialization.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t ub_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                             cudaStream_t stream, int cluster, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster; attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// drop-in for `kernel<<<grid, block, smem, stream>>>(args...)`; UB_POST_LAUNCH() follows as before
+#define UB_LAUNCH_NC(kernel, grid, block, smem, stream, ...)                                       \
+    UB_CHECK_CUDA(ub::ub_launch(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, 1, __VA_ARGS__))
 
 // ---- igemm.cu -------------------------------------------------------------------------------
 struct IgemmEpilogue {
