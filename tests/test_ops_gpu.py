@@ -390,3 +390,19 @@ def test_bn_apply_relu_fused_head(ops, n, h, w, c, nc):
     assert rel_l2(logits, ref) < 1e-4
     if c == 64:
         assert torch.equal(logits, logits2)      # same summation tree as the stand-alone head
+
+
+@pytest.mark.parametrize("n,h,w,c0,c1,co", [(1, 6, 128, 64, 0, 64), (2, 5, 254, 128, 0, 64),
+                                            (1, 7, 128, 64, 64, 64), (2, 40, 230, 64, 0, 64),
+                                            (3, 33, 330, 64, 64, 64)])
+def test_conv3x3_wgrad_wide_maps(ops, n, h, w, c0, c1, co):
+    """Weight gradient with Cout = 64 on wide maps (the shapes of inc.b / up4.a / up4.b), incl. the
+    zero-copy concat of two sources and ragged row ends."""
+    x0 = bf(rand(n, c0, h, w))
+    x1 = bf(rand(n, c1, h, w, seed=9)) if c1 else None
+    dy = bf(rand(n, co, h - 2, w - 2, seed=3))
+    dw = ops.conv3x3_wgrad(ops.nhwc(x0), ops.nhwc(x1) if c1 else None, ops.nhwc(dy))
+    x = torch.cat([x0, x1], 1) if c1 else x0
+    ref = torch.nn.grad.conv2d_weight(x, (co, c0 + c1, 3, 3), dy)
+    torch.cuda.synchronize()
+    assert rel_l2(dw, ref) < F32_TOL and cosine(dw, ref) > 0.9999
