@@ -8,6 +8,70 @@ namespace ub {
 
 constexpr int HEAD_MAX_CLASSES = 8;
 
+// Fast path of the 1x1 head for K in {64, 128, 256}: K/8 lanes per pixel (one coalesced 16-byte
+// load each, channel group fixed per thread so the weights live in registers), 4 pixels in flight per
+// thread, partial dot products combined with xor-shuffles — the same arithmetic order as the head
+// fused into the last BN-apply kernel (elementwise.cuh), so eval and training logits of identical
+// activations agree bit for bit.
+template <int NCT>
+static __global__ void __launch_bounds__(256)
+head_fwd_vec_kernel(const __nv_bfloat16* __restrict__ a, unsigned npix, unsigned HW, int K, int NC,
+                    const float* __restrict__ w, const float* __restrict__ b,
+                    float* __restrict__ logits, unsigned char* __restrict__ mask) {
+    pdl_entry();
+    const unsigned CG = (unsigned)K >> 3;
+    const unsigned cg = threadIdx.x % CG;
+    float wr[NCT][8];
+#pragma unroll
+    for (int c = 0; c < NCT; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wr[c][k] = c < NC ? w[c * K + cg * 8 + k] : 0.f;
+    const unsigned gstride = gridDim.x * 256u / CG;
+    const unsigned first = (blockIdx.x * 256u + threadIdx.x) / CG;
+    const unsigned iters = (npix + 4u * gstride - 1u) / (4u * gstride);   // uniform: shuffles inside
+    for (unsigned it = 0; it < iters; ++it) {
+        const unsigned p0 = first + it * 4u * gstride;
+        uint4 raw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned p = p0 + j * gstride;
+            if (p < npix) raw[j] = ldg16(a + (size_t)p * K + cg * 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned p = p0 + j * gstride;
+            const bool ok = p < npix;
+            float acc[NCT];
+#pragma unroll
+            for (int c = 0; c < NCT; ++c) acc[c] = 0.f;
+            if (ok) {
+                const Vec8 x = unpack8(raw[j]);
+#pragma unroll
+                for (int c = 0; c < NCT; ++c)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[c] = fmaf(x.v[k], wr[c][k], acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < NCT; ++c) {
+                if (c < NC) {
+                    for (unsigned off = 1; off < CG; off <<= 1)
+                        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+                }
+            }
+            if (ok && cg == 0) {
+                const unsigned n = p / HW, hw = p % HW;
+#pragma unroll
+                for (int c = 0; c < NCT; ++c) {
+                    acc[c] += (b && c < NC) ? b[c] : 0.f;
+                    if (c < NC) logits[((size_t)n * NC + c) * HW + hw] = acc[c];
+                }
+                if (mask) mask[p] = (NCT >= 2 && NC >= 2 && acc[1] > acc[0]) ? 255 : 0;
+            }
+        }
+    }
+}
+
+// Generic K (any multiple of 8): one thread per pixel, weights in shared memory.
 // logits[n][c][h][w] (fp32 NCHW) = sum_k a[n][h][w][k] * w[c][k] + b[c];  optional u8 mask for the
 // 2-class eval path: 255 where z1 > z0 (== softmax(z)[1] > 0.5, reference scripts/predict.py:85-92).
 static __global__ void __launch_bounds__(256)
@@ -15,63 +79,6 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ a, long long P, long long HW, 
                 const float* __restrict__ w, const float* __restrict__ b,
                 float* __restrict__ logits, unsigned char* __restrict__ mask) {
     pdl_entry();
-    if (K == 64) {
-        // Fast path (the reference's 64-channel head): 8 threads per pixel, one coalesced 16-byte
-        // load each, partial dot products combined with three shuffle steps.
-        const unsigned cg = threadIdx.x & 7u;
-        float wr[HEAD_MAX_CLASSES][8];
-#pragma unroll
-        for (int c = 0; c < HEAD_MAX_CLASSES; ++c)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) wr[c][k] = c < NC ? w[c * 64 + cg * 8 + k] : 0.f;
-        const unsigned gstride = gridDim.x * 32u;  // pixels per grid sweep (256 threads / 8)
-        const unsigned pend = ((unsigned)P + 3u) & ~3u;  // keep whole warps in the loop (shuffles)
-        for (unsigned p0 = blockIdx.x * 32u + (threadIdx.x >> 3); p0 < pend + 2 * gstride;
-             p0 += 2 * gstride) {
-            if (p0 >= pend) break;
-            uint4 raw[2];
-            bool ok[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const unsigned pj = p0 + j * gstride;
-                ok[j] = pj < (unsigned)P;
-                if (ok[j]) raw[j] = ldg16(a + (size_t)pj * 64 + cg * 8);
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const unsigned pj = p0 + j * gstride;
-                if (pj >= pend) continue;   // warp-uniform: a warp covers 4 consecutive pixels
-                Vec8 x;
-                if (ok[j]) x = unpack8(raw[j]);
-                else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) x.v[k] = 0.f;
-                }
-                float acc[HEAD_MAX_CLASSES];
-#pragma unroll
-                for (int c = 0; c < HEAD_MAX_CLASSES; ++c) {
-                    acc[c] = 0.f;
-                    if (c < NC) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) acc[c] = fmaf(x.v[k], wr[c][k], acc[c]);
-                        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
-                        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
-                        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
-                    }
-                }
-                if (cg == 0 && ok[j]) {
-                    const unsigned n = pj / (unsigned)HW, hw = pj % (unsigned)HW;
-#pragma unroll
-                    for (int c = 0; c < HEAD_MAX_CLASSES; ++c)
-                        if (c < NC) logits[((size_t)n * NC + c) * HW + hw] = acc[c] + (b ? b[c] : 0.f);
-                    if (mask)
-                        mask[pj] = (NC >= 2 && acc[1] + (b ? b[1] : 0.f) > acc[0] + (b ? b[0] : 0.f))
-                                       ? 255 : 0;
-                }
-            }
-        }
-        return;
-    }
     extern __shared__ float wsm[];  // [NC][K] + [NC]
     for (int i = threadIdx.x; i < NC * K; i += blockDim.x) wsm[i] = w[i];
     for (int i = threadIdx.x; i < NC; i += blockDim.x) wsm[NC * K + i] = b ? b[i] : 0.f;

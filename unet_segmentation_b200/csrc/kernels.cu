@@ -306,7 +306,19 @@ int launch_head_fwd(const __nv_bfloat16* a, int N, int H, int W, int K, int NC, 
     }
     const long long P = (long long)N * H * W;
     if (P >= 0x7FFFFFF0LL / 8) { set_last_error("head: too many pixels"); return UB_ERR_UNSUPPORTED; }
-    UB_LAUNCH_NC(head_fwd_kernel, ew_blocks(K == 64 ? P * 8 : P), 256, (size_t)(NC * K + NC) * 4, s, a, P, (long long)H * W, K, NC, w, b, logits, mask);
+    if (K == 64 || K == 128 || K == 256) {
+        const int blocks = ew_blocks(P * (K / 8));
+        const unsigned npix = (unsigned)P, HW = (unsigned)(H * W);
+        if (NC <= 2)
+            UB_LAUNCH_NC((head_fwd_vec_kernel<2>), blocks, 256, 0, s, a, npix, HW, K, NC, w, b, logits, mask);
+        else if (NC <= 4)
+            UB_LAUNCH_NC((head_fwd_vec_kernel<4>), blocks, 256, 0, s, a, npix, HW, K, NC, w, b, logits, mask);
+        else
+            UB_LAUNCH_NC((head_fwd_vec_kernel<8>), blocks, 256, 0, s, a, npix, HW, K, NC, w, b, logits, mask);
+        UB_POST_LAUNCH();
+        return UB_OK;
+    }
+    UB_LAUNCH_NC(head_fwd_kernel, ew_blocks(P), 256, (size_t)(NC * K + NC) * 4, s, a, P, (long long)H * W, K, NC, w, b, logits, mask);
     UB_POST_LAUNCH();
     return UB_OK;
 }
