@@ -160,6 +160,14 @@ int ub_op_conv3x3_forward(const ub_view* src0, const ub_view* src1, const void* 
                           const float* bias, int Co, int epilogue, const float* scale,
                           const float* shift, void* y, float* stats, int* info, void* stream);
 /* dx[N][H+2][W+2][Ci] = full correlation of dy[N][H][W][Co] with the rotated weights wd. */
+/* Eval path of the LAST conv unit (64 output channels): 3x3 conv + folded BN affine + ReLU with the
+ * 1x1 OutConv and the (z1 > z0) mask fused into the epilogue; the activation is never stored
+ * (reference models/unet_model.py:11-17,56-63,145; scripts/predict.py:85-92).
+ * head_w [n_classes][64], head_b [n_classes] fp32; logits NCHW fp32; mask (optional) u8 [N][H-2][W-2]. */
+int ub_op_conv3x3_affine_relu_head(const ub_view* src0, const ub_view* src1, const void* wf,
+                                   const float* scale, const float* shift, const float* head_w,
+                                   const float* head_b, int n_classes, float* logits,
+                                   uint8_t* mask, void* stream);
 int ub_op_conv3x3_dgrad(const ub_view* dy, const void* wd, int Ci, void* dx, void* stream);
 int64_t ub_op_wgrad_workspace_floats(int rows, int cols, int64_t pixels);
 /* dw[Co][C0+C1][3][3] fp32 = sum over pixels of x (concat of src0, src1) * dy[N][H-2][W-2][Co]. */

@@ -406,3 +406,26 @@ def test_conv3x3_wgrad_wide_maps(ops, n, h, w, c0, c1, co):
     ref = torch.nn.grad.conv2d_weight(x, (co, c0 + c1, 3, 3), dy)
     torch.cuda.synchronize()
     assert rel_l2(dw, ref) < F32_TOL and cosine(dw, ref) > 0.9999
+
+
+@pytest.mark.parametrize("n,h,w,ci,nc", [(1, 12, 12, 64, 2), (2, 20, 30, 64, 3), (1, 6, 130, 64, 2),
+                                         (2, 9, 260, 128, 2)])
+def test_conv3x3_eval_fused_head(ops, n, h, w, ci, nc):
+    """Eval last unit: conv + folded BN + ReLU + 1x1 OutConv + mask in ONE epilogue (im2col and
+    row-run / resident-weight kernels) == the unfused conv followed by the head kernel."""
+    x = bf(rand(n, ci, h, w))
+    wt = bf(rand(64, ci, 3, 3, scale=0.05, seed=1))
+    wf, _ = ops.pack_conv3x3(wt)
+    scale, shift = rand(64, seed=2) * 0.2 + 1.0, rand(64, seed=3) * 0.3
+    hw_, hb = rand(nc, 64, scale=0.2, seed=4), rand(nc, seed=5)
+    logits, mask = ops.conv3x3_affine_relu_head(ops.nhwc(x), None, wf, scale, shift, hw_, hb)
+    a, _, _ = ops.conv3x3_forward(ops.nhwc(x), None, wf, None, epilogue=2, scale=scale, shift=shift)
+    logits2, mask2 = ops.head_forward(a, hw_, hb, want_mask=True)
+    ref_a = bf(F.relu(F.conv2d(x, wt) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)))
+    ref = F.conv2d(ref_a, hw_.view(nc, 64, 1, 1), hb)
+    torch.cuda.synchronize()
+    assert rel_l2(logits, logits2) < 1e-5          # same bf16 activations, different summation order
+    assert rel_l2(logits, ref) < BF16_TOL
+    margin = (logits2[:, 1] - logits2[:, 0]).abs() if nc >= 2 else None
+    if nc >= 2:
+        assert torch.equal(mask[margin > 1e-4], mask2[margin > 1e-4])

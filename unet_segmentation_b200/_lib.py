@@ -66,6 +66,7 @@ _SIGNATURES = {
     "ub_op_conv_stats_floats": (c_int64, [c_int]),
     "ub_op_conv3x3_forward": (c_int, [_VP, _VP, _P, _P, c_int, c_int, _P, _P, _P, _P,
                                       C.POINTER(c_int), _P]),
+    "ub_op_conv3x3_affine_relu_head": (c_int, [_VP, _VP, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "ub_op_conv3x3_dgrad": (c_int, [_VP, _P, c_int, _P, _P]),
     "ub_op_wgrad_workspace_floats": (c_int64, [c_int, c_int, c_int64]),
     "ub_op_conv3x3_wgrad": (c_int, [_VP, _VP, _P, c_int, _P, c_int64, _P, _P]),

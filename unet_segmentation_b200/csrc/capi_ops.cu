@@ -86,6 +86,22 @@ int ub_op_conv3x3_forward(const ub_view* src0, const ub_view* src1, const void* 
     if (r == 0 && info) { info[0] = li.grid; info[1] = li.n_tiles; info[2] = li.BN; info[3] = li.M; }
     return r;
 }
+int ub_op_conv3x3_affine_relu_head(const ub_view* src0, const ub_view* src1, const void* wf,
+                                   const float* scale, const float* shift, const float* head_w,
+                                   const float* head_b, int n_classes, float* logits,
+                                   uint8_t* mask, void* stream) {
+    UB_REQUIRE(src0 && wf && scale && shift && head_w && logits,
+               "conv3x3_affine_relu_head: null pointer");
+    View v0 = to_view(src0), v1;
+    if (src1) v1 = to_view(src1);
+    IgemmEpilogue e;
+    memset(&e, 0, sizeof(e));
+    e.kind = EPI_AFFINE_RELU_HEAD; e.ldo = 64; e.scale = scale; e.shift = shift;
+    e.head_w = head_w; e.head_b = head_b; e.head_logits = logits; e.head_mask = mask;
+    e.head_nc = n_classes;
+    return launch_igemm(v0, src1 ? &v1 : nullptr, 0, -2, 1, 9, 3, (const __nv_bfloat16*)wf, 64, e,
+                        nullptr, S(stream));
+}
 int ub_op_conv3x3_dgrad(const ub_view* dy, const void* wd, int Ci, void* dx, void* stream) {
     UB_REQUIRE(dy && wd && dx, "conv3x3_dgrad: null pointer");
     IgemmEpilogue e;

@@ -101,6 +101,10 @@ static int launch_igemm_bn(int epi, const CUtensorMap& a0, const CUtensorMap& a1
         case EPI_STORE: return launch_igemm_t<BN, EPI_STORE, CG>(a0, a1, b, p, grid, stream);
         case EPI_AFFINE_RELU: return launch_igemm_t<BN, EPI_AFFINE_RELU, CG>(a0, a1, b, p, grid, stream);
         case EPI_CONVT: return launch_igemm_t<BN, EPI_CONVT, CG>(a0, a1, b, p, grid, stream);
+        case EPI_AFFINE_RELU_HEAD:
+            if (BN == 64 && CG == 1)
+                return launch_igemm_t<64, EPI_AFFINE_RELU_HEAD, 1>(a0, a1, b, p, grid, stream);
+            break;
     }
     set_last_error("unknown epilogue kind %d", epi);
     return UB_ERR_ARG;
@@ -145,6 +149,10 @@ static int launch_rowrun_bn(int epi, const CUtensorMap& a0, const CUtensorMap& a
         case EPI_STORE: return launch_rowrun_t<BN, EPI_STORE, CG, WRES>(a0, a1, b, p, grid, stream);
         case EPI_AFFINE_RELU:
             return launch_rowrun_t<BN, EPI_AFFINE_RELU, CG, WRES>(a0, a1, b, p, grid, stream);
+        case EPI_AFFINE_RELU_HEAD:
+            if (BN == 64 && CG == 1)
+                return launch_rowrun_t<64, EPI_AFFINE_RELU_HEAD, 1, WRES>(a0, a1, b, p, grid, stream);
+            break;
     }
     set_last_error("row-run: unsupported epilogue kind %d", epi);
     return UB_ERR_ARG;
@@ -173,6 +181,13 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
     const int BN = pick_bn(ncols);
     if (!BN) {
         set_last_error("igemm: %d output columns is not a multiple of 64", ncols);
+        return UB_ERR_UNSUPPORTED;
+    }
+    if (epi.kind == EPI_AFFINE_RELU_HEAD &&
+        (ncols != 64 || epi.head_nc < 1 || epi.head_nc > HEAD_EPI_MAX_CLASSES || !epi.head_w ||
+         !epi.head_logits)) {
+        set_last_error("igemm: the fused head epilogue needs 64 output channels and <= %d classes",
+                       HEAD_EPI_MAX_CLASSES);
         return UB_ERR_UNSUPPORTED;
     }
     const int Wo = (src0.W + upper - lower - 1) / tstride + 1;
@@ -212,6 +227,8 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
         if (rr) { set_last_error("row-run: tensor map encoding failed: %d", rr); return UB_ERR_TMAP; }
         q.epi.M = (int)M; q.epi.out = epi.out; q.epi.ldo = epi.ldo; q.epi.bias = epi.bias;
         q.epi.scale = epi.scale; q.epi.shift = epi.shift; q.epi.stats = epi.stats;
+        q.epi.head_w = epi.head_w; q.epi.head_b = epi.head_b; q.epi.head_logits = epi.head_logits;
+        q.epi.head_mask = epi.head_mask; q.epi.head_nc = epi.head_nc; q.epi.head_hw = Ho * Wo;
         static long long* dbg_buf = nullptr;
         static int dbg_on = -1;
         if (dbg_on < 0) { const char* e = getenv("UB_RR_PROFILE"); dbg_on = (e && atoi(e)) ? 1 : 0; }
@@ -278,6 +295,8 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
     (void)K;
     p.out = epi.out; p.ldo = epi.ldo; p.bias = epi.bias; p.scale = epi.scale; p.shift = epi.shift;
     p.stats = epi.stats;
+    p.head_w = epi.head_w; p.head_b = epi.head_b; p.head_logits = epi.head_logits;
+    p.head_mask = epi.head_mask; p.head_nc = epi.head_nc; p.head_hw = Ho * Wo;
     if (epi.kind == EPI_CONVT) {
         p.out = (__nv_bfloat16*)epi.ct_dst.ptr;
         p.ct_cout = ncols / 4; p.ct_H = src0.H; p.ct_W = src0.W;

@@ -14,7 +14,13 @@
 
 namespace ub {
 
-enum : int { EPI_CONV_STATS = 0, EPI_STORE = 1, EPI_AFFINE_RELU = 2, EPI_CONVT = 3 };
+// EPI_AFFINE_RELU_HEAD (eval, last conv unit, Cout = 64): folded BN + ReLU followed by the 1x1 output
+// convolution and the z1 > z0 mask in the SAME epilogue — every epilogue thread holds one pixel's 64
+// activations, so the logits are 64 FMAs per class and the activation tensor is never written
+// (reference models/unet_model.py:56-63,145; scripts/predict.py:85-92).
+enum : int { EPI_CONV_STATS = 0, EPI_STORE = 1, EPI_AFFINE_RELU = 2, EPI_CONVT = 3,
+             EPI_AFFINE_RELU_HEAD = 4 };
+constexpr int HEAD_EPI_MAX_CLASSES = 8;
 
 struct IgemmParams {
     int M;               // GEMM rows = base pixels = N*Ho*Wo
@@ -30,6 +36,12 @@ struct IgemmParams {
     const float* scale;  // EPI_AFFINE_RELU: y = relu(acc*scale + shift)
     const float* shift;
     float* stats;        // EPI_CONV_STATS: [gridDim.x][2][BN] per-CTA partial (sum, sumsq)
+    // EPI_AFFINE_RELU_HEAD: head weights [nc][64] + bias [nc] (fp32), logits NCHW fp32, u8 mask
+    const float* head_w;
+    const float* head_b;
+    float* head_logits;
+    unsigned char* head_mask;   // may be null
+    int head_nc, head_hw;       // classes, pixels per image (Ho*Wo)
     // EPI_CONVT: GEMM column = q*ct_cout + co, q = dy*2+dx; row = (n,h,w) of the input
     int ct_cout, ct_H, ct_W;
     long long ct_sN, ct_sH, ct_sW;  // element strides of the destination [N,2H,2W,*] view
@@ -46,7 +58,8 @@ struct IgemmCfg {
     static constexpr int STAGES = (CG == 2) ? (BN == 256 ? 6 : 8)
                                             : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
     static constexpr int BAR_BYTES = 256;
-    static constexpr int STAT_BYTES = 4 * 2 * BN * 4;   // BN-statistics rows of the 4 lane quadrants
+    // epilogue scratch: BN-statistics rows of the 4 lane quadrants, or the fused head's weights
+    static constexpr int STAT_BYTES = (BN == 64) ? 2304 : 4 * 2 * BN * 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + 1024;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
@@ -98,7 +111,8 @@ template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t trow, long long m,
                                               bool valid, int n0, int lane, int chalf,
                                               float (&ssum)[EpiCfg<BN>::NCH],
-                                              float (&ssq)[EpiCfg<BN>::NCH]) {
+                                              float (&ssq)[EpiCfg<BN>::NCH],
+                                              const float* hs = nullptr) {
                 long long ct_row = 0;
                 if (EPI == EPI_CONVT) {
                     const int w = (int)(m % p.ct_W);
@@ -106,6 +120,11 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                     const int h = (int)(t % p.ct_H);
                     const long long n = t / p.ct_H;
                     ct_row = n * p.ct_sN + (long long)(2 * h) * p.ct_sH + (long long)(2 * w) * p.ct_sW;
+                }
+                float hacc[HEAD_EPI_MAX_CLASSES];
+                if (EPI == EPI_AFFINE_RELU_HEAD) {
+    #pragma unroll
+                    for (int hc = 0; hc < HEAD_EPI_MAX_CLASSES; ++hc) hacc[hc] = 0.f;
                 }
     #pragma unroll
                 for (int cl = 0; cl < EpiCfg<BN>::NCH; ++cl) {
@@ -117,16 +136,36 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                     float v[32];
     #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (EPI == EPI_AFFINE_RELU) {
+                    if (EPI == EPI_AFFINE_RELU || EPI == EPI_AFFINE_RELU_HEAD) {
     #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             v[i] = fmaxf(fmaf(v[i], __ldg(p.scale + col0 + i), __ldg(p.shift + col0 + i)),
                                          0.f);
+                        if (EPI == EPI_AFFINE_RELU_HEAD) {
+                            // BN = 64: this thread sees all 64 channels of its pixel over the two chunks
+    #pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));   // as it would be stored
+    #pragma unroll
+                            for (int hc = 0; hc < HEAD_EPI_MAX_CLASSES; ++hc) {
+                                if (hc < p.head_nc) {
+                                    const float4* w4 = reinterpret_cast<const float4*>(hs + hc * 64 + c * 32);
+    #pragma unroll
+                                    for (int i4 = 0; i4 < 8; ++i4) {
+                                        const float4 wv = w4[i4];
+                                        hacc[hc] = fmaf(v[4 * i4 + 0], wv.x, hacc[hc]);
+                                        hacc[hc] = fmaf(v[4 * i4 + 1], wv.y, hacc[hc]);
+                                        hacc[hc] = fmaf(v[4 * i4 + 2], wv.z, hacc[hc]);
+                                        hacc[hc] = fmaf(v[4 * i4 + 3], wv.w, hacc[hc]);
+                                    }
+                                }
+                            }
+                        }
                     } else if (p.bias != nullptr) {
     #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col0 + i);
                     }
-                    if (valid) {
+                    if (valid && EPI != EPI_AFFINE_RELU_HEAD) {
                         __nv_bfloat16* dst;
                         if (EPI == EPI_CONVT) {
                             const int qd = col0 / p.ct_cout;
@@ -158,6 +197,29 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                         ssq[cl] += warp_column_sum(s2, lane);
                     }
                 }
+                if (EPI == EPI_AFFINE_RELU_HEAD && valid) {
+                    // consecutive lanes = consecutive pixels: coalesced NCHW logits / mask stores
+                    const long long n = m / p.head_hw, hw = m % p.head_hw;
+    #pragma unroll
+                    for (int hc = 0; hc < HEAD_EPI_MAX_CLASSES; ++hc) {
+                        if (hc < p.head_nc) {
+                            hacc[hc] += hs[HEAD_EPI_MAX_CLASSES * 64 + hc];
+                            p.head_logits[(n * p.head_nc + hc) * p.head_hw + hw] = hacc[hc];
+                        }
+                    }
+                    if (p.head_mask) p.head_mask[m] = (p.head_nc >= 2 && hacc[1] > hacc[0]) ? 255 : 0;
+                }
+}
+
+// Head weights of EPI_AFFINE_RELU_HEAD -> shared memory: hs[c*64 + k] (c < 8), bias at hs[512 + c].
+template <int EPI>
+__device__ __forceinline__ void stage_head_weights(const IgemmParams& p, float* hs) {
+    if (EPI != EPI_AFFINE_RELU_HEAD) return;
+    for (int i = threadIdx.x; i < HEAD_EPI_MAX_CLASSES * 64; i += blockDim.x)
+        hs[i] = i < p.head_nc * 64 ? p.head_w[i] : 0.f;
+    for (int i = threadIdx.x; i < HEAD_EPI_MAX_CLASSES; i += blockDim.x)
+        hs[HEAD_EPI_MAX_CLASSES * 64 + i] = (p.head_b && i < p.head_nc) ? p.head_b[i] : 0.f;
+    __syncthreads();
 }
 
 template <int BN, int EPI, int CG>
@@ -208,6 +270,8 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_g;
     pdl_wait();   // prologue done; from here on global memory of the preceding kernels is read
+    float* hs = reinterpret_cast<float*>(gbase + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+    stage_head_weights<EPI>(p, hs);
 
     const int cchunks = p.cchunks0 + p.cchunks1;
     const int kblocks = p.taps * cchunks;
@@ -332,7 +396,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 
-            epilogue_tile<BN, EPI>(p, trow, m, valid, n0, lane, chalf, ssum, ssq);
+            epilogue_tile<BN, EPI>(p, trow, m, valid, n0, lane, chalf, ssum, ssq, hs);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

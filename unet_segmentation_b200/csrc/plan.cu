@@ -60,7 +60,10 @@ struct ub_plan {
     std::vector<void*> allocs;
     size_t bytes = 0;
     float* scratch = nullptr;   // stats / reduction partials
-    float* fused_logits = nullptr;  // training forward: logits written by the last BN-apply (fused head)
+    // logits written by the last unit itself: the last BN-apply kernel (training) or the last conv's
+    // epilogue (eval, 64 channels) — the separate head kernel is skipped
+    float* fused_logits = nullptr;
+    unsigned char* fused_mask = nullptr;
     double* fc_cov = nullptr;   // patch moments of the single-channel first conv (forward -> backward)
     float* wgrad_ws = nullptr;
     size_t wgrad_ws_floats = 0;
@@ -439,6 +442,13 @@ static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const Vie
     UB_TRY(launch_bn_fold_eval(u.Co, P->params[u.p_b], P->params[u.p_g], P->params[u.p_be],
                                P->rm[u.bn], P->rv[u.bn], P->eps, u.scale, u.shift, s));
     e.kind = EPI_AFFINE_RELU; e.out = u.a; e.scale = u.scale; e.shift = u.shift;
+    if (P->fused_logits && &u == &P->dec[P->L - 2].u[1]) {
+        // eval, last unit (64 channels): the 1x1 head and the mask come out of the conv epilogue
+        const int np = (int)P->params.size();
+        e.kind = EPI_AFFINE_RELU_HEAD;
+        e.head_w = P->params[np - 2]; e.head_b = P->params[np - 1];
+        e.head_logits = P->fused_logits; e.head_mask = P->fused_mask; e.head_nc = P->NC;
+    }
     {
         ProfScope ps(P, CLS_FPROP, fl, by, s);
         UB_TRY(launch_igemm(in0, in1, 0, -2, 1, 9, 3, u.wf, u.Co, e, &u.info, s));
@@ -465,7 +475,13 @@ int ub_plan_forward(ub_plan* P, const float* x, float* logits, uint8_t* mask, vo
     cudaStream_t s = (cudaStream_t)stream;
     P->x = x;
     const int L = P->L;
-    P->fused_logits = (P->training && bn_apply_head_supported(P->base, P->NC)) ? logits : nullptr;
+    static int fuse_eval = -1;
+    if (fuse_eval < 0) { const char* e = getenv("UB_FUSE_EVAL_HEAD"); fuse_eval = (e && !atoi(e)) ? 0 : 1; }
+    if (P->training)
+        P->fused_logits = bn_apply_head_supported(P->base, P->NC) ? logits : nullptr;
+    else
+        P->fused_logits = (fuse_eval && P->base == 64 && P->NC <= HEAD_EPI_MAX_CLASSES) ? logits : nullptr;
+    P->fused_mask = P->training ? nullptr : mask;
     for (int i = 0; i < L; ++i) UB_TRY(block_forward(P, P->enc[i], s));
     for (int j = 0; j < L - 1; ++j) {
         UpT& t = P->ups[j];

@@ -84,6 +84,12 @@ struct IgemmEpilogue {
     const float* shift;
     float* stats;             // EPI_CONV_STATS partials; layout reported through stats_* below
     View ct_dst;              // EPI_CONVT destination view [N,2H,2W,>=Cout] (ptr at channel 0)
+    // EPI_AFFINE_RELU_HEAD: 1x1 head weights [nc][64] / bias [nc]; logits NCHW fp32; optional mask
+    const float* head_w;
+    const float* head_b;
+    float* head_logits;
+    unsigned char* head_mask;
+    int head_nc;
 };
 struct IgemmLaunchInfo {
     int grid, n_tiles, BN, M;

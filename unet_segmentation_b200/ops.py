@@ -108,6 +108,19 @@ def bn_apply_relu(y, scale, shift, pool=False):
     return (a, p, am) if pool else (a, p)
 
 
+def conv3x3_affine_relu_head(src0, src1, wf, scale, shift, head_w, head_b, want_mask=True):
+    """Eval last unit: conv + folded BN + ReLU + 1x1 head (+ mask) in one kernel -> (logits, mask)."""
+    lib = _lib.load()
+    n, h, w, _ = src0.shape
+    nc = head_w.shape[0]
+    logits = torch.empty(n, nc, h - 2, w - 2, dtype=torch.float32, device=src0.device)
+    mask = torch.empty(n, h - 2, w - 2, dtype=torch.uint8, device=src0.device) if want_mask else None
+    check(lib.ub_op_conv3x3_affine_relu_head(_vp(src0), _vp(src1), _p(wf), _p(scale), _p(shift),
+                                             _p(head_w.contiguous()), _p(head_b), nc, _p(logits),
+                                             _p(mask), _stream()), "conv3x3_affine_relu_head")
+    return logits, mask
+
+
 def bn_apply_relu_head(y, scale, shift, head_w, head_b):
     """BN-apply + ReLU with the 1x1 head fused: returns (a bf16 NHWC, logits fp32 NCHW)."""
     lib = _lib.load()
