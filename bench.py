@@ -358,16 +358,31 @@ def main():
         dom = max(breakdown, key=lambda k: breakdown[k]["ms_per_step"])
         d = breakdown[dom]
         tensor_bound = d["tflops"] is not None
+        # DRAM traffic of that kernel class per launch, from the committed ncu --set full capture
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+                tj = json.load(fh)
+            if dom in tj:
+                traffic = tj[dom]["dram_bytes_per_launch"]
+                traffic_src = tj["source"]
+        except Exception:
+            pass
         if tensor_bound:
             peak = float(peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"])
             roofline = {"kernel": dom, "bound": "tensor", "achieved": d["tflops"], "peak": peak,
-                        "unit": "TFLOP/s", "frac": d["tflops"] / peak, "traffic": None,
+                        "unit": "TFLOP/s", "frac": d["tflops"] / peak, "traffic": traffic,
+                        "traffic_source": traffic_src,
+                        "launches_per_step": d["groups_per_step"],
+                        "algorithmic_bytes_per_launch": d["gbs"] * 1e9 * d["ms_per_step"] * 1e-3
+                        / d["groups_per_step"],
                         "peak_source": f"{peaks['_source']} sustained bf16 (kernel timed in-step)",
                         "share_of_step": d["ms_per_step"] / ms_per_step}
         else:
             peak = float(peaks["hbm_gbs"])
             roofline = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": peak,
-                        "unit": "GB/s", "frac": d["gbs"] / peak, "traffic": None,
+                        "unit": "GB/s", "frac": d["gbs"] / peak, "traffic": traffic,
+                        "traffic_source": traffic_src,
                         "peak_source": f"{peaks['_source']} HBM copy",
                         "share_of_step": d["ms_per_step"] / ms_per_step}
 
