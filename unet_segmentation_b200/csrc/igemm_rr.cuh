@@ -46,7 +46,7 @@ __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bo
 // 21 % of it.
 template <int BN, int CG = 1, bool WRES = false>
 struct RowRunCfg {
-    static constexpr int btaps(int bn, int cg) { return (bn <= 128 || cg == 2) ? 3 : 1; }
+    static constexpr int btaps(int bn, int cg) { return bn <= 128 ? 3 : 1; }
     static constexpr int BTAPS = btaps(BN, CG);
     static constexpr int ROW_BYTES = 130 * 128;            // input rows are packed back to back
     static constexpr int A_TX = 3 * ROW_BYTES;             // bytes one A stage receives (49920)
@@ -54,9 +54,12 @@ struct RowRunCfg {
     static constexpr int B_ROWS = BN / CG;                 // weight rows staged by one CTA
     static constexpr int B_TILE = B_ROWS * 128;            // one tap: [B_ROWS][64] K-major
     static constexpr int B_STAGE = BTAPS * B_TILE;
-    static constexpr int SA = (CG == 2) ? (BN == 256 ? 2 : 3) : ((BN == 64) ? 3 : 2);
+    // Ring depths. A B stage of a BN = 128 pair is only 12 MMAs x 64 cycles = 768 cycles of cover
+    // against ~1 us of TMA latency: with two stages the MMA warp waited for weights a third of the
+    // time (role profile), so that ring gets four stages and the A ring, which had slack, two.
+    static constexpr int SA = (CG == 2) ? (BN == 64 ? 3 : 2) : ((BN == 64) ? 3 : 2);
     static constexpr int SB = WRES ? 1
-                                   : ((CG == 2) ? (BN == 64 ? 4 : 2) : ((BN == 64) ? 3 : (BN == 128 ? 2 : 3)));
+                                   : ((CG == 2) ? (BN == 256 ? 6 : 4) : ((BN == 64) ? 3 : (BN == 128 ? 2 : 3)));
     static constexpr int B_AREA = WRES ? 9 * B_TILE : SB * B_STAGE;
     static constexpr int BAR_BYTES = 256;
     // epilogue scratch: BN-statistics rows of the 4 lane quadrants, or the fused head's weights
