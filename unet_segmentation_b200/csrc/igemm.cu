@@ -52,13 +52,19 @@ size_t igemm_stats_floats(int ncols) {
     return (size_t)num_sms() * 2 * bn;   // one [2][BN] row per CTA
 }
 
-bool pdl_enabled() {
-    static int on = -1;
-    // Off by default: with every edge of the step programmatic, early-resident CTAs of the next
+bool pdl_allow(bool gemm, unsigned blocks) {
+    // Default 0: with every edge of the step programmatic (mode 1), early-resident CTAs of the next
     // kernel take registers / thread slots from the HBM-bound kernels and the step got 1 % SLOWER
-    // (15.55 -> 15.75 ms, same box). UB_PDL=1 enables it for experiments.
-    if (on < 0) { const char* e = getenv("UB_PDL"); on = (e && atoi(e)) ? 1 : 0; }
-    return on != 0;
+    // (15.55 -> 15.75 ms, same box).
+    static int mode = -1;
+    static thread_local int last_kind = 0;   // 0 tiny, 1 large elementwise, 2 tensor-core kernel
+    if (mode < 0) { const char* e = getenv("UB_PDL"); mode = e ? atoi(e) : 0; }
+    const int kind = gemm ? 2 : (blocks >= (unsigned)num_sms() ? 1 : 0);
+    const int prev = last_kind;
+    last_kind = kind;
+    if (mode == 1) return true;
+    if (mode == 2) return !(kind == 2 && prev == 1);
+    return false;
 }
 // cta_group::2 pairs: on unless UB_PAIR=0
 static bool pairs_enabled() {

@@ -47,7 +47,10 @@ long long launch_count();
 
 // Kernel launch with programmatic dependent launch (see common.cuh: pdl_*) and an optional
 // 2-CTA cluster (cta_group::2 pairs). UB_PDL=0 launches with plain stream serialization.
-bool pdl_enabled();
+// pdl_allow(): may this launch start while its predecessor drains? (UB_PDL: 0 never, 1 always,
+// 2 = every edge except a tensor-core kernel following a large elementwise kernel, whose early
+// resident CTAs (352 threads, ~47 K registers, 200 KB smem) would cut the elementwise occupancy.)
+bool pdl_allow(bool gemm, unsigned blocks);
 template <typename... KArgs, typename... Args>
 inline cudaError_t ub_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                              cudaStream_t stream, int cluster, Args&&... args) {
@@ -62,7 +65,7 @@ inline cudaError_t ub_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
         attr[n].val.clusterDim.z = 1;
         ++n;
     }
-    if (pdl_enabled()) {
+    if (pdl_allow(smem > 100 * 1024, grid.x * grid.y)) {   // the tensor-core kernels use > 100 KB smem
         attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;
