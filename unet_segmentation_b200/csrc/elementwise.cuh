@@ -354,8 +354,8 @@ struct BnBwdArgs {
     __nv_bfloat16* dy;       // apply: [N,H,W,C]
 };
 
-// PIX (POOL_SKIP only): the forward saved the pool arg-max, so the kernel runs per pixel like the
-// DIRECT path instead of recomputing whole 2x2 windows.
+// PIX (POOL_SKIP only): the forward saved the pool arg-max byte, so the window's winner is decoded
+// instead of being recomputed from y (one thread = one 2x2 window x 8 channels in both variants).
 template <bool POOL_SKIP, bool APPLY, bool PIX = false>
 static __global__ void __launch_bounds__(256, 2)
 bn_bwd_kernel(const BnBwdArgs A) {
@@ -399,69 +399,69 @@ bn_bwd_kernel(const BnBwdArgs A) {
     };
 
     if (POOL_SKIP && PIX) {
-        const unsigned npix = (unsigned)A.N * H * W;
+        // One thread = one 2x2 pooling window x 8 channels (arg-max saved by the forward pass): the
+        // pooled gradient and the arg-max byte are loaded and decoded ONCE per window instead of once
+        // per pixel, and the window coordinates advance incrementally (no division in the loop).
         const unsigned Hp = H >> 1, Wp = W >> 1;
+        const unsigned HW2 = (H + 1) >> 1, WW2 = (W + 1) >> 1;   // windows incl. the odd last row / col
+        const unsigned nwin = (unsigned)A.N * HW2 * WW2;
         const __nv_bfloat16* gpb = reinterpret_cast<const __nv_bfloat16*>(A.gp.ptr);
         const __nv_bfloat16* gsb = reinterpret_cast<const __nv_bfloat16*>(A.gs.ptr);
-        // (w, h, n) of the thread's current pixel is advanced incrementally by the grid stride:
-        // no integer division in the loop (it made this kernel issue-bound, 2.7 TB/s).
-        const unsigned dW = gstride % W, dH = (gstride / W) % H, dN = (gstride / W) / H;
-        unsigned w = first % W, h = (first / W) % H, n = (first / W) / H;
-        for (unsigned p0 = first; p0 < npix; p0 += 4 * gstride) {
-            uint4 yr[4], gpr[4], gsr[4];
-            uint2 amr[4];
-            bool full[4], ins[4];
-            unsigned dsel[4];
+        const unsigned dWq = gstride % WW2, dHq = (gstride / WW2) % HW2, dN = (gstride / WW2) / HW2;
+        unsigned wq = first % WW2, hq = (first / WW2) % HW2, n = (first / WW2) / HW2;
+        for (unsigned wi = first; wi < nwin; wi += gstride) {
+            uint4 yr[4], gsr[4], gpr;
+            uint2 amr;
+            bool inb[4], ins[4];
+            size_t pix[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const unsigned p = p0 + j * gstride;
-                full[j] = false; ins[j] = false;
-                if (p < npix) {
-                    yr[j] = ldg16(A.y + (size_t)p * C + cg * 8);
-                    const unsigned hq = h >> 1, wq = w >> 1;
-                    dsel[j] = ((h & 1u) << 1) | (w & 1u);
-                    full[j] = hq < Hp && wq < Wp;
-                    if (full[j]) {
-                        gpr[j] = ldg16(gpb + (size_t)(n * A.gp.sN + hq * A.gp.sH + wq * A.gp.sW) + cg * 8);
-                        amr[j] = __ldg(reinterpret_cast<const uint2*>(
-                            A.amax + ((size_t)(n * Hp + hq) * Wp + wq) * C + cg * 8));
-                    }
-                    const int hs = (int)h - A.crop_h, ws = (int)w - A.crop_w;
-                    ins[j] = A.has_skip && hs >= 0 && hs < A.gs.H && ws >= 0 && ws < A.gs.W;
-                    if (ins[j])
-                        gsr[j] = ldg16(gsb + (size_t)(n * A.gs.sN + hs * A.gs.sH + ws * A.gs.sW) + cg * 8);
-                }
-                // advance to pixel p + gstride
-                w += dW;
-                const unsigned cw = w >= W ? 1u : 0u;
-                w -= cw ? W : 0u;
-                h += dH + cw;
-                const unsigned chh = h >= H ? 1u : 0u;
-                h -= chh ? H : 0u;
-                n += dN + chh;
+            for (int d = 0; d < 4; ++d) {
+                const unsigned h = hq * 2 + (d >> 1), w = wq * 2 + (d & 1);
+                inb[d] = h < H && w < W;
+                pix[d] = (size_t)(n * H + h) * W + w;
+                if (inb[d]) yr[d] = ldg16(A.y + pix[d] * C + cg * 8);
+                const int hs = (int)h - A.crop_h, ws = (int)w - A.crop_w;
+                ins[d] = inb[d] && A.has_skip && hs >= 0 && hs < A.gs.H && ws >= 0 && ws < A.gs.W;
+                if (ins[d])
+                    gsr[d] = ldg16(gsb + (size_t)(n * A.gs.sN + hs * A.gs.sH + ws * A.gs.sW) + cg * 8);
+            }
+            const bool full = hq < Hp && wq < Wp;
+            if (full) {
+                gpr = ldg16(gpb + (size_t)(n * A.gp.sN + hq * A.gp.sH + wq * A.gp.sW) + cg * 8);
+                amr = __ldg(reinterpret_cast<const uint2*>(
+                    A.amax + ((size_t)(n * Hp + hq) * Wp + wq) * C + cg * 8));
+            }
+            Vec8 gpv;
+            unsigned a8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { gpv.v[k] = 0.f; a8[k] = 0xFFu; }
+            if (full) {
+                gpv = unpack8(gpr);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a8[k] = ((k < 4 ? amr.x : amr.y) >> (8 * (k & 3))) & 0xFFu;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const unsigned p = p0 + j * gstride;
-                if (p < npix) {
-                    Vec8 gv;
-                    if (ins[j]) {
-                        gv = unpack8(gsr[j]);
-                    } else {
+            for (int d = 0; d < 4; ++d) {
+                if (!inb[d]) continue;
+                Vec8 gv;
+                if (ins[d]) {
+                    gv = unpack8(gsr[d]);
+                } else {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) gv.v[k] = 0.f;
-                    }
-                    if (full[j]) {
-                        const Vec8 gpv = unpack8(gpr[j]);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const unsigned a8 = ((k < 4 ? amr[j].x : amr[j].y) >> (8 * (k & 3))) & 0xFFu;
-                            if (a8 == dsel[j]) gv.v[k] += gpv.v[k];
-                        }
-                    }
-                    process((size_t)p, unpack8(yr[j]), gv);
+                    for (int k = 0; k < 8; ++k) gv.v[k] = 0.f;
                 }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) gv.v[k] += (a8[k] == (unsigned)d) ? gpv.v[k] : 0.f;
+                process(pix[d], unpack8(yr[d]), gv);
             }
+            // advance to window wi + gstride
+            wq += dWq;
+            const unsigned cw = wq >= WW2 ? 1u : 0u;
+            wq -= cw ? WW2 : 0u;
+            hq += dHq + cw;
+            const unsigned chh = hq >= HW2 ? 1u : 0u;
+            hq -= chh ? HW2 : 0u;
+            n += dN + chh;
         }
     } else if (!POOL_SKIP) {
         const unsigned npix = (unsigned)A.N * H * W;

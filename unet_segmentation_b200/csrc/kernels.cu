@@ -145,8 +145,8 @@ int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
     A.dgamma = d.dgamma; A.dbeta = d.dbeta; A.dy = d.dy;
     const long long count = (long long)d.N * d.H * d.W;
     A.inv_count = (float)(1.0 / (double)count);
-    const bool pix = d.pool_skip && d.amax != nullptr;
-    const long long items = (d.pool_skip && !pix)
+    const bool pix = d.pool_skip && d.amax != nullptr;   // saved arg-max available
+    const long long items = d.pool_skip
                                 ? (long long)d.N * ((d.H + 1) / 2) * ((d.W + 1) / 2) * (d.C / 8)
                                 : count * (d.C / 8);
     const int blocks = red_blocks(items, 2);   // = resident CTAs (launch bounds 256 x 2): one wave
