@@ -362,16 +362,19 @@ bn_bwd_kernel(const BnBwdArgs A) {
     pdl_entry();
     const unsigned C = A.C, CG = C >> 3, H = A.H, W = A.W;
     const unsigned cg = threadIdx.x % CG;  // host guarantees 256 % CG == 0
-    float sc[8], sh[8], mu[8], rs[8], kb[8], kg[8];
+    // Per-channel constants folded so that the inner loop is 5-6 instructions per element:
+    //   reduce: dyh = g*[y*sc+sh > 0];  sum dyh;  sum dyh*(y - mean)   (rstd applied by the finalisation)
+    //   apply:  dy = sc*(dyh - dbeta/n - xhat*dgamma/n) = sc*dyh - (c1 + c2*y),
+    //           c2 = sc*rstd*dgamma/n,  c1 = sc*dbeta/n - c2*mean
+    float sc[8], sh[8], mu[8], c1[8], c2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         sc[k] = A.scale[cg * 8 + k];
         sh[k] = A.shift[cg * 8 + k];
         mu[k] = A.mean[cg * 8 + k];
-        rs[k] = A.rstd[cg * 8 + k];
         if (APPLY) {
-            kb[k] = A.dbeta[cg * 8 + k] * A.inv_count;
-            kg[k] = A.dgamma[cg * 8 + k] * A.inv_count;
+            c2[k] = sc[k] * A.rstd[cg * 8 + k] * (A.dgamma[cg * 8 + k] * A.inv_count);
+            c1[k] = sc[k] * (A.dbeta[cg * 8 + k] * A.inv_count) - c2[k] * mu[k];
         }
     }
     float acc_b[8], acc_g[8];
@@ -387,12 +390,11 @@ bn_bwd_kernel(const BnBwdArgs A) {
         for (int k = 0; k < 8; ++k) {
             const float act = fmaf(yv.v[k], sc[k], sh[k]);
             const float dyh = act > 0.f ? gv.v[k] : 0.f;
-            const float xh = (yv.v[k] - mu[k]) * rs[k];
             if (APPLY) {
-                o.v[k] = sc[k] * (dyh - kb[k] - xh * kg[k]);
+                o.v[k] = fmaf(sc[k], dyh, -fmaf(c2[k], yv.v[k], c1[k]));
             } else {
                 acc_b[k] += dyh;
-                acc_g[k] = fmaf(dyh, xh, acc_g[k]);
+                acc_g[k] = fmaf(dyh, yv.v[k] - mu[k], acc_g[k]);
             }
         }
         if (APPLY) *reinterpret_cast<uint4*>(A.dy + pix * C + cg * 8) = pack8(o);
@@ -575,10 +577,13 @@ bn_bwd_kernel(const BnBwdArgs A) {
     }
 }
 
-// dbeta/dgamma = sum over blocks of the partials (fixed order => deterministic).
+// dbeta = sum over blocks of the first partial, dgamma = rstd * (sum of the second) — the reduce pass
+// accumulates dyh*(y - mean); `rstd` null = the partials already hold dyh*xhat (first-conv path).
+// Fixed order => deterministic.
 static __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C,
-                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                       const float* __restrict__ rstd, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta) {
     pdl_entry();
     const int c = blockIdx.x * 32 + threadIdx.x;
     double b = 0.0, g = 0.0;
@@ -591,7 +596,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C,
     finalize_combine(b, g);
     if (threadIdx.y == 0 && c < C) {
         dbeta[c] = (float)b;
-        dgamma[c] = (float)g;
+        dgamma[c] = (float)(rstd ? g * (double)rstd[c] : g);
     }
 }
 

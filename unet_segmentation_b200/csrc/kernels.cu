@@ -154,7 +154,7 @@ int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
     else if (d.pool_skip) UB_LAUNCH_NC((bn_bwd_kernel<true, false>), blocks, 256, 0, s, A);
     else UB_LAUNCH_NC((bn_bwd_kernel<false, false>), blocks, 256, 0, s, A);
     UB_POST_LAUNCH();
-    UB_LAUNCH_NC(bn_bwd_finalize_kernel, (d.C + 31) / 32, dim3(32, FIN_SLICES), 0, s, d.partial, blocks, d.C, d.dgamma, d.dbeta);
+    UB_LAUNCH_NC(bn_bwd_finalize_kernel, (d.C + 31) / 32, dim3(32, FIN_SLICES), 0, s, d.partial, blocks, d.C, d.rstd, d.dgamma, d.dbeta);
     UB_POST_LAUNCH();
     const int ablocks = ew_blocks(items);
     if (pix) UB_LAUNCH_NC((bn_bwd_kernel<true, true, true>), ablocks, 256, 0, s, A);
@@ -283,7 +283,7 @@ int launch_first_conv_bwd(const FirstConvDesc& d, const float* scale, const floa
     A.partial = ws;
     int blocks = red_blocks(items);
     UB_TRY(fc_launch<FC_BWD_REDUCE>(A, blocks, s));
-    UB_LAUNCH_NC(bn_bwd_finalize_kernel, (d.Co + 31) / 32, dim3(32, FIN_SLICES), 0, s, ws, blocks, d.Co, dgamma, dbeta);
+    UB_LAUNCH_NC(bn_bwd_finalize_kernel, (d.Co + 31) / 32, dim3(32, FIN_SLICES), 0, s, ws, blocks, d.Co, (const float*)nullptr, dgamma, dbeta);
     UB_POST_LAUNCH();
     A.dgamma = dgamma; A.dbeta = dbeta; A.inv_count = (float)(1.0 / (double)count);
     A.wpartial = ws;
