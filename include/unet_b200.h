@@ -131,6 +131,19 @@ int ub_scale_by_device_scalar(const float* in, const float* scalar, float* out, 
                               void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Device-side input pipeline. One pass over a compactly transferred batch:
+ *   image_f32[N][1][H][W] = images_u8 / 255            (ToTensor, utils/dataset.py:92-94)
+ *   target[N][out_h][out_w] = (labels > 0) as int64      (utils/dataset.py:96-105), centre-cropped
+ *   weight[N][out_h][out_w] = (float)weight_maps         (utils/dataset.py:110), centre-cropped like
+ *                             center_crop_tensor (scripts/train.py:39-51,118-126)
+ * labels: uint8 (label_bytes 1) or uint16 (2), may be NULL; weight_maps: float32 (4) or float64
+ * (8), may be NULL. W must be a multiple of 4. Bit-exact against the torch ops it replaces.
+ * ---------------------------------------------------------------------------------------------- */
+int ub_prepare_batch(const uint8_t* images_u8, const void* labels, int label_bytes,
+                     const void* weight_maps, int weight_bytes, int N, int H, int W, int out_h,
+                     int out_w, float* image_f32, int64_t* target, float* weight, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * get_instance_masks (utils/metrics.py:42-72): 8-connected labelling in raster order, components
  * smaller than min_size zeroed, ids not compacted, uint16 output. Bit-exact.
  * ---------------------------------------------------------------------------------------------- */

@@ -429,3 +429,35 @@ def test_conv3x3_eval_fused_head(ops, n, h, w, ci, nc):
     margin = (logits2[:, 1] - logits2[:, 0]).abs() if nc >= 2 else None
     if nc >= 2:
         assert torch.equal(mask[margin > 1e-4], mask2[margin > 1e-4])
+
+
+@pytest.mark.parametrize("n,h,w,oh,lbl_dtype,w_dtype", [(2, 36, 40, 20, torch.uint8, torch.float32),
+                                                         (3, 64, 52, 40, torch.uint16, torch.float64),
+                                                         (1, 512, 512, 324, torch.uint16, torch.float64)])
+def test_device_input_pipeline(n, h, w, oh, lbl_dtype, w_dtype):
+    """uint8 frame / instance mask / stored weight map -> (image, target, weights)
+    bit-exactly as the reference builds them (utils/dataset.py:92-110, scripts/train.py:39-51,118-126)."""
+    from unet_segmentation_b200 import input_pipeline
+    g = torch.Generator().manual_seed(11)
+    img = torch.randint(0, 256, (n, h, w), generator=g, dtype=torch.uint8)
+    lbl = (torch.randint(0, 700, (n, h, w), generator=g) * (torch.rand(n, h, w, generator=g) > 0.5))
+    lbl = lbl.to(torch.int32).clamp(0, 255 if lbl_dtype == torch.uint8 else 65535).to(lbl_dtype)
+    wm = (10 + torch.rand(n, h, w, generator=g, dtype=torch.float64) * 3).to(w_dtype)
+    image, target, weight = input_pipeline.prepare_batch(img.cuda(), lbl.cuda(), wm.cuda(), (oh, oh))
+    # the reference's host pipeline + device crop
+    ref_img = img.float().div(255).unsqueeze(1)
+    ref_t = (lbl.to(torch.int32) > 0).long().unsqueeze(1)
+    ref_w = wm.float().unsqueeze(1)
+    s0h, s0w = max(0, (h - oh) // 2), max(0, (w - oh) // 2)
+    ref_t = ref_t[:, :, s0h:s0h + oh, s0w:s0w + oh].squeeze(1)
+    ref_w = ref_w[:, :, s0h:s0h + oh, s0w:s0w + oh].squeeze(1)
+    torch.cuda.synchronize()
+    assert torch.equal(image.cpu(), ref_img)
+    assert target.dtype == torch.int64 and torch.equal(target.cpu(), ref_t)
+    assert weight.dtype == torch.float32 and torch.equal(weight.cpu(), ref_w)
+    # double-buffered staging from pinned host memory gives the same tensors
+    prep = input_pipeline.DeviceBatchPreparer("cuda", (oh, oh))
+    k = prep.submit(img.pin_memory(), lbl.pin_memory(), wm.pin_memory())
+    image2, target2, weight2 = prep.get(k)
+    torch.cuda.synchronize()
+    assert torch.equal(image2, image) and torch.equal(target2, target) and torch.equal(weight2, weight)

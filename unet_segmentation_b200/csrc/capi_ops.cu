@@ -52,6 +52,12 @@ int ub_scale_by_device_scalar(const float* in, const float* scalar, float* out, 
     return launch_scale_by_scalar(in, scalar, out, n, S(stream));
 }
 
+int ub_prepare_batch(const uint8_t* images_u8, const void* labels, int label_bytes,
+                     const void* weight_maps, int weight_bytes, int N, int H, int W, int out_h,
+                     int out_w, float* image_f32, int64_t* target, float* weight, void* stream) {
+    return launch_prepare_batch(images_u8, labels, label_bytes, weight_maps, weight_bytes, N, H, W,
+                                out_h, out_w, image_f32, (long long*)target, weight, S(stream));
+}
 int64_t ub_ccl_workspace_bytes(int H, int W) { return (int64_t)ccl_ws_bytes(H, W); }
 int ub_ccl_label(const uint8_t* mask, int H, int W, int min_size, uint16_t* labels, void* workspace,
                  void* stream) {

@@ -4,6 +4,7 @@
 #include "elementwise.cuh"
 #include "first_conv.cuh"
 #include "head_loss.cuh"
+#include "input_pipeline.cuh"
 #include "igemm.cuh"
 #include "ub_internal.h"
 
@@ -373,6 +374,33 @@ int launch_scale_by_scalar(const float* in, const float* scalar, float* out, lon
 int launch_fill_zero(float* p, long long n, cudaStream_t s) {
     if (n <= 0) return UB_OK;
     UB_LAUNCH_NC(fill_zero_kernel, ew_blocks(n), 256, 0, s, p, n);
+    UB_POST_LAUNCH();
+    return UB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int launch_prepare_batch(const unsigned char* img, const void* labels, int label_bytes,
+                         const void* wmap, int wmap_bytes, int N, int H, int W, int oh, int ow,
+                         float* image, long long* target, float* weight, cudaStream_t s) {
+    if (!img || !image || N < 1 || H < 1 || W < 4 || W % 4 != 0) {
+        set_last_error("prepare_batch: need uint8 images with a width that is a multiple of 4");
+        return UB_ERR_ARG;
+    }
+    if (oh < 0 || ow < 0 || oh > H || ow > W || (labels && !target) || (wmap && !weight) ||
+        (labels && label_bytes != 1 && label_bytes != 2) || (wmap && wmap_bytes != 4 && wmap_bytes != 8)) {
+        set_last_error("prepare_batch: bad crop size or label / weight-map element size");
+        return UB_ERR_ARG;
+    }
+    if ((long long)N * H * W >= 0x7FFFFFFFLL) {
+        set_last_error("prepare_batch: batch too large for 32-bit indexing");
+        return UB_ERR_UNSUPPORTED;
+    }
+    PrepArgs A;
+    A.img = img; A.labels = labels; A.wmap = wmap; A.label_bytes = label_bytes; A.wmap_bytes = wmap_bytes;
+    A.N = N; A.H = H; A.W = W; A.oh = oh; A.ow = ow;
+    A.h0 = (H - oh) / 2; A.w0 = (W - ow) / 2;   // center_crop_tensor, scripts/train.py:39-51
+    A.image = image; A.target = target; A.weight = weight;
+    UB_LAUNCH_NC(prepare_batch_kernel, ew_blocks((long long)N * H * (W / 4)), 256, 0, s, A);
     UB_POST_LAUNCH();
     return UB_OK;
 }

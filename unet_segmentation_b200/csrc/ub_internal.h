@@ -200,6 +200,9 @@ int launch_scale_by_scalar(const float* in, const float* scalar, float* out, lon
                            cudaStream_t s);
 int launch_fill_zero(float* p, long long n, cudaStream_t s);
 
+int launch_prepare_batch(const unsigned char* img, const void* labels, int label_bytes,
+                         const void* wmap, int wmap_bytes, int N, int H, int W, int oh, int ow,
+                         float* image, long long* target, float* weight, cudaStream_t s);
 size_t ccl_ws_bytes(int H, int W);
 int launch_ccl(const unsigned char* mask, int H, int W, int min_size, unsigned short* out, void* ws,
                cudaStream_t s);
