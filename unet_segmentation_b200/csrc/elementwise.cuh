@@ -647,41 +647,47 @@ static __global__ void tile_bias4_kernel(const float* __restrict__ b, int Co, fl
 // (cols % 32 == 0, RC % 8 == 0):
 //   ws[split][row = tap*RC + rc][col]  ->  out[(col*RC + rc)*T + tap]
 //   conv3x3: RC = Ci, col = co, T = 9;   convT2x2: RC = Co, col = ci, T = 4
-// One block = 32 columns x 8 `rc` values x all T taps; blockDim = (32, 8). Thread (tx, ty) sums, over
-// the splits, the T values of (col0+tx, rc0+ty) — reads are coalesced along the columns and the T
-// chains are independent — then the block transposes through shared memory so that the torch-layout
-// rows out[col][rc0..rc0+8)[0..T) (8*T contiguous floats per column) are written with full sectors.
+// One block = 32 columns x 8 `rc` values x all T taps; blockDim = (32, 8, WGR_SLICES). Thread
+// (tx, ty, tz) sums, over every WGR_SLICES-th split, the T values of (col0+tx, rc0+ty) — reads are
+// coalesced along the columns, the T chains are independent and the split loop (a chain of dependent
+// load -> add steps) is cut WGR_SLICES ways — then the block combines the slices and transposes
+// through shared memory so that the torch-layout rows out[col][rc0..rc0+8)[0..T) (8*T contiguous
+// floats per column) are written with full sectors. Fixed summation order: deterministic.
+constexpr int WGR_SLICES = 4;
 template <int T>
-static __global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256 * WGR_SLICES)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long split_stride, int cols,
                     int RC, float* __restrict__ out, float* zero0, int nzero0, float* zero1,
                     int nzero1) {
     pdl_entry();
-    __shared__ float sm[32][8 * T + 1];
-    const int tx = threadIdx.x, ty = threadIdx.y;
+    __shared__ float sm[WGR_SLICES][32][8 * T + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+    const int tid = (tz * 8 + ty) * 32 + tx;
     if (blockIdx.x == 0 && blockIdx.y == 0) {
         // bias gradients that are analytically zero in training mode (a bias ahead of a BatchNorm is
         // removed by the mean subtraction) are cleared here instead of by extra launches
-        for (int i = ty * 32 + tx; i < nzero0; i += 256) zero0[i] = 0.f;
-        for (int i = ty * 32 + tx; i < nzero1; i += 256) zero1[i] = 0.f;
+        for (int i = tid; i < nzero0; i += 256 * WGR_SLICES) zero0[i] = 0.f;
+        for (int i = tid; i < nzero1; i += 256 * WGR_SLICES) zero1[i] = 0.f;
     }
     const int col0 = blockIdx.x * 32, rc0 = blockIdx.y * 8;
     float acc[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.f;
     const float* base = ws + (long long)(rc0 + ty) * cols + col0 + tx;
-    for (int k = 0; k < splits; ++k) {
+    for (int k = tz; k < splits; k += WGR_SLICES) {
         const float* p = base + (long long)k * split_stride;
 #pragma unroll
         for (int t = 0; t < T; ++t) acc[t] += __ldg(p + (long long)t * RC * cols);
     }
 #pragma unroll
-    for (int t = 0; t < T; ++t) sm[tx][ty * T + t] = acc[t];
+    for (int t = 0; t < T; ++t) sm[tz][tx][ty * T + t] = acc[t];
     __syncthreads();
-    const int tid = ty * 32 + tx;
-    for (int i = tid; i < 32 * 8 * T; i += 256) {
+    for (int i = tid; i < 32 * 8 * T; i += 256 * WGR_SLICES) {
         const int c = i / (8 * T), r = i % (8 * T);
-        out[((long long)(col0 + c) * RC + rc0) * T + r] = sm[c][r];
+        float v = sm[0][c][r];
+#pragma unroll
+        for (int z = 1; z < WGR_SLICES; ++z) v += sm[z][c][r];
+        out[((long long)(col0 + c) * RC + rc0) * T + r] = v;
     }
 }
 

@@ -439,9 +439,9 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
     UB_TRY(rc);
     const dim3 rgrid(cols / 32, ctot / 8);
     if (taps == 9)
-        UB_LAUNCH_NC((wgrad_reduce_kernel<9>), rgrid, dim3(32, 8), 0, stream, ws, splits, p.split_stride, cols, ctot, out, zero0, nzero0, zero1, nzero1);
+        UB_LAUNCH_NC((wgrad_reduce_kernel<9>), rgrid, dim3(32, 8, WGR_SLICES), 0, stream, ws, splits, p.split_stride, cols, ctot, out, zero0, nzero0, zero1, nzero1);
     else if (taps == 4)
-        UB_LAUNCH_NC((wgrad_reduce_kernel<4>), rgrid, dim3(32, 8), 0, stream, ws, splits, p.split_stride, cols, ctot, out, zero0, nzero0, zero1, nzero1);
+        UB_LAUNCH_NC((wgrad_reduce_kernel<4>), rgrid, dim3(32, 8, WGR_SLICES), 0, stream, ws, splits, p.split_stride, cols, ctot, out, zero0, nzero0, zero1, nzero1);
     else {
         set_last_error("wgrad: unsupported tap count %d", taps);
         return UB_ERR_UNSUPPORTED;
