@@ -447,6 +447,9 @@ def main():
                                      "refresh in one kernel), inside the step" if args.optimizer == "fused"
                                      else "SGD(lr=1e-4, momentum=0.99) torch foreach, inside the step"),
                        "bn": "per-rank batch statistics", "l2": "per-step working set 11 GB >> 126 MB L2",
+                       "streams": "weight gradients on an internal side stream, overlapping the "
+                                  "BN-backward / data-gradient chain (kernel_breakdown is measured "
+                                  "with that overlap off)",
                        "first_conv": "fp32 CUDA-core (SURVEY F4)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps},

@@ -109,6 +109,12 @@ int ub_plan_sgd_step(ub_plan* plan, const float* const* grads, float* const* mom
  * CUDA events on the launching stream; collect() synchronises them and returns, per kernel class
  * (ub_plan_profile_class_name), the summed duration [ms], algorithmic FLOPs / bytes and the number
  * of timed groups. Arrays hold ub_plan_profile_classes() entries. */
+/* Weight gradients run on an internal low-priority stream, concurrently with the BatchNorm-backward
+ * / data-gradient chain of the caller's stream. mode 0: off (everything on the caller's stream);
+ * 1 (default): joined at the end of every ub_plan_backward_stage call, so a stage's gradients are
+ * complete in stream order when it returns (data-parallel all-reduce hooks); 2: joined only at the
+ * end of the last stage (single-GPU training). */
+int ub_plan_set_overlap(ub_plan* plan, int mode);
 int64_t ub_launch_count(void);
 int ub_plan_profile_enable(ub_plan* plan, int on);
 int ub_plan_profile_classes(void);

@@ -71,6 +71,16 @@ struct ub_plan {
     const float* x = nullptr;   // input of the last forward (kept by the caller)
     bool packed = false;
     float momentum = 0.1f, eps = 1e-5f;
+    // Weight gradients run on a low-priority side stream: they are off the backward critical path
+    // (BN backward -> data gradient -> BN backward ...), tensor-bound, and small enough in registers
+    // (256 threads x 74) to share an SM with the HBM-bound BN-backward CTAs, so the two overlap.
+    //   overlap: 0 = everything on the caller's stream, 1 = join at the end of every backward stage
+    //   (a stage's gradients are complete when the call returns its work to the stream: what the
+    //   data-parallel all-reduce hook needs), 2 = join only at the end of the last stage.
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int overlap = 1;
+    bool side_used = false;
     // optional in-step kernel timing (CUDA events on the launching stream)
     struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
     bool prof_on = false;
@@ -92,6 +102,9 @@ struct ub_plan {
         return 0;
     }
     ~ub_plan() {
+        if (side) cudaStreamDestroy(side);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         for (void* q : allocs) cudaFree(q);
         for (auto& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     }
@@ -316,6 +329,17 @@ int ub_plan_create(ub_plan** out, int N, int n_channels, int H, int W, int base,
     if (int r = P->alloc(&P->scratch, scratch)) return fail(r);
     if (int r = P->alloc(&P->fc_cov, (size_t)FIRST_CONV_COV_DOUBLES)) return fail(r);
     if (P->training) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = lowest priority (numerically greatest)
+        if (cudaStreamCreateWithPriority(&P->side, cudaStreamNonBlocking, lo) != cudaSuccess ||
+            cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            set_last_error("plan: could not create the weight-gradient side stream");
+            cudaGetLastError();
+            return fail(ub::UB_ERR_CUDA);
+        }
+        const char* ov = getenv("UB_WGRAD_OVERLAP");
+        if (ov) P->overlap = atoi(ov);
         P->wgrad_ws_floats = wws;
         if (int r = P->alloc(&P->wgrad_ws, wws)) return fail(r);
         if (int r = P->alloc(&P->head_da, (size_t)N * P->outH * P->outW * base)) return fail(r);
@@ -529,6 +553,22 @@ int ub_plan_stage_params(const ub_plan* P, int stage, int* first, int* count) {
     return 0;
 }
 
+// Stream for a weight-gradient launch: the side stream, ordered after everything enqueued on `s` so
+// far (its inputs dy / d(concat) were just produced there), or `s` itself when overlap is off.
+static cudaStream_t wgrad_stream(ub_plan* P, cudaStream_t s) {
+    if (P->overlap == 0 || P->prof_on || !P->side) return s;
+    cudaEventRecord(P->ev_fork, s);
+    cudaStreamWaitEvent(P->side, P->ev_fork, 0);
+    P->side_used = true;
+    return P->side;
+}
+static void wgrad_join(ub_plan* P, cudaStream_t s) {
+    if (!P->side_used) return;
+    cudaEventRecord(P->ev_join, P->side);
+    cudaStreamWaitEvent(s, P->ev_join, 0);
+    P->side_used = false;
+}
+
 struct Upstream {
     bool pool_skip = false;
     View g{}, gp{}, gs{};
@@ -559,10 +599,11 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
     }
     View a0 = make_view(u0.a, N, u0.Ho(), u0.Wo(), u0.Co);
     {
-        ProfScope ps(P, CLS_WGRAD, fl1, 2.0 * (pi1 * u1.Ci + po1 * u1.Co) + 4.0 * 9 * u1.Ci * u1.Co, s);
+        cudaStream_t ws = wgrad_stream(P, s);
+        ProfScope ps(P, CLS_WGRAD, fl1, 2.0 * (pi1 * u1.Ci + po1 * u1.Co) + 4.0 * 9 * u1.Ci * u1.Co, ws);
         // both conv biases of the block sit ahead of a BatchNorm: analytically zero gradients
         UB_TRY(launch_wgrad(a0, nullptr, 0, -2, 1, 9, 3, u1.dy, u1.Co, u1.Co, P->wgrad_ws,
-                            P->wgrad_ws_floats, grads[u1.p_w], s, grads[u1.p_b], u1.Co,
+                            P->wgrad_ws_floats, grads[u1.p_w], ws, grads[u1.p_b], u1.Co,
                             grads[u0.p_b], u0.Co));
     }
     {
@@ -597,9 +638,10 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
         UB_TRY(launch_bn_bwd(d, s));
     }
     {
-        ProfScope ps(P, CLS_WGRAD, fl0, 2.0 * (pi0 * u0.Ci + po0 * u0.Co) + 4.0 * 9 * u0.Ci * u0.Co, s);
+        cudaStream_t ws = wgrad_stream(P, s);
+        ProfScope ps(P, CLS_WGRAD, fl0, 2.0 * (pi0 * u0.Ci + po0 * u0.Co) + 4.0 * 9 * u0.Ci * u0.Co, ws);
         UB_TRY(launch_wgrad(b.in0, b.two ? &b.in1 : nullptr, 0, -2, 1, 9, 3, u0.dy, u0.Co, u0.Co,
-                            P->wgrad_ws, P->wgrad_ws_floats, grads[u0.p_w], s));
+                            P->wgrad_ws, P->wgrad_ws_floats, grads[u0.p_w], ws));
     }
     IgemmEpilogue e;
     memset(&e, 0, sizeof(e));
@@ -609,8 +651,8 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
     return launch_igemm(dyv, nullptr, -2, 0, 1, 9, 3, u0.wd, u0.Ci, e, nullptr, s);
 }
 
-int ub_plan_backward_stage(ub_plan* P, int stage, const float* dlogits, float* const* grads,
-                           void* stream) {
+static int backward_stage_impl(ub_plan* P, int stage, const float* dlogits, float* const* grads,
+                               void* stream) {
     if (!P || !grads) { set_last_error("backward: null pointer"); return ub::UB_ERR_ARG; }
     if (!P->training) {
         set_last_error("backward: plan was created for inference (training=0)");
@@ -658,10 +700,11 @@ int ub_plan_backward_stage(ub_plan* P, int stage, const float* dlogits, float* c
             UB_TRY(launch_igemm(dup, nullptr, 0, -1, 2, 4, 2, t.wb, t.Ci, e, nullptr, s));
         }
         const ConvUnit& prev = j == 0 ? P->enc[L - 1].u[1] : P->dec[j - 1].u[1];
-        ProfScope ps(P, CLS_CT_WGRAD, flt, 2.0 * mt * (4.0 * t.Co + t.Ci) + 16.0 * t.Co * t.Ci, s);
+        cudaStream_t ws = wgrad_stream(P, s);   // after the data gradient that produced d(concat)
+        ProfScope ps(P, CLS_CT_WGRAD, flt, 2.0 * mt * (4.0 * t.Co + t.Ci) + 16.0 * t.Co * t.Ci, ws);
         // the transposed-conv bias is removed by the following BatchNorm: zero gradient
         return launch_wgrad(dup, nullptr, 0, -1, 2, 4, 2, prev.a, t.Ci, t.Ci, P->wgrad_ws,
-                            P->wgrad_ws_floats, grads[t.p_w], s, grads[t.p_b], t.Co);
+                            P->wgrad_ws_floats, grads[t.p_w], ws, grads[t.p_b], t.Co);
     }
     const int i = 2 * L - 2 - stage;
     Block& b = P->enc[i];
@@ -686,6 +729,19 @@ int ub_plan_backward_stage(ub_plan* P, int stage, const float* dlogits, float* c
     return block_backward(P, b, up, grads, s);
 }
 
+
+int ub_plan_backward_stage(ub_plan* P, int stage, const float* dlogits, float* const* grads,
+                           void* stream) {
+    const int rc = backward_stage_impl(P, stage, dlogits, grads, stream);
+    // weight gradients of this stage ran on the side stream: join where the caller needs them
+    if (P && (rc != 0 || P->overlap == 1 || stage == 2 * P->L - 2)) wgrad_join(P, (cudaStream_t)stream);
+    return rc;
+}
+int ub_plan_set_overlap(ub_plan* P, int mode) {
+    if (!P || mode < 0 || mode > 2) { set_last_error("set_overlap: mode must be 0, 1 or 2"); return ub::UB_ERR_ARG; }
+    if (!getenv("UB_WGRAD_OVERLAP")) P->overlap = mode;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Fused SGD step over all parameters + refresh of the packed bf16 operands (sgd.cuh).

@@ -175,6 +175,9 @@ class _Plan:
         views = [flat[self.offsets[i]:self.offsets[i + 1]] for i in range(self.num_params)]
         arr = (C.c_void_p * self.num_params)(*[v.data_ptr() for v in views])
         dl = C.c_void_p(dlogits.data_ptr())
+        # weight gradients overlap the BN-backward / data-gradient chain on an internal stream; with a
+        # per-stage hook (data-parallel all-reduce) every stage is joined, otherwise only the last
+        check(self.lib.ub_plan_set_overlap(self.handle, 1 if stage_hook is not None else 2))
         for s in range(self.num_stages):
             check(self.lib.ub_plan_backward_stage(self.handle, s, dl, arr, _stream()),
                   f"ub_plan_backward_stage({s})")
