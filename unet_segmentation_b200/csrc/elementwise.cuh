@@ -356,8 +356,10 @@ struct BnBwdArgs {
 
 // PIX (POOL_SKIP only): the forward saved the pool arg-max byte, so the window's winner is decoded
 // instead of being recomputed from y (one thread = one 2x2 window x 8 channels in both variants).
+// Launch bounds: the direct variant is held to 85 registers (3 CTAs per SM) so that two of its CTAs
+// still fit beside a weight-gradient CTA (256 threads x 74 registers) when the two kernels overlap.
 template <bool POOL_SKIP, bool APPLY, bool PIX = false>
-static __global__ void __launch_bounds__(256, 2)
+static __global__ void __launch_bounds__(256, POOL_SKIP ? 2 : 3)
 bn_bwd_kernel(const BnBwdArgs A) {
     pdl_entry();
     const unsigned C = A.C, CG = C >> 3, H = A.H, W = A.W;
