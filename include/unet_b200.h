@@ -115,6 +115,9 @@ int ub_plan_sgd_step(ub_plan* plan, const float* const* grads, float* const* mom
  * complete in stream order when it returns (data-parallel all-reduce hooks); 2: joined only at the
  * end of the last stage (single-GPU training). */
 int ub_plan_set_overlap(ub_plan* plan, int mode);
+/* Makes `stream` wait for the weight gradients issued so far (mode 2 + a communication stream: the
+ * all-reduce of a stage waits for that stage's weight gradients while the backward itself goes on). */
+int ub_plan_join_side(ub_plan* plan, void* stream);
 int64_t ub_launch_count(void);
 int ub_plan_profile_enable(ub_plan* plan, int on);
 int ub_plan_profile_classes(void);

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "ub_plan_stage_params": (c_int, [_P, c_int, C.POINTER(c_int), C.POINTER(c_int)]),
     "ub_plan_backward_stage": (c_int, [_P, c_int, _P, C.POINTER(c_void_p), _P]),
     "ub_plan_set_overlap": (c_int, [_P, c_int]),
+    "ub_plan_join_side": (c_int, [_P, _P]),
     "ub_plan_sgd_step": (c_int, [_P, C.POINTER(c_void_p), C.POINTER(c_void_p), c_float, c_float,
                                  c_float, c_float, c_int, c_int, _P]),
     "ub_launch_count": (c_int64, []),

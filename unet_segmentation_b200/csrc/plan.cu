@@ -737,6 +737,15 @@ int ub_plan_backward_stage(ub_plan* P, int stage, const float* dlogits, float* c
     if (P && (rc != 0 || P->overlap == 1 || stage == 2 * P->L - 2)) wgrad_join(P, (cudaStream_t)stream);
     return rc;
 }
+// Makes `stream` (e.g. a communication stream) wait for the weight gradients enqueued so far on the
+// internal stream, without stalling the stream the backward runs on.
+int ub_plan_join_side(ub_plan* P, void* stream) {
+    if (!P) return ub::UB_ERR_ARG;
+    if (!P->side || P->overlap == 0) return 0;
+    UB_CHECK_CUDA(cudaEventRecord(P->ev_join, P->side));
+    UB_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, P->ev_join, 0));
+    return 0;
+}
 int ub_plan_set_overlap(ub_plan* P, int mode) {
     if (!P || mode < 0 || mode > 2) { set_last_error("set_overlap: mode must be 0, 1 or 2"); return ub::UB_ERR_ARG; }
     if (!getenv("UB_WGRAD_OVERLAP")) P->overlap = mode;

@@ -62,8 +62,15 @@ class StageGradAllReducer:
         self.comm_stream = None
         self.n_collectives = 0
         self.bytes_reduced = 0
+        self.model = model
         if model is not None:
             model.set_backward_hooks(self.on_stage, self.on_done)
+
+    # The library computes weight gradients on its own side stream; this hook orders the
+    # communication stream after it itself (plan.join_side), so the backward stream never stalls.
+    @property
+    def joins_side_stream(self) -> bool:
+        return self.model is not None and hasattr(self.model, "_latest_training_plan")
 
     def on_stage(self, stage: int, flat_grads: torch.Tensor) -> None:
         if self.world == 1:
@@ -76,6 +83,10 @@ class StageGradAllReducer:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(flat_grads.device))
             self.comm_stream.wait_event(ready)
+            if self.joins_side_stream:
+                plan = self.model._latest_training_plan()
+                if plan is not None:
+                    plan.join_side(self.comm_stream)
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(flat_grads, op=dist.ReduceOp.AVG, group=self.group)
             flat_grads.record_stream(self.comm_stream)

@@ -170,6 +170,10 @@ class _Plan:
         self.generation += 1
         return logits, mask
 
+    def join_side(self, stream: "torch.cuda.Stream") -> None:
+        """Make ``stream`` wait for the weight gradients issued so far on the library's side stream."""
+        check(self.lib.ub_plan_join_side(self.handle, C.c_void_p(stream.cuda_stream)), "ub_plan_join_side")
+
     def backward(self, dlogits, stage_hook: Optional[Callable] = None):
         flat = torch.empty(self.offsets[-1], dtype=torch.float32, device=dlogits.device)
         views = [flat[self.offsets[i]:self.offsets[i + 1]] for i in range(self.num_params)]
@@ -177,7 +181,10 @@ class _Plan:
         dl = C.c_void_p(dlogits.data_ptr())
         # weight gradients overlap the BN-backward / data-gradient chain on an internal stream; with a
         # per-stage hook (data-parallel all-reduce) every stage is joined, otherwise only the last
-        check(self.lib.ub_plan_set_overlap(self.handle, 1 if stage_hook is not None else 2))
+        # (a hook that orders its own stream after the side stream — join_side — keeps full overlap)
+        joins_itself = bool(getattr(getattr(stage_hook, "__self__", None), "joins_side_stream", False))
+        check(self.lib.ub_plan_set_overlap(self.handle,
+                                           1 if (stage_hook is not None and not joins_itself) else 2))
         for s in range(self.num_stages):
             check(self.lib.ub_plan_backward_stage(self.handle, s, dl, arr, _stream()),
                   f"ub_plan_backward_stage({s})")
