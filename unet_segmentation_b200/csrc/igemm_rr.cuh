@@ -10,7 +10,7 @@
 // reads exactly the rows TMA wrote — scripts_dev/shift_probe.py.) A-operand ingest drops 2.9x.
 //
 // Pipelines: A ring (SA stages of 3 row buffers) fed by warp 0, B ring (SB stages of one
-// (tap, chunk) weight tile) fed by warp 6, MMA issue by warp 1, epilogue warps 2-5 on a
+// (tap, chunk) weight tile) fed by warp 6, MMA issue by warp 1, epilogue warps 2-5 (and 7-10) on a
 // double-buffered TMEM accumulator — same epilogues as igemm_kmajor_kernel.
 #pragma once
 #include "igemm.cuh"
