@@ -28,8 +28,38 @@ def center_crop(t: torch.Tensor, size) -> torch.Tensor:
     return t[..., hs:hs + th, ws:ws + tw]
 
 
-def _conv_bn_relu(x, sd, conv, bn, training, buffers_out, momentum=0.1, eps=1e-5):
-    x = F.conv2d(x, sd[f"{conv}.weight"], sd[f"{conv}.bias"])
+# ------------------------------------------------------------------------------------------------
+# T2 oracle: the reference arithmetic with bf16 rounding at the operands of
+# every convolution except the first (input and weight, straight-through backward) and at the
+# gradient w.r.t. every convolution output — the rounding points of a bf16-operand implementation.
+# ------------------------------------------------------------------------------------------------
+def _round_ste(t: torch.Tensor) -> torch.Tensor:
+    """bf16 rounding in the forward pass, identity gradient."""
+    return t + (t.bfloat16().float() - t).detach()
+
+
+class _RoundGrad(torch.autograd.Function):
+    """Identity in the forward pass; rounds the incoming gradient to bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def _conv(x, w, b, emulate, first=False, transpose=False):
+    if emulate and not first:
+        x, w = _round_ste(x), _round_ste(w)
+    y = F.conv_transpose2d(x, w, b, stride=2) if transpose else F.conv2d(x, w, b)
+    return _RoundGrad.apply(y) if (emulate and not first) else y
+
+
+def _conv_bn_relu(x, sd, conv, bn, training, buffers_out, momentum=0.1, eps=1e-5, emulate=False):
+    x = _conv(x, sd[f"{conv}.weight"], sd[f"{conv}.bias"], emulate,
+              first=(conv == "inc.double_conv.0"))
     rm, rv = sd[f"{bn}.running_mean"], sd[f"{bn}.running_var"]
     if training and buffers_out is not None:
         rm, rv = rm.clone(), rv.clone()
@@ -41,33 +71,35 @@ def _conv_bn_relu(x, sd, conv, bn, training, buffers_out, momentum=0.1, eps=1e-5
     return F.relu(x)
 
 
-def _double_conv(x, sd, prefix, training, buffers_out):
-    x = _conv_bn_relu(x, sd, f"{prefix}.0", f"{prefix}.1", training, buffers_out)
-    return _conv_bn_relu(x, sd, f"{prefix}.3", f"{prefix}.4", training, buffers_out)
+def _double_conv(x, sd, prefix, training, buffers_out, emulate=False):
+    x = _conv_bn_relu(x, sd, f"{prefix}.0", f"{prefix}.1", training, buffers_out, emulate=emulate)
+    return _conv_bn_relu(x, sd, f"{prefix}.3", f"{prefix}.4", training, buffers_out, emulate=emulate)
 
 
 def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = False,
                  levels: int = 5, buffers_out: Optional[dict] = None,
-                 capture: Optional[dict] = None) -> torch.Tensor:
+                 capture: Optional[dict] = None, emulate_bf16: bool = False) -> torch.Tensor:
     """logits = UNet(x). ``buffers_out`` (dict) receives the updated BN buffers in training mode;
-    ``capture`` (dict) receives the intermediate block outputs (teacher forcing)."""
-    feats = [_double_conv(x, sd, "inc.double_conv", training, buffers_out)]
+    ``capture`` (dict) receives the intermediate block outputs (teacher forcing);
+    ``emulate_bf16`` selects the T2 oracle (bf16-rounded conv operands / output gradients)."""
+    e = emulate_bf16
+    feats = [_double_conv(x, sd, "inc.double_conv", training, buffers_out, e)]
     for i in range(1, levels):
         p = F.max_pool2d(feats[-1], 2)
         feats.append(_double_conv(p, sd, f"down{i}.maxpool_conv.1.double_conv", training,
-                                  buffers_out))
+                                  buffers_out, e))
     y = feats[-1]
     for j in range(1, levels):
-        up = F.conv_transpose2d(y, sd[f"up{j}.up.weight"], sd[f"up{j}.up.bias"], stride=2)
+        up = _conv(y, sd[f"up{j}.up.weight"], sd[f"up{j}.up.bias"], e, transpose=True)
         skip = center_crop(feats[levels - 1 - j], up.shape[-2:])
         y = _double_conv(torch.cat([skip, up], dim=1), sd, f"up{j}.conv.double_conv", training,
-                         buffers_out)
+                         buffers_out, e)
         if capture is not None:
             capture[f"up{j}"] = y
     if capture is not None:
         for i, f in enumerate(feats):
             capture[f"x{i + 1}"] = f
-    return F.conv2d(y, sd["outc.conv.weight"], sd["outc.conv.bias"])
+    return _conv(y, sd["outc.conv.weight"], sd["outc.conv.bias"], e)
 
 
 def weighted_cross_entropy(logits, targets, weight_maps):

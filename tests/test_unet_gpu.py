@@ -39,13 +39,14 @@ def make_model(seed, n_classes=2):
     return m.cuda(), {k: v.cuda() for k, v in sd.items()}
 
 
-def oracle_step(sd, img, t, w, training=True):
+def oracle_step(sd, img, t, w, training=True, emulate_bf16=False):
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
               if v.is_floating_point() and "running" not in k}
     full = dict(sd)
     full.update(params)
     bufs = {}
-    logits = unet_ref.unet_forward(full, img, training=training, buffers_out=bufs)
+    logits = unet_ref.unet_forward(full, img, training=training, buffers_out=bufs,
+                                   emulate_bf16=emulate_bf16)
     loss = unet_ref.weighted_cross_entropy(logits, t, w)
     loss.backward()
     return logits.detach(), loss.detach(), {k: p.grad for k, p in params.items()}, bufs
@@ -99,6 +100,48 @@ def test_training_step_vs_fp32_oracle_512():
             assert int(new[k]) == int(v), k
         else:
             assert rel_l2(new[k], v) < 2e-2, (k, rel_l2(new[k], v))
+
+
+def test_training_step_vs_bf16_rounding_oracle_512():
+    """T2: against the reference arithmetic with bf16 rounding at the operand points of
+    a bf16 implementation (conv inputs / weights except the first conv, conv-output gradients). The
+    result must be at least as close to this oracle as to the fp32 one; far outside the band means
+    a kernel bug, not number-format drift."""
+    from unet_segmentation_b200.loss import WeightedCrossEntropyLoss
+
+    model, sd = make_model(seed=0)
+    img, t, w = unet_ref.synthetic_batch(2, size=512, seed=1234, device="cuda")
+    ref_logits, ref_loss, ref_grads, _ = oracle_step(sd, img, t, w, emulate_bf16=True)
+    fp_logits, _, fp_grads, _ = oracle_step(sd, img, t, w)
+    model.train()
+    logits = model(img)
+    loss = WeightedCrossEntropyLoss()(logits, t, w)
+    loss.backward()
+    torch.cuda.synchronize()
+    e_logits = rel_l2(logits, ref_logits)
+    e_loss = abs(float(loss) - float(ref_loss)) / abs(float(ref_loss))
+    agree = float(((logits[:, 1] > logits[:, 0]) == (ref_logits[:, 1] > ref_logits[:, 0]))
+                  .float().mean())
+    cos, cos_fp = {}, {}
+    for name, p in model.named_parameters():
+        if name.endswith(ZERO_GRAD_BIASES):
+            continue
+        cos[name] = cosine(p.grad, ref_grads[name])
+        cos_fp[name] = cosine(p.grad, fp_grads[name])
+    vals, vals_fp = np.array(list(cos.values())), np.array(list(cos_fp.values()))
+    print(f"\n[T2 512^2 N=2] vs bf16-rounding oracle: logits rel-L2 {e_logits:.3e}  loss rel "
+          f"{e_loss:.3e}  mask agree {agree:.5f}  grad cos min {vals.min():.4f} median "
+          f"{np.median(vals):.4f}  >=0.999: {(vals >= 0.999).sum()}/{len(vals)}   "
+          f"(vs fp32: logits {rel_l2(logits, fp_logits):.3e}, cos min {vals_fp.min():.4f} median "
+          f"{np.median(vals_fp):.4f})")
+    # Measured: logits 1.39e-2 (vs 1.46e-2 against fp32), masks 99.60 %, cos min 0.895 / median 0.958.
+    # The library has one rounding point more than this oracle (the conv output y is stored in bf16
+    # before BatchNorm), and runs with identical rounding points already differ by ~5e-3 through
+    # ReLU / max-pool mask flips (SURVEY Appendix B), so the band is "no worse than against fp32".
+    assert e_logits < 1.8e-2 and e_loss < 1e-3 and agree > 0.995
+    assert e_logits <= 1.02 * rel_l2(logits, fp_logits)
+    assert vals.min() > 0.87 and np.median(vals) > 0.95
+    assert np.median(vals) >= np.median(vals_fp) - 1e-3   # closer to the same-rounding oracle
 
 
 @pytest.mark.parametrize("name", ["train_n2_s188", "train_n1_s220", "eval_n1_s252"])
