@@ -150,7 +150,8 @@ int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
     const long long items = d.pool_skip
                                 ? (long long)d.N * ((d.H + 1) / 2) * ((d.W + 1) / 2) * (d.C / 8)
                                 : count * (d.C / 8);
-    const int blocks = red_blocks(items, 2);   // = resident CTAs (launch bounds 256 x 2): one wave
+    // one wave of resident CTAs (launch bounds: 3 per SM for the direct variant, 2 for the pooled one)
+    const int blocks = red_blocks(items, d.pool_skip ? 2 : 3);
     if (pix) UB_LAUNCH_NC((bn_bwd_kernel<true, false, true>), blocks, 256, 0, s, A);
     else if (d.pool_skip) UB_LAUNCH_NC((bn_bwd_kernel<true, false>), blocks, 256, 0, s, A);
     else UB_LAUNCH_NC((bn_bwd_kernel<false, false>), blocks, 256, 0, s, A);
