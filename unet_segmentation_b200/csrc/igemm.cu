@@ -92,7 +92,7 @@ static int launch_igemm_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    UB_CHECK_CUDA(ub_launch(igemm_kmajor_kernel<BN, EPI, CG>, dim3(grid), dim3(IGEMM_THREADS),
+    UB_CHECK_CUDA(ub_launch(igemm_kmajor_kernel<BN, EPI, CG>, dim3(grid), dim3(igemm_threads(BN)),
                                    Cfg::SMEM_BYTES, stream, CG, a0, a1, b, p));
     UB_POST_LAUNCH();
     return UB_OK;
@@ -141,7 +141,7 @@ static int launch_rowrun_t(const CUtensorMap& a0, const CUtensorMap& a1, const C
         attr_set = true;
     }
     UB_CHECK_CUDA(ub_launch(igemm_rowrun_kernel<BN, EPI, CG, WRES>, dim3(grid),
-                                   dim3(IGEMM_THREADS), Cfg::SMEM_BYTES, stream, CG, a0, a1, b, p));
+                                   dim3(igemm_threads(BN)), Cfg::SMEM_BYTES, stream, CG, a0, a1, b, p));
     UB_POST_LAUNCH();
     return UB_OK;
 }

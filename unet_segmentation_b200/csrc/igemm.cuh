@@ -69,6 +69,7 @@ struct IgemmCfg {
 // BN = 64 keeps four epilogue warps (one 32-column chunk pair each): its tiles are MMA-issue bound
 // and a second epilogue warp on the MMA warp's scheduler costs more than it saves (measured).
 constexpr int IGEMM_THREADS = 352;
+constexpr int igemm_threads(int bn) { return bn == 64 ? 224 : IGEMM_THREADS; }   // BN = 64: warps 0-6
 template <int BN> struct EpiCfg {
     static constexpr int HALVES = (BN == 64) ? 1 : 2;      // column halves = epilogue warps / 4
     static constexpr int NCH = BN / 32 / HALVES;           // 32-column chunks per warp
@@ -77,6 +78,23 @@ template <int BN>
 __device__ __forceinline__ bool is_epilogue_warp(int warp) {
     return warp >= 2 && warp != 6 && (EpiCfg<BN>::HALVES == 2 || warp < 6);
 }
+
+// BN = 64 statistics epilogue: per-thread register accumulators (row of the thread x 64 columns, sum
+// and sum of squares) across ALL tiles of the CTA, reduced across lanes once at the end — 64
+// instructions per tile and chunk instead of the ~250 of a per-tile warp transpose-reduction, which
+// paced the resident-weight kernel (its MMA warp waited 23 % of the time for a free accumulator).
+// The 224-thread launch of BN = 64 leaves the registers for it.
+template <int BN, int EPI> struct StatRegs {
+    static constexpr bool ON = (BN == 64 && EPI == 0 /* EPI_CONV_STATS */);
+    float s[ON ? 2 : 1][ON ? 32 : 1];
+    float q[ON ? 2 : 1][ON ? 32 : 1];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int a = 0; a < (ON ? 2 : 1); ++a)
+#pragma unroll
+            for (int b = 0; b < (ON ? 32 : 1); ++b) { s[a][b] = 0.f; q[a][b] = 0.f; }
+    }
+};
 
 // End of a CONV_STATS kernel: the epilogue warps of a CTA combine their per-quadrant column sums in
 // shared memory (fixed order) and write ONE partial row [2][BN] per CTA, so the finalisation kernel
@@ -100,6 +118,19 @@ __device__ __forceinline__ void write_cta_stats(float* red, float* dst_row, int 
         dst_row[i] = ((red[i] + red[2 * BN + i]) + red[4 * BN + i]) + red[6 * BN + i];
 }
 
+template <int BN, int EPI>
+__device__ __forceinline__ void finish_stat_regs(StatRegs<BN, EPI>& sr, int lane,
+                                                 float (&ssum)[EpiCfg<BN>::NCH],
+                                                 float (&ssq)[EpiCfg<BN>::NCH]) {
+    if constexpr (StatRegs<BN, EPI>::ON) {
+#pragma unroll
+        for (int cl = 0; cl < 2; ++cl) {
+            ssum[cl] = warp_column_sum(sr.s[cl], lane);
+            ssq[cl] = warp_column_sum(sr.q[cl], lane);
+        }
+    }
+}
+
 // Epilogue of one 128 x BN accumulator tile: TMEM -> registers (32 columns at a time), bias /
 // folded-BN affine, bf16 store (row-major, or 2x2 pixel-shuffle scatter for the transposed conv),
 // and the per-channel sum / sum-of-squares of the BatchNorm statistics.
@@ -112,7 +143,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                                               bool valid, int n0, int lane, int chalf,
                                               float (&ssum)[EpiCfg<BN>::NCH],
                                               float (&ssq)[EpiCfg<BN>::NCH],
-                                              const float* hs = nullptr) {
+                                              StatRegs<BN, EPI>& sr, const float* hs = nullptr) {
                 long long ct_row = 0;
                 if (EPI == EPI_CONVT) {
                     const int w = (int)(m % p.ct_W);
@@ -186,7 +217,15 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                             d4[j] = o;
                         }
                     }
-                    if (EPI == EPI_CONV_STATS) {
+                    if (EPI == EPI_CONV_STATS && StatRegs<BN, EPI>::ON) {
+    #pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float x = valid ? v[i] : 0.f;
+                            sr.s[StatRegs<BN, EPI>::ON ? cl : 0][StatRegs<BN, EPI>::ON ? i : 0] += x;
+                            sr.q[StatRegs<BN, EPI>::ON ? cl : 0][StatRegs<BN, EPI>::ON ? i : 0] =
+                                fmaf(x, x, sr.q[StatRegs<BN, EPI>::ON ? cl : 0][StatRegs<BN, EPI>::ON ? i : 0]);
+                        }
+                    } else if (EPI == EPI_CONV_STATS) {
                         float s2[32];
     #pragma unroll
                         for (int i = 0; i < 32; ++i) {
@@ -223,7 +262,7 @@ __device__ __forceinline__ void stage_head_weights(const IgemmParams& p, float* 
 }
 
 template <int BN, int EPI, int CG>
-__global__ void __launch_bounds__(IGEMM_THREADS, 1)
+__global__ void __launch_bounds__(igemm_threads(BN), 1)
 igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const IgemmParams p) {
@@ -388,6 +427,8 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
         float ssum[NCH], ssq[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+        StatRegs<BN, EPI> sr;
+        sr.clear();
 
         for (int mu = m_first; mu < m_units; mu += m_step) {
             const long long m = (long long)(mu * CG + (int)rank) * 128 + row_in_tile;
@@ -396,7 +437,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 
-            epilogue_tile<BN, EPI>(p, trow, m, valid, n0, lane, chalf, ssum, ssq, hs);
+            epilogue_tile<BN, EPI>(p, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, hs);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -405,6 +446,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             }
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
+        finish_stat_regs<BN, EPI>(sr, lane, ssum, ssq);
         if (EPI == EPI_CONV_STATS) {
             // partial row of "virtual CTA" rank*nunits + unit: nunits % n_tiles == 0, so the channel
             // tile of a row is still (row index % n_tiles) for bn_finalize_kernel

@@ -70,7 +70,7 @@ struct RowRunCfg {
 };
 
 template <int BN, int EPI, int CG, bool WRES>
-__global__ void __launch_bounds__(IGEMM_THREADS, 1)
+__global__ void __launch_bounds__(igemm_threads(BN), 1)
 igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const RowRunParams p) {
@@ -289,6 +289,8 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         float ssum[NCH], ssq[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+        StatRegs<BN, EPI> sr;
+        sr.clear();
         const bool prof = p.dbg != nullptr;
         long long wE = 0;
         const long long tstart = clock64();
@@ -302,7 +304,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             mbar_wait_prof(tfull_bar(as), aphase, prof, wE);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-            epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, chalf, ssum, ssq, hs);
+            epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, hs);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -315,6 +317,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             atomicAdd((unsigned long long*)&p.dbg[8], (unsigned long long)wE);
             atomicAdd((unsigned long long*)&p.dbg[9], (unsigned long long)(clock64() - tstart));
         }
+        finish_stat_regs<BN, EPI>(sr, lane, ssum, ssq);
         if (EPI == EPI_CONV_STATS) {
             float* red = reinterpret_cast<float*>(gbase + Cfg::SA * Cfg::A_STAGE + Cfg::B_AREA +
                                                   Cfg::BAR_BYTES);
