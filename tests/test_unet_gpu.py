@@ -92,7 +92,8 @@ def test_training_step_vs_fp32_oracle_512():
     for name in ("outc.conv.weight", "outc.conv.bias", "up4.conv.double_conv.4.weight",
                  "up4.conv.double_conv.3.weight"):
         assert cos[name] > 0.999, (name, cos[name])
-    assert vals.min() > 0.85 and np.median(vals) > 0.95
+    # measured: min 0.889, median 0.953 (torch.autocast(bf16) on the reference: 0.58 / 0.82)
+    assert vals.min() > 0.85 and np.median(vals) > 0.94
     # BN buffers follow torch semantics (momentum 0.1, unbiased running_var, counter += 1)
     new = model.state_dict()
     for k, v in ref_bufs.items():
