@@ -60,7 +60,8 @@ struct IgemmCfg {
     static constexpr int BAR_BYTES = 256;
     // epilogue scratch: BN-statistics rows of the 4 lane quadrants, or the fused head's weights
     static constexpr int STAT_BYTES = (BN == 64) ? 2304 : 4 * 2 * BN * 4;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + 1024;
+    static constexpr int CONST_BYTES = 2 * BN * 4;   // per-column epilogue constants of the n tile
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + CONST_BYTES + 1024;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
@@ -143,7 +144,8 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                                               bool valid, int n0, int lane, int chalf,
                                               float (&ssum)[EpiCfg<BN>::NCH],
                                               float (&ssq)[EpiCfg<BN>::NCH],
-                                              StatRegs<BN, EPI>& sr, const float* hs = nullptr) {
+                                              StatRegs<BN, EPI>& sr, const float* cs,
+                                              const float* hs = nullptr) {
                 long long ct_row = 0;
                 if (EPI == EPI_CONVT) {
                     const int w = (int)(m % p.ct_W);
@@ -169,9 +171,14 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
                     if (EPI == EPI_AFFINE_RELU || EPI == EPI_AFFINE_RELU_HEAD) {
     #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            v[i] = fmaxf(fmaf(v[i], __ldg(p.scale + col0 + i), __ldg(p.shift + col0 + i)),
-                                         0.f);
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 a4 = reinterpret_cast<const float4*>(cs + c * 32)[i4];
+                            const float4 b4 = reinterpret_cast<const float4*>(cs + BN + c * 32)[i4];
+                            v[4 * i4 + 0] = fmaxf(fmaf(v[4 * i4 + 0], a4.x, b4.x), 0.f);
+                            v[4 * i4 + 1] = fmaxf(fmaf(v[4 * i4 + 1], a4.y, b4.y), 0.f);
+                            v[4 * i4 + 2] = fmaxf(fmaf(v[4 * i4 + 2], a4.z, b4.z), 0.f);
+                            v[4 * i4 + 3] = fmaxf(fmaf(v[4 * i4 + 3], a4.w, b4.w), 0.f);
+                        }
                         if (EPI == EPI_AFFINE_RELU_HEAD) {
                             // BN = 64: this thread sees all 64 channels of its pixel over the two chunks
     #pragma unroll
@@ -194,7 +201,11 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                         }
                     } else if (p.bias != nullptr) {
     #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col0 + i);
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 a4 = reinterpret_cast<const float4*>(cs + c * 32)[i4];
+                            v[4 * i4 + 0] += a4.x; v[4 * i4 + 1] += a4.y;
+                            v[4 * i4 + 2] += a4.z; v[4 * i4 + 3] += a4.w;
+                        }
                     }
                     if (valid && EPI != EPI_AFFINE_RELU_HEAD) {
                         __nv_bfloat16* dst;
@@ -248,6 +259,23 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                     }
                     if (p.head_mask) p.head_mask[m] = (p.head_nc >= 2 && hacc[1] > hacc[0]) ? 255 : 0;
                 }
+}
+
+// Per-column epilogue constants of n tile [n0, n0+BN) -> shared memory (broadcast LDS.128 reads
+// instead of 32-64 cached global loads per 32-column chunk and tile):
+//   cs[0..BN) = scale (AFFINE_RELU kinds) or bias (other kinds, 0 if absent), cs[BN..2BN) = shift.
+template <int BN, int EPI>
+__device__ __forceinline__ void stage_epilogue_consts(const IgemmParams& p, int n0, float* cs) {
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+        if (EPI == EPI_AFFINE_RELU || EPI == EPI_AFFINE_RELU_HEAD) {
+            cs[i] = p.scale[n0 + i];
+            cs[BN + i] = p.shift[n0 + i];
+        } else {
+            cs[i] = p.bias ? p.bias[n0 + i] : 0.f;
+            cs[BN + i] = 0.f;
+        }
+    }
+    __syncthreads();
 }
 
 // Head weights of EPI_AFFINE_RELU_HEAD -> shared memory: hs[c*64 + k] (c < 8), bias at hs[512 + c].
@@ -310,7 +338,10 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
     const uint32_t tmem_base = *tmem_slot_g;
     pdl_wait();   // prologue done; from here on global memory of the preceding kernels is read
     float* hs = reinterpret_cast<float*>(gbase + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+    float* cs = reinterpret_cast<float*>(gbase + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES +
+                                         Cfg::STAT_BYTES);
     stage_head_weights<EPI>(p, hs);
+    stage_epilogue_consts<BN, EPI>(p, (unit % p.n_tiles) * BN, cs);
 
     const int cchunks = p.cchunks0 + p.cchunks1;
     const int kblocks = p.taps * cchunks;
@@ -437,7 +468,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 
-            epilogue_tile<BN, EPI>(p, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, hs);
+            epilogue_tile<BN, EPI>(p, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, cs, hs);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

@@ -64,7 +64,8 @@ struct RowRunCfg {
     static constexpr int BAR_BYTES = 256;
     // epilogue scratch: BN-statistics rows of the 4 lane quadrants, or the fused head's weights
     static constexpr int STAT_BYTES = (BN == 64) ? 2304 : 4 * 2 * BN * 4;
-    static constexpr int SMEM_BYTES = SA * A_STAGE + B_AREA + BAR_BYTES + STAT_BYTES + 1024;
+    static constexpr int CONST_BYTES = 2 * BN * 4;   // per-column epilogue constants of the n tile
+    static constexpr int SMEM_BYTES = SA * A_STAGE + B_AREA + BAR_BYTES + STAT_BYTES + CONST_BYTES + 1024;
     static_assert(!WRES || (BN == 64 && CG == 1), "resident weights: BN = 64, single CTA");
     static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
@@ -116,7 +117,10 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
     const uint32_t tmem_base = *tmem_slot_g;
     pdl_wait();   // prologue done; from here on global memory of the preceding kernels is read
     float* hs = reinterpret_cast<float*>(gbase + Cfg::SA * Cfg::A_STAGE + Cfg::B_AREA + Cfg::BAR_BYTES);
+    float* cs = reinterpret_cast<float*>(gbase + Cfg::SA * Cfg::A_STAGE + Cfg::B_AREA + Cfg::BAR_BYTES +
+                                         Cfg::STAT_BYTES);
     stage_head_weights<EPI>(p.epi, hs);
+    stage_epilogue_consts<BN, EPI>(p.epi, (unit % p.n_tiles) * BN, cs);
 
     const int cchunks = p.cchunks0 + p.cchunks1;
     const int cta_n = unit % p.n_tiles;
@@ -304,7 +308,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             mbar_wait_prof(tfull_bar(as), aphase, prof, wE);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-            epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, hs);
+            epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, cs, hs);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
