@@ -153,6 +153,20 @@ int ub_prepare_batch(const uint8_t* images_u8, const void* labels, int label_byt
                      int out_w, float* image_f32, int64_t* target, float* weight, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Weight-map generation: calculate_weight_map(mask, w0, sigma) of
+ * scripts/preprocess_data.py:17-77 for a batch of instance-label masks, on the device.
+ *   labels      [N][H][W] uint8 (label_bytes 1) or uint16 (2) instance ids, 0 = background
+ *   weight_maps [N][H][W] float64 (weight_bytes 8: what the reference stores as .npy) or float32
+ *               (4: torch.from_numpy(map).float(), utils/dataset.py:110)
+ *   counts      N uint32 of device scratch (foreground pixel counts; zeroed by the call)
+ * The reference's border term is identically w0 (its distance maps vanish for every mask, SURVEY
+ * F6), so the map is float32(1 / class fraction) + w0 per pixel; bit-exact against the stored maps.
+ * The result feeds ub_prepare_batch (weight_maps argument).
+ * ---------------------------------------------------------------------------------------------- */
+int ub_weight_map(const void* labels, int label_bytes, int N, int H, int W, double w0, double sigma,
+                  void* weight_maps, int weight_bytes, uint32_t* counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * get_instance_masks (utils/metrics.py:42-72): 8-connected labelling in raster order, components
  * smaller than min_size zeroed, ids not compacted, uint16 output. Bit-exact.
  * ---------------------------------------------------------------------------------------------- */

@@ -4,7 +4,8 @@
 
 Imports /root/reference (read-only, bytecode writing disabled) and records, for seeded weights and
 inputs, what the reference's own UNet + WeightedCrossEntropyLoss compute on CPU in fp32, plus a
-subset of the reference's shipped mask -> instance-label pairs for get_instance_masks.
+subset of the reference's shipped mask -> instance-label pairs for get_instance_masks and of its
+instance mask -> stored weight map pairs for calculate_weight_map.
 The GPU box has no /root/reference: tests there compare against these fixtures.
 """
 import importlib.util
@@ -104,6 +105,16 @@ def main():
         ccl[f"mask{i:03d}"] = m.astype(np.uint8)
         ccl[f"inst{i:03d}"] = inst.astype(np.uint16)
     np.savez_compressed(os.path.join(OUT, "ccl_golden.npz"), **ccl)
+
+    # calculate_weight_map (scripts/preprocess_data.py): instance masks + the maps the reference stores
+    train = os.path.join(REF, "data/raw/train/DIC-C2DH-HeLa")
+    wm = {}
+    for seq, num in (("01", "002"), ("01", "041"), ("01", "067")):
+        wm[f"labels{seq}_{num}"] = np.array(
+            Image.open(os.path.join(train, f"{seq}_ST", "SEG", f"man_seg{num}.tif"))).astype(np.uint16)
+        wm[f"wmap{seq}_{num}"] = np.load(
+            os.path.join(train, f"{seq}_ST", "WEIGHT_MAPS", f"weight_map_{num}.npy"))
+    np.savez_compressed(os.path.join(OUT, "weight_map_golden.npz"), **wm)
     for f in os.listdir(OUT):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

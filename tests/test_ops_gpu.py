@@ -2,6 +2,8 @@
 ABI, against the single torch op it replaces, in fp32 on the same bf16-rounded inputs. Only the
 accumulation order differs, so the bars are tight: rel-L2 <= 4e-3 for bf16 outputs (one bf16
 rounding), <= 1e-3 and cosine >= 0.999 for fp32 gradients."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -461,3 +463,57 @@ def test_device_input_pipeline(n, h, w, oh, lbl_dtype, w_dtype):
     image2, target2, weight2 = prep.get(k)
     torch.cuda.synchronize()
     assert torch.equal(image2, image) and torch.equal(target2, target) and torch.equal(weight2, weight)
+
+
+@pytest.mark.parametrize("lbl_dtype,out_dtype", [(torch.uint16, torch.float64), (torch.uint8, torch.float32),
+                                                 (torch.uint16, torch.float32)])
+def test_device_weight_map_bit_exact(lbl_dtype, out_dtype):
+    """calculate_weight_map (scripts/preprocess_data.py:17-77) on the device — the
+    reference's stored maps (golden) and the oracle on random / empty / full / odd-sized masks."""
+    from oracle import weight_map_ref
+    from unet_segmentation_b200 import input_pipeline
+    np_out = np.float64 if out_dtype == torch.float64 else np.float32
+    if lbl_dtype == torch.uint16:
+        blob = np.load(os.path.join(os.path.dirname(__file__), "golden", "weight_map_golden.npz"))
+        ids = sorted(k[len("labels"):] for k in blob.files if k.startswith("labels"))
+        lab = torch.from_numpy(np.stack([blob[f"labels{i}"] for i in ids]).astype(np.int32)).to(torch.uint16)
+        got = input_pipeline.weight_maps_from_labels(lab.cuda(), dtype=out_dtype).cpu().numpy()
+        for k, i in enumerate(ids):
+            assert np.array_equal(got[k], blob[f"wmap{i}"].astype(np_out)), i
+    rng = np.random.default_rng(21)
+    top = 255 if lbl_dtype == torch.uint8 else 40000
+    for (n, h, w), w0, sigma in [((3, 36, 40), 10, 5), ((2, 33, 17), 10, 5), ((1, 7, 9), 2.5, 0.0),
+                                 ((4, 512, 512), 10, 5)]:
+        lab = (rng.integers(1, top + 1, (n, h, w)) * (rng.random((n, h, w)) < rng.random((n, 1, 1)))).astype(np.int32)
+        lab[0] = 0                      # an image without any instance
+        if n > 1:
+            lab[1] = 9                  # an image without background
+        got = input_pipeline.weight_maps_from_labels(torch.from_numpy(lab).to(lbl_dtype).cuda(), w0, sigma,
+                                                     out_dtype)
+        assert got.dtype == out_dtype and tuple(got.shape) == (n, h, w)
+        got = got.cpu().numpy()
+        for k in range(n):
+            ref = weight_map_ref.weight_map_closed_form(lab[k], w0, sigma).astype(np_out)
+            assert np.array_equal(got[k], ref), (n, h, w, k)
+    one = torch.from_numpy(lab[-1]).to(lbl_dtype).cuda()     # (H, W) input keeps its shape
+    assert tuple(input_pipeline.weight_maps_from_labels(one).shape) == tuple(one.shape)
+
+
+def test_device_batch_preparer_computes_missing_weight_maps():
+    """Labels without stored maps: DeviceBatchPreparer derives the weights on the device (N4 -> N3)
+    and yields what the reference's dataset + train-loop crop would."""
+    from oracle import weight_map_ref
+    from unet_segmentation_b200 import input_pipeline
+    g = torch.Generator().manual_seed(5)
+    n, h, w, oh = 2, 64, 64, 40
+    img = torch.randint(0, 256, (n, h, w), generator=g, dtype=torch.uint8)
+    lbl = (torch.randint(1, 30, (n, h, w), generator=g) * (torch.rand(n, h, w, generator=g) > 0.6)).to(torch.uint8)
+    prep = input_pipeline.DeviceBatchPreparer("cuda", (oh, oh))
+    image, target, weight = prep.get(prep.submit(img.pin_memory(), lbl.pin_memory(), None))
+    torch.cuda.synchronize()
+    s0 = (h - oh) // 2
+    ref_w = torch.stack([torch.from_numpy(weight_map_ref.weight_map_closed_form(lbl[k].numpy())).float()
+                         for k in range(n)])[:, s0:s0 + oh, s0:s0 + oh]
+    assert torch.equal(weight.cpu(), ref_w)
+    assert torch.equal(target.cpu(), (lbl > 0).long()[:, s0:s0 + oh, s0:s0 + oh])
+    assert torch.equal(image.cpu(), img.float().div(255).unsqueeze(1))

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 REF = "/root/reference"
 
-from oracle import ccl_ref, unet_ref  # noqa: E402
+from oracle import ccl_ref, unet_ref, weight_map_ref  # noqa: E402
 
 
 def _case(blob, name):
@@ -149,6 +149,65 @@ def test_ccl_oracle_matches_all_shipped_pairs():
         assert np.array_equal(ccl_ref.get_instance_masks(m, 15), inst.astype(np.uint16))
         n += 1
     assert n == 12
+
+
+def test_weight_map_oracle_matches_reference_stored_maps():
+    """calculate_weight_map (scripts/preprocess_data.py:17-77): the step-by-step restatement (real
+    distance transforms) and the closed form the CUDA kernel implements both reproduce the maps the
+    reference stores, bit for bit."""
+    blob = np.load(os.path.join(GOLD, "weight_map_golden.npz"))
+    ids = sorted(k[len("labels"):] for k in blob.files if k.startswith("labels"))
+    assert len(ids) >= 3
+    for i in ids:
+        lab, stored = blob[f"labels{i}"], blob[f"wmap{i}"]
+        assert stored.dtype == np.float64 and len(np.unique(stored)) == 2   # SURVEY F6
+        closed = weight_map_ref.weight_map_closed_form(lab)
+        assert closed.dtype == np.float64 and np.array_equal(closed, stored), i
+    full = weight_map_ref.weight_map_full(blob[f"labels{ids[0]}"])
+    assert full.dtype == np.float64 and np.array_equal(full, blob[f"wmap{ids[0]}"])
+
+
+def test_weight_map_closed_form_equals_full_restatement_on_edge_cases():
+    rng = np.random.default_rng(5)
+    cases = [np.zeros((12, 20), np.uint16), np.full((9, 7), 3, np.uint8)]
+    one = np.zeros((24, 31), np.uint16); one[5:14, 8:20] = 7; cases.append(one)
+    three = one.copy(); three[16:22, 2:30] = 2; three[0:3, 0:4] = 300; cases.append(three)
+    cases.append((rng.integers(0, 6, (33, 17)) * (rng.random((33, 17)) < 0.4)).astype(np.uint16))
+    for lab in cases:
+        for w0, sigma in ((10, 5), (3.5, 0.0)):
+            full = weight_map_ref.weight_map_full(lab, w0, sigma)
+            closed = weight_map_ref.weight_map_closed_form(lab, w0, sigma)
+            assert np.array_equal(full.astype(np.float64), closed), (lab.shape, w0, sigma)
+    wbg, wfg = weight_map_ref.class_balance_weights(0, 100)
+    assert (wbg, wfg) == (np.float32(1.0), np.float32(0.0))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_weight_map_oracle_matches_live_reference_and_all_stored_maps():
+    import glob
+
+    from PIL import Image
+
+    sys.dont_write_bytecode = True
+    spec = importlib.util.spec_from_file_location(
+        "ref_preprocess", os.path.join(REF, "scripts", "preprocess_data.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    lab = np.zeros((40, 56), np.uint16)
+    for k, (y, x, h, w) in enumerate([(3, 4, 10, 12), (20, 30, 15, 20), (25, 2, 8, 9)]):
+        lab[y:y + h, x:x + w] = 5 * k + 1
+        got = ref.calculate_weight_map(lab, 10, 5)
+        assert np.array_equal(got, weight_map_ref.weight_map_full(lab))
+        assert np.array_equal(got, weight_map_ref.weight_map_closed_form(lab))
+    empty = ref.calculate_weight_map(np.zeros((8, 8), np.uint16), 10, 5)
+    assert empty.dtype == np.float32 == weight_map_ref.weight_map_full(np.zeros((8, 8), np.uint16)).dtype
+    base = os.path.join(REF, "data/raw/train/DIC-C2DH-HeLa/01_ST")
+    files = sorted(glob.glob(os.path.join(base, "WEIGHT_MAPS", "weight_map_*.npy")))
+    assert len(files) == 84
+    for f in files:
+        num = os.path.basename(f)[len("weight_map_"):-4]
+        m = np.array(Image.open(os.path.join(base, "SEG", f"man_seg{num}.tif")))
+        assert np.array_equal(weight_map_ref.weight_map_closed_form(m), np.load(f)), f
 
 
 def test_c_abi_exports_every_declared_symbol():

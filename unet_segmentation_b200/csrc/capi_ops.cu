@@ -58,6 +58,11 @@ int ub_prepare_batch(const uint8_t* images_u8, const void* labels, int label_byt
     return launch_prepare_batch(images_u8, labels, label_bytes, weight_maps, weight_bytes, N, H, W,
                                 out_h, out_w, image_f32, (long long*)target, weight, S(stream));
 }
+int ub_weight_map(const void* labels, int label_bytes, int N, int H, int W, double w0, double sigma,
+                  void* weight_maps, int weight_bytes, uint32_t* counts, void* stream) {
+    return launch_weight_map(labels, label_bytes, N, H, W, w0, sigma, weight_maps, weight_bytes,
+                             counts, S(stream));
+}
 int64_t ub_ccl_workspace_bytes(int H, int W) { return (int64_t)ccl_ws_bytes(H, W); }
 int ub_ccl_label(const uint8_t* mask, int H, int W, int min_size, uint16_t* labels, void* workspace,
                  void* stream) {

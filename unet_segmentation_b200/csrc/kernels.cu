@@ -1,5 +1,7 @@
 // Host-side launchers of the HBM-bound kernels (elementwise.cuh, first_conv.cuh, head_loss.cuh,
 // ccl.cuh). Grids are sized in multiples of the SM count; no launcher synchronises.
+#include <cmath>
+
 #include "ccl.cuh"
 #include "elementwise.cuh"
 #include "first_conv.cuh"
@@ -7,6 +9,7 @@
 #include "input_pipeline.cuh"
 #include "igemm.cuh"
 #include "ub_internal.h"
+#include "weight_map.cuh"
 
 namespace ub {
 
@@ -404,6 +407,54 @@ int launch_prepare_batch(const unsigned char* img, const void* labels, int label
     UB_LAUNCH_NC(prepare_batch_kernel, ew_blocks((long long)N * H * (W / 4)), 256, 0, s, A);
     UB_POST_LAUNCH();
     return UB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename LabelT, int VEC>
+static int weight_map_typed(const LabelT* labels, int N, unsigned P, double border, void* out,
+                            int out_bytes, unsigned* counts, cudaStream_t s) {
+    // one image per grid row; enough blocks per image to fill the machine with the whole batch
+    int per_image = ew_blocks((long long)(P / VEC));
+    const int want = (num_sms() * 8 + N - 1) / N;
+    if (per_image > want) per_image = want;
+    const dim3 grid((unsigned)per_image, (unsigned)N);
+    UB_LAUNCH_NC((wmap_count_kernel<LabelT, VEC>), grid, 256, 0, s, labels, P, counts);
+    UB_POST_LAUNCH();
+    if (out_bytes == 8)
+        UB_LAUNCH_NC((wmap_emit_kernel<LabelT, double, VEC>), grid, 256, 0, s, labels, P, counts, border, (double*)out);
+    else
+        UB_LAUNCH_NC((wmap_emit_kernel<LabelT, float, VEC>), grid, 256, 0, s, labels, P, counts, border, (float*)out);
+    UB_POST_LAUNCH();
+    return UB_OK;
+}
+int launch_weight_map(const void* labels, int label_bytes, int N, int H, int W, double w0,
+                      double sigma, void* out, int out_bytes, unsigned* counts, cudaStream_t s) {
+    if (!labels || !out || !counts || N < 1 || H < 1 || W < 1 || N > 65535) {
+        set_last_error("weight_map: null pointer or bad shape (N=%d H=%d W=%d)", N, H, W);
+        return UB_ERR_ARG;
+    }
+    if ((label_bytes != 1 && label_bytes != 2) || (out_bytes != 4 && out_bytes != 8)) {
+        set_last_error("weight_map: labels must be uint8 / uint16, output float32 / float64");
+        return UB_ERR_ARG;
+    }
+    if (!(w0 == w0) || !(sigma == sigma) || !(sigma * sigma + 1e-8 > 0.0)) {
+        set_last_error("weight_map: w0 / sigma must be finite numbers");
+        return UB_ERR_ARG;
+    }
+    const long long P = (long long)H * W;
+    if (P >= 0x7FFFFFFFLL) {
+        set_last_error("weight_map: image too large for 32-bit indexing");
+        return UB_ERR_UNSUPPORTED;
+    }
+    // w0 * exp(-((d1 + d2)^2) / (2 (sigma^2 + 1e-8))) with d1 = d2 = 0 (see weight_map.cuh)
+    const double border = w0 * std::exp(-0.0 / (2.0 * (sigma * sigma + 1e-8)));
+    UB_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)N * sizeof(unsigned), s));
+    const bool vec = P % 4 == 0;
+    if (label_bytes == 1)
+        return vec ? weight_map_typed<unsigned char, 4>((const unsigned char*)labels, N, (unsigned)P, border, out, out_bytes, counts, s)
+                   : weight_map_typed<unsigned char, 1>((const unsigned char*)labels, N, (unsigned)P, border, out, out_bytes, counts, s);
+    return vec ? weight_map_typed<unsigned short, 4>((const unsigned short*)labels, N, (unsigned)P, border, out, out_bytes, counts, s)
+               : weight_map_typed<unsigned short, 1>((const unsigned short*)labels, N, (unsigned)P, border, out, out_bytes, counts, s);
 }
 
 // ---------------------------------------------------------------------------------------------

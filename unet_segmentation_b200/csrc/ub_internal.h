@@ -204,6 +204,8 @@ int launch_prepare_batch(const unsigned char* img, const void* labels, int label
                          const void* wmap, int wmap_bytes, int N, int H, int W, int oh, int ow,
                          float* image, long long* target, float* weight, cudaStream_t s);
 size_t ccl_ws_bytes(int H, int W);
+int launch_weight_map(const void* labels, int label_bytes, int N, int H, int W, double w0,
+                      double sigma, void* out, int out_bytes, unsigned* counts, cudaStream_t s);
 int launch_ccl(const unsigned char* mask, int H, int W, int min_size, unsigned short* out, void* ws,
                cudaStream_t s);
 

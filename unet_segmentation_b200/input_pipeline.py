@@ -12,6 +12,11 @@ kernel (``ub_prepare_batch``) produces the three tensors the training step consu
 
 bit-exactly what the reference pipeline yields, with 6–11 bytes per pixel crossing PCIe instead of
 16. ``DeviceBatchPreparer`` double-buffers the host→device copies on a side stream.
+
+Row N4: ``weight_maps_from_labels`` computes the weight maps themselves on the device
+(``ub_weight_map`` = ``calculate_weight_map`` of ``scripts/preprocess_data.py:17-77``, bit-exact
+against the reference's stored ``.npy`` maps), so the host ships 3 bytes per pixel (uint8 frame +
+uint16 labels) and ``DeviceBatchPreparer.submit(images, labels, None)`` needs no stored maps.
 """
 from __future__ import annotations
 
@@ -63,21 +68,53 @@ def prepare_batch(images_u8: torch.Tensor, labels: Optional[torch.Tensor],
     return image, target, weight
 
 
+def weight_maps_from_labels(labels: torch.Tensor, w0: float = 10, sigma: float = 5,
+                            dtype: torch.dtype = torch.float64) -> torch.Tensor:
+    """``calculate_weight_map(mask, w0, sigma)`` (reference scripts/preprocess_data.py:17-77, defaults
+    W0 = 10, SIGMA = 5 of :14-15) for a batch: labels (N, H, W) or (H, W) uint8|uint16|int16 CUDA
+    instance masks -> weight maps of the same shape, float64 as the reference stores them (or
+    float32 = what ``utils/dataset.py:110`` hands to the loss). Bit-exact; see
+    ``csrc/weight_map.cuh`` for why the reference's border term is the constant ``w0``."""
+    if not labels.is_cuda or labels.dtype not in (torch.uint8, torch.uint16, torch.int16) \
+            or labels.dim() not in (2, 3):
+        raise ValueError("weight_maps_from_labels expects a CUDA uint8 / uint16 tensor of shape "
+                         "(N, H, W) or (H, W); the B200 input pipeline has no CPU path")
+    if dtype not in (torch.float32, torch.float64):
+        raise ValueError("dtype must be torch.float32 or torch.float64")
+    lab = labels.contiguous()
+    if lab.dim() == 2:
+        lab = lab.unsqueeze(0)
+    n, h, w = lab.shape
+    out = torch.empty(n, h, w, dtype=dtype, device=lab.device)
+    if out.numel() == 0:
+        return out.reshape(labels.shape)
+    counts = torch.empty(n, dtype=torch.int32, device=lab.device)
+    lib = _lib.load()
+    with torch.cuda.device(lab.device):
+        check(lib.ub_weight_map(_p(lab), lab.element_size(), n, h, w, float(w0), float(sigma), _p(out),
+                                out.element_size(), _p(counts),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+              "ub_weight_map")
+    return out.reshape(labels.shape)
+
+
 class DeviceBatchPreparer:
     """Double-buffered host→device staging + ``prepare_batch``: ``submit`` enqueues the compact
     copies of the NEXT batch on a side stream while the current step computes; ``get`` makes the
     compute stream wait for them and runs the kernel."""
 
-    def __init__(self, device, out_hw: Tuple[int, int]):
+    def __init__(self, device, out_hw: Tuple[int, int], w0: float = 10, sigma: float = 5):
         self.device = torch.device(device)
         self.out_hw = out_hw
+        self.w0, self.sigma = w0, sigma   # used when a batch is submitted without stored maps
         self.stream = torch.cuda.Stream(device=self.device)
         self.slots = [None, None]
         self.free = [None, None]
         self.k = 0
 
     def submit(self, images_u8, labels, weight_maps):
-        """Pinned host tensors (uint8 images, uint8/uint16 labels, float32/float64 weight maps)."""
+        """Pinned host tensors (uint8 images, uint8/uint16 labels, float32/float64 weight maps).
+        ``weight_maps=None`` with labels present: the maps are computed on the device (row N4)."""
         k = self.k
         self.k ^= 1
         with torch.cuda.stream(self.stream):
@@ -94,7 +131,10 @@ class DeviceBatchPreparer:
         dev, ev = self.slots[k]
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)
-        out = prepare_batch(dev[0], dev[1], dev[2], self.out_hw)
+        wmaps = dev[2]
+        if wmaps is None and dev[1] is not None:
+            wmaps = weight_maps_from_labels(dev[1], self.w0, self.sigma, torch.float32)
+        out = prepare_batch(dev[0], dev[1], wmaps, self.out_hw)
         self.free[k] = torch.cuda.Event()
         self.free[k].record(cur)
         for t in dev:
