@@ -14,5 +14,9 @@ Pinning status:
     (data/raw/processed/predictions/DIC-C2DH-HeLa/01_RES{,_INST}); a subset is committed as
     tests/golden/ccl_golden.npz.
   * overlap-tile inference: absent from the reference -> PARITY UNPINNED; semantics
-    are defined in ``overlap_tile_ref.py`` and checked through the aligned-tile invariant.
+    are defined in ``overlap_tile_ref.py`` and checked through the aligned-tile invariant
+    (tests/test_overlap_tile_cpu.py on the oracle itself, tests/test_tiling_gpu.py on the library).
+  * calculate_weight_map (row N4): ``weight_map_ref.py`` is pinned by the 84 float64 weight maps the
+    reference stores next to its instance masks (data/raw/train/DIC-C2DH-HeLa/01_ST/WEIGHT_MAPS; all
+    checked live, three committed in tests/golden/weight_map_golden.npz) and by the live function.
 """
