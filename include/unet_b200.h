@@ -167,6 +167,27 @@ int ub_weight_map(const void* labels, int label_bytes, int N, int H, int W, doub
                   void* weight_maps, int weight_bytes, uint32_t* counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Elastic deformation: elastic_deform_image_and_mask(image, mask, alpha, sigma,
+ * random_state) of utils/augmentations.py:4-39 for a batch, on the device, bit-exact against the
+ * reference (scipy.ndimage.gaussian_filter(mode="constant") + map_coordinates(mode="reflect")).
+ *   images      [N][H][W] uint8 (may be NULL)      -> images_out uint8: bilinear, rounded half up
+ *   labels      [N][H][W] uint8 / uint16 (may be NULL) -> labels_out, nearest neighbour;
+ *               label_out_bytes 1 with uint16 input wraps modulo 256 like the reference's
+ *               mask.astype(np.uint8) (utils/dataset.py:93)
+ *   noise       [2][N][H][W] float64 uniform [0, 1) draws: the reference's random_state.rand(*shape)
+ *               for dx (first draw, augmentations.py:27) then for dy (:28) of every sample
+ *   taps        2 * radius + 1 float64 Gaussian weights (only the first radius + 1 are read):
+ *               exp(-0.5 / sigma^2 * x^2) / sum for x = -radius … radius, radius = int(4 sigma + .5)
+ *               (scipy's _gaussian_kernel1d; computed by the caller so that exp is numpy's)
+ *   workspace   ub_elastic_workspace_bytes(N, H, W) bytes of device scratch
+ * ---------------------------------------------------------------------------------------------- */
+int64_t ub_elastic_workspace_bytes(int N, int H, int W);
+int ub_elastic_deform(const uint8_t* images, const void* labels, int label_bytes, int N, int H, int W,
+                      const double* noise, const double* taps, int radius, double alpha,
+                      uint8_t* images_out, void* labels_out, int label_out_bytes, void* workspace,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * get_instance_masks (utils/metrics.py:42-72): 8-connected labelling in raster order, components
  * smaller than min_size zeroed, ids not compacted, uint16 output. Bit-exact.
  * ---------------------------------------------------------------------------------------------- */

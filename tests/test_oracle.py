@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 REF = "/root/reference"
 
-from oracle import ccl_ref, unet_ref, weight_map_ref  # noqa: E402
+from oracle import ccl_ref, elastic_ref, unet_ref, weight_map_ref  # noqa: E402
 
 
 def _case(blob, name):
@@ -208,6 +208,48 @@ def test_weight_map_oracle_matches_live_reference_and_all_stored_maps():
         num = os.path.basename(f)[len("weight_map_"):-4]
         m = np.array(Image.open(os.path.join(base, "SEG", f"man_seg{num}.tif")))
         assert np.array_equal(weight_map_ref.weight_map_closed_form(m), np.load(f)), f
+
+
+_ELASTIC_CASES = [((96, 80), 2000, 20, 123), ((64, 48), 300, 3, 7), ((33, 17), 2000, 2, 9),
+                  ((5, 7), 50, 0.8, 1), ((1, 9), 20, 1, 2)]
+
+
+def _elastic_inputs(shape, seed):
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, shape).astype(np.uint8)
+    lab = (rng.integers(0, 60000, shape) * (rng.random(shape) < 0.5)).astype(np.uint16)
+    return img, lab
+
+
+@pytest.mark.parametrize("shape,alpha,sigma,seed", _ELASTIC_CASES)
+def test_elastic_step_by_step_oracle_equals_scipy_restatement(shape, alpha, sigma, seed):
+    """The plain-numpy arithmetic the CUDA kernels mirror is bit-identical to the reference's scipy
+    calls (utils/augmentations.py:27-37), incl. displacements of several image sizes (repeated
+    reflection) and one-pixel-high images."""
+    img, lab = _elastic_inputs(shape, seed)
+    si, sm = elastic_ref.elastic_deform_scipy(img, lab, alpha, sigma, seed)
+    u, v = elastic_ref.reference_noise(seed, shape)
+    ti, tm = elastic_ref.elastic_deform_steps(img, lab, u, v, alpha, sigma)
+    assert si.dtype == ti.dtype == np.uint8 and sm.dtype == tm.dtype == np.uint16
+    assert np.array_equal(si, ti) and np.array_equal(sm, tm)
+    assert not np.array_equal(si, img)                      # the deformation does something
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_elastic_oracle_matches_live_reference():
+    sys.dont_write_bytecode = True
+    spec = importlib.util.spec_from_file_location(
+        "ref_augmentations", os.path.join(REF, "utils", "augmentations.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    for shape, alpha, sigma, seed in _ELASTIC_CASES + [((512, 512), 2000, 20, 2024)]:
+        img, lab = _elastic_inputs(shape, seed)
+        ri, rm = ref.elastic_deform_image_and_mask(img, lab, alpha, sigma, random_state=seed)
+        si, sm = elastic_ref.elastic_deform_scipy(img, lab, alpha, sigma, seed)
+        u, v = elastic_ref.reference_noise(seed, shape)
+        ti, tm = elastic_ref.elastic_deform_steps(img, lab, u, v, alpha, sigma)
+        assert np.array_equal(ri, si) and np.array_equal(rm, sm), shape
+        assert np.array_equal(ri, ti) and np.array_equal(rm, tm), shape
 
 
 def test_c_abi_exports_every_declared_symbol():

@@ -65,6 +65,9 @@ _SIGNATURES = {
                                  _P, _P]),
     "ub_weight_map": (c_int, [_P, c_int, c_int, c_int, c_int, C.c_double, C.c_double, _P, c_int, _P,
                               _P]),
+    "ub_elastic_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "ub_elastic_deform": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, C.c_double, _P, _P,
+                                  c_int, _P, _P]),
     "ub_ccl_workspace_bytes": (c_int64, [c_int, c_int]),
     "ub_ccl_label": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
     "ub_op_pack_conv3x3": (c_int, [_P, c_int, c_int, _P, _P, _P]),

@@ -63,6 +63,16 @@ int ub_weight_map(const void* labels, int label_bytes, int N, int H, int W, doub
     return launch_weight_map(labels, label_bytes, N, H, W, w0, sigma, weight_maps, weight_bytes,
                              counts, S(stream));
 }
+int64_t ub_elastic_workspace_bytes(int N, int H, int W) {
+    return N > 0 && H > 0 && W > 0 ? (int64_t)elastic_ws_bytes(N, H, W) : 0;
+}
+int ub_elastic_deform(const uint8_t* images, const void* labels, int label_bytes, int N, int H, int W,
+                      const double* noise, const double* taps, int radius, double alpha,
+                      uint8_t* images_out, void* labels_out, int label_out_bytes, void* workspace,
+                      void* stream) {
+    return launch_elastic(images, labels, label_bytes, N, H, W, noise, taps, radius, alpha, images_out,
+                          labels_out, label_out_bytes, workspace, S(stream));
+}
 int64_t ub_ccl_workspace_bytes(int H, int W) { return (int64_t)ccl_ws_bytes(H, W); }
 int ub_ccl_label(const uint8_t* mask, int H, int W, int min_size, uint16_t* labels, void* workspace,
                  void* stream) {

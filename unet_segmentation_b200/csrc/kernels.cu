@@ -3,6 +3,7 @@
 #include <cmath>
 
 #include "ccl.cuh"
+#include "elastic.cuh"
 #include "elementwise.cuh"
 #include "first_conv.cuh"
 #include "head_loss.cuh"
@@ -455,6 +456,69 @@ int launch_weight_map(const void* labels, int label_bytes, int N, int H, int W, 
                    : weight_map_typed<unsigned char, 1>((const unsigned char*)labels, N, (unsigned)P, border, out, out_bytes, counts, s);
     return vec ? weight_map_typed<unsigned short, 4>((const unsigned short*)labels, N, (unsigned)P, border, out, out_bytes, counts, s)
                : weight_map_typed<unsigned short, 1>((const unsigned short*)labels, N, (unsigned)P, border, out, out_bytes, counts, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Elastic deformation: noise [2][N][H][W] (dx draws, then dy draws) -> workspace halves
+// [0] = after the row pass, [1] = displacement fields [2][N][H][W]; then one sampling pass.
+size_t elastic_ws_bytes(int N, int H, int W) { return (size_t)4 * N * H * W * sizeof(double); }
+template <typename LI, typename LO>
+static int elastic_sample_typed(const unsigned char* img, const void* labels, const double* dx,
+                                const double* dy, int N, int H, int W, unsigned char* img_out,
+                                void* labels_out, cudaStream_t s) {
+    UB_LAUNCH_NC((elastic_sample_kernel<LI, LO>), ew_blocks((long long)N * H * W), 256, 0, s, img,
+                 (const LI*)labels, dx, dy, N, H, W, img_out, (LO*)labels_out);
+    UB_POST_LAUNCH();
+    return UB_OK;
+}
+int launch_elastic(const unsigned char* img, const void* labels, int label_bytes, int N, int H, int W,
+                   const double* noise, const double* taps, int radius, double alpha,
+                   unsigned char* img_out, void* labels_out, int label_out_bytes, void* ws,
+                   cudaStream_t s) {
+    if (!noise || !taps || !ws || N < 1 || H < 1 || W < 1 || radius < 0) {
+        set_last_error("elastic_deform: null pointer or bad shape (N=%d H=%d W=%d radius=%d)", N, H, W, radius);
+        return UB_ERR_ARG;
+    }
+    if ((img && !img_out) || (labels && !labels_out) || (!img && !labels) ||
+        (labels && ((label_bytes != 1 && label_bytes != 2) || (label_out_bytes != 1 && label_out_bytes != 2)))) {
+        set_last_error("elastic_deform: need images and / or labels (uint8 / uint16) with their outputs");
+        return UB_ERR_ARG;
+    }
+    if ((long long)N * H * W >= 0x7FFFFFFFLL || 2LL * N > 65535) {
+        set_last_error("elastic_deform: batch too large for 32-bit indexing");
+        return UB_ERR_UNSUPPORTED;
+    }
+    const size_t smem_v = elastic_v_smem(radius), smem_h = elastic_h_smem(radius);
+    if (smem_v > 200 * 1024 || smem_h > 200 * 1024) {
+        set_last_error("elastic_deform: Gaussian radius %d (sigma too large) exceeds the shared-memory tile", radius);
+        return UB_ERR_UNSUPPORTED;
+    }
+    // opt-in to > 48 KB of dynamic shared memory (per device, so not cached in a static)
+    UB_CHECK_CUDA(cudaFuncSetAttribute(elastic_blur_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    UB_CHECK_CUDA(cudaFuncSetAttribute(elastic_blur_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const size_t field = (size_t)N * H * W;
+    double* tmp = reinterpret_cast<double*>(ws);
+    double* disp = tmp + 2 * field;
+    const dim3 gv((W + 31) / 32, (H + EL_V_ROWS - 1) / EL_V_ROWS, 2 * N);
+    const dim3 gh((W + EL_H_COLS - 1) / EL_H_COLS, (H + EL_H_ROWS - 1) / EL_H_ROWS, 2 * N);
+    if (gv.y > 65535 || gh.y > 65535) {
+        set_last_error("elastic_deform: image too tall");
+        return UB_ERR_UNSUPPORTED;
+    }
+    UB_LAUNCH_NC(elastic_blur_rows_kernel, gv, dim3(32, 8), smem_v, s, noise, tmp, H, W, taps, radius, 1);
+    UB_POST_LAUNCH();
+    UB_LAUNCH_NC(elastic_blur_cols_kernel, gh, dim3(128, 2), smem_h, s, (const double*)tmp, disp, H, W, taps, radius, alpha);
+    UB_POST_LAUNCH();
+    const double* dx = disp;
+    const double* dy = disp + field;
+    if (!labels) return elastic_sample_typed<unsigned char, unsigned char>(img, nullptr, dx, dy, N, H, W, img_out, nullptr, s);
+    if (label_bytes == 1)
+        return label_out_bytes == 1
+                   ? elastic_sample_typed<unsigned char, unsigned char>(img, labels, dx, dy, N, H, W, img_out, labels_out, s)
+                   : elastic_sample_typed<unsigned char, unsigned short>(img, labels, dx, dy, N, H, W, img_out, labels_out, s);
+    return label_out_bytes == 1
+               ? elastic_sample_typed<unsigned short, unsigned char>(img, labels, dx, dy, N, H, W, img_out, labels_out, s)
+               : elastic_sample_typed<unsigned short, unsigned short>(img, labels, dx, dy, N, H, W, img_out, labels_out, s);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -206,6 +206,11 @@ int launch_prepare_batch(const unsigned char* img, const void* labels, int label
 size_t ccl_ws_bytes(int H, int W);
 int launch_weight_map(const void* labels, int label_bytes, int N, int H, int W, double w0,
                       double sigma, void* out, int out_bytes, unsigned* counts, cudaStream_t s);
+size_t elastic_ws_bytes(int N, int H, int W);
+int launch_elastic(const unsigned char* img, const void* labels, int label_bytes, int N, int H, int W,
+                   const double* noise, const double* taps, int radius, double alpha,
+                   unsigned char* img_out, void* labels_out, int label_out_bytes, void* ws,
+                   cudaStream_t s);
 int launch_ccl(const unsigned char* mask, int H, int W, int min_size, unsigned short* out, void* ws,
                cudaStream_t s);
 

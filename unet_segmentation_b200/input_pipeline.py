@@ -16,13 +16,18 @@ bit-exactly what the reference pipeline yields, with 6–11 bytes per pixel cros
 Row N4: ``weight_maps_from_labels`` computes the weight maps themselves on the device
 (``ub_weight_map`` = ``calculate_weight_map`` of ``scripts/preprocess_data.py:17-77``, bit-exact
 against the reference's stored ``.npy`` maps), so the host ships 3 bytes per pixel (uint8 frame +
-uint16 labels) and ``DeviceBatchPreparer.submit(images, labels, None)`` needs no stored maps.
+uint16 labels) and ``DeviceBatchPreparer.submit(images, labels, None)`` needs no stored maps;
+``elastic_deform`` is the reference's training augmentation (``utils/augmentations.py:4-39``,
+``elastic_deform_image_and_mask``; enabled in ``scripts/train.py:34-36`` with alpha 2000, sigma 20)
+for a whole batch in three kernels (``ub_elastic_deform``), bit-exact against scipy given the same
+uniform draws.
 """
 from __future__ import annotations
 
 import ctypes as C
 from typing import Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -96,6 +101,81 @@ def weight_maps_from_labels(labels: torch.Tensor, w0: float = 10, sigma: float =
                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)),
               "ub_weight_map")
     return out.reshape(labels.shape)
+
+
+def gaussian_taps(sigma: float, truncate: float = 4.0) -> np.ndarray:
+    """The 1-D kernel ``scipy.ndimage.gaussian_filter`` builds (``_gaussian_kernel1d``): radius
+    int(truncate * sigma + 0.5), exp(-0.5 / sigma^2 * x^2) normalised by its sum. Evaluated with
+    numpy on the host so that the weights carry numpy's ``exp`` rounding (2 r + 1 doubles per
+    call — plumbing, not a compute path)."""
+    sd = float(sigma)
+    if not sd > 0.0:
+        raise ValueError("sigma must be positive")
+    radius = int(truncate * sd + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sd * sd) * x ** 2)
+    return phi / phi.sum()
+
+
+def reference_noise(seeds, shape: Tuple[int, int]) -> torch.Tensor:
+    """The uniform draws the reference makes for each sample (``np.random.RandomState(seed)``,
+    ``rand(*shape)`` for dx then for dy; utils/augmentations.py:19-28, seeds from
+    utils/dataset.py:84) as a pinned float64 host tensor (2, N, H, W) for ``elastic_deform(noise=)``.
+    Use it to reproduce a reference run; leave ``noise=None`` to draw on the device instead."""
+    out = np.empty((2, len(seeds)) + tuple(shape), np.float64)
+    for k, seed in enumerate(seeds):
+        rs = np.random.RandomState(seed)
+        out[0, k] = rs.rand(*shape)
+        out[1, k] = rs.rand(*shape)
+    t = torch.from_numpy(out)
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+def elastic_deform(images_u8: Optional[torch.Tensor], labels: Optional[torch.Tensor],
+                   alpha: float = 2000, sigma: float = 20, noise: Optional[torch.Tensor] = None,
+                   generator: Optional[torch.Generator] = None, labels_as_uint8: bool = False):
+    """``elastic_deform_image_and_mask`` (reference utils/augmentations.py:4-39) for a batch:
+    images_u8 (N, H, W) uint8 -> bilinear-resampled uint8; labels (N, H, W) uint8|uint16 ->
+    nearest-neighbour-resampled labels (``labels_as_uint8`` wraps uint16 ids modulo 256 like the
+    ``astype(np.uint8)`` of utils/dataset.py:93). ``noise``: (2, N, H, W) float64 CUDA tensor of
+    uniform [0, 1) draws (``reference_noise`` reproduces the reference's seeds); None draws them on
+    the device with ``generator``. Returns (images, labels); an absent input gives None."""
+    ref = images_u8 if images_u8 is not None else labels
+    if ref is None or not ref.is_cuda or ref.dim() != 3:
+        raise ValueError("elastic_deform expects CUDA tensors of shape (N, H, W); the B200 input "
+                         "pipeline has no CPU path")
+    n, h, w = ref.shape
+    dev = ref.device
+    if images_u8 is not None and (images_u8.dtype != torch.uint8 or images_u8.shape != ref.shape):
+        raise ValueError("images must be (N, H, W) uint8")
+    if labels is not None and (labels.shape != ref.shape or labels.device != dev or
+                               labels.dtype not in (torch.uint8, torch.uint16, torch.int16)):
+        raise ValueError("labels must be (N, H, W) uint8 / uint16 on the images' device")
+    if noise is None:
+        noise = torch.rand(2, n, h, w, dtype=torch.float64, device=dev, generator=generator)
+    if noise.shape != (2, n, h, w) or noise.dtype != torch.float64 or noise.device != dev:
+        raise ValueError("noise must be a (2, N, H, W) float64 tensor on the images' device")
+    taps_np = gaussian_taps(sigma)
+    radius = (len(taps_np) - 1) // 2
+    taps = torch.from_numpy(taps_np).to(dev)
+    images_u8 = images_u8.contiguous() if images_u8 is not None else None
+    labels = labels.contiguous() if labels is not None else None
+    noise = noise.contiguous()
+    img_out = torch.empty_like(images_u8) if images_u8 is not None else None
+    lab_out = None
+    if labels is not None:
+        lab_out = torch.empty(n, h, w, dtype=torch.uint8 if labels_as_uint8 else labels.dtype, device=dev)
+    if n * h * w == 0:
+        return img_out, lab_out
+    lib = _lib.load()
+    ws = torch.empty(int(lib.ub_elastic_workspace_bytes(n, h, w)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.ub_elastic_deform(_p(images_u8), _p(labels), labels.element_size() if labels is not None else 0,
+                                    n, h, w, _p(noise), _p(taps), radius, float(alpha), _p(img_out),
+                                    _p(lab_out), lab_out.element_size() if lab_out is not None else 0,
+                                    _p(ws), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+              "ub_elastic_deform")
+    return img_out, lab_out
 
 
 class DeviceBatchPreparer:
