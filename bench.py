@@ -358,16 +358,19 @@ def main():
         dom = max(breakdown, key=lambda k: breakdown[k]["ms_per_step"])
         d = breakdown[dom]
         tensor_bound = d["tflops"] is not None
-        # DRAM traffic of that kernel class per launch, from the committed ncu --set full capture
+        # DRAM traffic of that kernel class per launch (= per layer), from the committed ncu captures:
+        # the per-class capture of one step (scripts_dev/traffic_by_class.py), else the --set full one
         traffic, traffic_src = None, None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-                tj = json.load(fh)
-            if dom in tj:
-                traffic = tj[dom]["dram_bytes_per_launch"]
-                traffic_src = tj["source"]
-        except Exception:
-            pass
+        for fname in ("r01_traffic_by_class.json", "r01_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", fname)) as fh:
+                    tj = json.load(fh)
+                if dom in tj:
+                    traffic = tj[dom]["dram_bytes_per_step"] / d["groups_per_step"]
+                    traffic_src = f"profiles/{fname}: {tj['source']}"
+                    break
+            except Exception:
+                pass
         if tensor_bound:
             peak = float(peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"])
             roofline = {"kernel": dom, "bound": "tensor", "achieved": d["tflops"], "peak": peak,

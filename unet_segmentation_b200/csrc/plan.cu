@@ -2,7 +2,11 @@
 // backward as a fixed sequence of kernel launches over a pre-allocated NHWC bf16 activation arena.
 // No allocation, no host synchronisation and no tensor-map-independent host work happens after
 // ub_plan_create, so a step can be captured into a CUDA graph.
+#include <stdlib.h>
+
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/unet_b200.h"
 #include "igemm.cuh"
@@ -113,10 +117,20 @@ struct ub_plan {
 enum : int { CLS_FPROP = 0, CLS_DGRAD, CLS_WGRAD, CLS_CT_FPROP, CLS_CT_DGRAD, CLS_CT_WGRAD,
              CLS_BN_APPLY, CLS_BN_BWD, CLS_FIRST, CLS_HEAD, CLS_COUNT };
 
-// Brackets the launches issued inside its scope with two CUDA events when profiling is enabled.
+static const char* const kClassNames[CLS_COUNT] = {
+    "conv3x3_fprop", "conv3x3_dgrad", "conv3x3_wgrad", "convT_fprop", "convT_dgrad", "convT_wgrad",
+    "bn_apply_relu_pool", "bn_relu_backward", "first_conv_fp32", "head_1x1"};
+static bool nvtx_on() {   // UB_NVTX=1: name every kernel class for `ncu --nvtx --print-nvtx-rename kernel`
+    static const bool on = [] { const char* e = getenv("UB_NVTX"); return e && e[0] == '1'; }();
+    return on;
+}
+
+// Brackets the launches issued inside its scope with two CUDA events when profiling is enabled
+// (and with an NVTX range named after the kernel class under UB_NVTX=1).
 struct ProfScope {
-    ub_plan* P; cudaStream_t s; cudaEvent_t e1 = nullptr;
+    ub_plan* P; cudaStream_t s; cudaEvent_t e1 = nullptr; bool range = false;
     ProfScope(ub_plan* P_, int cls, double flops, double bytes, cudaStream_t s_) : P(P_), s(s_) {
+        if (nvtx_on()) { nvtxRangePushA(kClassNames[cls]); range = true; }
         if (!P->prof_on) return;
         ub_plan::ProfRec r;
         r.cls = cls; r.flops = flops; r.bytes = bytes;
@@ -125,7 +139,10 @@ struct ProfScope {
         e1 = r.e1;
         P->prof.push_back(r);
     }
-    ~ProfScope() { if (e1) cudaEventRecord(e1, s); }
+    ~ProfScope() {
+        if (e1) cudaEventRecord(e1, s);
+        if (range) nvtxRangePop();
+    }
 };
 static inline double gemm_bytes(double rows_in, double cin, double cout, double taps, double rows_out) {
     return 2.0 * (rows_in * cin + cout * taps * cin + rows_out * cout);
@@ -830,11 +847,7 @@ int ub_plan_profile_enable(ub_plan* P, int on) {
 }
 int ub_plan_profile_classes(void) { return CLS_COUNT; }
 const char* ub_plan_profile_class_name(int cls) {
-    static const char* names[CLS_COUNT] = {"conv3x3_fprop", "conv3x3_dgrad", "conv3x3_wgrad",
-                                           "convT_fprop", "convT_dgrad", "convT_wgrad",
-                                           "bn_apply_relu_pool", "bn_relu_backward", "first_conv_fp32",
-                                           "head_1x1"};
-    return (cls >= 0 && cls < CLS_COUNT) ? names[cls] : "";
+    return (cls >= 0 && cls < CLS_COUNT) ? kClassNames[cls] : "";
 }
 int ub_plan_profile_collect(ub_plan* P, double* ms, double* flops, double* bytes, int* launches) {
     if (!P || !ms || !flops || !bytes || !launches) return ub::UB_ERR_ARG;
