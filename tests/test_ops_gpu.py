@@ -557,3 +557,24 @@ def test_device_elastic_deformation_bit_exact(n, h, w, alpha, sigma, lbl_dtype):
     a = input_pipeline.elastic_deform(d_img, d_lab, alpha, sigma, generator=g1)
     b = input_pipeline.elastic_deform(d_img, d_lab, alpha, sigma, generator=g2)
     assert torch.equal(a[0], b[0]) and np.array_equal(a[1].cpu().numpy(), b[1].cpu().numpy())
+
+
+def test_device_batch_preparer_with_augmentation_matches_the_manual_sequence():
+    """augment=(alpha, sigma): weight maps of the UNDEFORMED labels (the reference keeps the stored
+    map, utils/dataset.py:81-94), elastic deformation of frame + labels, uint8 cast of the deformed
+    mask, then tensor conversion and crop."""
+    from unet_segmentation_b200 import input_pipeline as ip
+    g = torch.Generator().manual_seed(8)
+    n, h, w, oh = 2, 96, 96, 52
+    img = torch.randint(0, 256, (n, h, w), generator=g, dtype=torch.uint8)
+    lbl = (torch.randint(1, 600, (n, h, w), generator=g) * (torch.rand(n, h, w, generator=g) > 0.5)).to(torch.int32).to(torch.uint16)
+    prep = ip.DeviceBatchPreparer("cuda", (oh, oh), augment=(300, 4),
+                                  generator=torch.Generator(device="cuda").manual_seed(77))
+    image, target, weight = prep.get(prep.submit(img.pin_memory(), lbl.pin_memory(), None))
+    wm = ip.weight_maps_from_labels(lbl.cuda(), dtype=torch.float32)
+    d_img, d_lbl = ip.elastic_deform(img.cuda(), lbl.cuda(), 300, 4, labels_as_uint8=True,
+                                     generator=torch.Generator(device="cuda").manual_seed(77))
+    image2, target2, weight2 = ip.prepare_batch(d_img, d_lbl, wm, (oh, oh))
+    torch.cuda.synchronize()
+    assert torch.equal(image, image2) and torch.equal(target, target2) and torch.equal(weight, weight2)
+    assert not torch.equal(image[:, 0], img.cuda().float().div(255))      # it did deform

@@ -183,10 +183,17 @@ class DeviceBatchPreparer:
     copies of the NEXT batch on a side stream while the current step computes; ``get`` makes the
     compute stream wait for them and runs the kernel."""
 
-    def __init__(self, device, out_hw: Tuple[int, int], w0: float = 10, sigma: float = 5):
+    def __init__(self, device, out_hw: Tuple[int, int], w0: float = 10, sigma: float = 5,
+                 augment: Optional[Tuple[float, float]] = None,
+                 generator: Optional[torch.Generator] = None):
+        """``augment=(alpha, sigma)`` applies the reference's elastic deformation to frame and
+        labels on the device (utils/dataset.py:83-94; (2000, 20) in scripts/train.py:35-36), with
+        uniform draws from ``generator``. As in the reference, the weight map is NOT deformed: it
+        is the stored map, or — when none is submitted — the map of the undeformed labels."""
         self.device = torch.device(device)
         self.out_hw = out_hw
         self.w0, self.sigma = w0, sigma   # used when a batch is submitted without stored maps
+        self.augment, self.generator = augment, generator
         self.stream = torch.cuda.Stream(device=self.device)
         self.slots = [None, None]
         self.free = [None, None]
@@ -211,10 +218,14 @@ class DeviceBatchPreparer:
         dev, ev = self.slots[k]
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)
-        wmaps = dev[2]
-        if wmaps is None and dev[1] is not None:
-            wmaps = weight_maps_from_labels(dev[1], self.w0, self.sigma, torch.float32)
-        out = prepare_batch(dev[0], dev[1], wmaps, self.out_hw)
+        images, labels, wmaps = dev
+        if wmaps is None and labels is not None:
+            wmaps = weight_maps_from_labels(labels, self.w0, self.sigma, torch.float32)
+        if self.augment is not None:
+            # the reference casts the deformed mask to uint8 (utils/dataset.py:93)
+            images, labels = elastic_deform(images, labels, self.augment[0], self.augment[1],
+                                            generator=self.generator, labels_as_uint8=True)
+        out = prepare_batch(images, labels, wmaps, self.out_hw)
         self.free[k] = torch.cuda.Event()
         self.free[k].record(cur)
         for t in dev:
