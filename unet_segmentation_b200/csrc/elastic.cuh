@@ -14,21 +14,67 @@
 //   3. per pixel: (y + dy, x + dx) folded back into the image ('reflect'), image sampled
 //      bilinearly and rounded half up into uint8, instance mask sampled at the nearest pixel.
 // The Gaussian passes stage a tile plus its 2 r halo rows / columns in shared memory (each input
-// element is read from HBM ~once instead of 2 r + 1 times); taps come from the host (numpy's exp).
+// element is read from HBM ~once instead of 2 r + 1 times) and every thread slides two 4-element
+// register windows along the filter axis (2 shared-memory loads per 4 outputs and tap instead of
+// 8); taps come from the host (numpy's exp).
 #pragma once
 #include "common.cuh"
 
 namespace ub {
 
-constexpr int EL_V_ROWS = 64;    // vertical pass: output rows per CTA (x 32 columns)
-constexpr int EL_H_COLS = 128;   // horizontal pass: output columns per CTA (x 8 rows)
-constexpr int EL_H_ROWS = 8;
+constexpr int EL_V_ROWS = 64;    // row pass: output rows per CTA (x 32 columns)
+constexpr int EL_H_COLS = 128;   // column pass: output columns per CTA (x 32 rows)
+constexpr int EL_H_ROWS = 32;
+constexpr int EL_H_PITCH = 33;   // transposed tile [column][row], padded against bank conflicts
+constexpr int EL_RUN = 4;        // consecutive outputs per thread along the filter axis
 
 __host__ __device__ inline size_t elastic_v_smem(int r) { return ((size_t)(EL_V_ROWS + 2 * r) * 32 + r + 1) * 8; }
-__host__ __device__ inline size_t elastic_h_smem(int r) { return ((size_t)EL_H_ROWS * (EL_H_COLS + 2 * r) + r + 1) * 8; }
+__host__ __device__ inline size_t elastic_h_smem(int r) { return ((size_t)(EL_H_COLS + 2 * r) * EL_H_PITCH + r + 1) * 8; }
+
+// EL_RUN consecutive outputs along the filter axis from a zero-padded shared-memory line:
+//   acc[k] = x[k] w[r];  acc[k] += (x[k - d] + x[k + d]) w[r - d]  for d = r … 1   (scipy's order)
+// c0 points at x[0], consecutive positions are `stride` doubles apart, w[r - d] is the weight of
+// distance d. The two operand windows x[k - d] and x[k + d] (k = 0 … 3) move by one position per
+// step, so they live in two 4-register rings and each step loads 2 new values instead of 8 (the
+// first cut read every operand from shared memory and ran at 88-95 % of the shared-memory
+// wavefront peak with the FP64 pipe at 28 %, profiles/r01_summary.md). Ring slot of logical
+// element k after s steps: (k + s) & 3 on the left, (k - s) & 3 on the right.
+template <int S>
+__device__ __forceinline__ void el_blur_step(const double* c0, int stride, double wd, int d,
+                                             double (&acc)[EL_RUN], double (&L)[EL_RUN],
+                                             double (&R)[EL_RUN]) {
+#pragma unroll
+    for (int k = 0; k < EL_RUN; ++k)
+        acc[k] = __dadd_rn(acc[k], __dmul_rn(__dadd_rn(L[(k + S) & 3], R[(k - S) & 3]), wd));
+    // windows of distance d - 1: the left one gains x[3 - (d - 1)], the right one x[d - 1]
+    L[S & 3] = c0[(EL_RUN - d) * stride];
+    R[(3 - S) & 3] = c0[(d - 1) * stride];
+}
+__device__ __forceinline__ void el_blur_run(const double* c0, int stride, const double* w, int r,
+                                            double (&acc)[EL_RUN]) {
+    static_assert(EL_RUN == 4, "ring indexing assumes runs of 4");
+    double L[EL_RUN], R[EL_RUN];
+#pragma unroll
+    for (int k = 0; k < EL_RUN; ++k) {
+        acc[k] = __dmul_rn(c0[k * stride], w[r]);
+        L[k] = c0[(k - r) * stride];
+        R[k] = c0[(k + r) * stride];
+    }
+    int d = r;
+    for (; d >= 4; d -= 4) {
+        el_blur_step<0>(c0, stride, w[r - d], d, acc, L, R);
+        el_blur_step<1>(c0, stride, w[r - d + 1], d - 1, acc, L, R);
+        el_blur_step<2>(c0, stride, w[r - d + 2], d - 2, acc, L, R);
+        el_blur_step<3>(c0, stride, w[r - d + 3], d - 3, acc, L, R);
+    }
+    if (d >= 1) el_blur_step<0>(c0, stride, w[r - d], d, acc, L, R);
+    if (d >= 2) el_blur_step<1>(c0, stride, w[r - d + 1], d - 1, acc, L, R);
+    if (d >= 3) el_blur_step<2>(c0, stride, w[r - d + 2], d - 2, acc, L, R);
+}
 
 // Axis-0 pass. in / out: [images][H][W]; block (32, 8); grid (ceil(W/32), ceil(H/EL_V_ROWS), images).
-// taps[0..r] = weights of distance r … 0 (the first half of the symmetric kernel).
+// taps[0..r] = weights of distance r … 0 (the first half of the symmetric kernel). Thread (tx, ty)
+// computes column tx of the tile, rows ty * 8 … ty * 8 + 7 as two runs of 4.
 static __global__ void __launch_bounds__(256)
 elastic_blur_rows_kernel(const double* __restrict__ in, double* __restrict__ out, int H, int W,
                          const double* __restrict__ taps, int r, int affine) {
@@ -51,48 +97,53 @@ elastic_blur_rows_kernel(const double* __restrict__ in, double* __restrict__ out
     }
     __syncthreads();
     if (x >= W) return;
-    for (int k = ty; k < EL_V_ROWS; k += 8) {
-        const int y = y0 + k;
-        if (y >= H) break;
-        const double* c = tile + (k + r) * 32 + tx;
-        double acc = __dmul_rn(c[0], w[r]);
-        for (int d = r; d >= 1; --d)
-            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(c[-d * 32], c[d * 32]), w[r - d]));
-        out[img + (size_t)y * W + x] = acc;
+#pragma unroll 1
+    for (int g = 0; g < 8 / EL_RUN; ++g) {
+        const int k0 = ty * 8 + g * EL_RUN;
+        if (y0 + k0 >= H) break;
+        double acc[EL_RUN];
+        el_blur_run(tile + (k0 + r) * 32 + tx, 32, w, r, acc);
+#pragma unroll
+        for (int k = 0; k < EL_RUN; ++k)
+            if (y0 + k0 + k < H) out[img + (size_t)(y0 + k0 + k) * W + x] = acc[k];
     }
 }
 
-// Axis-1 pass, result times alpha. block (128, 2); grid (ceil(W/EL_H_COLS), ceil(H/EL_H_ROWS), images).
+// Axis-1 pass, result times alpha. block (32, 8); grid (ceil(W/EL_H_COLS), ceil(H/EL_H_ROWS), images).
+// The tile is stored transposed ([column][row], pitch 33) so that the 32 lanes of a warp = 32 rows
+// read consecutive words while each thread slides along its row: thread (tr, tg) computes row tr,
+// columns tg * 16 … tg * 16 + 15 as four runs of 4.
 static __global__ void __launch_bounds__(256)
 elastic_blur_cols_kernel(const double* __restrict__ in, double* __restrict__ out, int H, int W,
                          const double* __restrict__ taps, int r, double alpha) {
     pdl_entry();
     extern __shared__ double el_smem[];
-    const int pitch = EL_H_COLS + 2 * r;
-    double* tile = el_smem;                               // [EL_H_ROWS][pitch]
-    double* w = el_smem + (size_t)EL_H_ROWS * pitch;      // [r + 1]
-    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int cols = EL_H_COLS + 2 * r;
+    double* tile = el_smem;                                   // [cols][EL_H_PITCH]
+    double* w = el_smem + (size_t)cols * EL_H_PITCH;          // [r + 1]
+    const int tr = threadIdx.x, tg = threadIdx.y;
     const int x0 = blockIdx.x * EL_H_COLS, y0 = blockIdx.y * EL_H_ROWS;
     const size_t img = (size_t)blockIdx.z * H * W;
-    for (int i = ty * 128 + tx; i <= r; i += 256) w[i] = taps[i];
-    for (int row = ty; row < EL_H_ROWS; row += 2) {
+    for (int i = tg * 32 + tr; i <= r; i += 256) w[i] = taps[i];
+    for (int row = tg; row < EL_H_ROWS; row += 8) {           // a warp loads one row, coalesced
         const int y = y0 + row;
-        for (int j = tx; j < pitch; j += 128) {
+        for (int j = tr; j < cols; j += 32) {
             const int x = x0 - r + j;
-            tile[row * pitch + j] = (y < H && x >= 0 && x < W) ? in[img + (size_t)y * W + x] : 0.0;
+            tile[j * EL_H_PITCH + row] = (y < H && x >= 0 && x < W) ? in[img + (size_t)y * W + x] : 0.0;
         }
     }
     __syncthreads();
-    const int x = x0 + tx;
-    if (x >= W) return;
-    for (int row = ty; row < EL_H_ROWS; row += 2) {
-        const int y = y0 + row;
-        if (y >= H) break;
-        const double* c = tile + row * pitch + tx + r;
-        double acc = __dmul_rn(c[0], w[r]);
-        for (int d = r; d >= 1; --d)
-            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(c[-d], c[d]), w[r - d]));
-        out[img + (size_t)y * W + x] = __dmul_rn(acc, alpha);
+    const int y = y0 + tr;
+    if (y >= H) return;
+#pragma unroll 1
+    for (int g = 0; g < 16 / EL_RUN; ++g) {
+        const int k0 = tg * 16 + g * EL_RUN;
+        if (x0 + k0 >= W) break;
+        double acc[EL_RUN];
+        el_blur_run(tile + (k0 + r) * EL_H_PITCH + tr, EL_H_PITCH, w, r, acc);
+#pragma unroll
+        for (int k = 0; k < EL_RUN; ++k)
+            if (x0 + k0 + k < W) out[img + (size_t)y * W + x0 + k0 + k] = __dmul_rn(acc[k], alpha);
     }
 }
 

@@ -507,7 +507,7 @@ int launch_elastic(const unsigned char* img, const void* labels, int label_bytes
     }
     UB_LAUNCH_NC(elastic_blur_rows_kernel, gv, dim3(32, 8), smem_v, s, noise, tmp, H, W, taps, radius, 1);
     UB_POST_LAUNCH();
-    UB_LAUNCH_NC(elastic_blur_cols_kernel, gh, dim3(128, 2), smem_h, s, (const double*)tmp, disp, H, W, taps, radius, alpha);
+    UB_LAUNCH_NC(elastic_blur_cols_kernel, gh, dim3(32, 8), smem_h, s, (const double*)tmp, disp, H, W, taps, radius, alpha);
     UB_POST_LAUNCH();
     const double* dx = disp;
     const double* dy = disp + field;
