@@ -117,6 +117,21 @@ def gaussian_taps(sigma: float, truncate: float = 4.0) -> np.ndarray:
     return phi / phi.sum()
 
 
+_TAPS_CACHE: dict = {}
+
+
+def _device_taps(sigma: float, device: torch.device) -> Tuple[torch.Tensor, int]:
+    """Gaussian taps as a device tensor, cached per (sigma, device): the upload is a synchronous
+    pageable copy that should not sit in a per-batch loop."""
+    key = (float(sigma), str(device))
+    hit = _TAPS_CACHE.get(key)
+    if hit is None:
+        taps_np = gaussian_taps(sigma)
+        hit = (torch.from_numpy(taps_np).to(device), (len(taps_np) - 1) // 2)
+        _TAPS_CACHE[key] = hit
+    return hit
+
+
 def reference_noise(seeds, shape: Tuple[int, int]) -> torch.Tensor:
     """The uniform draws the reference makes for each sample (``np.random.RandomState(seed)``,
     ``rand(*shape)`` for dx then for dy; utils/augmentations.py:19-28, seeds from
@@ -155,9 +170,7 @@ def elastic_deform(images_u8: Optional[torch.Tensor], labels: Optional[torch.Ten
         noise = torch.rand(2, n, h, w, dtype=torch.float64, device=dev, generator=generator)
     if noise.shape != (2, n, h, w) or noise.dtype != torch.float64 or noise.device != dev:
         raise ValueError("noise must be a (2, N, H, W) float64 tensor on the images' device")
-    taps_np = gaussian_taps(sigma)
-    radius = (len(taps_np) - 1) // 2
-    taps = torch.from_numpy(taps_np).to(dev)
+    taps, radius = _device_taps(sigma, dev)
     images_u8 = images_u8.contiguous() if images_u8 is not None else None
     labels = labels.contiguous() if labels is not None else None
     noise = noise.contiguous()
