@@ -477,6 +477,40 @@ def main():
             infer[f"{size}x{size}"] = {"mpix_per_s": size * size / (ms_i * 1e-3) / 1e6, "ms": ms_i,
                                        "tiles": n_tiles, "tile_in": tile_in, "tile_out": tile_out,
                                        "batch_tiles": bt, "fg_fraction": float((mask > 0).float().mean())}
+        # the reference's per-frame predict loop (scripts/predict.py:73-112): one 512^2 frame from host
+        # memory -> eval forward -> (softmax[1] > 0.5) mask -> get_instance_masks -> both back on the host
+        if rank == 0:
+            try:
+                from unet_segmentation_b200.postprocess import get_instance_masks
+
+                frame_h = ((frame - 0.5) / 0.5).reshape(1, 1, 512, 512).pin_memory()   # Normalize(.5,.5)
+                mask_hb = torch.empty(324, 324, dtype=torch.uint8).pin_memory()
+                inst_hb = torch.empty(324, 324, dtype=torch.uint16).pin_memory()
+
+                def predict_frame():
+                    x = frame_h.to(dev, non_blocking=True)
+                    _, mk = model.predict_mask(x)
+                    inst = get_instance_masks(mk[0], min_size=15)
+                    mask_hb.copy_(mk[0], non_blocking=True)
+                    inst_hb.copy_(inst, non_blocking=True)
+
+                for _ in range(3):
+                    predict_frame()
+                torch.cuda.synchronize()
+                reps_f = 20
+                e0.record()
+                for _ in range(reps_f):
+                    predict_frame()
+                e1.record()
+                torch.cuda.synchronize()
+                ms_f = e0.elapsed_time(e1) / reps_f
+                infer["predict_frame_512"] = {"ms_per_frame": ms_f, "frames_per_s": 1e3 / ms_f,
+                                              "stages": "H2D 1x1x512x512 f32 -> eval forward (mask fused) -> "
+                                                        "8-connected labelling + <15 px filter -> D2H "
+                                                        "324x324 uint8 + uint16",
+                                              "max_label": int(inst_hb.numpy().max())}
+            except Exception as exc:   # an extra measurement must not take the contract line down
+                infer["predict_frame_512"] = {"error": f"{type(exc).__name__}: {exc}"}
         model.train()
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
