@@ -165,6 +165,7 @@ __device__ __forceinline__ double el_fold_coordinate(double c, int n) {
 }
 // d c b a | a b c d | d c b a for integer footprint positions
 __device__ __forceinline__ int el_fold_index(long long i, int n) {
+    if ((unsigned long long)i < (unsigned long long)n) return (int)i;   // in range: the common case
     if (n <= 1) return 0;
     if (i < 0) i = -i - 1;
     i %= 2LL * n;

@@ -192,9 +192,11 @@ def elastic_deform(images_u8: Optional[torch.Tensor], labels: Optional[torch.Ten
 
 
 class DeviceBatchPreparer:
-    """Double-buffered host→device staging + ``prepare_batch``: ``submit`` enqueues the compact
-    copies of the NEXT batch on a side stream while the current step computes; ``get`` makes the
-    compute stream wait for them and runs the kernel."""
+    """Double-buffered host→device staging + the device-side sample pipeline on a side stream:
+    ``submit`` enqueues, for the NEXT batch, the compact copies and every kernel of the pipeline
+    (weight maps, elastic deformation, ``prepare_batch``) on the preparer's own stream, so that they
+    overlap the training step running on the compute stream; ``get`` only makes the compute stream
+    wait for the finished tensors."""
 
     def __init__(self, device, out_hw: Tuple[int, int], w0: float = 10, sigma: float = 5,
                  augment: Optional[Tuple[float, float]] = None,
@@ -209,39 +211,41 @@ class DeviceBatchPreparer:
         self.augment, self.generator = augment, generator
         self.stream = torch.cuda.Stream(device=self.device)
         self.slots = [None, None]
-        self.free = [None, None]
         self.k = 0
 
-    def submit(self, images_u8, labels, weight_maps):
-        """Pinned host tensors (uint8 images, uint8/uint16 labels, float32/float64 weight maps).
-        ``weight_maps=None`` with labels present: the maps are computed on the device (row N4)."""
-        k = self.k
-        self.k ^= 1
-        with torch.cuda.stream(self.stream):
-            if self.free[k] is not None:
-                self.stream.wait_event(self.free[k])
-            dev = [t.to(self.device, non_blocking=True) if t is not None else None
-                   for t in (images_u8, labels, weight_maps)]
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        self.slots[k] = (dev, ev)
-        return k
-
-    def get(self, k):
-        dev, ev = self.slots[k]
-        cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(ev)
-        images, labels, wmaps = dev
+    def _process(self, images, labels, wmaps):
         if wmaps is None and labels is not None:
             wmaps = weight_maps_from_labels(labels, self.w0, self.sigma, torch.float32)
         if self.augment is not None:
             # the reference casts the deformed mask to uint8 (utils/dataset.py:93)
             images, labels = elastic_deform(images, labels, self.augment[0], self.augment[1],
                                             generator=self.generator, labels_as_uint8=True)
-        out = prepare_batch(images, labels, wmaps, self.out_hw)
-        self.free[k] = torch.cuda.Event()
-        self.free[k].record(cur)
-        for t in dev:
+        return prepare_batch(images, labels, wmaps, self.out_hw)
+
+    def submit(self, images_u8, labels, weight_maps):
+        """Pinned host tensors (uint8 images, uint8/uint16 labels, float32/float64 weight maps).
+        ``weight_maps=None`` with labels present: the maps are computed on the device (row N4).
+        Returns a slot index for ``get``; at most two batches may be in flight."""
+        k = self.k
+        self.k ^= 1
+        with torch.cuda.stream(self.stream):
+            # staging copies and intermediates are allocated, used and freed on this stream only
+            dev = [t.to(self.device, non_blocking=True) if t is not None else None
+                   for t in (images_u8, labels, weight_maps)]
+            out = self._process(*dev)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.slots[k] = (out, ev)
+        return k
+
+    def get(self, k):
+        """(images fp32 (N,1,H,W), targets int64 (N,h,w), weights fp32 (N,h,w)) of slot ``k``, ordered
+        after the preparer's stream on the current stream."""
+        out, ev = self.slots[k]
+        self.slots[k] = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in out:
             if t is not None:
-                t.record_stream(cur)
+                t.record_stream(cur)   # produced on the side stream, consumed (and freed) on this one
         return out
