@@ -365,21 +365,29 @@ def main():
                 loss_h.copy_(loss.detach(), non_blocking=True)
 
         pipe_loop(2)
-        barrier()
+        torch.cuda.synchronize()
         l0 = int(lib.ub_launch_count())
-        e0.record()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
         pipe_loop(args.steps)
-        e1.record()
-        barrier()
-        pipe_ms = max_over_ranks(e0.elapsed_time(e1))
-        pipeline = {"value": world * N * args.steps / (pipe_ms * 1e-3), "unit": "img/s",
-                    "ms_per_step": pipe_ms / args.steps,
+        pe1.record()
+        torch.cuda.synchronize()
+        pipe_local_ms = pe0.elapsed_time(pe1)
+        pipeline = {"unit": "img/s",
                     "h2d_bytes_per_step": img8_h.numel() + lbl_h.numel() * 2, "d2h_bytes_per_step": 4,
                     "gpu_launches_per_step": (int(lib.ub_launch_count()) - l0) / args.steps,
                     "stages": "uint8 frames + uint16 labels from pinned host memory -> ub_weight_map "
-                              "-> ub_elastic_deform(2000, 20) -> ub_prepare_batch -> training step"}
+                              "-> ub_elastic_deform(2000, 20) -> ub_prepare_batch (all on the preparer's "
+                              "stream, overlapping the previous step) -> training step"}
     except Exception as exc:   # the extra measurement must never take the contract line down
+        pipe_local_ms = float("nan")
         pipeline = {"error": f"{type(exc).__name__}: {exc}"}
+    # collectives stay outside the try block so that every rank reaches them
+    barrier()
+    pipe_ms = max_over_ranks(pipe_local_ms)
+    if "error" not in pipeline:
+        pipeline["value"] = world * N * args.steps / (pipe_ms * 1e-3)
+        pipeline["ms_per_step"] = pipe_ms / args.steps
 
     # ---------------- in-step kernel timing (roofline) ----------------
     roofline, breakdown = None, None
