@@ -62,6 +62,12 @@ typedef struct ub_plan ub_plan;
 
 int ub_plan_create(ub_plan** plan, int N, int n_channels, int H, int W, int base_channels,
                    int levels, int n_classes, int training);
+/* bilinear != 0: the Up blocks of UNet(..., bilinear=True) (models/unet_model.py:40-43,78-81):
+ * nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) keeps the channel count, the
+ * first convolution of the block then takes C_skip + C_prev channels (1536 -> 512 ...), and the
+ * up.{w, b} entries drop out of the parameter order (8 parameters per decoder stage). */
+int ub_plan_create_ex(ub_plan** plan, int N, int n_channels, int H, int W, int base_channels,
+                      int levels, int n_classes, int training, int bilinear);
 int ub_plan_destroy(ub_plan* plan);
 int ub_plan_out_hw(const ub_plan* plan, int* out_h, int* out_w);
 int ub_plan_num_params(const ub_plan* plan);
@@ -288,6 +294,11 @@ int64_t ub_op_head_bwd_workspace_floats(int K, int n_classes);
 int ub_op_head_backward(const float* dlogits, const void* a, int N, int H, int W, int K,
                         int n_classes, const float* w, void* da, float* workspace, float* dw,
                         float* db, void* stream);
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (Up with bilinear=True,
+ * models/unet_model.py:40-43): x view [N,H,W,C] -> out contiguous [N,2H,2W,C]; backward: g view
+ * [N,2H,2W,C] -> dx contiguous [N,H,W,C] (exact adjoint, gather form). bf16, C % 8 == 0. */
+int ub_op_upsample2x_forward(const ub_view* x, void* out, void* stream);
+int ub_op_upsample2x_backward(const ub_view* g, void* dx, void* stream);
 int ub_op_maxpool2(const void* a, void* pooled, int N, int H, int W, int C, void* stream);
 
 #ifdef __cplusplus

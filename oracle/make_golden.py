@@ -45,12 +45,12 @@ def sample_idx(numel, k=64):
     return np.unique(np.linspace(0, numel - 1, num=min(k, numel)).astype(np.int64))
 
 
-def unet_case(UNet, Loss, train_mod, n, size, seed_w, seed_x, training):
+def unet_case(UNet, Loss, train_mod, n, size, seed_w, seed_x, training, bilinear=False):
     sys.path.insert(0, ROOT)
     from oracle.unet_ref import synthetic_batch
 
     torch.manual_seed(seed_w)
-    model = UNet(n_channels=1, n_classes=2)
+    model = UNet(n_channels=1, n_classes=2, bilinear=bilinear)
     model.apply(train_mod.init_weights)
     img, t, w = synthetic_batch(n, size=size, seed=seed_x)
     out = {}
@@ -94,6 +94,11 @@ def main():
             blob[f"{name}/{k}"] = v
         blob[f"{name}/meta"] = np.array([n, size, sw, sx, int(tr)])
     np.savez_compressed(os.path.join(OUT, "unet_golden.npz"), **blob)
+    bil = {}     # UNet(1, 2, bilinear=True): nn.Upsample branch of the reference's Up block
+    for k, v in unet_case(UNet, Loss, train_mod, 1, 220, 3, 12, True, bilinear=True).items():
+        bil[f"train_n1_s220_bilinear/{k}"] = v
+    bil["train_n1_s220_bilinear/meta"] = np.array([1, 220, 3, 12, 1])
+    np.savez_compressed(os.path.join(OUT, "unet_bilinear_golden.npz"), **bil)
 
     from PIL import Image
 

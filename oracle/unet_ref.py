@@ -90,7 +90,10 @@ def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = 
                                   buffers_out, e))
     y = feats[-1]
     for j in range(1, levels):
-        up = _conv(y, sd[f"up{j}.up.weight"], sd[f"up{j}.up.bias"], e, transpose=True)
+        if f"up{j}.up.weight" in sd:
+            up = _conv(y, sd[f"up{j}.up.weight"], sd[f"up{j}.up.bias"], e, transpose=True)
+        else:   # bilinear=True: nn.Upsample has no parameters (models/unet_model.py:40-41)
+            up = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True)
         skip = center_crop(feats[levels - 1 - j], up.shape[-2:])
         y = _double_conv(torch.cat([skip, up], dim=1), sd, f"up{j}.conv.double_conv", training,
                          buffers_out, e)
@@ -132,7 +135,7 @@ def _double_conv_modules(cin, cout):
 
 
 def make_state_dict(n_channels=1, n_classes=2, seed=0, base=64, levels=5, init=True,
-                    device="cpu"):
+                    device="cpu", bilinear=False):
     import torch.nn as nn
 
     torch.manual_seed(seed)
@@ -142,8 +145,11 @@ def make_state_dict(n_channels=1, n_classes=2, seed=0, base=64, levels=5, init=T
         mods[f"down{i}.maxpool_conv.1.double_conv"] = _double_conv_modules(c[i - 1], c[i])
     for j in range(1, levels):
         cp = c[levels - j]
-        mods[f"up{j}.up"] = nn.ConvTranspose2d(cp, cp // 2, kernel_size=2, stride=2)
-        mods[f"up{j}.conv.double_conv"] = _double_conv_modules(cp, cp // 2)
+        if bilinear:    # Up(cp, cp/2, cp/2, True): DoubleConv(cp + cp/2, cp/2), models/unet_model.py:41-43
+            mods[f"up{j}.conv.double_conv"] = _double_conv_modules(cp + cp // 2, cp // 2)
+        else:
+            mods[f"up{j}.up"] = nn.ConvTranspose2d(cp, cp // 2, kernel_size=2, stride=2)
+            mods[f"up{j}.conv.double_conv"] = _double_conv_modules(cp, cp // 2)
     mods["outc.conv"] = nn.Conv2d(c[0], n_classes, kernel_size=1)
     if init:  # scripts/train.py:54-61 — nn.Conv2d only (ConvTranspose2d keeps torch's default)
         for m in mods.values():

@@ -578,3 +578,25 @@ def test_device_batch_preparer_with_augmentation_matches_the_manual_sequence():
     torch.cuda.synchronize()
     assert torch.equal(image, image2) and torch.equal(target, target2) and torch.equal(weight, weight2)
     assert not torch.equal(image[:, 0], img.cuda().float().div(255))      # it did deform
+
+
+@pytest.mark.parametrize("n,h,w,c,coff,ctot", [(2, 24, 24, 128, 0, 128), (1, 7, 5, 64, 64, 192),
+                                               (2, 1, 3, 8, 0, 8), (1, 41, 82, 256, 128, 384)])
+def test_bilinear_upsample_forward_backward(ops, n, h, w, c, coff, ctot):
+    """nn.Upsample(scale_factor=2, bilinear, align_corners=True) (Up with bilinear=True,
+    models/unet_model.py:40-43) and its adjoint, on a channel slice of a wider NHWC buffer (the
+    up-sampled range of d(concat)), against torch in fp32 on the same bf16-rounded inputs."""
+    x_full = bf(rand(n, h, w, ctot, seed=1)).to(torch.bfloat16)
+    x = x_full[..., coff:coff + c]
+    up = ops.upsample2x(x)
+    ref_in = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    ref = F.interpolate(ref_in, scale_factor=2, mode="bilinear", align_corners=True)
+    assert up.shape == (n, 2 * h, 2 * w, c)
+    assert rel_l2(up.float(), ref.detach().permute(0, 2, 3, 1)) < BF16_TOL
+    g_full = bf(rand(n, 2 * h, 2 * w, ctot, seed=2)).to(torch.bfloat16)
+    g = g_full[..., coff:coff + c]
+    dx = ops.upsample2x_backward(g)
+    ref.backward(g.float().permute(0, 3, 1, 2))
+    assert dx.shape == (n, h, w, c)
+    assert rel_l2(dx.float(), ref_in.grad.permute(0, 2, 3, 1)) < BF16_TOL
+    assert cosine(dx.float(), ref_in.grad.permute(0, 2, 3, 1)) > 0.9999

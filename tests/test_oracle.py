@@ -24,11 +24,15 @@ def golden():
     return np.load(os.path.join(GOLD, "unet_golden.npz"))
 
 
-@pytest.mark.parametrize("name", ["train_n2_s188", "train_n1_s220", "eval_n1_s252"])
+@pytest.mark.parametrize("name", ["train_n2_s188", "train_n1_s220", "eval_n1_s252",
+                                  "train_n1_s220_bilinear"])
 def test_unet_oracle_matches_reference_golden(golden, name):
+    bilinear = name.endswith("_bilinear")
+    if bilinear:
+        golden = np.load(os.path.join(GOLD, "unet_bilinear_golden.npz"))
     c = _case(golden, name)
     n, size, sw, sx, training = [int(v) for v in c["meta"]]
-    sd = unet_ref.make_state_dict(1, 2, seed=sw)
+    sd = unet_ref.make_state_dict(1, 2, seed=sw, bilinear=bilinear)
     img, t, w = unet_ref.synthetic_batch(n, size=size, seed=sx)
     if training:
         params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()
@@ -104,18 +108,65 @@ def test_drop_in_module_tree_matches_reference_state_dict():
     assert [id(b) for b in m._ordered_bns()] == [id(dict(m.named_modules())[n]) for n in bn_names]
 
 
-def test_drop_in_rejects_cpu_and_bilinear():
+def test_drop_in_rejects_cpu():
     from unet_segmentation_b200.loss import WeightedCrossEntropyLoss
     from unet_segmentation_b200.unet import UNet
 
-    m = UNet(1, 2)
-    with pytest.raises(RuntimeError, match="no CPU fallback"):
-        m(torch.zeros(1, 1, 188, 188))
+    for m in (UNet(1, 2), UNet(1, 2, bilinear=True)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m(torch.zeros(1, 1, 188, 188))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         WeightedCrossEntropyLoss()(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, dtype=torch.long),
                                    torch.ones(1, 4, 4))
-    with pytest.raises(NotImplementedError):
-        UNet(1, 2, bilinear=True)
+
+
+def test_drop_in_bilinear_module_tree_matches_reference_state_dict():
+    """UNet(..., bilinear=True) (models/unet_model.py:40-43,78-81): nn.Upsample up-sampling without
+    parameters, first decoder convolutions over prev + skip channels (1536 -> 512 ...)."""
+    from unet_segmentation_b200.unet import UNet
+
+    torch.manual_seed(0)
+    m = UNet(1, 2, bilinear=True)
+    ours = m.state_dict()
+    ref = unet_ref.make_state_dict(1, 2, seed=0, init=False, bilinear=True)
+    assert list(ours.keys()) == list(ref.keys())
+    assert len(list(m.parameters())) == 74
+    for k in ref:
+        assert ours[k].shape == ref[k].shape and torch.equal(ours[k], ref[k]), k
+    assert tuple(ours["up1.conv.double_conv.0.weight"].shape) == (512, 1536, 3, 3)
+    assert isinstance(m.up1.up, torch.nn.Upsample) and m.up1.up.align_corners is True
+    assert [id(p) for p in m._ordered_params()] == [id(p) for p in m.parameters()]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_bilinear_oracle_matches_live_reference():
+    sys.dont_write_bytecode = True
+    spec = importlib.util.spec_from_file_location("ref_unet_bilinear",
+                                                  os.path.join(REF, "models", "unet_model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(5)
+    ref = mod.UNet(1, 2, bilinear=True)
+    sd = unet_ref.make_state_dict(1, 2, seed=5, init=False, bilinear=True)
+    rsd = ref.state_dict()
+    assert list(sd) == list(rsd) and all(torch.equal(sd[k], rsd[k]) for k in sd)
+    img, t, w = unet_ref.synthetic_batch(1, size=220, seed=3)
+    ref.train()
+    logits = ref(img)
+    loss = (torch.nn.functional.cross_entropy(logits, t, reduction="none") * w).mean()
+    loss.backward()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and "running" not in k}
+    full = dict(sd)
+    full.update(params)
+    o_logits = unet_ref.unet_forward(full, img, training=True, buffers_out={})
+    o_loss = unet_ref.weighted_cross_entropy(o_logits, t, w)
+    o_loss.backward()
+    assert torch.allclose(logits, o_logits, atol=1e-5, rtol=1e-5)
+    assert abs(float(loss) - float(o_loss)) <= 1e-6 * abs(float(loss))
+    for name, p in ref.named_parameters():
+        g, og = p.grad, params[name].grad
+        assert float((g - og).norm()) <= 1e-4 * float(g.norm()) + 1e-7, name
 
 
 def test_ccl_oracle_matches_reference_golden_pairs():

@@ -23,11 +23,12 @@ def cosine(a, b):
     return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
 
 
-def build(n_channels, n_classes, base, levels, seed):
+def build(n_channels, n_classes, base, levels, seed, bilinear=False):
     from unet_segmentation_b200.unet import UNet
 
-    sd = unet_ref.make_state_dict(n_channels, n_classes, seed=seed, base=base, levels=levels)
-    m = UNet(n_channels, n_classes, base_channels=base, levels=levels)
+    sd = unet_ref.make_state_dict(n_channels, n_classes, seed=seed, base=base, levels=levels,
+                                  bilinear=bilinear)
+    m = UNet(n_channels, n_classes, bilinear, base_channels=base, levels=levels)
     m.load_state_dict(sd)                      # same keys / shapes as the reference-style tree
     return m.cuda(), {k: v.cuda() for k, v in sd.items()}
 
@@ -43,16 +44,18 @@ def oracle_step(sd, img, t, w, levels):
     return logits.detach(), loss.detach(), {k: p.grad for k, p in params.items()}
 
 
-@pytest.mark.parametrize("n_channels,n_classes,base,levels,n,size", [
-    (1, 2, 128, 5, 2, 252),      # BASELINE configs[4]: wide U-Net (base 128, depth 5)
-    (1, 2, 64, 4, 2, 196),       # shallower net
-    (3, 3, 64, 3, 2, 132),       # RGB input (generic first conv), 3 classes, depth 3
-    (1, 2, 64, 6, 2, 444),       # deeper net (2048 channels at the bottleneck)
+@pytest.mark.parametrize("n_channels,n_classes,base,levels,n,size,bilinear", [
+    (1, 2, 128, 5, 2, 252, False),      # BASELINE configs[4]: wide U-Net (base 128, depth 5)
+    (1, 2, 64, 4, 2, 196, False),       # shallower net
+    (3, 3, 64, 3, 2, 132, False),       # RGB input (generic first conv), 3 classes, depth 3
+    (1, 2, 64, 6, 2, 444, False),       # deeper net (2048 channels at the bottleneck)
+    (1, 2, 64, 5, 2, 252, True),        # UNet(1, 2, bilinear=True): nn.Upsample branch (:40-43)
+    (1, 2, 64, 3, 2, 132, True),
 ])
-def test_training_step_other_configurations(n_channels, n_classes, base, levels, n, size):
+def test_training_step_other_configurations(n_channels, n_classes, base, levels, n, size, bilinear):
     from unet_segmentation_b200.loss import WeightedCrossEntropyLoss
 
-    model, sd = build(n_channels, n_classes, base, levels, seed=2)
+    model, sd = build(n_channels, n_classes, base, levels, seed=2, bilinear=bilinear)
     img, t, w = unet_ref.synthetic_batch(n, size=size, seed=31, levels=levels, device="cuda")
     if n_channels > 1:
         g = torch.Generator(device="cuda").manual_seed(5)
@@ -73,7 +76,7 @@ def test_training_step_other_configurations(n_channels, n_classes, base, levels,
             continue
         cos[name] = cosine(p.grad, ref_grads[name])
     vals = np.array(list(cos.values()))
-    print(f"\n[C={n_channels} K={n_classes} base={base} levels={levels} {n}x{size}^2] logits rel-L2 "
+    print(f"\n[C={n_channels} K={n_classes} base={base} levels={levels} bilinear={bilinear} {n}x{size}^2] logits rel-L2 "
           f"{e_logits:.3e}  loss rel {e_loss:.3e}  grad cos min {vals.min():.4f} median "
           f"{np.median(vals):.4f}  out {tuple(logits.shape)}")
     # measured: logits 1.1e-2 … 1.7e-2, loss 2e-6 … 4e-4, cosine median 0.91 … 0.99 (the deeper the
@@ -103,3 +106,42 @@ def test_single_class_eval_forward():
     p, pr = torch.sigmoid(logits), torch.sigmoid(ref)
     conf = (pr - 0.5).abs() > 0.02
     assert float(((p > 0.5) == (pr > 0.5))[conf].float().mean()) >= 0.999
+
+
+def test_bilinear_unet_against_reference_golden_and_sgd_steps():
+    """UNet(1, 2, bilinear=True) against the golden vector recorded from the reference itself, then
+    three optimizer steps (FusedSGD must cope with a parameter table without up.weight / up.bias)."""
+    import os
+
+    from unet_segmentation_b200.loss import WeightedCrossEntropyLoss
+    from unet_segmentation_b200.optim import FusedSGD
+
+    blob = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet_bilinear_golden.npz"))
+    name = "train_n1_s220_bilinear"
+    c = {k[len(name) + 1:]: blob[k] for k in blob.files if k.startswith(name + "/")}
+    n, size, sw, sx, _ = [int(v) for v in c["meta"]]
+    model, _ = build(1, 2, 64, 5, seed=sw, bilinear=True)
+    img, t, w = unet_ref.synthetic_batch(n, size=size, seed=sx, device="cuda")
+    model.train()
+    crit = WeightedCrossEntropyLoss()
+    logits = model(img)
+    loss = crit(logits, t, w)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(c["loss"])) / float(c["loss"]) < 2e-2
+    assert rel_l2(logits, torch.from_numpy(c["logits"]).cuda()) < 8e-2   # 36x36 logits, N = 1
+    g = model.outc.conv.bias.grad.cpu().double()
+    assert abs(float(g.norm()) - float(c["gnorm/outc.conv.bias"])) < 5e-2 * float(c["gnorm/outc.conv.bias"])
+    opt = FusedSGD(model, lr=1e-3, momentum=0.9)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(img), t, w)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    model.eval()
+    with torch.no_grad():
+        z = model(img)
+    assert z.shape == logits.shape and torch.isfinite(z).all()

@@ -33,6 +33,7 @@ _SIGNATURES = {
     "ub_version": (c_int, []),
     "ub_device_sm_count": (c_int, []),
     "ub_plan_create": (c_int, [C.POINTER(c_void_p)] + [c_int] * 8),
+    "ub_plan_create_ex": (c_int, [C.POINTER(c_void_p)] + [c_int] * 9),
     "ub_plan_destroy": (c_int, [_P]),
     "ub_plan_out_hw": (c_int, [_P, C.POINTER(c_int), C.POINTER(c_int)]),
     "ub_plan_num_params": (c_int, [_P]),
@@ -77,6 +78,8 @@ _SIGNATURES = {
                                       C.POINTER(c_int), _P]),
     "ub_op_conv3x3_affine_relu_head": (c_int, [_VP, _VP, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "ub_op_conv3x3_dgrad": (c_int, [_VP, _P, c_int, _P, _P]),
+    "ub_op_upsample2x_forward": (c_int, [_VP, _P, _P]),
+    "ub_op_upsample2x_backward": (c_int, [_VP, _P, _P]),
     "ub_op_wgrad_workspace_floats": (c_int64, [c_int, c_int, c_int64]),
     "ub_op_conv3x3_wgrad": (c_int, [_VP, _VP, _P, c_int, _P, c_int64, _P, _P]),
     "ub_op_convT_forward": (c_int, [_VP, _P, _P, c_int, _VP, _P]),

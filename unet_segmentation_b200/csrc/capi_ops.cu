@@ -250,6 +250,14 @@ int ub_op_head_backward(const float* dlogits, const void* a, int N, int H, int W
     return launch_head_bwd(dlogits, (const __nv_bfloat16*)a, N, H, W, K, n_classes, w,
                            (__nv_bfloat16*)da, workspace, dw, db, S(stream));
 }
+int ub_op_upsample2x_forward(const ub_view* x, void* out, void* stream) {
+    UB_REQUIRE(x && out, "upsample2x_forward: null pointer");
+    return launch_upsample2x_fwd(to_view(x), (__nv_bfloat16*)out, S(stream));
+}
+int ub_op_upsample2x_backward(const ub_view* g, void* dx, void* stream) {
+    UB_REQUIRE(g && dx, "upsample2x_backward: null pointer");
+    return launch_upsample2x_bwd(to_view(g), (__nv_bfloat16*)dx, S(stream));
+}
 int ub_op_maxpool2(const void* a, void* pooled, int N, int H, int W, int C, void* stream) {
     return launch_maxpool2((const __nv_bfloat16*)a, (__nv_bfloat16*)pooled, N, H, W, C, S(stream));
 }

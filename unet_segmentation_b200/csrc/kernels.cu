@@ -10,6 +10,7 @@
 #include "input_pipeline.cuh"
 #include "igemm.cuh"
 #include "ub_internal.h"
+#include "upsample.cuh"
 #include "weight_map.cuh"
 
 namespace ub {
@@ -406,6 +407,35 @@ int launch_prepare_batch(const unsigned char* img, const void* labels, int label
     A.h0 = (H - oh) / 2; A.w0 = (W - ow) / 2;   // center_crop_tensor, scripts/train.py:39-51
     A.image = image; A.target = target; A.weight = weight;
     UB_LAUNCH_NC(prepare_batch_kernel, ew_blocks((long long)N * H * (W / 4)), 256, 0, s, A);
+    UB_POST_LAUNCH();
+    return UB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int check_up_view(const View& v, const char* what) {
+    if (!v.ptr || v.N < 1 || v.H < 1 || v.W < 1 || v.C < 8 || v.C % 8 != 0 || v.sW % 8 != 0 ||
+        v.sH % 8 != 0 || v.sN % 8 != 0 || ((uintptr_t)v.ptr & 15) != 0) {
+        set_last_error("%s: need an NHWC bf16 view with C %% 8 == 0 and 16-byte aligned pixels", what);
+        return UB_ERR_ARG;
+    }
+    return UB_OK;
+}
+int launch_upsample2x_fwd(const View& x, __nv_bfloat16* out, cudaStream_t s) {
+    UB_TRY(check_up_view(x, "upsample2x forward"));
+    if (!out) { set_last_error("upsample2x forward: null output"); return UB_ERR_ARG; }
+    const long long items = (long long)x.N * 4 * x.H * x.W * (x.C / 8);
+    UB_LAUNCH_NC(upsample2x_fwd_kernel, ew_blocks(items), 256, 0, s, x, out);
+    UB_POST_LAUNCH();
+    return UB_OK;
+}
+int launch_upsample2x_bwd(const View& g, __nv_bfloat16* dx, cudaStream_t s) {
+    UB_TRY(check_up_view(g, "upsample2x backward"));
+    if (!dx || g.H % 2 != 0 || g.W % 2 != 0) {
+        set_last_error("upsample2x backward: null output or odd gradient size %dx%d", g.H, g.W);
+        return UB_ERR_ARG;
+    }
+    const long long items = (long long)g.N * (g.H / 2) * (g.W / 2) * (g.C / 8);
+    UB_LAUNCH_NC(upsample2x_bwd_kernel, ew_blocks(items), 256, 0, s, g, dx, g.H / 2, g.W / 2);
     UB_POST_LAUNCH();
     return UB_OK;
 }

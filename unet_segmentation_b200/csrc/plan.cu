@@ -53,6 +53,7 @@ struct UpT {
 struct ub_plan {
     int N = 0, Cin = 0, H = 0, W = 0, base = 0, L = 0, NC = 0;
     bool training = false;
+    bool bilinear = false;   // Up blocks use nn.Upsample(bilinear, align_corners) instead of ConvTranspose2d
     int outH = 0, outW = 0;
     std::vector<Block> enc, dec;
     std::vector<UpT> ups;
@@ -172,6 +173,10 @@ extern "C" {
 
 int ub_plan_create(ub_plan** out, int N, int n_channels, int H, int W, int base, int levels,
                    int n_classes, int training) {
+    return ub_plan_create_ex(out, N, n_channels, H, W, base, levels, n_classes, training, 0);
+}
+int ub_plan_create_ex(ub_plan** out, int N, int n_channels, int H, int W, int base, int levels,
+                      int n_classes, int training, int bilinear) {
     if (!out) return ub::UB_ERR_ARG;
     *out = nullptr;
     int ndev = 0;
@@ -194,13 +199,14 @@ int ub_plan_create(ub_plan** out, int N, int n_channels, int H, int W, int base,
     }
     ub_plan* P = new ub_plan();
     P->N = N; P->Cin = n_channels; P->H = H; P->W = W; P->base = base; P->L = levels;
-    P->NC = n_classes; P->training = training != 0;
+    P->NC = n_classes; P->training = training != 0; P->bilinear = bilinear != 0;
     const int L = levels;
+    const int UPP = P->bilinear ? 0 : 2;          // parameters of the up-sampling op of a decoder stage
     P->enc.resize(L);
     P->dec.resize(L - 1);
     P->ups.resize(L - 1);
     P->crop.resize(L - 1);
-    const int nparams = 8 * L + 10 * (L - 1) + 2;
+    const int nparams = 8 * L + (8 + UPP) * (L - 1) + 2;
     P->params.assign(nparams, nullptr);
     P->param_numel.assign(nparams, 0);
     P->rm.assign(2 * L + 2 * (L - 1), nullptr);
@@ -241,11 +247,14 @@ int ub_plan_create(ub_plan** out, int N, int n_channels, int H, int W, int base,
         UpT& t = P->ups[j];
         Block& b = P->dec[j];
         const int cp = base << (L - 1 - j);
-        t.Ci = cp; t.Co = cp / 2; t.Hin = h; t.Win = w;
-        const int pb = 8 * L + 10 * j;
-        t.p_w = pb; t.p_b = pb + 1;
-        P->param_numel[t.p_w] = (long long)t.Ci * t.Co * 4;
-        P->param_numel[t.p_b] = t.Co;
+        // ConvTranspose2d(cp, cp / 2, 2, 2)  |  Upsample: channels unchanged (models/unet_model.py:40-46)
+        t.Ci = cp; t.Co = P->bilinear ? cp : cp / 2; t.Hin = h; t.Win = w;
+        const int pb = 8 * L + (8 + UPP) * j;
+        if (!P->bilinear) {
+            t.p_w = pb; t.p_b = pb + 1;
+            P->param_numel[t.p_w] = (long long)t.Ci * t.Co * 4;
+            P->param_numel[t.p_b] = t.Co;
+        }
         h *= 2; w *= 2;
         const Block& sk = P->enc[L - 2 - j];
         const int sh = sk.u[1].Ho(), sw = sk.u[1].Wo();
@@ -255,10 +264,10 @@ int ub_plan_create(ub_plan** out, int N, int n_channels, int H, int W, int base,
             return fail(ub::UB_ERR_ARG);
         }
         b.two = true;
-        b.u[0].Ci = cp; b.u[0].Co = cp / 2; b.u[0].Hin = h; b.u[0].Win = w;
+        b.u[0].Ci = cp / 2 + t.Co; b.u[0].Co = cp / 2; b.u[0].Hin = h; b.u[0].Win = w;
         b.u[1].Ci = cp / 2; b.u[1].Co = cp / 2; b.u[1].Hin = h - 2; b.u[1].Win = w - 2;
-        set_unit_params(b.u[0], pb + 2, 2 * L + 2 * j);
-        set_unit_params(b.u[1], pb + 6, 2 * L + 2 * j + 1);
+        set_unit_params(b.u[0], pb + UPP, 2 * L + 2 * j);
+        set_unit_params(b.u[1], pb + UPP + 4, 2 * L + 2 * j + 1);
         h -= 4; w -= 4;
         if (h < 1 || w < 1) {
             set_last_error("plan: input %dx%d too small for %d levels", H, W, L);
@@ -301,13 +310,17 @@ int ub_plan_create(ub_plan** out, int N, int n_channels, int H, int W, int base,
     for (int j = 0; j < L - 1; ++j) {
         UpT& t = P->ups[j];
         Block& b = P->dec[j];
-        if (int r = P->alloc(&t.wf, (size_t)4 * t.Co * t.Ci)) return fail(r);
-        if (int r = P->alloc(&t.bias4, (size_t)4 * t.Co)) return fail(r);
+        if (!P->bilinear) {
+            if (int r = P->alloc(&t.wf, (size_t)4 * t.Co * t.Ci)) return fail(r);
+            if (int r = P->alloc(&t.bias4, (size_t)4 * t.Co)) return fail(r);
+        }
         if (int r = P->alloc(&t.out, (size_t)N * 4 * t.Hin * t.Win * t.Co)) return fail(r);
         if (P->training) {
-            if (int r = P->alloc(&t.wb, (size_t)4 * t.Co * t.Ci)) return fail(r);
+            if (!P->bilinear) {
+                if (int r = P->alloc(&t.wb, (size_t)4 * t.Co * t.Ci)) return fail(r);
+                upd(wws, wgrad_ws_floats(4 * t.Co, t.Ci, (long long)N * t.Hin * t.Win));
+            }
             if (int r = P->alloc(&t.dx, (size_t)N * t.Hin * t.Win * t.Ci)) return fail(r);
-            upd(wws, wgrad_ws_floats(4 * t.Co, t.Ci, (long long)N * t.Hin * t.Win));
         }
         for (int k = 0; k < 2; ++k) {
             ConvUnit& u = b.u[k];
@@ -425,9 +438,10 @@ int ub_plan_pack_weights(ub_plan* P, void* stream) {
     };
     for (auto& b : P->enc) UB_TRY(pack_block(b));
     for (auto& b : P->dec) UB_TRY(pack_block(b));
-    for (auto& t : P->ups)
-        UB_TRY(launch_pack_convT(P->params[t.p_w], t.Ci, t.Co, t.wf, t.wb, P->params[t.p_b], t.bias4,
-                                 s));
+    if (!P->bilinear)
+        for (auto& t : P->ups)
+            UB_TRY(launch_pack_convT(P->params[t.p_w], t.Ci, t.Co, t.wf, t.wb, P->params[t.p_b],
+                                     t.bias4, s));
     P->packed = true;
     return 0;
 }
@@ -528,6 +542,13 @@ int ub_plan_forward(ub_plan* P, const float* x, float* logits, uint8_t* mask, vo
         UpT& t = P->ups[j];
         const ConvUnit& prev = j == 0 ? P->enc[L - 1].u[1] : P->dec[j - 1].u[1];
         View xin = make_view(prev.a, P->N, t.Hin, t.Win, t.Ci);
+        if (P->bilinear) {   // nn.Upsample(scale_factor=2, bilinear, align_corners=True), :41
+            const double m = (double)P->N * t.Hin * t.Win * t.Ci;
+            ProfScope ps(P, CLS_CT_FPROP, 0, 2.0 * m * 5, s);
+            UB_TRY(launch_upsample2x_fwd(xin, t.out, s));
+            UB_TRY(block_forward(P, P->dec[j], s));
+            continue;
+        }
         IgemmEpilogue e;
         memset(&e, 0, sizeof(e));
         e.kind = EPI_CONVT; e.bias = t.bias4;
@@ -558,8 +579,9 @@ int ub_plan_stage_params(const ub_plan* P, int stage, int* first, int* count) {
     int f, c;
     if (stage < L - 1) {
         const int j = L - 2 - stage;  // decoder block index
-        f = 8 * L + 10 * j;
-        c = 10 + (stage == 0 ? 2 : 0);  // the head's two parameters follow the last up block
+        const int per = P->bilinear ? 8 : 10;
+        f = 8 * L + per * j;
+        c = per + (stage == 0 ? 2 : 0);  // the head's two parameters follow the last up block
     } else {
         const int i = 2 * L - 2 - stage;  // encoder block index
         f = 8 * i;
@@ -708,6 +730,11 @@ static int backward_stage_impl(ub_plan* P, int stage, const float* dlogits, floa
         View dup = make_view(b.din, N, b.u[0].Hin, b.u[0].Win, b.u[0].Ci);
         dup.ptr = b.din + cs;
         dup.C = t.Co;
+        if (P->bilinear) {   // adjoint of the bilinear up-sampling; no parameters
+            const double m = (double)N * t.Hin * t.Win * t.Ci;
+            ProfScope ps(P, CLS_CT_DGRAD, 0, 2.0 * m * 5, s);
+            return launch_upsample2x_bwd(dup, t.dx, s);
+        }
         IgemmEpilogue e;
         memset(&e, 0, sizeof(e));
         e.kind = EPI_STORE; e.out = t.dx; e.ldo = t.Ci;
@@ -808,6 +835,7 @@ int ub_plan_sgd_step(ub_plan* P, const float* const* grads, float* const* moment
     for (auto& b : P->enc) conv_units(b);
     for (auto& b : P->dec) conv_units(b);
     for (auto& u : P->ups) {
+        if (P->bilinear) break;
         SgdTensor& t = all[u.p_w];
         t.kind = SGD_CONVT; t.d0 = u.Ci; t.d1 = u.Co; t.T = 4; t.outA = u.wb; t.outB = u.wf;
         SgdTensor& tb = all[u.p_b];

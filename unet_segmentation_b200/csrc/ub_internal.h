@@ -204,6 +204,8 @@ int launch_prepare_batch(const unsigned char* img, const void* labels, int label
                          const void* wmap, int wmap_bytes, int N, int H, int W, int oh, int ow,
                          float* image, long long* target, float* weight, cudaStream_t s);
 size_t ccl_ws_bytes(int H, int W);
+int launch_upsample2x_fwd(const View& x, __nv_bfloat16* out, cudaStream_t s);
+int launch_upsample2x_bwd(const View& g, __nv_bfloat16* dx, cudaStream_t s);
 int launch_weight_map(const void* labels, int label_bytes, int N, int H, int W, double w0,
                       double sigma, void* out, int out_bytes, unsigned* counts, cudaStream_t s);
 size_t elastic_ws_bytes(int N, int H, int W);

@@ -255,6 +255,24 @@ def head_backward(dlogits, a, w):
     return da, dw, db
 
 
+def upsample2x(x):
+    """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) on an NHWC bf16 view."""
+    lib = _lib.load()
+    n, h, w, c = x.shape
+    out = torch.empty(n, 2 * h, 2 * w, c, dtype=torch.bfloat16, device=x.device)
+    check(lib.ub_op_upsample2x_forward(_vp(x), _p(out), _stream()), "upsample2x_forward")
+    return out
+
+
+def upsample2x_backward(g):
+    """Adjoint of ``upsample2x``: g (N, 2H, 2W, C) NHWC bf16 view -> (N, H, W, C)."""
+    lib = _lib.load()
+    n, h2, w2, c = g.shape
+    dx = torch.empty(n, h2 // 2, w2 // 2, c, dtype=torch.bfloat16, device=g.device)
+    check(lib.ub_op_upsample2x_backward(_vp(g), _p(dx), _stream()), "upsample2x_backward")
+    return dx
+
+
 def maxpool2(a):
     lib = _lib.load()
     n, h, w, c = a.shape

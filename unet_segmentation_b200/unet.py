@@ -51,18 +51,20 @@ class Down(nn.Module):
 
 
 class Up(nn.Module):
-    """ConvTranspose2d(k=2,s=2) then DoubleConv over [cropped skip, up] (reference :35-54)."""
+    """Up-sampling then DoubleConv over [cropped skip, up] (reference :35-54): ConvTranspose2d(k=2,
+    s=2) halving the channels, or — ``bilinear=True`` — nn.Upsample(scale_factor=2, bilinear,
+    align_corners=True) keeping them (so the DoubleConv takes prev + skip channels, :41-43)."""
 
     def __init__(self, in_channels_from_prev_decoder: int, skip_channels: int, out_channels: int,
                  bilinear: bool = True):
         super().__init__()
         if bilinear:
-            raise NotImplementedError(
-                "bilinear=True (nn.Upsample) is outside the B200 hot path; the reference's "
-                "train.py / predict.py use the transposed-convolution branch")
-        half = in_channels_from_prev_decoder // 2
-        self.up = nn.ConvTranspose2d(in_channels_from_prev_decoder, half, kernel_size=2, stride=2)
-        self.conv = DoubleConv(half + skip_channels, out_channels)
+            self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+            self.conv = DoubleConv(in_channels_from_prev_decoder + skip_channels, out_channels)
+        else:
+            half = in_channels_from_prev_decoder // 2
+            self.up = nn.ConvTranspose2d(in_channels_from_prev_decoder, half, kernel_size=2, stride=2)
+            self.conv = DoubleConv(half + skip_channels, out_channels)
 
     def forward(self, x1, x2_cropped):  # pragma: no cover
         raise NotImplementedError(_NO_SUBMODULE_FWD)
@@ -83,14 +85,15 @@ class OutConv(nn.Module):
 class _Plan:
     """Python handle of a ``ub_plan`` (one per input shape / mode / device)."""
 
-    def __init__(self, n, cin, h, w, base, levels, n_classes, training, device):
+    def __init__(self, n, cin, h, w, base, levels, n_classes, training, device, bilinear=False):
         self.lib = _lib.load()
         self.device = device
         self.training = training
         handle = C.c_void_p()
         with torch.cuda.device(device):
-            check(self.lib.ub_plan_create(C.byref(handle), n, cin, h, w, base, levels, n_classes,
-                                          1 if training else 0), "ub_plan_create")
+            check(self.lib.ub_plan_create_ex(C.byref(handle), n, cin, h, w, base, levels, n_classes,
+                                             1 if training else 0, 1 if bilinear else 0),
+                  "ub_plan_create")
         self.handle = handle
         oh, ow = C.c_int(), C.c_int()
         check(self.lib.ub_plan_out_hw(handle, C.byref(oh), C.byref(ow)))
@@ -291,7 +294,8 @@ class UNet(nn.Module):
         for b in enc:
             dc(b)
         for u in ups:
-            out.extend([u.up.weight, u.up.bias])
+            if not self.bilinear:      # nn.Upsample has no parameters
+                out.extend([u.up.weight, u.up.bias])
             dc(u.conv)
         out.extend([self.outc.conv.weight, self.outc.conv.bias])
         return out
@@ -311,7 +315,7 @@ class UNet(nn.Module):
             if len(self._plans) >= 8:  # keep the arena bounded when shapes vary
                 self._plans.pop(next(iter(self._plans)))
             plan = _Plan(n, c, h, w, self.base_channels, self.levels, self.n_classes, training,
-                         x.device)
+                         x.device, bilinear=self.bilinear)
             self._plans[key] = plan
         plan.bind(self._ordered_params(), self._ordered_bns(), self._weights_epoch)
         if training:
