@@ -87,14 +87,16 @@ def test_conv3x3_forward_stats_and_bn(ops):
     assert torch.equal(ops.nchw(p), F.max_pool2d(ops.nchw(a), 2))
 
 
-def test_conv3x3_concat_sources(ops):
-    """Zero-copy crop + concat: src0 = centre crop of a larger skip tensor, src1 = up-sampled."""
-    n, hs, ws_, cs, h, w, cu, co = 2, 30, 28, 64, 20, 18, 64, 128
+@pytest.mark.parametrize("cs,cu,co", [(64, 64, 128), (64, 128, 64), (128, 256, 128), (256, 512, 256)])
+def test_conv3x3_concat_sources(ops, cs, cu, co):
+    """Zero-copy crop + concat: src0 = centre crop of a larger skip tensor, src1 = up-sampled.
+    Unequal channel counts are the bilinear=True decoder (C_skip + 2 C_skip -> C_skip)."""
+    n, hs, ws_, h, w = 2, 30, 28, 20, 18
     skip = bf(rand(n, cs, hs, ws_))
     up = bf(rand(n, cu, h, w, seed=5))
     ch, cw = (hs - h) // 2, (ws_ - w) // 2
-    wt = bf(rand(co, cs + cu, 3, 3, scale=0.04, seed=1))
-    wf, _ = ops.pack_conv3x3(wt)
+    wt = bf(rand(co, cs + cu, 3, 3, scale=(2.0 / (9 * (cs + cu))) ** 0.5, seed=1))
+    wf, wd = ops.pack_conv3x3(wt)
     skip_nhwc = ops.nhwc(skip)
     y, _, _ = ops.conv3x3_forward(skip_nhwc[:, ch:ch + h, cw:cw + w, :], ops.nhwc(up), wf, None)
     ref = F.conv2d(torch.cat([skip[:, :, ch:ch + h, cw:cw + w], up], 1), wt)
@@ -107,6 +109,11 @@ def test_conv3x3_concat_sources(ops):
         torch.cat([skip[:, :, ch:ch + h, cw:cw + w], up], 1), wt.shape, dy)
     torch.cuda.synchronize()
     assert rel_l2(dw, ref_dw) < F32_TOL and cosine(dw, ref_dw) > 0.9999
+    # data gradient of the concatenated input: one tensor whose channel ranges are the two sources'
+    dx = ops.conv3x3_dgrad(ops.nhwc(dy), wd)
+    ref_dx = torch.nn.grad.conv2d_input((n, cs + cu, h, w), wt, dy)
+    torch.cuda.synchronize()
+    assert rel_l2(ops.nchw(dx), ref_dx) < BF16_TOL
 
 
 def test_conv3x3_eval_epilogue(ops):
