@@ -30,7 +30,7 @@ typedef enum ub_status {
     UB_OK = 0,
     UB_ERR_CUDA = -1,        /* CUDA runtime / driver failure (includes "no device") */
     UB_ERR_ARG = -2,         /* invalid argument */
-    UB_ERR_UNSUPPORTED = -3, /* configuration outside the supported envelope (e.g. bilinear=True) */
+    UB_ERR_UNSUPPORTED = -3, /* configuration outside the supported envelope (e.g. base_channels = 96) */
     UB_ERR_TMAP = -4,        /* TMA descriptor encoding failed */
     UB_ERR_NOMEM = -5
 } ub_status;

@@ -141,7 +141,7 @@ def test_bilinear_unet_against_reference_golden_and_sgd_steps():
     print(f"\n[bilinear golden 1x220^2] loss rel {e_loss:.3e}  logits rel-L2 {e_logits:.3e}  "
           f"outc.bias grad-norm rel {e_g:.3e}")
     # 36x36 logits from N = 1: bf16 noise of the bilinear net (see above) on tiny batch statistics
-    assert e_loss < 3e-2 and e_logits < 0.15 and e_g < 0.1
+    assert e_loss < 5e-3 and e_logits < 0.15 and e_g < 1e-2   # measured 3.7e-4 / 9.2e-2 / 8e-5
     opt = FusedSGD(model, lr=1e-3, momentum=0.9)
     losses = []
     for _ in range(3):
