@@ -313,3 +313,28 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), f"libunetb200.so does not export {name}"
     assert set(declared) == set(_lib._SIGNATURES)
     assert lib.ub_version() >= 100
+
+
+def test_host_side_helpers_of_the_elastic_pipeline():
+    """The two host-side pieces of input_pipeline.elastic_deform: the Gaussian taps are scipy's own
+    kernel (impulse response of gaussian_filter1d), and reference_noise replays the reference's
+    RandomState draws (dx first, then dy; utils/augmentations.py:27-28)."""
+    from scipy.ndimage import gaussian_filter1d
+
+    from unet_segmentation_b200 import input_pipeline as ip
+
+    for sigma in (20, 5, 2.5, 0.8):
+        taps = ip.gaussian_taps(sigma)
+        r = (len(taps) - 1) // 2
+        assert r == int(4.0 * sigma + 0.5)
+        impulse = np.zeros(2 * r + 1)
+        impulse[r] = 1.0
+        assert np.array_equal(gaussian_filter1d(impulse, sigma, mode="constant"), taps)
+        assert np.array_equal(taps, elastic_ref.gaussian_taps(sigma))
+    with pytest.raises(ValueError):
+        ip.gaussian_taps(0.0)
+    noise = ip.reference_noise([11, 12], (6, 5))
+    assert noise.shape == (2, 2, 6, 5) and noise.dtype == torch.float64
+    for k, seed in enumerate((11, 12)):
+        u, v = elastic_ref.reference_noise(seed, (6, 5))
+        assert np.array_equal(noise[0, k].numpy(), u) and np.array_equal(noise[1, k].numpy(), v)
