@@ -321,3 +321,15 @@ def test_fused_sgd_matches_torch_sgd():
         l2 = m2(img); l3 = m3(img)
         torch.cuda.synchronize()
         assert torch.equal(l2, l3), kw                      # training plan uses the fused-written caches
+
+
+def test_input_gradient_request_fails_loudly():
+    """The library never computes d loss / d image (the first layer needs no data
+    gradient); asking for it must raise instead of leaving x.grad silently empty."""
+    model, _ = make_model(seed=0)
+    model.train()
+    img, _, _ = unet_ref.synthetic_batch(1, size=188, seed=1, device="cuda")
+    with pytest.raises(RuntimeError, match="gradient with respect to the input"):
+        model(img.clone().requires_grad_(True))
+    with torch.no_grad():                      # fine without autograd, and in eval mode
+        assert model(img.clone().requires_grad_(True)).shape == (1, 2, 4, 4)

@@ -341,6 +341,11 @@ class UNet(nn.Module):
 
     def forward(self, x):
         x = self._check_input(x)
+        if x.requires_grad and self.training and torch.is_grad_enabled():
+            # the first layer's data gradient is never computed (no reference caller needs it,
+            # SURVEY §2.3); returning None silently would be a quiet wrong answer
+            raise RuntimeError("UNet (B200): the gradient with respect to the input image is not "
+                               "computed; detach the input (x.detach()) before the forward pass")
         with torch.cuda.device(x.device):
             if self.training and torch.is_grad_enabled():
                 return _UNetFunction.apply(self, x, *self._ordered_params())
