@@ -111,51 +111,91 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_step_time(steps: int, warmup: int, threads: int | None = None):
-    """The reference's CPU path (oracle port, fp32 torch): BASELINE.json configs[0], one
-    1x1x512x512 sample per step: zero_grad -> forward -> loss -> backward."""
+    """The reference's CPU path on BASELINE.json configs[0]: one 1x1x512x512 sample per step,
+    zero_grad -> forward -> centre-crop + squeeze -> loss -> backward -> SGD(1e-4, 0.99).step()
+    (scripts/train.py:114-131).
+
+    Runs the UNMODIFIED reference (`models/unet_model.py` UNet + `utils/losses.py`
+    WeightedCrossEntropyLoss + `scripts/train.py` init_weights / center_crop_tensor) from
+    baseline/_ref/ (oracle/install_ref.py) or /root/reference when either is present -> kind
+    "reference"; otherwise the oracle port (oracle/unet_ref.py, pinned to the reference) -> "port".
+    Returns (median s/step, total s, threads, kind)."""
     import torch
 
-    from oracle import unet_ref
+    from oracle import ref_loader, unet_ref
 
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sd = unet_ref.make_state_dict(1, 2, seed=0)
-    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
-              if v.is_floating_point() and "running" not in k}
-    full = dict(sd)
-    full.update(params)
-    img, t, w = unet_ref.synthetic_batch(1, size=SIZE, seed=1234)
+    img, t, w = unet_ref.synthetic_batch(1, size=SIZE, seed=1234, cropped=False)
+    ref = ref_loader.load_reference()
     times = []
-    for it in range(warmup + steps):
-        for p in params.values():
-            p.grad = None
-        t0 = time.perf_counter()
-        bufs = {}
-        logits = unet_ref.unet_forward(full, img, training=True, buffers_out=bufs)
-        loss = unet_ref.weighted_cross_entropy(logits, t, w)
-        loss.backward()
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
+    if ref is not None and ref.init_weights is not None:
+        kind = "reference"
+        torch.manual_seed(0)
+        model = ref.UNet(1, 2)
+        model.apply(ref.init_weights)
+        model.train()
+        crit = ref.WeightedCrossEntropyLoss()
+        opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.99)     # scripts/train.py:97
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            out = model(img)
+            size = out.shape[2:]
+            tt = ref.center_crop_tensor(t, size).squeeze(1)
+            ww = ref.center_crop_tensor(w, size).squeeze(1)
+            loss = crit(out, tt, ww)
+            loss.backward()
+            opt.step()
+            float(loss.item())
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    else:
+        kind = "port"
+        sd = unet_ref.make_state_dict(1, 2, seed=0)
+        params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+                  if v.is_floating_point() and "running" not in k}
+        full = dict(sd)
+        full.update(params)
+        opt = torch.optim.SGD(list(params.values()), lr=1e-4, momentum=0.99)
+        size = (unet_ref.out_size(SIZE),) * 2
+        tt = unet_ref.center_crop(t, size).squeeze(1)
+        ww = unet_ref.center_crop(w, size).squeeze(1)
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            bufs = {}
+            logits = unet_ref.unet_forward(full, img, training=True, buffers_out=bufs)
+            loss = unet_ref.weighted_cross_entropy(logits, tt, ww)
+            loss.backward()
+            opt.step()
+            float(loss.item())
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
     med = statistics.median(times)
-    return med, sum(times), torch.get_num_threads()
+    return med, sum(times), torch.get_num_threads(), kind
 
 
 def run_reference_arm(args, rank: int):
     if rank != 0:
         return
-    med, total, threads = cpu_reference_step_time(args.steps, max(args.warmup, 1))
+    med, total, threads, kind = cpu_reference_step_time(args.steps, max(args.warmup, 1))
     value = 1.0 / med
     sample = (f"{args.steps} timed steps of one 1x1x{SIZE}x{SIZE} sample (batch-16 workload sampled "
-              f"at 1 image/step), fp32 torch CPU, median step {med:.3f} s")
+              f"at 1 image/step; zero_grad + fwd + weighted CE + bwd + SGD step), fp32 torch CPU, "
+              f"median step {med:.3f} s")
+    what = ("the unmodified reference (models/unet_model.py, utils/losses.py, scripts/train.py "
+            "helpers from baseline/_ref)" if kind == "reference" else "CPU oracle port of the reference")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": med * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "UNet(1,2) 64->1024 train step (fwd + weighted CE + bwd), 512x512, "
-                               "CPU oracle port of the reference", "batch_per_step": 1},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+        "config": {"workload": "UNet(1,2) 64->1024 train step (fwd + weighted CE + bwd + SGD), "
+                               f"512x512, {what}", "batch_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -524,11 +564,12 @@ def main():
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        med, total, threads = cpu_reference_step_time(steps=5, warmup=2)
-        cpu_baseline = {"value": 1.0 / med, "unit": UNIT, "cores": threads, "kind": "port",
+        med, total, threads, kind = cpu_reference_step_time(steps=5, warmup=2)
+        cpu_baseline = {"value": 1.0 / med, "unit": UNIT, "cores": threads, "kind": kind,
                         "sample": f"5 timed + 2 warm-up steps of one 1x1x{SIZE}x{SIZE} sample "
-                                  f"(configs[0]); oracle port of the reference on "
-                                  f"{os.cpu_count()} host CPUs, median {med:.3f} s/step"}
+                                  f"(configs[0]: zero_grad + fwd + weighted CE + bwd + SGD step); "
+                                  f"{'the unmodified reference from baseline/_ref' if kind == 'reference' else 'oracle port of the reference'}"
+                                  f" on {os.cpu_count()} host CPUs, median {med:.3f} s/step"}
 
     if rank == 0:
         sus = float(peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"])

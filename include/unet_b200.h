@@ -79,6 +79,10 @@ int64_t ub_plan_device_bytes(const ub_plan* plan);
 int ub_plan_bind_params(ub_plan* plan, const float* const* params, int count);
 int ub_plan_bind_bn_buffers(ub_plan* plan, float* const* running_mean, float* const* running_var,
                             int64_t* const* num_batches_tracked, int count);
+/* Per-layer BatchNorm2d hyper-parameters (host arrays of ub_plan_num_bn() floats): `momentum` of the
+ * running-statistics update and `eps` (reference models/unet_model.py:12,16 uses the nn.BatchNorm2d
+ * defaults 0.1 / 1e-5, which are also the plan's defaults). */
+int ub_plan_set_bn_config(ub_plan* plan, const float* momentum, const float* eps, int count);
 /* Refresh the packed bf16 operand caches from the bound masters (after optimizer.step() /
  * load_state_dict()). */
 int ub_plan_pack_weights(ub_plan* plan, void* stream);

@@ -57,9 +57,22 @@ def _conv(x, w, b, emulate, first=False, transpose=False):
     return _RoundGrad.apply(y) if (emulate and not first) else y
 
 
-def _conv_bn_relu(x, sd, conv, bn, training, buffers_out, momentum=0.1, eps=1e-5, emulate=False):
+def _keep(capture, key, t):
+    """Teacher forcing: remember an intermediate and, when it is part of an autograd
+    graph, ask autograd to keep its gradient (the upstream gradient of the producing layer)."""
+    if capture is not None:
+        if t.requires_grad:
+            t.retain_grad()
+        capture[key] = t
+    return t
+
+
+def _conv_bn_relu(x, sd, conv, bn, training, buffers_out, momentum=0.1, eps=1e-5, emulate=False,
+                  capture=None):
+    _keep(capture, f"{conv}.in", x)
     x = _conv(x, sd[f"{conv}.weight"], sd[f"{conv}.bias"], emulate,
               first=(conv == "inc.double_conv.0"))
+    _keep(capture, f"{conv}.y", x)
     rm, rv = sd[f"{bn}.running_mean"], sd[f"{bn}.running_var"]
     if training and buffers_out is not None:
         rm, rv = rm.clone(), rv.clone()
@@ -68,35 +81,42 @@ def _conv_bn_relu(x, sd, conv, bn, training, buffers_out, momentum=0.1, eps=1e-5
     elif training:
         rm = rv = None
     x = F.batch_norm(x, rm, rv, sd[f"{bn}.weight"], sd[f"{bn}.bias"], training, momentum, eps)
-    return F.relu(x)
+    return _keep(capture, f"{conv}.a", F.relu(x))
 
 
-def _double_conv(x, sd, prefix, training, buffers_out, emulate=False):
-    x = _conv_bn_relu(x, sd, f"{prefix}.0", f"{prefix}.1", training, buffers_out, emulate=emulate)
-    return _conv_bn_relu(x, sd, f"{prefix}.3", f"{prefix}.4", training, buffers_out, emulate=emulate)
+def _double_conv(x, sd, prefix, training, buffers_out, emulate=False, capture=None):
+    x = _conv_bn_relu(x, sd, f"{prefix}.0", f"{prefix}.1", training, buffers_out, emulate=emulate,
+                      capture=capture)
+    return _conv_bn_relu(x, sd, f"{prefix}.3", f"{prefix}.4", training, buffers_out, emulate=emulate,
+                         capture=capture)
 
 
 def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = False,
                  levels: int = 5, buffers_out: Optional[dict] = None,
                  capture: Optional[dict] = None, emulate_bf16: bool = False) -> torch.Tensor:
     """logits = UNet(x). ``buffers_out`` (dict) receives the updated BN buffers in training mode;
-    ``capture`` (dict) receives the intermediate block outputs (teacher forcing);
+    ``capture`` (dict) receives the intermediate block outputs and, per conv unit ``<prefix>.{0,3}``,
+    its input ``.in``, pre-BN output ``.y`` and post-ReLU activation ``.a`` (plus ``upJ.up.in/.out`` of the
+    transposed convs) with ``retain_grad`` — after ``backward()`` their ``.grad`` are the upstream
+    gradients each layer saw (teacher forcing, SURVEY §8c T0);
     ``emulate_bf16`` selects the T2 oracle (bf16-rounded conv operands / output gradients)."""
     e = emulate_bf16
-    feats = [_double_conv(x, sd, "inc.double_conv", training, buffers_out, e)]
+    feats = [_double_conv(x, sd, "inc.double_conv", training, buffers_out, e, capture)]
     for i in range(1, levels):
         p = F.max_pool2d(feats[-1], 2)
         feats.append(_double_conv(p, sd, f"down{i}.maxpool_conv.1.double_conv", training,
-                                  buffers_out, e))
+                                  buffers_out, e, capture))
     y = feats[-1]
     for j in range(1, levels):
         if f"up{j}.up.weight" in sd:
+            _keep(capture, f"up{j}.up.in", y)
             up = _conv(y, sd[f"up{j}.up.weight"], sd[f"up{j}.up.bias"], e, transpose=True)
         else:   # bilinear=True: nn.Upsample has no parameters (models/unet_model.py:40-41)
             up = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True)
+        _keep(capture, f"up{j}.up.out", up)
         skip = center_crop(feats[levels - 1 - j], up.shape[-2:])
         y = _double_conv(torch.cat([skip, up], dim=1), sd, f"up{j}.conv.double_conv", training,
-                         buffers_out, e)
+                         buffers_out, e, capture)
         if capture is not None:
             capture[f"up{j}"] = y
     if capture is not None:
@@ -168,7 +188,7 @@ def make_state_dict(n_channels=1, n_classes=2, seed=0, base=64, levels=5, init=T
     return sd
 
 
-def synthetic_batch(n, size=512, out=None, seed=1234, levels=5, device="cpu"):
+def synthetic_batch(n, size=512, out=None, seed=1234, levels=5, device="cpu", cropped=True):
     """DIC-C2DH-HeLa-shaped synthetic sample: low-contrast image in [0,1], target =
     union of random ellipses (fg ~0.45), two-valued class-balance weight map, target and
     weights centre-cropped + squeezed exactly like scripts/train.py:118-126 (non-contiguous)."""
@@ -184,6 +204,8 @@ def synthetic_batch(n, size=512, out=None, seed=1234, levels=5, device="cpu"):
             mask[b, 0] |= ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1.0
     f_fg = mask.float().mean().clamp(0.05, 0.95)
     wmap = torch.where(mask, 10 + 1 / f_fg, 10 + 1 / (1 - f_fg)).float()
+    if not cropped:   # as the dataset hands them over: (N,1,size,size) (utils/dataset.py:96-115)
+        return img.to(device), mask.long().to(device), wmap.to(device)
     t = center_crop(mask.long(), (out, out)).squeeze(1)
     w = center_crop(wmap, (out, out)).squeeze(1)
     return img.to(device), t.to(device), w.to(device)

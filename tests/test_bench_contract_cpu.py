@@ -1,11 +1,14 @@
-"""bench.py contract checks that need no GPU: the reference arm (`--impl reference`) runs the oracle
-port on the host cores and prints ONE JSON line with the keys the driver reads."""
+"""bench.py contract checks that need no GPU: the reference arm (`--impl reference`) runs the
+unmodified reference (baseline/_ref or /root/reference; the oracle port only when neither exists) on
+the host cores and prints ONE JSON line with the keys the driver reads."""
 import json
 import os
 import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def test_reference_arm_prints_one_contract_line():
@@ -20,7 +23,10 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "unet_512x512_train_images_per_sec"
     assert d["unit"] == "img/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["value"] > 0 and abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-6 * d["value"] + 1e-9
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_loader
+
+    expect = "reference" if ref_loader.reference_root() else "port"
+    assert d["cpu_baseline"]["kind"] == expect and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
@@ -43,3 +49,32 @@ def test_gpu_arm_fails_loudly_without_a_device():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"],
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_reference_loader_runs_the_unmodified_reference_files():
+    """oracle/ref_loader.py executes the reference's own files (never the drop-in shims): the classes
+    come from modules whose __file__ lies under baseline/_ref or /root/reference, byte-identical to the
+    reference tree when that is mounted, and their seeded init equals the oracle's state dict."""
+    import hashlib
+
+    import torch
+
+    from oracle import ref_loader, unet_ref
+
+    ref = ref_loader.load_reference()
+    if ref is None:
+        return                                   # GPU box without baseline/_ref: nothing to check
+    mod = sys.modules[ref.UNet.__module__] if ref.UNet.__module__ in sys.modules else None
+    path = ref.UNet.__init__.__code__.co_filename
+    assert path.startswith(ref.root) and "unet_segmentation_b200" not in path
+    if os.path.isdir("/root/reference") and ref.root != "/root/reference":
+        for f in ("models/unet_model.py", "utils/losses.py", "scripts/train.py"):
+            a = hashlib.sha256(open(os.path.join(ref.root, f), "rb").read()).hexdigest()
+            b = hashlib.sha256(open(os.path.join("/root/reference", f), "rb").read()).hexdigest()
+            assert a == b, f
+    torch.manual_seed(0)
+    m = ref.UNet(1, 2)
+    m.apply(ref.init_weights)
+    sd = unet_ref.make_state_dict(1, 2, seed=0)
+    assert all(torch.equal(sd[k], v) for k, v in m.state_dict().items())
+    del mod

@@ -1,0 +1,228 @@
+"""TRUE T0: teacher-forced per-layer parity AT THE REAL LAYER GEOMETRY.
+
+The fp32 oracle runs ONE training step at N = 2 x 512^2 with `capture=` (oracle/unet_ref.py): every conv
+unit's input, pre-BN output, post-ReLU activation and — after backward() — the upstream gradients it
+saw. Each captured (input, upstream-gradient) pair, rounded to bf16 exactly as the library would store
+it, is then fed to the single `ub_op_*` kernel through the C ABI and compared with the single torch op
+in fp32 (TF32 off) on the SAME rounded tensors, so only the accumulation order differs:
+
+    bf16 outputs (y, dX, dY of BN)   rel-L2 <= 4e-3   (one bf16 rounding of the result)
+    fp32 weight gradients / dgamma   rel-L2 <= 4e-3 and cosine >= 0.999   <- the north-star
+                                     "per-layer gradients >= 0.999" bar, where it is attainable
+
+This covers every tile configuration the benchmarked network selects, including the ones the small
+random-tensor cases of test_ops_gpu.py never reach: d4.b (1024 -> 1024, K = 9216, 24^2 maps), up1.a
+(zero-copy concat 512 + 512 -> 512 over a cropped skip), the cta_group::2 pair kernels, the row-run
+kernels on 508 / 326-pixel rows, the resident-weight 64 -> 64 kernel and the split-K weight gradients
+over 4.1 M pixels.  Reference ops: models/unet_model.py:11-17 (conv, BN, ReLU), :28 (pool), :45 (ConvT).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import unet_ref  # noqa: E402
+
+BF16_TOL = 4e-3
+GRAD_TOL = 4e-3
+COS_BAR = 0.999
+
+ENC = ["inc.double_conv"] + [f"down{i}.maxpool_conv.1.double_conv" for i in range(1, 5)]
+DEC = [f"up{j}.conv.double_conv" for j in range(1, 5)]
+UNITS = [f"{p}.{k}" for p in ENC + DEC for k in (0, 3)]
+CONV_UNITS = [u for u in UNITS if u != "inc.double_conv.0"]        # the first conv has its own kernels
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cosine(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from unet_segmentation_b200 import _lib, ops as _ops
+
+    _lib.require_cuda()
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def cap():
+    """One oracle training step at N=2 x 512^2 with every intermediate and its gradient kept."""
+    sd = {k: v.cuda() for k, v in unet_ref.make_state_dict(1, 2, seed=0).items()}
+    img, t, w = unet_ref.synthetic_batch(2, size=512, seed=1234, device="cuda")
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and "running" not in k}
+    full = dict(sd)
+    full.update(params)
+    c = {}
+    logits = unet_ref.unet_forward(full, img, training=True, buffers_out={}, capture=c)
+    unet_ref.weighted_cross_entropy(logits, t, w).backward()
+    torch.cuda.synchronize()
+    out = {"sd": sd, "img": img}
+    for k, v in c.items():
+        out[k] = v.detach()
+        if v.grad is not None:
+            out[k + ".grad"] = v.grad
+    return out
+
+
+def _sources(cap, ops, unit):
+    """(src0 view, src1 or None, fp32 NCHW input as torch sees it). The first conv of a decoder block
+    reads the zero-copy concat: src0 = centre-crop VIEW of the full skip tensor, src1 = up-sampled."""
+    if unit.startswith("up") and unit.endswith(".0"):
+        j = int(unit[2])
+        skip_full = bf(cap[f"x{5 - j}"])
+        up = bf(cap[f"up{j}.up.out"])
+        h, w = up.shape[-2:]
+        ch, cw = (skip_full.shape[2] - h) // 2, (skip_full.shape[3] - w) // 2
+        src0 = ops.nhwc(skip_full)[:, ch:ch + h, cw:cw + w, :]
+        x = torch.cat([skip_full[:, :, ch:ch + h, cw:cw + w], up], 1)
+        assert torch.equal(x, bf(cap[f"{unit}.in"]))
+        return src0, ops.nhwc(up), x
+    x = bf(cap[f"{unit}.in"])
+    return ops.nhwc(x), None, x
+
+
+@pytest.mark.parametrize("unit", CONV_UNITS)
+def test_conv3x3_fprop_dgrad_wgrad_at_layer_geometry(ops, cap, unit):
+    sd = cap["sd"]
+    wt, b = bf(sd[f"{unit}.weight"]), sd[f"{unit}.bias"] + 0.01       # non-zero bias exercises the add
+    src0, src1, x = _sources(cap, ops, unit)
+    wf, wd = ops.pack_conv3x3(wt)
+    # forward (+ BN statistics epilogue: the training kernel)
+    y, stats, info = ops.conv3x3_forward(src0, src1, wf, b, epilogue=0)
+    ref_y = F.conv2d(x, wt, b)
+    torch.cuda.synchronize()
+    e_y = rel_l2(ops.nchw(y), ref_y)
+    gamma = torch.ones(wt.shape[0], device="cuda")
+    scale, shift, mean, rstd = ops.bn_finalize(stats, info, gamma, torch.zeros_like(gamma))
+    e_mean = float((mean - ref_y.mean((0, 2, 3))).abs().max() / ref_y.std())
+    e_var = rel_l2(1 / rstd ** 2, ref_y.var((0, 2, 3), unbiased=False) + 1e-5)
+    # data gradient and weight gradient from the upstream gradient the oracle saw at this layer
+    dy = bf(cap[f"{unit}.y.grad"])
+    dy = dy / dy.abs().max().clamp_min(1e-30)          # scale-free (true grads are ~1e-7)
+    dy = bf(dy)
+    dx = ops.conv3x3_dgrad(ops.nhwc(dy), wd)
+    ref_dx = torch.nn.grad.conv2d_input(x.shape, wt, dy)
+    dw = ops.conv3x3_wgrad(src0, src1, ops.nhwc(dy))
+    ref_dw = torch.nn.grad.conv2d_weight(x, wt.shape, dy)
+    torch.cuda.synchronize()
+    e_dx, e_dw, c_dw = rel_l2(ops.nchw(dx), ref_dx), rel_l2(dw, ref_dw), cosine(dw, ref_dw)
+    print(f"\n[T0 {unit}: {tuple(x.shape)} -> {wt.shape[0]}] y {e_y:.2e}  mean {e_mean:.1e} var {e_var:.1e}"
+          f"  dX {e_dx:.2e}  dW rel {e_dw:.2e} cos {c_dw:.6f}")
+    assert e_y < BF16_TOL and e_mean < 1e-3 and e_var < 2e-3
+    assert e_dx < BF16_TOL
+    assert e_dw < GRAD_TOL and c_dw >= COS_BAR
+
+
+@pytest.mark.parametrize("unit", CONV_UNITS)
+def test_bn_relu_backward_at_layer_geometry(ops, cap, unit):
+    """BN + ReLU backward fed the oracle's own pre-BN tensor and upstream gradient d(a) (which already
+    contains the max-pool routing and the skip gradient, so the DIRECT kernel variant is the one under
+    test here; the pooled + skip variant is covered at geometry by the end-to-end tests)."""
+    sd = cap["sd"]
+    bn = unit[:-1] + str(int(unit[-1]) + 1)
+    gamma, beta = sd[f"{bn}.weight"] * 1.0, sd[f"{bn}.bias"] + 0.05
+    y = bf(cap[f"{unit}.y"])
+    g = cap[f"{unit}.a.grad"]
+    g = bf(g / g.abs().max().clamp_min(1e-30))
+    mean = y.mean((0, 2, 3)); var = y.var((0, 2, 3), unbiased=False)
+    rstd = (var + 1e-5).rsqrt(); scale = gamma * rstd; shift = beta - mean * scale
+    dy, dgamma, dbeta = ops.bn_relu_backward(ops.nhwc(y), scale, shift, mean, rstd, g=ops.nhwc(g))
+    yv = y.clone().requires_grad_(True)
+    gv, bv = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    F.relu(F.batch_norm(yv, None, None, gv, bv, True, 0.1, 1e-5)).backward(g)
+    torch.cuda.synchronize()
+    e_dy = rel_l2(ops.nchw(dy), yv.grad)
+    print(f"\n[T0 BN-bwd {unit}: {tuple(y.shape)}] dY {e_dy:.2e}  dgamma {rel_l2(dgamma, gv.grad):.2e} "
+          f"cos {cosine(dgamma, gv.grad):.6f}  dbeta {rel_l2(dbeta, bv.grad):.2e}")
+    assert e_dy < 6e-3          # ReLU-boundary flips of the re-computed activation (fp32 vs torch order)
+    assert rel_l2(dgamma, gv.grad) < GRAD_TOL and cosine(dgamma, gv.grad) >= COS_BAR
+    assert rel_l2(dbeta, bv.grad) < GRAD_TOL and cosine(dbeta, bv.grad) >= COS_BAR
+
+
+@pytest.mark.parametrize("j", [1, 2, 3, 4])
+def test_conv_transpose_at_layer_geometry(ops, cap, j):
+    """ConvTranspose2d(k=2, s=2) of up1..up4 (1024->512 at 24^2 ... 128->64 at 164^2): forward written
+    into the channel slice of a concat-shaped buffer, data gradient and weight gradient."""
+    sd = cap["sd"]
+    wt, b = bf(sd[f"up{j}.up.weight"]), sd[f"up{j}.up.bias"]
+    x = bf(cap[f"up{j}.up.in"])
+    n, ci, h, w = x.shape
+    co = wt.shape[1]
+    wf, wb, b4 = ops.pack_convT(wt, b)
+    cat = torch.zeros(n, 2 * h, 2 * w, 2 * co, dtype=torch.bfloat16, device="cuda")
+    ops.convT_forward(ops.nhwc(x), wf, b4, cat[..., co:])
+    ref = F.conv_transpose2d(x, wt, b, stride=2)
+    torch.cuda.synchronize()
+    e_y = rel_l2(ops.nchw(cat[..., co:]), ref)
+    assert float(cat[..., :co].float().abs().max()) == 0.0       # the skip half is untouched
+    dup = cap[f"up{j}.up.out.grad"]
+    dup = bf(dup / dup.abs().max().clamp_min(1e-30))
+    dcat = torch.zeros(n, 2 * h, 2 * w, 2 * co, dtype=torch.bfloat16, device="cuda")
+    dcat[..., co:] = ops.nhwc(dup)
+    dx = ops.convT_dgrad(dcat[..., co:], wb)
+    dw = ops.convT_wgrad(dcat[..., co:], ops.nhwc(x))
+    ref_dx = F.conv2d(dup, wt, stride=2)                         # adjoint of the transposed conv
+    xv = wt.clone().requires_grad_(True)
+    F.conv_transpose2d(x, xv, None, stride=2).backward(dup)
+    torch.cuda.synchronize()
+    e_dx, e_dw, c_dw = rel_l2(ops.nchw(dx), ref_dx), rel_l2(dw, xv.grad), cosine(dw, xv.grad)
+    print(f"\n[T0 up{j}.up: {tuple(x.shape)} -> {co}] y {e_y:.2e}  dX {e_dx:.2e}  dW rel {e_dw:.2e} "
+          f"cos {c_dw:.6f}")
+    assert e_y < BF16_TOL and e_dx < BF16_TOL
+    assert e_dw < GRAD_TOL and c_dw >= COS_BAR
+
+
+def test_first_conv_at_layer_geometry(ops, cap):
+    """inc.double_conv.0 (1 -> 64 on 2 x 512^2, fp32 CUDA cores) + its BN / ReLU, forward
+    and the one-pass backward, fed the oracle's upstream gradient."""
+    sd, x = cap["sd"], cap["img"]
+    u = "inc.double_conv.0"
+    wt, b = sd[f"{u}.weight"], sd[f"{u}.bias"] + 0.02
+    gamma, beta = sd["inc.double_conv.1.weight"] * 1.0, sd["inc.double_conv.1.bias"] + 0.05
+    a, st = ops.first_conv_forward(x, wt, b, gamma, beta)
+    wr = wt.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref_a = F.relu(F.batch_norm(F.conv2d(x, wr, b), None, None, gr, br, True, 0.1, 1e-5))
+    g = cap[f"{u}.a.grad"]
+    g = bf(g / g.abs().max().clamp_min(1e-30))
+    # the library's ReLU mask is its own stored activation: teacher-force the same mask into torch
+    dw, dgamma, dbeta = ops.first_conv_backward(x, wt, b, st, ops.nhwc(g), a)
+    ref_a.backward(g)
+    torch.cuda.synchronize()
+    e_a = rel_l2(ops.nchw(a), ref_a.detach())
+    print(f"\n[T0 {u}] a {e_a:.2e}  dW rel {rel_l2(dw, wr.grad):.2e} cos {cosine(dw, wr.grad):.6f}  "
+          f"dgamma {rel_l2(dgamma, gr.grad):.2e}  dbeta {rel_l2(dbeta, br.grad):.2e}")
+    assert e_a < BF16_TOL
+    assert cosine(dw, wr.grad) >= COS_BAR and rel_l2(dw, wr.grad) < 1e-2
+    assert cosine(dgamma, gr.grad) >= COS_BAR and cosine(dbeta, br.grad) >= COS_BAR
+
+
+def test_head_and_loss_at_layer_geometry(ops, cap):
+    """OutConv 1x1 (64 -> 2 on 2 x 324^2) forward / backward fed the oracle's last activation."""
+    sd = cap["sd"]
+    a = bf(cap["up4.conv.double_conv.3.a"])
+    wt, b = sd["outc.conv.weight"].flatten(1), sd["outc.conv.bias"]
+    logits, _ = ops.head_forward(ops.nhwc(a), wt, b)
+    ref = F.conv2d(a, sd["outc.conv.weight"], b)
+    dl = torch.randn_like(ref)
+    da, dw, db = ops.head_backward(dl, ops.nhwc(a), wt)
+    wv = sd["outc.conv.weight"].clone().requires_grad_(True)
+    av = a.clone().requires_grad_(True)
+    F.conv2d(av, wv, b).backward(dl)
+    torch.cuda.synchronize()
+    assert rel_l2(logits, ref) < 1e-4
+    assert rel_l2(ops.nchw(da), av.grad) < BF16_TOL
+    assert cosine(dw, wv.grad.flatten(1)) >= 0.9999 and rel_l2(db, dl.sum((0, 2, 3))) < 1e-4

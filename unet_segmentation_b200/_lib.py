@@ -43,6 +43,7 @@ _SIGNATURES = {
     "ub_plan_bind_params": (c_int, [_P, C.POINTER(c_void_p), c_int]),
     "ub_plan_bind_bn_buffers": (c_int, [_P, C.POINTER(c_void_p), C.POINTER(c_void_p),
                                         C.POINTER(c_void_p), c_int]),
+    "ub_plan_set_bn_config": (c_int, [_P, C.POINTER(c_float), C.POINTER(c_float), c_int]),
     "ub_plan_pack_weights": (c_int, [_P, _P]),
     "ub_plan_forward": (c_int, [_P, _P, _P, _P, _P]),
     "ub_plan_num_stages": (c_int, [_P]),
@@ -121,12 +122,20 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _build
+
     if not os.path.exists(LIB_PATH):
         if not build_if_missing:
             raise RuntimeError(f"{LIB_PATH} is missing; run `python -m unet_segmentation_b200.build`")
-        from . import build as _build
-
         _build.build()
+    elif not _build.is_current():
+        # a library from older sources must never load silently; rebuild when nvcc is here (the
+        # authoring container), otherwise refuse (a GPU box receives the in-tree .so with its stamp)
+        if build_if_missing and _build.have_nvcc():
+            _build.build()
+        else:
+            raise RuntimeError(f"{LIB_PATH} does not match the sources under csrc/ (hash stamp "
+                               "differs); run `python -m unet_segmentation_b200.build`")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol

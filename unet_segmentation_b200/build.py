@@ -45,14 +45,35 @@ def _source_hash() -> str:
     return h.hexdigest()
 
 
+STAMP_PATH = os.path.join(LIB_DIR, "libunetb200.hash")
+LAST_ACTION = ""     # "rebuilt (hash ...)" / "reused (hash ...)": what the last build() call did
+
+
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
+def is_current() -> bool:
+    """Does the in-tree library carry the hash stamp of the sources as they are now?"""
+    try:
+        return os.path.exists(LIB_PATH) and open(STAMP_PATH).read().strip() == _source_hash()
+    except OSError:
+        return False
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    global LAST_ACTION
     os.makedirs(BUILD_DIR, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
-    stamp = os.path.join(LIB_DIR, "libunetb200.hash")
+    stamp = STAMP_PATH
     digest = _source_hash()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
-        if open(stamp).read().strip() == digest:
-            return LIB_PATH
+    if not force and is_current():
+        LAST_ACTION = f"reused (hash {digest[:16]})"
+        return LIB_PATH
     nvcc = _nvcc()
 
     def compile_one(src: str) -> str:
@@ -74,8 +95,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as fh:
         fh.write(digest)
+    LAST_ACTION = f"rebuilt (hash {digest[:16]})"
     return LIB_PATH
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True), LAST_ACTION)

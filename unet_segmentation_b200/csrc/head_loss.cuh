@@ -65,7 +65,9 @@ head_fwd_vec_kernel(const __nv_bfloat16* __restrict__ a, unsigned npix, unsigned
                     acc[c] += (b && c < NC) ? b[c] : 0.f;
                     if (c < NC) logits[((size_t)n * NC + c) * HW + hw] = acc[c];
                 }
-                if (mask) mask[p] = (NCT >= 2 && NC >= 2 && acc[1] > acc[0]) ? 255 : 0;
+                // 2+ classes: softmax[1] > 0.5 == z1 > z0 (scripts/predict.py:85-92); one class: the
+                // stale callers' sigmoid(z) > 0.5 == z > 0 (scripts/inference.py:39,85)
+                if (mask) mask[p] = (NC >= 2 ? (NCT >= 2 && acc[1] > acc[0]) : acc[0] > 0.f) ? 255 : 0;
             }
         }
     }
@@ -102,7 +104,7 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ a, long long P, long long HW, 
 #pragma unroll
         for (int c = 0; c < HEAD_MAX_CLASSES; ++c)
             if (c < NC) logits[((size_t)n * NC + c) * HW + hw] = acc[c];
-        if (mask) mask[p] = (NC >= 2 && acc[1] > acc[0]) ? 255 : 0;
+        if (mask) mask[p] = (NC >= 2 ? acc[1] > acc[0] : acc[0] > 0.f) ? 255 : 0;
     }
 }
 
@@ -242,7 +244,16 @@ wce_fwd_bwd_kernel(const WceArgs A) {
         const long long tgt = A.t[n * A.tN + h * A.tH + w * A.tW];
         const float wt = A.wm[n * A.wN + h * A.wH + w * A.wW];
         const bool ignored = tgt == -100;
-        if (!ignored && (tgt < 0 || tgt >= A.C)) { *A.err = 1; continue; }
+        if (!ignored && (tgt < 0 || tgt >= A.C)) {
+            // The reference's nn.CrossEntropyLoss faults here (device-side assert). This path raises
+            // the error flag (read by the Python module), poisons the loss with NaN so that the step
+            // cannot pass for a valid one, and writes a defined (zero) gradient for the pixel.
+            *A.err = 1;
+            local = __int_as_float(0x7fc00000);
+            if (A.dz)
+                for (int c = 0; c < A.C; ++c) A.dz[((long long)n * A.C + c) * HW + hw] = 0.f;
+            continue;
+        }
         float loss, zt = 0.f;
         if (A.C == 2) {
             const float z0 = zp[0], z1 = zp[A.zC];

@@ -235,14 +235,6 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
         q.epi.scale = epi.scale; q.epi.shift = epi.shift; q.epi.stats = epi.stats;
         q.epi.head_w = epi.head_w; q.epi.head_b = epi.head_b; q.epi.head_logits = epi.head_logits;
         q.epi.head_mask = epi.head_mask; q.epi.head_nc = epi.head_nc; q.epi.head_hw = Ho * Wo;
-        static long long* dbg_buf = nullptr;
-        static int dbg_on = -1;
-        if (dbg_on < 0) { const char* e = getenv("UB_RR_PROFILE"); dbg_on = (e && atoi(e)) ? 1 : 0; }
-        if (dbg_on) {
-            if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
-            cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), stream);
-            q.dbg = dbg_buf;
-        }
         int units = (num_sms() / CG / q.n_tiles) * q.n_tiles;
         if (units <= 0) units = q.n_tiles;
         const long long tiles = (long long)((q.m_tiles + CG - 1) / CG) * q.n_tiles;
@@ -265,16 +257,6 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
                     else rc = launch_rowrun_bn<64, 1>(epi.kind, mA0, mA1, mB, q, grid, stream);
                     break;
             }
-        }
-        if (dbg_on && rc == 0) {  // debugging aid only: synchronises
-            long long h[10];
-            cudaStreamSynchronize(stream);
-            cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-            const double g = grid;
-            fprintf(stderr, "[rr BN=%d epi=%d tiles/cta=%.1f] cycles/cta: A-prod wait %.0f of %.0f | "
-                    "B-prod wait %.0f of %.0f | MMA wait A %.0f B %.0f tmem %.0f of %.0f | epi wait %.0f of %.0f\n",
-                    BN, epi.kind, (double)tiles / g, h[0] / g, h[1] / g, h[2] / g, h[3] / g, h[4] / g,
-                    h[5] / g, h[6] / g, h[7] / g, h[8] / g, h[9] / g);
         }
         return rc;
     }

@@ -257,7 +257,8 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                             p.head_logits[(n * p.head_nc + hc) * p.head_hw + hw] = hacc[hc];
                         }
                     }
-                    if (p.head_mask) p.head_mask[m] = (p.head_nc >= 2 && hacc[1] > hacc[0]) ? 255 : 0;
+                    if (p.head_mask)   // one class: sigmoid(z) > 0.5 == z > 0 (scripts/inference.py:39,85)
+                        p.head_mask[m] = (p.head_nc >= 2 ? hacc[1] > hacc[0] : hacc[0] > 0.f) ? 255 : 0;
                 }
 }
 

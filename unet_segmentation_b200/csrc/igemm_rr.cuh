@@ -24,17 +24,7 @@ struct RowRunParams {
     int qtiles;           // ceil(Wo / 128)
     int m_tiles, n_tiles; // m_tiles = N * Ho * qtiles
     IgemmParams epi;      // epilogue fields (out, ldo, bias, scale, shift, stats); M = N*Ho*Wo
-    long long* dbg;       // optional role profile: [role][0] = cycles waiting, [role][1] = total
 };
-
-// mbarrier wait that optionally accounts the cycles spent waiting (role profiling, UB_RR_PROFILE=1)
-__device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bool prof,
-                                               long long& waited) {
-    if (!prof) { mbar_wait(bar, parity); return; }
-    const long long t0 = clock64();
-    mbar_wait(bar, parity);
-    waited += clock64() - t0;
-}
 
 // One TMA operation costs the issuing thread a few hundred cycles whatever its size, and one
 // barrier wait + tcgen05 fence costs the MMA thread ~230 cycles, so operations are made as large as
@@ -134,9 +124,6 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         // ---------------- A producer: 3 input rows x 130 pixels x 64 channels per chunk ----------
         int stage = 0;
         uint32_t phase = 0;
-        const bool prof = p.dbg != nullptr;
-        long long waited = 0;
-        const long long tstart = clock64();
         for (int mu = m_first; mu < m_units; mu += m_step) {
             int mt = mu * CG + (int)rank;
             if (mt >= p.m_tiles) mt = p.m_tiles - 1;   // odd tail: reload a valid tile, rows masked
@@ -147,7 +134,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             const int w0 = qt * 128 + p.lower;
             const int h0 = pr + p.lower;
             for (int cc = 0; cc < cchunks; ++cc) {
-                mbar_wait_prof(emptyA(stage), phase ^ 1u, prof, waited);
+                mbar_wait(emptyA(stage), phase ^ 1u);
                 const uint32_t sa = base + stage * Cfg::A_STAGE;
                 const uint32_t fb = (CG == 2) ? mapa_rank(fullA(stage), 0) : fullA(stage);
                 if (elect_one()) {
@@ -161,17 +148,10 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                 if (++stage == Cfg::SA) { stage = 0; phase ^= 1u; }
             }
         }
-        if (prof && lane == 0) {
-            atomicAdd((unsigned long long*)&p.dbg[0], (unsigned long long)waited);
-            atomicAdd((unsigned long long*)&p.dbg[1], (unsigned long long)(clock64() - tstart));
-        }
     } else if (warp == 6) {
         // ---------------- B producer: BTAPS (tap, chunk) weight tiles per stage --------------------
         int stage = 0;
         uint32_t phase = 0;
-        const bool prof = p.dbg != nullptr;
-        long long waited = 0;
-        const long long tstart = clock64();
         const int nrow0 = n0 + (int)rank * Cfg::B_ROWS;
         if (WRES) {   // all nine taps once: three boxes of (64 ch, 64 rows, 3 taps)
             if (elect_one()) {
@@ -186,7 +166,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             for (int cc = 0; cc < cchunks; ++cc) {
 #pragma unroll 1
                 for (int tap = 0; tap < 9; tap += Cfg::BTAPS) {
-                    mbar_wait_prof(emptyB(stage), phase ^ 1u, prof, waited);
+                    mbar_wait(emptyB(stage), phase ^ 1u);
                     const uint32_t fb = (CG == 2) ? mapa_rank(fullB(stage), 0) : fullB(stage);
                     if (elect_one()) {
                         if (rank == 0) mbar_expect_tx(fullB(stage), CG * Cfg::B_STAGE);
@@ -198,10 +178,6 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                 }
             }
         }
-        if (prof && lane == 0) {
-            atomicAdd((unsigned long long*)&p.dbg[2], (unsigned long long)waited);
-            atomicAdd((unsigned long long*)&p.dbg[3], (unsigned long long)(clock64() - tstart));
-        }
     } else if (warp == 1 && rank == 0) {
         // ---------------- MMA issuer (leader CTA) ---------------------------------------------------
         constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN, 0, 0);
@@ -209,18 +185,15 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         uint32_t pa = 0, pb = 0;
         int as = 0;
         uint32_t aphase = 0;
-        const bool prof = p.dbg != nullptr;
-        long long wA = 0, wB = 0, wT = 0;
-        const long long tstart = clock64();
-        if (WRES) mbar_wait_prof(fullB(0), 0, prof, wB);
+        if (WRES) mbar_wait(fullB(0), 0);
         for (int mu = m_first; mu < m_units; mu += m_step) {
-            mbar_wait_prof(tempty_bar(as), aphase ^ 1u, prof, wT);
+            mbar_wait(tempty_bar(as), aphase ^ 1u);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
             uint32_t acc = 0;
             if (WRES) {
                 // one chunk, resident weights: all 36 MMAs of the tile behind a single wait
-                mbar_wait_prof(fullA(sa_i), pa, prof, wA);
+                mbar_wait(fullA(sa_i), pa);
                 tc_fence_after();
                 const uint32_t sa = base + sa_i * Cfg::A_STAGE;
                 if (elect_one()) {
@@ -242,11 +215,11 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                 if (++sa_i == Cfg::SA) { sa_i = 0; pa ^= 1u; }
             } else
             for (int cc = 0; cc < cchunks; ++cc) {
-                mbar_wait_prof(fullA(sa_i), pa, prof, wA);
+                mbar_wait(fullA(sa_i), pa);
                 const uint32_t sa = base + sa_i * Cfg::A_STAGE;
 #pragma unroll 1
                 for (int tap = 0; tap < 9; tap += Cfg::BTAPS) {
-                    mbar_wait_prof(fullB(sb_i), pb, prof, wB);
+                    mbar_wait(fullB(sb_i), pb);
                     tc_fence_after();
                     if (elect_one()) {
 #pragma unroll
@@ -276,12 +249,6 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             }
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
-        if (prof && lane == 0) {
-            atomicAdd((unsigned long long*)&p.dbg[4], (unsigned long long)wA);
-            atomicAdd((unsigned long long*)&p.dbg[5], (unsigned long long)wB);
-            atomicAdd((unsigned long long*)&p.dbg[6], (unsigned long long)wT);
-            atomicAdd((unsigned long long*)&p.dbg[7], (unsigned long long)(clock64() - tstart));
-        }
     } else if (is_epilogue_warp<BN>(warp)) {
         // ---------------- epilogue (lane quadrant x column half) --------------------------------------
         const int quad = warp & 3;
@@ -295,9 +262,6 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         for (int c = 0; c < NCH; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
         StatRegs<BN, EPI> sr;
         sr.clear();
-        const bool prof = p.dbg != nullptr;
-        long long wE = 0;
-        const long long tstart = clock64();
         for (int mu = m_first; mu < m_units; mu += m_step) {
             const int mt = mu * CG + (int)rank;
             const int qt = mt % p.qtiles;
@@ -305,7 +269,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             const int q = qt * 128 + row_in_tile;
             const bool valid = q < p.Wo && mt < p.m_tiles;
             const long long m = (long long)t * p.Wo + q;
-            mbar_wait_prof(tfull_bar(as), aphase, prof, wE);
+            mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
             epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, cs, hs);
@@ -316,10 +280,6 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                 else mbar_arrive(tempty_bar(as));
             }
             if (++as == 2) { as = 0; aphase ^= 1u; }
-        }
-        if (prof && warp == 2 && lane == 0) {
-            atomicAdd((unsigned long long*)&p.dbg[8], (unsigned long long)wE);
-            atomicAdd((unsigned long long*)&p.dbg[9], (unsigned long long)(clock64() - tstart));
         }
         finish_stat_regs<BN, EPI>(sr, lane, ssum, ssq);
         if (EPI == EPI_CONV_STATS) {

@@ -75,7 +75,8 @@ struct ub_plan {
     bf16* head_da = nullptr;
     const float* x = nullptr;   // input of the last forward (kept by the caller)
     bool packed = false;
-    float momentum = 0.1f, eps = 1e-5f;
+    // per BatchNorm layer (ub_plan_set_bn_config): nn.BatchNorm2d defaults unless the module says otherwise
+    std::vector<float> bn_mom, bn_eps;
     // Weight gradients run on a low-priority side stream: they are off the backward critical path
     // (BN backward -> data gradient -> BN backward ...), tensor-bound, and small enough in registers
     // (256 threads x 74) to share an SM with the HBM-bound BN-backward CTAs, so the two overlap.
@@ -212,6 +213,8 @@ int ub_plan_create_ex(ub_plan** out, int N, int n_channels, int H, int W, int ba
     P->rm.assign(2 * L + 2 * (L - 1), nullptr);
     P->rv.assign(2 * L + 2 * (L - 1), nullptr);
     P->nbt.assign(2 * L + 2 * (L - 1), nullptr);
+    P->bn_mom.assign(2 * L + 2 * (L - 1), 0.1f);
+    P->bn_eps.assign(2 * L + 2 * (L - 1), 1e-5f);
 
     auto fail = [&](int code) { delete P; return code; };
     auto set_unit_params = [&](ConvUnit& u, int pbase, int bn) {
@@ -423,6 +426,23 @@ int ub_plan_bind_bn_buffers(ub_plan* P, float* const* rm, float* const* rv,
     return 0;
 }
 
+int ub_plan_set_bn_config(ub_plan* P, const float* momentum, const float* eps, int count) {
+    if (!P || !momentum || !eps || count != (int)P->rm.size()) {
+        set_last_error("set_bn_config: expected %d BatchNorm layers, got %d",
+                       P ? (int)P->rm.size() : -1, count);
+        return ub::UB_ERR_ARG;
+    }
+    for (int i = 0; i < count; ++i) {
+        if (!(momentum[i] >= 0.f && momentum[i] <= 1.f) || !(eps[i] > 0.f)) {
+            set_last_error("set_bn_config: layer %d: momentum %g must lie in [0, 1] and eps %g be "
+                           "positive", i, (double)momentum[i], (double)eps[i]);
+            return ub::UB_ERR_ARG;
+        }
+    }
+    for (int i = 0; i < count; ++i) { P->bn_mom[i] = momentum[i]; P->bn_eps[i] = eps[i]; }
+    return 0;
+}
+
 int ub_plan_pack_weights(ub_plan* P, void* stream) {
     if (!P) return ub::UB_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
@@ -461,12 +481,12 @@ static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const Vie
             d.bias = P->params[u.p_b];
             UB_TRY(launch_first_conv_train_stats(d, P->scratch, P->params[u.p_g], P->params[u.p_be],
                                                  P->rm[u.bn], P->rv[u.bn], P->nbt[u.bn],
-                                                 P->momentum, P->eps, u.scale, u.shift, u.mean,
-                                                 u.rstd, P->fc_cov, s));
+                                                 P->bn_mom[u.bn], P->bn_eps[u.bn], u.scale, u.shift,
+                                                 u.mean, u.rstd, P->fc_cov, s));
         } else {
             d.bias = nullptr;
             UB_TRY(launch_bn_fold_eval(u.Co, P->params[u.p_b], P->params[u.p_g], P->params[u.p_be],
-                                       P->rm[u.bn], P->rv[u.bn], P->eps, u.scale, u.shift, s));
+                                       P->rm[u.bn], P->rv[u.bn], P->bn_eps[u.bn], u.scale, u.shift, s));
         }
         return launch_first_conv_apply(d, u.scale, u.shift, u.a, s);
     }
@@ -484,7 +504,7 @@ static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const Vie
         ProfScope ps(P, CLS_BN_APPLY, 0, pix_out * u.Co * (pooled ? 4.5 : 4.0), s);
         UB_TRY(launch_bn_finalize(P->scratch, u.info, u.Co, (double)u.info.M, P->params[u.p_g],
                                   P->params[u.p_be], P->rm[u.bn], P->rv[u.bn], P->nbt[u.bn],
-                                  P->momentum, P->eps, u.scale, u.shift, u.mean, u.rstd, s));
+                                  P->bn_mom[u.bn], P->bn_eps[u.bn], u.scale, u.shift, u.mean, u.rstd, s));
         if (P->fused_logits && &u == &P->dec[P->L - 2].u[1]) {   // last unit: 1x1 head fused in
             const int np = (int)P->params.size();
             return launch_bn_apply_relu_head(u.y, u.a, N, u.Ho(), u.Wo(), u.Co, u.scale, u.shift,
@@ -495,7 +515,7 @@ static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const Vie
                                     u.shift, s);
     }
     UB_TRY(launch_bn_fold_eval(u.Co, P->params[u.p_b], P->params[u.p_g], P->params[u.p_be],
-                               P->rm[u.bn], P->rv[u.bn], P->eps, u.scale, u.shift, s));
+                               P->rm[u.bn], P->rv[u.bn], P->bn_eps[u.bn], u.scale, u.shift, s));
     e.kind = EPI_AFFINE_RELU; e.out = u.a; e.scale = u.scale; e.shift = u.shift;
     if (P->fused_logits && &u == &P->dec[P->L - 2].u[1]) {
         // eval, last unit (64 channels): the 1x1 head and the mask come out of the conv epilogue

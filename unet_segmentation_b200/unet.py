@@ -112,6 +112,7 @@ class _Plan:
             self.stage_ranges.append((f.value, c.value))
         self.bound_ptrs = None
         self.bound_buf_ptrs = None
+        self.bound_bn_cfg = None
         self.packed_versions = None
         self.generation = 0
 
@@ -156,6 +157,13 @@ class _Plan:
             check(self.lib.ub_plan_bind_bn_buffers(self.handle, rm, rv, nb, k),
                   "ub_plan_bind_bn_buffers")
             self.bound_buf_ptrs = bptrs
+        cfg = tuple((float(m.momentum), float(m.eps)) for m in bn_modules)
+        if cfg != self.bound_bn_cfg:
+            k = len(cfg)
+            mom = (C.c_float * k)(*[c[0] for c in cfg])
+            eps = (C.c_float * k)(*[c[1] for c in cfg])
+            check(self.lib.ub_plan_set_bn_config(self.handle, mom, eps, k), "ub_plan_set_bn_config")
+            self.bound_bn_cfg = cfg
         versions = (tuple(p._version for p in params), epoch)
         if versions != self.packed_versions:
             check(self.lib.ub_plan_pack_weights(self.handle, _stream()), "ub_plan_pack_weights")
@@ -307,6 +315,50 @@ class UNet(nn.Module):
             out.extend([b.double_conv[1], b.double_conv[4]])
         return out
 
+    def _check_bn_modules(self, bns, training: bool) -> None:
+        """The library implements nn.BatchNorm2d as the reference configures it (running statistics,
+        exponential moving average, the whole net in one mode); anything else must not run silently
+        with different semantics."""
+        for m in bns:
+            if not m.track_running_stats or m.running_mean is None:
+                raise RuntimeError("UNet (B200): BatchNorm2d(track_running_stats=False) is not supported")
+            if m.momentum is None:
+                raise RuntimeError("UNet (B200): BatchNorm2d(momentum=None) (cumulative moving "
+                                   "average) is not supported; use a float momentum")
+            if not m.affine:
+                raise RuntimeError("UNet (B200): BatchNorm2d(affine=False) is not supported")
+            if m.training != training:
+                raise RuntimeError("UNet (B200): a BatchNorm2d layer is in "
+                                   f"{'train' if m.training else 'eval'} mode while the network runs in "
+                                   f"{'train' if training else 'eval'} mode; per-layer frozen BatchNorm "
+                                   "is not supported (call model.train() / model.eval() on the whole net)")
+
+    def invalidate_weights(self) -> None:
+        """Force a refresh of the packed bf16 operand caches at the next forward. Needed after
+        writing parameters in a way torch's version counters do not see (``p.data`` assignment /
+        in-place edits through ``.data``, raw-pointer writers); optimizers, ``load_state_dict`` and
+        ordinary in-place tensor ops are picked up automatically."""
+        self._weights_epoch += 1
+
+    # plans hold ctypes handles of device arenas: they are per-process caches, not state
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_plans"] = {}
+        state["_stage_hook"] = None
+        state["_backward_done_hook"] = None
+        state.pop("_last_train_key", None)
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
     def _plan_for(self, x: torch.Tensor, training: bool) -> _Plan:
         n, c, h, w = x.shape
         key = (n, c, h, w, training, x.device.index)
@@ -317,7 +369,9 @@ class UNet(nn.Module):
             plan = _Plan(n, c, h, w, self.base_channels, self.levels, self.n_classes, training,
                          x.device, bilinear=self.bilinear)
             self._plans[key] = plan
-        plan.bind(self._ordered_params(), self._ordered_bns(), self._weights_epoch)
+        bns = self._ordered_bns()
+        self._check_bn_modules(bns, training)
+        plan.bind(self._ordered_params(), bns, self._weights_epoch)
         if training:
             self._last_train_key = key
         return plan
