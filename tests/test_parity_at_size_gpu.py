@@ -129,7 +129,9 @@ def test_training_step_vs_fp32_oracle_and_autocast_control_512(n):
     print(fmt(f"[T1 N={n} x 512^2] torch.autocast(bf16) ctl", ctrl))
     # north-star bars a bf16 implementation can meet end to end
     assert ours["logits"] < 2e-2 and ours["loss"] < 2e-3
-    assert ours["mask"] > 0.99 and ours["mask_conf"] > 0.99      # tightened to the measured values below
+    # measured (N=2 / N=16): masks 0.99568 / 0.99574 overall, 0.99745 / 0.99751 where |z1-z0| > 0.05;
+    # the torch.autocast control: 0.9823 / 0.9842. 99.9 % is met in eval mode only.
+    assert ours["mask"] > 0.995 and ours["mask_conf"] > 0.997
     for name in ("outc.conv.weight", "outc.conv.bias", "up4.conv.double_conv.4.weight",
                  "up4.conv.double_conv.3.weight"):
         assert ours["cos"][name] > 0.999, (name, ours["cos"][name])
@@ -149,7 +151,7 @@ def test_wide_unet_base128_1024_vs_fp32_oracle():
     ours = t1_metrics(logits, loss, grads, *ref)
     print("\n" + fmt("[T1 base128 1 x 1024^2] libunetb200          ", ours))
     print(fmt("[T1 base128 1 x 1024^2] torch.autocast(bf16) ctl", ctrl))
-    assert ours["logits"] < 2e-2 and ours["loss"] < 2e-3 and ours["mask"] > 0.99
+    assert ours["logits"] < 2e-2 and ours["loss"] < 2e-3 and ours["mask"] > 0.996   # measured 0.99676
     assert ours["cos"]["outc.conv.weight"] > 0.999 and ours["cos"]["outc.conv.bias"] > 0.999
     assert_no_worse_than_control(ours, ctrl, "base128")
 
@@ -238,7 +240,7 @@ def test_against_reference_golden_512(name):
         agree = mask_agreement(logits, ref_logits)
         print(f"\n[reference golden {name}] logits rel-L2 {e_logits:.3e}  loss rel {e_loss:.3e}  "
               f"mask agree {agree:.5f}")
-        assert e_logits < 2e-2 and e_loss < 2e-3 and agree > 0.99
+        assert e_logits < 2e-2 and e_loss < 2e-3 and agree > 0.995     # measured 0.99566
         grads = dict(model.named_parameters())
         for k in ("outc.conv.weight", "outc.conv.bias", "up4.conv.double_conv.4.weight",
                   "up4.conv.double_conv.4.bias"):
