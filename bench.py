@@ -54,6 +54,31 @@ def load_peaks():
         return d
 
 
+def forward_flops(size: int, base: int = 64, levels: int = 5, n_classes: int = 2) -> float:
+    """Executed FLOPs (2 per MAC) of one eval forward of a size x size single-channel tile through
+    the reference architecture (models/unet_model.py:73-85,105-146), layer by layer."""
+    fl, h, cin = 0.0, size, 1
+    skips = []
+    for i in range(levels):
+        co = base << i
+        fl += 2.0 * (h - 2) ** 2 * co * 9 * cin
+        fl += 2.0 * (h - 4) ** 2 * co * 9 * co
+        h -= 4
+        cin = co
+        if i < levels - 1:
+            skips.append(co)
+            h //= 2
+    for j in range(levels - 1):
+        co = cin // 2
+        fl += 2.0 * h * h * cin * 4 * co           # ConvTranspose2d(k=2, s=2)
+        h *= 2
+        fl += 2.0 * (h - 2) ** 2 * co * 9 * (co + skips[-1 - j])
+        fl += 2.0 * (h - 4) ** 2 * co * 9 * co
+        h -= 4
+        cin = co
+    return fl + 2.0 * h * h * n_classes * cin
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -213,6 +238,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-infer", action="store_true")
+    ap.add_argument("--no-wide", action="store_true", help="skip the BASELINE configs[4] wide-U-Net step")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused = unet_segmentation_b200.optim.FusedSGD, torch = torch.optim.SGD")
     args = ap.parse_args()
@@ -461,7 +487,7 @@ def main():
         # DRAM traffic of that kernel class per launch (= per layer), from the committed ncu captures:
         # the per-class capture of one step (scripts_dev/traffic_by_class.py), else the --set full one
         traffic, traffic_src = None, None
-        for fname in ("r01_traffic_by_class.json", "r01_traffic.json"):
+        for fname in ("r02_traffic_by_class.json", "r01_traffic_by_class.json", "r01_traffic.json"):
             try:
                 with open(os.path.join(ROOT, "profiles", fname)) as fh:
                     tj = json.load(fh)
@@ -474,7 +500,9 @@ def main():
         if tensor_bound:
             peak = float(peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"])
             roofline = {"kernel": dom, "bound": "tensor", "achieved": d["tflops"], "peak": peak,
-                        "unit": "TFLOP/s", "frac": d["tflops"] / peak, "traffic": traffic,
+                        "unit": "TFLOP/s", "frac": d["tflops"] / peak,
+                        "frac_of_measured_burst": d["tflops"] / float(peaks["bf16_tflops"]),
+                        "frac_of_datasheet_2250": d["tflops"] / 2250.0, "traffic": traffic,
                         "traffic_source": traffic_src,
                         "launches_per_step": d["groups_per_step"],
                         "algorithmic_bytes_per_launch": d["gbs"] * 1e9 * d["ms_per_step"] * 1e-3
@@ -489,6 +517,61 @@ def main():
                         "peak_source": f"{peaks['_source']} HBM copy",
                         "share_of_step": d["ms_per_step"] / ms_per_step}
 
+    # ---------------- BASELINE configs[4]: wide U-Net (base 128) on 1024^2 crops, batch 8 per GPU ----------
+    wide = None
+    if not args.no_wide:
+        try:
+            wide_model = UNet(1, 2, base_channels=128)
+            wide_model.load_state_dict(unet_ref.make_state_dict(1, 2, seed=0, base=128))
+            wide_model = wide_model.to(dev).train()
+            parallel.broadcast_parameters(wide_model)
+            wide_red = parallel.StageGradAllReducer(wide_model) if world > 1 else None
+            from unet_segmentation_b200.optim import FusedSGD as _FSGD
+
+            wopt = _FSGD(wide_model, lr=1e-4, momentum=0.99)
+            WN, WS = 8, 1024
+            gw = torch.Generator().manual_seed(4321 + rank)
+            wimg = (0.4 + 0.2 * torch.rand(WN, 1, WS, WS, generator=gw)).to(dev)
+            wo = unet_ref.out_size(WS)
+            wt = (torch.rand(WN, wo, wo, generator=gw) > 0.55).long().to(dev)
+            ww = torch.where(wt > 0, 12.5, 11.66).float()
+
+            def wide_step():
+                wopt.zero_grad(set_to_none=True)
+                loss = criterion(wide_model(wimg), wt, ww)
+                loss.backward()
+                wopt.step()
+                return loss
+
+            for _ in range(3):
+                wide_step()
+            wsteps = 5
+            barrier()
+            we0, we1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            we0.record()
+            for _ in range(wsteps):
+                wl = wide_step()
+            we1.record()
+            barrier()
+            wide_local = we0.elapsed_time(we1)
+            wide = {"final_loss": float(wl), "arena_gb": wide_model.arena_bytes() / 1e9}
+            del wide_model, wopt, wide_red, wimg, wt, ww
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            wide_local = float("nan")
+            wide = {"error": f"{type(exc).__name__}: {exc}"}
+        barrier()
+        wide_ms = max_over_ranks(wide_local)
+        if "error" not in wide:
+            WIDE_FLOP_PER_IMG = 14234.6e9          # base 128 at 1024^2, 3 x fwd - first dgrad
+            wide.update({"workload": "UNet(1,2, base 128, depth 5) training step, batch 8/GPU x 1x1024x1024 "
+                                     "(BASELINE configs[4]), FusedSGD inside the step",
+                         "ms_per_step": wide_ms / 5, "img_per_s": world * 8 * 5 / (wide_ms * 1e-3),
+                         "step_tflops_per_gpu": 8 * WIDE_FLOP_PER_IMG / (wide_ms / 5 * 1e-3) / 1e12,
+                         "frac_of_bf16_sustained": 8 * WIDE_FLOP_PER_IMG / (wide_ms / 5 * 1e-3) / 1e12
+                         / float(peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]),
+                         "n_gpus": world, "steps": 5, "warmup": 3})
+
     # ---------------- overlap-tile inference (BASELINE metric ii), tiles sharded over ranks ----------
     infer = None
     if not args.no_infer:
@@ -501,30 +584,83 @@ def main():
                 mod.running_mean.copy_((torch.randn(mod.num_features, generator=gen) * 0.1).to(dev))
                 mod.running_var.copy_((0.5 + torch.rand(mod.num_features, generator=gen)).to(dev))
         infer = {}
+        burst = float(peaks["bf16_tflops"])
+        USEFUL_FLOP_PER_PX = 1.468e6          # halo-free lower bound
         for size in (1024, 8192):
             gi = torch.Generator().manual_seed(99)
             frame = 0.4 + 0.2 * torch.rand(512, 512, generator=gi)
             img = frame.repeat(size // 512, size // 512).to(dev)   # mosaic of 512^2 frames
-            tile_in = tiling.choose_tile(size, size, world)    # least executed work per rank
+            tile_in, ranks_used, bt = tiling.choose_plan(size, size, world)   # least modelled time
             tile_out, _, origins = tiling.plan_tiles(size, size, tile_in)
             n_tiles = len(origins)
-            if n_tiles < world:
-                continue
-            bt = min(8, max(1, n_tiles // world))
-            tiling.overlap_tile_predict(model, img, tile_in=tile_in, batch_tiles=bt, rank=rank,
-                                        world=world)  # warm-up
+            for _ in range(3):           # plain launches, graph capture, first replay
+                tiling.overlap_tile_predict(model, img, tile_in=tile_in, batch_tiles=bt, rank=rank,
+                                            world=world, ranks_used=ranks_used)
             barrier()
-            reps = 3
+            reps = 5
+            l0 = int(lib.ub_launch_count())
             e0.record()
             for _ in range(reps):
                 mask = tiling.overlap_tile_predict(model, img, tile_in=tile_in, batch_tiles=bt,
-                                                   rank=rank, world=world)
+                                                   rank=rank, world=world, ranks_used=ranks_used)
             e1.record()
             barrier()
             ms_i = max_over_ranks(e0.elapsed_time(e1)) / reps
-            infer[f"{size}x{size}"] = {"mpix_per_s": size * size / (ms_i * 1e-3) / 1e6, "ms": ms_i,
-                                       "tiles": n_tiles, "tile_in": tile_in, "tile_out": tile_out,
-                                       "batch_tiles": bt, "fg_fraction": float((mask > 0).float().mean())}
+            exec_flop = n_tiles * forward_flops(tile_in)
+            mpix = size * size / (ms_i * 1e-3) / 1e6
+            bound = world * burst * 1e12 / USEFUL_FLOP_PER_PX / 1e6
+            infer[f"{size}x{size}"] = {
+                "mpix_per_s": mpix, "ms": ms_i, "tiles": n_tiles, "tile_in": tile_in,
+                "tile_out": tile_out, "batch_tiles": bt, "ranks_used": ranks_used,
+                "input_px_per_output_px": n_tiles * tile_in * tile_in / (size * size),
+                "useful_tflops": size * size * USEFUL_FLOP_PER_PX / (ms_i * 1e-3) / 1e12,
+                "executed_tflops": exec_flop / (ms_i * 1e-3) / 1e12,
+                "halo_free_bound_mpix_per_s": bound, "frac_of_halo_free_bound": mpix / bound,
+                "executed_frac_of_bf16_burst": exec_flop / (ms_i * 1e-3) / 1e12 / (ranks_used * burst),
+                "gpu_launches_per_image": (int(lib.ub_launch_count()) - l0) / reps,
+                "fg_fraction": float((mask > 0).float().mean()),
+                "path": "ub_extract_tiles (mirror gather) -> eval forward replayed from a CUDA graph "
+                        "(head + mask fused into the last conv) -> all-gather of uint8 tiles (N > 1) "
+                        "-> ub_stitch_tiles"}
+        # whole-image post-processing on a stitched 8192^2 mask: the reference's shipped
+        # binary masks (~1 700 speckly components per 324^2 frame) tiled to the full image
+        if rank == 0:
+            try:
+                import numpy as np
+
+                from unet_segmentation_b200.postprocess import get_instance_masks
+
+                blob = np.load(os.path.join(ROOT, "tests", "golden", "ccl_golden.npz"))
+                keys = sorted(k for k in blob.files if k.startswith("mask"))
+                reps_t = -(-8192 // 324)
+                big = np.concatenate([np.concatenate([blob[keys[(r + c) % len(keys)]]
+                                                      for c in range(reps_t)], axis=1)
+                                      for r in range(reps_t)], axis=0)[:8192, :8192]
+                big_d = torch.from_numpy(np.ascontiguousarray(big)).to(dev)
+                for _ in range(2):
+                    inst = get_instance_masks(big_d, min_size=15)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(5):
+                    inst = get_instance_masks(big_d, min_size=15)
+                e1.record()
+                torch.cuda.synchronize()
+                ms_c = e0.elapsed_time(e1) / 5
+                blob_ms = None
+                e0.record()
+                inst2 = get_instance_masks(mask, min_size=15)      # the network's own (one-blob) mask
+                e1.record()
+                torch.cuda.synchronize()
+                blob_ms = e0.elapsed_time(e1)
+                infer["ccl_stitched_8192"] = {
+                    "ms": ms_c, "mpix_per_s": 8192 * 8192 / (ms_c * 1e-3) / 1e6,
+                    "foreground_fraction": float((big_d > 0).float().mean()),
+                    "labels_wrap_uint16": True,
+                    "mask": "reference's shipped 01_RES masks (tests/golden/ccl_golden.npz) tiled to 8192^2",
+                    "one_blob_mask_ms": blob_ms, "one_blob_max_label": int(inst2.max())}
+                del big_d, inst, inst2
+            except Exception as exc:
+                infer["ccl_stitched_8192"] = {"error": f"{type(exc).__name__}: {exc}"}
         # the reference's per-frame predict loop (scripts/predict.py:73-112): one 512^2 frame from host
         # memory -> eval forward -> (softmax[1] > 0.5) mask -> get_instance_masks -> both back on the host
         if rank == 0:
@@ -534,10 +670,11 @@ def main():
                 frame_h = ((frame - 0.5) / 0.5).reshape(1, 1, 512, 512).pin_memory()   # Normalize(.5,.5)
                 mask_hb = torch.empty(324, 324, dtype=torch.uint8).pin_memory()
                 inst_hb = torch.empty(324, 324, dtype=torch.uint16).pin_memory()
+                x_dev = torch.empty(1, 1, 512, 512, device=dev)
 
                 def predict_frame():
-                    x = frame_h.to(dev, non_blocking=True)
-                    _, mk = model.predict_mask(x)
+                    x_dev.copy_(frame_h, non_blocking=True)
+                    _, mk = model.predict_mask(x_dev)
                     inst = get_instance_masks(mk[0], min_size=15)
                     mask_hb.copy_(mk[0], non_blocking=True)
                     inst_hb.copy_(inst, non_blocking=True)
@@ -545,7 +682,7 @@ def main():
                 for _ in range(3):
                     predict_frame()
                 torch.cuda.synchronize()
-                reps_f = 20
+                reps_f = 50
                 e0.record()
                 for _ in range(reps_f):
                     predict_frame()
@@ -553,9 +690,9 @@ def main():
                 torch.cuda.synchronize()
                 ms_f = e0.elapsed_time(e1) / reps_f
                 infer["predict_frame_512"] = {"ms_per_frame": ms_f, "frames_per_s": 1e3 / ms_f,
-                                              "stages": "H2D 1x1x512x512 f32 -> eval forward (mask fused) -> "
-                                                        "8-connected labelling + <15 px filter -> D2H "
-                                                        "324x324 uint8 + uint16",
+                                              "stages": "H2D 1x1x512x512 f32 -> eval forward (CUDA-graph replay, "
+                                                        "mask fused) -> 8-connected labelling + <15 px filter "
+                                                        "-> D2H 324x324 uint8 + uint16",
                                               "max_label": int(inst_hb.numpy().max())}
             except Exception as exc:   # an extra measurement must not take the contract line down
                 infer["predict_frame_512"] = {"error": f"{type(exc).__name__}: {exc}"}
@@ -599,6 +736,7 @@ def main():
             "step_frac_of_bf16_sustained": N * FLOP_PER_IMG_STEP / (ms_per_step * 1e-3) / 1e12 / sus,
             "kernel_breakdown": breakdown,
             "infer_overlap_tile": infer,
+            "wide_unet": wide,
             "final_loss": final_loss,
             "e2e_device_pipeline": pipeline,
             "allreduce": ({"collectives_per_step": reducer.n_collectives / steps_run[0],

@@ -91,8 +91,12 @@ int ub_plan_pack_weights(ub_plan* plan, void* stream);
  * training plan: batch statistics, running-stat update (momentum 0.1, unbiased variance),
  * activations saved for backward. eval plan: running statistics folded into the conv epilogues;
  * `mask` (optional, may be NULL; [N][out_h][out_w] uint8) receives 255 where logit1 > logit0,
- * i.e. softmax(logits)[:,1] > 0.5 (reference scripts/predict.py:85-92). */
+ * i.e. softmax(logits)[:,1] > 0.5 (reference scripts/predict.py:85-92).
+ * An eval plan called repeatedly with the SAME x / logits / mask pointers (and unchanged parameter
+ * binding) captures its launch sequence into a CUDA graph on the second call and replays it from
+ * then on (UB_EVAL_GRAPH=0 disables); ub_plan_graph_replays counts the replays. */
 int ub_plan_forward(ub_plan* plan, const float* x, float* logits, uint8_t* mask, void* stream);
+int64_t ub_plan_graph_replays(const ub_plan* plan);
 
 /* Backward, split into stages so that a data-parallel caller can all-reduce the gradients of a
  * finished stage while the next one runs. Stage 0 = outc + last up block, then the remaining up
@@ -204,6 +208,23 @@ int ub_elastic_deform(const uint8_t* images, const void* labels, int label_bytes
 int64_t ub_ccl_workspace_bytes(int H, int W);
 int ub_ccl_label(const uint8_t* mask, int H, int W, int min_size, uint16_t* labels, void* workspace,
                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Overlap-tile inference helpers (BASELINE configs[3]; the reference describes the strategy in prose
+ * only — README.md:104-106, images/old readme unet.txt:73-87 — semantics in DESIGN.md §5).
+ *   origins_yx  T pairs (row, column) of int32 on the DEVICE: top-left corners of the tiles' OUTPUT
+ *               windows in image coordinates; a negative row marks an unused slot.
+ * ub_extract_tiles: tiles[t][y][x] = image[reflect(row_t - margin + y)][reflect(col_t - margin + x)]
+ *   (numpy 'reflect' mirroring, any extension length), image [H][W] fp32, tiles [T][tile_in][tile_in]
+ *   fp32 = the (T,1,tile_in,tile_in) network input; tile_in % 4 == 0.
+ * ub_stitch_tiles: full[row_t + y][col_t + x] = tiles[t][y][x] clipped to the H x W image; tiles
+ *   [T][tile_out][tile_out] uint8 masks as ub_plan_forward writes them; tile_out % 4 == 0.
+ * One launch per call for all T tiles; no host work per tile.
+ * ---------------------------------------------------------------------------------------------- */
+int ub_extract_tiles(const float* image, int H, int W, const int32_t* origins_yx, int T, int tile_in,
+                     int margin, float* tiles, void* stream);
+int ub_stitch_tiles(const uint8_t* tiles, const int32_t* origins_yx, int T, int tile_out,
+                    uint8_t* full, int H, int W, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Operator-level entry points (teacher-forced per-layer parity tests). bf16 NHWC

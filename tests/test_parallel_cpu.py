@@ -99,27 +99,37 @@ def test_reflect_extension_matches_numpy():
     assert np.array_equal(tiles[0, 0].numpy(), ref)
 
 
-def test_choose_tile_minimises_executed_work():
-    """tiling.choose_tile: aligned tile sizes (≡ 12 mod 16), full coverage, never more executed
-    input pixels per rank than the 572-tile default, whole batches accounted for."""
+def test_choose_plan_minimises_modelled_time_and_never_loses_with_more_ranks():
+    """tiling.choose_plan: aligned tile sizes (≡ 12 mod 16), full coverage, modelled time no worse
+    than the 572-tile default and monotone in the number of ranks offered (it may leave ranks idle:
+    a 1024^2 image has work for four GPUs, not eight)."""
     from unet_segmentation_b200 import tiling
 
+    def cost(size, tile_in, ranks, bt):
+        n = len(tiling.plan_tiles(size, size, tile_in)[2])
+        per_rank = -(-n // ranks)
+        bt = max(1, min(bt, per_rank))
+        c = -(-per_rank // bt) * (tiling._MS_PER_FORWARD + tiling._MS_PER_PIXEL * bt * tile_in * tile_in)
+        return c + (tiling._MS_PER_GATHER if ranks > 1 else 0.0)
+
     for size in (600, 1024, 2048, 8192):
+        prev = None
         for world in (1, 2, 4, 8):
-            t = tiling.choose_tile(size, size, world)
-            assert t % 16 == 12
+            t, ranks, bt = tiling.choose_plan(size, size, world)
+            assert t == tiling.choose_tile(size, size, world)
+            assert t % 16 == 12 and 1 <= ranks <= world and 1 <= bt <= 8
             tile_out, stride, origins = tiling.plan_tiles(size, size, t)
             assert stride % 16 == 0 and all(y % 16 == 0 and x % 16 == 0 for y, x in origins)
-            assert max(y for y, _ in origins) + tile_out >= size
-
-            def slots(tile_in):
-                n = len(tiling.plan_tiles(size, size, tile_in)[2])
-                per_rank = -(-n // world)
-                bt = max(1, min(8, per_rank))
-                return -(-per_rank // bt) * bt * tile_in * tile_in
-
-            assert slots(t) <= slots(572)
-    assert tiling.choose_tile(8192, 8192, 8) == 1212     # 64 tiles of 1028: 8 per rank, no waste
+            assert max(y for y, _ in origins) + tile_out >= size and ranks <= len(origins)
+            c = cost(size, t, ranks, bt)
+            assert c <= cost(size, 572, min(world, len(tiling.plan_tiles(size, size, 572)[2])), 8) + 1e-9
+            assert prev is None or c <= prev + 1e-9          # more GPUs never model slower
+            prev = c
+    # 8192^2: 16 tiles of 2236 -> 2052 (stride 2048, 1.19 input pixels per output pixel; 64 tiles of
+    # 1212 -> 1028 execute 1.40), two per rank on eight GPUs
+    assert tiling.choose_plan(8192, 8192, 8) == (2236, 8, 2)
+    assert tiling.choose_plan(8192, 8192, 1) == (2236, 1, 8)
+    assert tiling.choose_plan(1024, 1024, 1)[:2] == (1212, 1)
 
 
 def test_bf16_rounding_oracle_is_a_small_perturbation_of_the_fp32_oracle():

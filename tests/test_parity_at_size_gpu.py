@@ -3,7 +3,7 @@ the C ABI against the fp32 oracle on the same GPU (TF32 off, tests/conftest.py) 
 
   * configs[1]: batch 16 x 1 x 512 x 512 training step (the shape bench.py times),
   * configs[4]: the wide U-Net (base 128, depth 5) on a 1024 x 1024 crop,
-  * configs[3]: the 8192 x 8192 overlap-tile plan bench.py runs (tiles 1212 -> 1028, batch 8),
+  * configs[3]: the 8192 x 8192 overlap-tile plan bench.py runs (16 tiles 2236 -> 2052, batch 8),
   * configs[0]: reference-held golden vectors at 512 x 512 (recorded from the unmodified reference by
     oracle/make_golden.py) at the north-star tolerance itself,
 
@@ -167,9 +167,9 @@ def _eval_sd(seed):
 
 
 def test_overlap_tile_8192_benchmarked_plan_vs_whole_image_forward():
-    """BASELINE configs[3] at full size with the plan bench.py uses (choose_tile -> 1212 -> 1028
-    tiles, batch 8): (a) the stitched logits equal ONE forward pass of the library over a
-    2068 x 2068-output window that straddles 3 x 3 tiles (the aligned-tile invariant, bit-exact);
+    """BASELINE configs[3] at full size with the plan bench.py uses (choose_plan -> 16 tiles of
+    2236 -> 2052, batch 8): (a) the stitched logits equal ONE forward pass of the library over a
+    2068 x 2068-output window that straddles 2 x 2 tiles (the aligned-tile invariant, bit-exact);
     (b) the same window against the fp32 oracle at the bf16 tolerance; (c) the mask is the
     thresholded stitched logits everywhere."""
     from unet_segmentation_b200 import tiling
@@ -186,17 +186,17 @@ def test_overlap_tile_8192_benchmarked_plan_vs_whole_image_forward():
     # mosaic of 512^2 frames with a smooth illumination ramp so tiles are not identical
     ramp = torch.linspace(-0.05, 0.05, size)
     img = (frame.repeat(size // 512, size // 512) + ramp[None, :] + ramp[:, None]).cuda()
-    tile_in = tiling.choose_tile(size, size, 1)
+    tile_in, _, bt = tiling.choose_plan(size, size, 1)
     tile_out, stride, origins = tiling.plan_tiles(size, size, tile_in)
-    assert (tile_in, tile_out, len(origins)) == (1212, 1028, 64)
+    assert (tile_in, tile_out, len(origins), bt) == (2236, 2052, 16, 8)
     mask, logits = tiling.overlap_tile_predict(model, img, tile_in=tile_in, batch_tiles=8,
                                                return_logits=True)
     torch.cuda.synchronize()
     assert mask.shape == (size, size) and logits.shape == (2, size, size)
     assert torch.equal(mask > 0, logits[1] > logits[0])
-    # one whole-window forward: output rows/cols [a, a + S), a = 512 (multiple of 16),
-    # S = 2068 (S + 184 = 2252 = 12 mod 16) covers parts of tiles 0, 1 and 2 in both directions
-    a, S = 512, 2068
+    # one whole-window forward: output rows/cols [a, a + S), a = 1008 (multiple of 16),
+    # S = 2068 (S + 184 = 2252 = 12 mod 16) covers parts of tiles 0 and 1 in both directions
+    a, S = 1008, 2068
     margin = tiling.network_margin(5)
     big = tiling.extract_tiles(img, [(a, a)], tile_in=S + 2 * margin, margin=margin).contiguous()
     whole, wmask = model.predict_mask(big)
@@ -210,7 +210,7 @@ def test_overlap_tile_8192_benchmarked_plan_vs_whole_image_forward():
     agree = float(((whole[0, 1] > whole[0, 0]) == (ref[1] > ref[0])).float().mean())
     conf = (ref[1] - ref[0]).abs() > 0.05
     agree_conf = float(((whole[0, 1] > whole[0, 0]) == (ref[1] > ref[0]))[conf].float().mean())
-    print(f"\n[overlap-tile 8192^2, 64 tiles 1212->1028] window {S}^2 vs fp32 oracle: logits rel-L2 "
+    print(f"\n[overlap-tile 8192^2, 16 tiles 2236->2052] window {S}^2 vs fp32 oracle: logits rel-L2 "
           f"{rel:.3e}, mask agreement {agree:.5f} ({agree_conf:.5f} on the "
           f"{float(conf.float().mean()):.3f} of pixels with |z1-z0| > 0.05)")
     assert rel < 2e-2 and agree_conf >= 0.999

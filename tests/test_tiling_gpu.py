@@ -103,3 +103,145 @@ def test_ccl_on_reference_golden_pairs():
     blob = np.load(os.path.join(os.path.dirname(__file__), "golden", "ccl_golden.npz"))
     for i in sorted(k[4:] for k in blob.files if k.startswith("mask")):
         assert np.array_equal(get_instance_masks(blob[f"mask{i}"], 15), blob[f"inst{i}"]), i
+
+
+def _native_extract(img, origins, tile_in, margin):
+    import ctypes as C
+
+    from unet_segmentation_b200 import _lib
+
+    lib = _lib.load()
+    table = torch.tensor([[y, x] for y, x in origins], dtype=torch.int32, device=img.device)
+    out = torch.empty(len(origins), 1, tile_in, tile_in, dtype=torch.float32, device=img.device)
+    _lib.check(lib.ub_extract_tiles(C.c_void_p(img.data_ptr()), img.shape[0], img.shape[1],
+                                    C.c_void_p(table.data_ptr()), len(origins), tile_in, margin,
+                                    C.c_void_p(out.data_ptr()),
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "extract")
+    return out
+
+
+@pytest.mark.parametrize("h,w,tile_in", [(500, 420, 572), (97, 131, 252), (1024, 1024, 700), (7, 5, 28)])
+def test_native_tile_gather_and_stitch_match_the_host_reference(h, w, tile_in):
+    """ub_extract_tiles (mirror rule, any extension length: the 7 x 5 image is reflected several
+    times) against tiling.extract_tiles (torch indexing, itself checked against numpy.pad and the
+    oracle on the CPU), and ub_stitch_tiles against a slice-by-slice stitch; unused slots skipped."""
+    import ctypes as C
+
+    from unet_segmentation_b200 import _lib, tiling
+
+    g = torch.Generator().manual_seed(h * w)
+    img = torch.rand(h, w, generator=g).cuda()
+    margin = 92 if tile_in > 200 else 9
+    tile_out = tile_in - 2 * margin
+    stride = (tile_out // 16) * 16 if tile_out >= 16 else tile_out
+    origins = [(y, x) for y in range(0, h, max(stride, 1)) for x in range(0, w, max(stride, 1))]
+    got = _native_extract(img, origins + [(-1, 0)], tile_in, margin)
+    ref = tiling.extract_tiles(img, origins, tile_in, margin)
+    torch.cuda.synchronize()
+    assert torch.equal(got[:-1], ref)
+    assert float(got[-1].abs().max()) == 0.0                    # unused slot: zeros
+    if tile_out % 4:
+        return
+    lib = _lib.load()
+    tiles = (torch.rand(len(origins) + 1, tile_out, tile_out, generator=g) * 255).to(torch.uint8).cuda()
+    # make overlapping regions agree (the invariant the real pipeline guarantees): tiles = crops of one image
+    canvas = (torch.rand(h + tile_out, w + tile_out, generator=g) * 255).to(torch.uint8).cuda()
+    for k, (y, x) in enumerate(origins):
+        tiles[k] = canvas[y:y + tile_out, x:x + tile_out]
+    table = torch.tensor([[y, x] for y, x in origins] + [[-1, 0]], dtype=torch.int32, device="cuda")
+    full = torch.full((h, w), 7, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.ub_stitch_tiles(C.c_void_p(tiles.data_ptr()), C.c_void_p(table.data_ptr()),
+                                   len(origins) + 1, tile_out, C.c_void_p(full.data_ptr()), h, w,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "stitch")
+    torch.cuda.synchronize()
+    assert torch.equal(full, canvas[:h, :w])
+
+
+def test_eval_forward_replays_from_a_cuda_graph_bit_identically():
+    """An eval plan called again with its own static buffers is captured on the second call and
+    replayed afterwards (ub_plan_forward); the replays equal the plain launches bit for bit, follow
+    weight and BN-buffer updates (the graph reads them through the bound pointers), and a new input
+    shape gets its own plan."""
+    model, _ = _eval_model(seed=8)
+    img = (0.4 + 0.2 * torch.rand(2, 1, 252, 252, generator=torch.Generator().manual_seed(3))).cuda()
+    first, m1 = model.predict_mask(img)                       # plain launches
+    plan = next(p for k, p in model._plans.items() if not k[4])
+    assert plan.graph_replays() == 0
+    second, m2 = model.predict_mask(img)                      # capture + first replay
+    third, m3 = model.predict_mask(img)
+    torch.cuda.synchronize()
+    assert plan.graph_replays() == 2
+    assert torch.equal(first, second) and torch.equal(first, third)
+    assert torch.equal(m1, m2) and torch.equal(m1, m3)
+    other = (0.4 + 0.2 * torch.rand(2, 1, 252, 252, generator=torch.Generator().manual_seed(4))).cuda()
+    o1, _ = model.predict_mask(other)                         # same plan, new data: still the graph
+    assert plan.graph_replays() == 3 and not torch.equal(o1, first)
+    assert torch.equal(model.predict_mask(img)[0], first)
+    with torch.no_grad():                                     # weights change -> operands re-packed
+        model.up4.conv.double_conv[3].weight.mul_(0.5)
+        model.inc.double_conv[1].running_mean.add_(0.05)
+    changed, _ = model.predict_mask(img)
+    torch.cuda.synchronize()
+    assert not torch.equal(changed, first)
+    from unet_segmentation_b200.unet import UNet
+
+    twin = UNet(1, 2).cuda().eval()
+    twin.load_state_dict(model.state_dict())
+    fresh, _ = twin.predict_mask(img)                         # plain launches on a fresh plan
+    torch.cuda.synchronize()
+    assert torch.equal(changed, fresh)
+
+
+def _tiled_golden_mask(size):
+    import os
+
+    blob = np.load(os.path.join(os.path.dirname(__file__), "golden", "ccl_golden.npz"))
+    keys = sorted(k for k in blob.files if k.startswith("mask"))
+    reps = -(-size // 324)
+    rows = []
+    for r in range(reps):
+        rows.append(np.concatenate([blob[keys[(r + c) % len(keys)]] for c in range(reps)], axis=1))
+    return np.ascontiguousarray(np.concatenate(rows, axis=0)[:size, :size])
+
+
+@pytest.mark.parametrize("size", [2048, 8192])
+def test_ccl_on_a_stitched_whole_image_mask(size):
+    """Whole-image post-processing (scripts/predict.py:85-98 on the stitched mask):
+    the reference's shipped binary masks (~1 700 speckly components per 324^2 frame) tiled to the
+    full image — about 10^6 components at 8192^2, far beyond uint16, so the wrap-around of the
+    reference's astype(uint16) is exercised too — labelled on the GPU, bit-exact against the oracle."""
+    from unet_segmentation_b200.postprocess import get_instance_masks
+
+    mask = _tiled_golden_mask(size)
+    ref = ccl_ref.get_instance_masks(mask, 15)
+    dev = get_instance_masks(torch.from_numpy(mask).cuda(), min_size=15)
+    torch.cuda.synchronize()
+    got = dev.cpu().numpy()
+    assert got.dtype == np.uint16 and got.shape == (size, size)
+    assert np.array_equal(got, ref)
+    # one giant component (a solid mask with a few holes): the contended-atomics case
+    solid = np.full((size, size), 255, dtype=np.uint8)
+    solid[::97, ::89] = 0
+    solid[size // 2, :] = 0                                   # split into two components
+    ref2 = ccl_ref.get_instance_masks(solid, 15)
+    got2 = get_instance_masks(torch.from_numpy(solid).cuda(), min_size=15).cpu().numpy()
+    assert np.array_equal(got2, ref2) and int(ref2.max()) == 2
+
+
+def test_overlap_tile_to_instance_labels_end_to_end():
+    """predict path on a large image entirely on the device: overlap-tile mask -> stitched-mask
+    connected components, equal to running the oracle's labelling on the same stitched mask, and
+    identical when the tiles are dealt to 3 emulated ranks of which only 2 are used."""
+    from unet_segmentation_b200 import tiling
+    from unet_segmentation_b200.postprocess import get_instance_masks
+
+    model, _ = _eval_model(seed=4)
+    img = (0.4 + 0.2 * torch.rand(1100, 900, generator=torch.Generator().manual_seed(1))).cuda()
+    full = tiling.overlap_tile_predict(model, img, tile_in=572, batch_tiles=4)
+    again = tiling.overlap_tile_predict(model, img, tile_in=572, batch_tiles=4)   # graph replays
+    auto = tiling.overlap_tile_predict(model, img, tile_in=None)                  # choose_plan
+    torch.cuda.synchronize()
+    assert torch.equal(full, again) and torch.equal(full, auto)
+    labels = get_instance_masks(full, min_size=15)
+    torch.cuda.synchronize()
+    assert np.array_equal(labels.cpu().numpy(), ccl_ref.get_instance_masks(full.cpu().numpy(), 15))

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "ub_plan_set_bn_config": (c_int, [_P, C.POINTER(c_float), C.POINTER(c_float), c_int]),
     "ub_plan_pack_weights": (c_int, [_P, _P]),
     "ub_plan_forward": (c_int, [_P, _P, _P, _P, _P]),
+    "ub_plan_graph_replays": (c_int64, [_P]),
     "ub_plan_num_stages": (c_int, [_P]),
     "ub_plan_stage_params": (c_int, [_P, c_int, C.POINTER(c_int), C.POINTER(c_int)]),
     "ub_plan_backward_stage": (c_int, [_P, c_int, _P, C.POINTER(c_void_p), _P]),
@@ -72,6 +73,8 @@ _SIGNATURES = {
                                   c_int, _P, _P]),
     "ub_ccl_workspace_bytes": (c_int64, [c_int, c_int]),
     "ub_ccl_label": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
+    "ub_extract_tiles": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P]),
+    "ub_stitch_tiles": (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, _P]),
     "ub_op_pack_conv3x3": (c_int, [_P, c_int, c_int, _P, _P, _P]),
     "ub_op_pack_convT": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P]),
     "ub_op_conv_stats_floats": (c_int64, [c_int]),

@@ -80,6 +80,15 @@ int ub_ccl_label(const uint8_t* mask, int H, int W, int min_size, uint16_t* labe
     return launch_ccl(mask, H, W, min_size, labels, workspace, S(stream));
 }
 
+int ub_extract_tiles(const float* image, int H, int W, const int32_t* origins_yx, int T, int tile_in,
+                     int margin, float* tiles, void* stream) {
+    return launch_extract_tiles(image, H, W, origins_yx, T, tile_in, margin, tiles, S(stream));
+}
+int ub_stitch_tiles(const uint8_t* tiles, const int32_t* origins_yx, int T, int tile_out,
+                    uint8_t* full, int H, int W, void* stream) {
+    return launch_stitch_tiles(tiles, origins_yx, T, tile_out, full, H, W, S(stream));
+}
+
 int ub_op_pack_conv3x3(const float* w, int Co, int Ci, void* wf, void* wd, void* stream) {
     return launch_pack_conv3x3(w, Co, Ci, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, S(stream));
 }

@@ -7,6 +7,7 @@
 #include "elementwise.cuh"
 #include "first_conv.cuh"
 #include "head_loss.cuh"
+#include "tiling.cuh"
 #include "input_pipeline.cuh"
 #include "igemm.cuh"
 #include "ub_internal.h"
@@ -555,7 +556,8 @@ int launch_elastic(const unsigned char* img, const void* labels, int label_bytes
 size_t ccl_ws_bytes(int H, int W) {
     const size_t n = (size_t)H * W;
     const size_t nb = (n + 1023) / 1024;
-    return (3 * n + nb + 16) * sizeof(int);
+    const size_t nc = (nb + 1023) / 1024;
+    return (3 * n + nb + nc + 16) * sizeof(int);
 }
 int launch_ccl(const unsigned char* mask, int H, int W, int min_size, unsigned short* out, void* ws,
                cudaStream_t s) {
@@ -563,17 +565,49 @@ int launch_ccl(const unsigned char* mask, int H, int W, int min_size, unsigned s
     if (n <= 0) return UB_OK;
     if (n > 0x7FFFFFFFLL) { set_last_error("ccl: image too large"); return UB_ERR_UNSUPPORTED; }
     const int nb = (int)((n + 1023) / 1024);
+    const int nc = (nb + 1023) / 1024;
     int* L = reinterpret_cast<int*>(ws);
     int* area = L + n;
     int* rank = area + n;
     int* block_roots = rank + n;
-    ccl_init_kernel<<<ew_blocks(n), 256, 0, s>>>(mask, L, area, n);
+    int* chunk_tot = block_roots + nb;
+    ccl_init_kernel<<<ew_blocks(n), 256, 0, s>>>(mask, L, area, n, W);
     ccl_merge_kernel<<<ew_blocks(n), 256, 0, s>>>(mask, L, H, W);
     ccl_flatten_kernel<<<nb, 1024, 0, s>>>(L, area, block_roots, n);
-    ccl_scan_kernel<<<1, 1024, 0, s>>>(block_roots, nb);
+    ccl_scan_chunks_kernel<<<nc, 1024, 0, s>>>(block_roots, nb, chunk_tot);
+    int extra = 0;
+    if (nc > 1) {     // more than 1024 blocks of 1024 pixels (images beyond 1 Mpix)
+        ccl_scan_kernel<<<1, 1024, 0, s>>>(chunk_tot, nc);
+        ccl_scan_add_kernel<<<nc, 1024, 0, s>>>(block_roots, nb, chunk_tot);
+        extra = 2;
+    }
     ccl_rank_kernel<<<nb, 1024, 0, s>>>(L, block_roots, rank, n);
     ccl_emit_kernel<<<ew_blocks(n), 256, 0, s>>>(L, area, rank, min_size, out, n);
-    count_launch(5);
+    count_launch(5 + extra);
+    UB_POST_LAUNCH();
+    return UB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int launch_extract_tiles(const float* image, int H, int W, const int* origins_yx, int T, int S,
+                         int margin, float* tiles, cudaStream_t s) {
+    if (!image || !origins_yx || !tiles || H < 1 || W < 1 || T < 1 || S < 4 || S % 4 != 0 || margin < 0) {
+        set_last_error("extract_tiles: null pointer or bad shape (H=%d W=%d T=%d tile=%d)", H, W, T, S);
+        return UB_ERR_ARG;
+    }
+    UB_LAUNCH_NC(extract_tiles_kernel, ew_blocks((long long)T * S * (S / 4)), 256, 0, s, image, H, W,
+                 reinterpret_cast<const int2*>(origins_yx), T, S, margin, tiles);
+    UB_POST_LAUNCH();
+    return UB_OK;
+}
+int launch_stitch_tiles(const unsigned char* tiles, const int* origins_yx, int T, int TO,
+                        unsigned char* full, int H, int W, cudaStream_t s) {
+    if (!tiles || !origins_yx || !full || H < 1 || W < 1 || T < 1 || TO < 4 || TO % 4 != 0) {
+        set_last_error("stitch_tiles: null pointer or bad shape (H=%d W=%d T=%d tile_out=%d)", H, W, T, TO);
+        return UB_ERR_ARG;
+    }
+    UB_LAUNCH_NC(stitch_tiles_kernel, ew_blocks((long long)T * TO * (TO / 4)), 256, 0, s, tiles,
+                 reinterpret_cast<const int2*>(origins_yx), T, TO, full, H, W);
     UB_POST_LAUNCH();
     return UB_OK;
 }

@@ -213,6 +213,12 @@ int launch_elastic(const unsigned char* img, const void* labels, int label_bytes
                    const double* noise, const double* taps, int radius, double alpha,
                    unsigned char* img_out, void* labels_out, int label_out_bytes, void* ws,
                    cudaStream_t s);
+// overlap-tile helpers (tiling.cuh): origins_yx = T pairs (row, column) of output-space tile origins
+// on the device; a negative row marks an unused slot
+int launch_extract_tiles(const float* image, int H, int W, const int* origins_yx, int T, int S,
+                         int margin, float* tiles, cudaStream_t s);
+int launch_stitch_tiles(const unsigned char* tiles, const int* origins_yx, int T, int TO,
+                        unsigned char* full, int H, int W, cudaStream_t s);
 int launch_ccl(const unsigned char* mask, int H, int W, int min_size, unsigned short* out, void* ws,
                cudaStream_t s);
 

@@ -98,7 +98,8 @@ class _Plan:
         oh, ow = C.c_int(), C.c_int()
         check(self.lib.ub_plan_out_hw(handle, C.byref(oh), C.byref(ow)))
         self.out_hw = (oh.value, ow.value)
-        self.n, self.n_classes = n, n_classes
+        self.n, self.n_classes, self.cin, self.in_hw = n, n_classes, cin, (h, w)
+        self._static = None
         self.num_params = self.lib.ub_plan_num_params(handle)
         self.num_stages = self.lib.ub_plan_num_stages(handle)
         self.numels = [int(self.lib.ub_plan_param_numel(handle, i)) for i in range(self.num_params)]
@@ -169,17 +170,43 @@ class _Plan:
             check(self.lib.ub_plan_pack_weights(self.handle, _stream()), "ub_plan_pack_weights")
             self.packed_versions = versions
 
-    def forward(self, x, want_mask=False):
+    def static_io(self, device):
+        """Eval plans own their input / logits / mask buffers: stable pointers let the library replay
+        the forward pass from a CUDA graph (ub_plan_forward) and let overlap-tile inference gather
+        tiles straight into the network input and stitch straight out of the mask buffer."""
+        if self._static is None:
+            oh, ow = self.out_hw
+            self._static = (
+                torch.empty(self.n, self.cin, self.in_hw[0], self.in_hw[1], dtype=torch.float32, device=device),
+                torch.empty(self.n, self.n_classes, oh, ow, dtype=torch.float32, device=device),
+                torch.empty(self.n, oh, ow, dtype=torch.uint8, device=device))
+        return self._static
+
+    def forward(self, x, want_mask=False, static_out=False):
+        """Training plans: fresh output tensors. Eval plans: run on the plan's static buffers (x is
+        copied in unless it IS the static input) and return clones — or the static buffers
+        themselves with ``static_out=True`` (valid until the next forward of this plan)."""
         oh, ow = self.out_hw
+        if not self.training:
+            xs, logits, mask = self.static_io(x.device)
+            if x.data_ptr() != xs.data_ptr():
+                xs.copy_(x)
+            check(self.lib.ub_plan_forward(self.handle, C.c_void_p(xs.data_ptr()),
+                                           C.c_void_p(logits.data_ptr()), C.c_void_p(mask.data_ptr()),
+                                           _stream()), "ub_plan_forward")
+            self.generation += 1
+            if static_out:
+                return logits, (mask if want_mask else None)
+            return logits.clone(), (mask.clone() if want_mask else None)
         logits = torch.empty(self.n, self.n_classes, oh, ow, dtype=torch.float32, device=x.device)
-        mask = (torch.empty(self.n, oh, ow, dtype=torch.uint8, device=x.device)
-                if want_mask else None)
         check(self.lib.ub_plan_forward(self.handle, C.c_void_p(x.data_ptr()),
-                                       C.c_void_p(logits.data_ptr()),
-                                       C.c_void_p(mask.data_ptr() if mask is not None else 0),
-                                       _stream()), "ub_plan_forward")
+                                       C.c_void_p(logits.data_ptr()), C.c_void_p(0), _stream()),
+              "ub_plan_forward")
         self.generation += 1
-        return logits, mask
+        return logits, None
+
+    def graph_replays(self) -> int:
+        return int(self.lib.ub_plan_graph_replays(self.handle))
 
     def join_side(self, stream: "torch.cuda.Stream") -> None:
         """Make ``stream`` wait for the weight gradients issued so far on the library's side stream."""
@@ -361,13 +388,16 @@ class UNet(nn.Module):
 
     def _plan_for(self, x: torch.Tensor, training: bool) -> _Plan:
         n, c, h, w = x.shape
-        key = (n, c, h, w, training, x.device.index)
+        return self._plan_for_shape(n, c, h, w, training, x.device)
+
+    def _plan_for_shape(self, n, c, h, w, training: bool, device) -> _Plan:
+        key = (n, c, h, w, training, device.index)
         plan = self._plans.get(key)
         if plan is None:
             if len(self._plans) >= 8:  # keep the arena bounded when shapes vary
                 self._plans.pop(next(iter(self._plans)))
             plan = _Plan(n, c, h, w, self.base_channels, self.levels, self.n_classes, training,
-                         x.device, bilinear=self.bilinear)
+                         device, bilinear=self.bilinear)
             self._plans[key] = plan
         bns = self._ordered_bns()
         self._check_bn_modules(bns, training)
