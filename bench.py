@@ -657,7 +657,8 @@ def main():
                     "foreground_fraction": float((big_d > 0).float().mean()),
                     "labels_wrap_uint16": True,
                     "mask": "reference's shipped 01_RES masks (tests/golden/ccl_golden.npz) tiled to 8192^2",
-                    "one_blob_mask_ms": blob_ms, "one_blob_max_label": int(inst2.max())}
+                    "one_blob_mask_ms": blob_ms, "one_blob_max_label": int(inst2.to(torch.int32).max()),
+                    "max_label": int(inst.to(torch.int32).max())}
                 del big_d, inst, inst2
             except Exception as exc:
                 infer["ccl_stitched_8192"] = {"error": f"{type(exc).__name__}: {exc}"}

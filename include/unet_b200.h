@@ -306,6 +306,10 @@ int ub_op_first_conv_forward(const float* x, int N, int Ci, int H, int W, const 
                              int64_t* num_batches_tracked, float momentum, float eps,
                              float* workspace, float* scale, float* shift, float* mean,
                              float* rstd, void* a, void* stream);
+/* Eval form: a = relu(conv(x, w) * scale + shift) with the caller's per-channel affine (BatchNorm
+ * running statistics and the conv bias folded in), bf16 NHWC out. */
+int ub_op_first_conv_affine_relu(const float* x, int N, int Ci, int H, int W, const float* w, int Co,
+                                 const float* scale, const float* shift, void* a, void* stream);
 int ub_op_first_conv_backward(const float* x, int N, int Ci, int H, int W, const float* w,
                               const float* bias, int Co, const float* scale, const float* shift,
                               const float* mean, const float* rstd, const ub_view* g,

@@ -100,6 +100,7 @@ _SIGNATURES = {
     "ub_op_first_conv_workspace_floats": (c_int64, [c_int]),
     "ub_op_first_conv_forward": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P,
                                          _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "ub_op_first_conv_affine_relu": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P]),
     "ub_op_first_conv_backward": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P,
                                           _P, _VP, _P, _P, _P, _P, _P, _P]),
     "ub_op_head_forward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),

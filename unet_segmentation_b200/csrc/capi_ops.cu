@@ -233,6 +233,13 @@ int ub_op_first_conv_forward(const float* x, int N, int Ci, int H, int W, const 
                                          S(stream)));
     return launch_first_conv_apply(d, scale, shift, (__nv_bfloat16*)a, S(stream));
 }
+int ub_op_first_conv_affine_relu(const float* x, int N, int Ci, int H, int W, const float* w, int Co,
+                                 const float* scale, const float* shift, void* a, void* stream) {
+    UB_REQUIRE(x && w && scale && shift && a, "first_conv_affine_relu: null pointer");
+    FirstConvDesc d;
+    d.x = x; d.N = N; d.Ci = Ci; d.H = H; d.W = W; d.Co = Co; d.w = w; d.bias = nullptr;
+    return launch_first_conv_apply(d, scale, shift, (__nv_bfloat16*)a, S(stream));
+}
 int ub_op_first_conv_backward(const float* x, int N, int Ci, int H, int W, const float* w,
                               const float* bias, int Co, const float* scale, const float* shift,
                               const float* mean, const float* rstd, const ub_view* g,

@@ -27,6 +27,13 @@ __device__ __forceinline__ int ccl_find(int* L, int i) {
     }
     return cur;
 }
+// Read-only find for the flatten pass: there every thread stores the ROOT into its own L[i], so no
+// other thread may re-point L[i] to a mere ancestor (which the halving stores above would do).
+__device__ __forceinline__ int ccl_find_ro(const int* L, int i) {
+    int r = L[i];
+    while (r != L[r]) r = L[r];
+    return r;
+}
 __device__ __forceinline__ void ccl_union(int* L, int a, int b) {
     bool done;
     do {
@@ -114,7 +121,7 @@ ccl_flatten_kernel(int* L, int* area, int* __restrict__ block_roots, long long n
     int is_root = 0;
     int r = -1;
     if (i < n && L[i] >= 0) {
-        r = ccl_find(L, (int)i);
+        r = ccl_find_ro(L, (int)i);
         L[i] = r;
         is_root = (r == (int)i);
     }

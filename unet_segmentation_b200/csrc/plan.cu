@@ -92,11 +92,13 @@ struct ub_plan {
     // mask) pointers and parameter binding, and replayed afterwards: per-frame prediction
     // (scripts/predict.py:73-112) is otherwise bound by host launch work, not by the GPU.
     cudaGraphExec_t fwd_graph = nullptr;
+    cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's may be the legacy stream)
     const float* g_x = nullptr;
     float* g_logits = nullptr;
     uint8_t* g_mask = nullptr;
     unsigned long long bind_epoch = 0, g_epoch = 0;
     int g_calls = 0;
+    bool g_disabled = false;             // a capture attempt failed: stay on plain launches
     long long g_nodes = 0;
     long long g_replays = 0;
     // optional in-step kernel timing (CUDA events on the launching stream)
@@ -126,6 +128,7 @@ struct ub_plan {
     }
     ~ub_plan() {
         drop_graph();
+        if (cap_stream) cudaStreamDestroy(cap_stream);
         if (side) cudaStreamDestroy(side);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
@@ -617,7 +620,7 @@ int ub_plan_forward(ub_plan* P, const float* x, float* logits, uint8_t* mask, vo
     for (size_t i = 0; i < P->rm.size(); ++i)
         if (!P->rm[i] || !P->rv[i]) { set_last_error("forward: BN buffers not bound"); return ub::UB_ERR_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
-    bool graphable = !P->training && eval_graph_enabled() && !P->prof_on && !nvtx_on();
+    bool graphable = !P->training && !P->g_disabled && eval_graph_enabled() && !P->prof_on && !nvtx_on();
     if (graphable) {
         cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
@@ -639,15 +642,29 @@ int ub_plan_forward(ub_plan* P, const float* x, float* logits, uint8_t* mask, vo
         P->g_x = x; P->g_logits = logits; P->g_mask = mask; P->g_epoch = P->bind_epoch;
     }
     if (++P->g_calls < 2) return forward_impl(P, x, logits, mask, s);   // first sight: plain launches
-    UB_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    // Capture on an internal stream: nothing executes during capture, and the caller's stream may be
+    // the legacy default stream, which cannot be captured. The graph is launched on the caller's.
+    if (!P->cap_stream &&
+        cudaStreamCreateWithFlags(&P->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        P->cap_stream = nullptr;
+        P->g_disabled = true;
+        return forward_impl(P, x, logits, mask, s);
+    }
+    if (cudaStreamBeginCapture(P->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        P->g_disabled = true;
+        return forward_impl(P, x, logits, mask, s);
+    }
     const long long before = ub::launch_count();
-    const int rc = forward_impl(P, x, logits, mask, s);
+    const int rc = forward_impl(P, x, logits, mask, P->cap_stream);
     cudaGraph_t g = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(s, &g);
+    const cudaError_t ce = cudaStreamEndCapture(P->cap_stream, &g);
     if (rc != 0 || ce != cudaSuccess || !g) {
         if (g) cudaGraphDestroy(g);
         cudaGetLastError();
         P->drop_graph();
+        P->g_disabled = true;
         if (rc != 0) return rc;
         return forward_impl(P, x, logits, mask, s);      // capture refused: stay on plain launches
     }
@@ -657,6 +674,7 @@ int ub_plan_forward(ub_plan* P, const float* x, float* logits, uint8_t* mask, vo
     if (ie != cudaSuccess) {
         cudaGetLastError();
         P->fwd_graph = nullptr;
+        P->g_disabled = true;
         ub::count_launch(-(int)P->g_nodes);
         return forward_impl(P, x, logits, mask, s);
     }

@@ -215,6 +215,17 @@ def first_conv_forward(x, w, bias, gamma, beta, running_mean=None, running_var=N
     return a, st
 
 
+def first_conv_affine_relu(x, w, scale, shift):
+    """Eval form of the first conv: relu(conv(x, w) * scale + shift) -> bf16 NHWC."""
+    lib = _lib.load()
+    n, ci, h, wd_ = x.shape
+    co = w.shape[0]
+    a = torch.empty(n, h - 2, wd_ - 2, co, dtype=torch.bfloat16, device=x.device)
+    check(lib.ub_op_first_conv_affine_relu(_p(x), n, ci, h, wd_, _p(w), co, _p(scale), _p(shift),
+                                           _p(a), _stream()), "first_conv_affine_relu")
+    return a
+
+
 def first_conv_backward(x, w, bias, st, g, a):
     lib = _lib.load()
     n, ci, h, wd_ = x.shape

@@ -20,12 +20,76 @@ import torch.nn as nn
 from . import _lib
 from ._lib import check
 
-_NO_SUBMODULE_FWD = ("only UNet.forward is implemented by the B200 library; the building blocks "
-                     "are parameter holders (there is no ATen/cuDNN fallback path)")
+# ------------------------------------------------------------------------------------------------
+# Stand-alone forwards of the building blocks. The reference's DoubleConv / Down / Up / OutConv are
+# public modules with their own forward (models/unet_model.py:20-21, 32-33, 50-54, 62-63) although
+# UNet.forward is their only caller. Here they run the same sm_100a kernels as the network executor
+# through the operator-level C ABI (ub_op_*): NCHW fp32 in / out like the reference, NHWC bf16 inside,
+# train mode = batch statistics + running-stat update, eval mode = folded BatchNorm. They build NO
+# autograd graph (training goes through UNet.forward, which owns the backward pass).
+# ------------------------------------------------------------------------------------------------
+def _require_inference(mod: nn.Module, *inputs) -> None:
+    if torch.is_grad_enabled() and (any(isinstance(t, torch.Tensor) and t.requires_grad for t in inputs)
+                                    or any(p.requires_grad for p in mod.parameters())):
+        raise RuntimeError(f"{type(mod).__name__}.forward (B200) runs the inference kernels and builds no "
+                           "autograd graph; call it under torch.no_grad(), or train through "
+                           "UNet.forward, which implements the backward pass")
+    for t in inputs:
+        if not isinstance(t, torch.Tensor) or t.dim() != 4 or not t.is_cuda:
+            raise RuntimeError(f"{type(mod).__name__}.forward (B200) needs (N, C, H, W) CUDA tensors; "
+                               "there is no CPU fallback")
+
+
+def _to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    return x.float().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _to_nchw(a: torch.Tensor) -> torch.Tensor:
+    return a.permute(0, 3, 1, 2).float().contiguous()
+
+
+def _folded_affine(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+    bias = conv.bias.float() if conv.bias is not None else torch.zeros_like(scale)
+    return scale.contiguous(), (bn.bias.float() + (bias - bn.running_mean.float()) * scale).contiguous()
+
+
+def _conv_bn_relu(conv: nn.Conv2d, bn: nn.BatchNorm2d, src0, src1=None, x_fp32=None) -> torch.Tensor:
+    """One [conv3x3 -> BN -> ReLU] unit on NHWC bf16 sources (src1 = second channel range of a
+    zero-copy concat), or on the fp32 NCHW image for a first conv whose C_in is not a multiple of 64."""
+    from . import ops
+
+    training = bn.training
+    if training and (bn.momentum is None or not bn.track_running_stats):
+        raise RuntimeError("BatchNorm2d(momentum=None / track_running_stats=False) is not supported")
+    w = conv.weight.detach().float().contiguous()
+    gamma, beta = bn.weight.detach().float(), bn.bias.detach().float()
+    if x_fp32 is not None:
+        if training:
+            a, _ = ops.first_conv_forward(x_fp32, w, conv.bias.detach().float(), gamma, beta,
+                                          bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                                          float(bn.momentum), float(bn.eps))
+            return a
+        scale, shift = _folded_affine(conv, bn)
+        return ops.first_conv_affine_relu(x_fp32, w, scale, shift)
+    wf, _ = ops.pack_conv3x3(w, with_dgrad=False)
+    if training:
+        y, stats, info = ops.conv3x3_forward(src0, src1, wf, conv.bias.detach().float(), epilogue=0)
+        scale, shift, _, _ = ops.bn_finalize(stats, info, gamma, beta, bn.running_mean,
+                                             bn.running_var, bn.num_batches_tracked,
+                                             float(bn.momentum), float(bn.eps))
+        return ops.bn_apply_relu(y, scale, shift)[0]
+    scale, shift = _folded_affine(conv, bn)
+    return ops.conv3x3_forward(src0, src1, wf, None, epilogue=2, scale=scale, shift=shift)[0]
+
+
+def _double_conv(seq: nn.Sequential, src0, src1=None, x_fp32=None) -> torch.Tensor:
+    a = _conv_bn_relu(seq[0], seq[1], src0, src1, x_fp32)
+    return _conv_bn_relu(seq[3], seq[4], a)
 
 
 class DoubleConv(nn.Module):
-    """[Conv3x3(valid) -> BatchNorm2d -> ReLU] x 2 — parameter holder (reference :5-21)."""
+    """[Conv3x3(valid) -> BatchNorm2d -> ReLU] x 2 (reference :5-21)."""
 
     def __init__(self, in_channels: int, out_channels: int):
         super().__init__()
@@ -35,19 +99,28 @@ class DoubleConv(nn.Module):
                        nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True)]
         self.double_conv = nn.Sequential(*layers)
 
-    def forward(self, x):  # pragma: no cover - never on the product path
-        raise NotImplementedError(_NO_SUBMODULE_FWD)
+    def forward(self, x):
+        _require_inference(self, x)
+        with torch.cuda.device(x.device):
+            if self.double_conv[0].in_channels % 64:      # image-side block: fp32 first conv
+                return _to_nchw(_double_conv(self.double_conv, None, None, x.float().contiguous()))
+            return _to_nchw(_double_conv(self.double_conv, _to_nhwc(x)))
 
 
 class Down(nn.Module):
-    """MaxPool2d(2) then DoubleConv — parameter holder (reference :23-33)."""
+    """MaxPool2d(2) then DoubleConv (reference :23-33)."""
 
     def __init__(self, in_channels: int, out_channels: int):
         super().__init__()
         self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), DoubleConv(in_channels, out_channels))
 
-    def forward(self, x):  # pragma: no cover
-        raise NotImplementedError(_NO_SUBMODULE_FWD)
+    def forward(self, x):
+        from . import ops
+
+        _require_inference(self, x)
+        with torch.cuda.device(x.device):
+            pooled = ops.maxpool2(_to_nhwc(x))              # floor mode, like nn.MaxPool2d(2)
+            return _to_nchw(_double_conv(self.maxpool_conv[1].double_conv, pooled))
 
 
 class Up(nn.Module):
@@ -66,8 +139,27 @@ class Up(nn.Module):
             self.up = nn.ConvTranspose2d(in_channels_from_prev_decoder, half, kernel_size=2, stride=2)
             self.conv = DoubleConv(half + skip_channels, out_channels)
 
-    def forward(self, x1, x2_cropped):  # pragma: no cover
-        raise NotImplementedError(_NO_SUBMODULE_FWD)
+    def forward(self, x1, x2_cropped):
+        """x1: previous decoder output, x2_cropped: the skip tensor already centre-cropped to the
+        up-sampled size (reference :50-54: ``x1 = self.up(x1); cat([x2_cropped, x1]); self.conv``).
+        The concat is never materialised: the conv reads the two tensors as two channel sources."""
+        from . import ops
+
+        _require_inference(self, x1, x2_cropped)
+        with torch.cuda.device(x1.device):
+            x1n = _to_nhwc(x1)
+            if isinstance(self.up, nn.ConvTranspose2d):
+                wf, _, b4 = ops.pack_convT(self.up.weight.detach().float(), self.up.bias.detach().float())
+                n, h, w, _ = x1n.shape
+                up = torch.empty(n, 2 * h, 2 * w, self.up.out_channels, dtype=torch.bfloat16,
+                                 device=x1.device)
+                ops.convT_forward(x1n, wf, b4, up)
+            else:
+                up = ops.upsample2x(x1n)
+            if tuple(x2_cropped.shape[2:]) != tuple(up.shape[1:3]):
+                raise RuntimeError(f"Sizes of tensors must match: skip {tuple(x2_cropped.shape[2:])} vs "
+                                   f"up-sampled {tuple(up.shape[1:3])} (crop the skip first)")
+            return _to_nchw(_double_conv(self.conv.double_conv, _to_nhwc(x2_cropped), up))
 
 
 class OutConv(nn.Module):
@@ -77,8 +169,14 @@ class OutConv(nn.Module):
         super().__init__()
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
 
-    def forward(self, x):  # pragma: no cover
-        raise NotImplementedError(_NO_SUBMODULE_FWD)
+    def forward(self, x):
+        from . import ops
+
+        _require_inference(self, x)
+        with torch.cuda.device(x.device):
+            w = self.conv.weight.detach().float().flatten(1).contiguous()
+            b = self.conv.bias.detach().float() if self.conv.bias is not None else None
+            return ops.head_forward(_to_nhwc(x), w, b)[0]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -371,6 +469,7 @@ class UNet(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_plans"] = {}
+        state.pop("_tile_sessions", None)
         state["_stage_hook"] = None
         state["_backward_done_hook"] = None
         state.pop("_last_train_key", None)
