@@ -245,3 +245,37 @@ def test_overlap_tile_to_instance_labels_end_to_end():
     labels = get_instance_masks(full, min_size=15)
     torch.cuda.synchronize()
     assert np.array_equal(labels.cpu().numpy(), ccl_ref.get_instance_masks(full.cpu().numpy(), 15))
+
+
+def test_frame_predictor_graph_equals_the_eager_predict_loop():
+    """unet_segmentation_b200.predict.FramePredictor (scripts/predict.py:73-112 as one CUDA-graph launch per
+    frame) against the same steps issued one by one, and its labels against the oracle."""
+    from unet_segmentation_b200.postprocess import get_instance_masks
+    from unet_segmentation_b200.predict import FramePredictor
+
+    model, _ = _eval_model(seed=6)
+    with torch.no_grad():          # move the decision boundary into the logits' range: a speckly mask
+        img0 = (0.4 + 0.2 * torch.rand(1, 1, 512, 512, generator=torch.Generator().manual_seed(2))).cuda()
+        z = model(img0)
+        model.outc.conv.bias[1] += (z[:, 0] - z[:, 1]).median()
+    fp = FramePredictor(model, (512, 512), min_size=15)
+    for seed in (2, 3, 4):
+        frame = (0.4 + 0.2 * torch.rand(512, 512, generator=torch.Generator().manual_seed(seed))).numpy()
+        mask, labels = fp(frame)
+        mask, labels = mask.copy(), labels.copy()
+        x = torch.from_numpy(frame).reshape(1, 1, 512, 512).cuda()
+        _, ref_mask = model.predict_mask(x)
+        ref_labels = get_instance_masks(ref_mask[0], 15)
+        torch.cuda.synchronize()
+        assert mask.shape == (324, 324) and mask.dtype == np.uint8 and labels.dtype == np.uint16
+        assert np.array_equal(mask, ref_mask[0].cpu().numpy())
+        assert np.array_equal(labels, ref_labels.cpu().numpy())
+        assert np.array_equal(labels, ccl_ref.get_instance_masks(mask, 15))
+        assert 0.02 < (mask > 0).mean() < 0.98 and labels.max() > 1
+    # weights change: the predictor re-records (packed operands are refreshed outside the graph)
+    with torch.no_grad():
+        model.outc.conv.weight.mul_(-1.0)
+    mask2, _ = fp(frame)
+    _, ref2 = model.predict_mask(x)
+    torch.cuda.synchronize()
+    assert np.array_equal(mask2, ref2[0].cpu().numpy())

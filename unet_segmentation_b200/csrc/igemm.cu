@@ -76,9 +76,10 @@ static bool pairs_enabled() {
 // Pairs pay off for BN >= 128 (a 2-CTA MMA with N = 64 issues slower than two 1-CTA MMAs, measured)
 // with at least 16 k-blocks per tile (short-K tiles are epilogue-bound) and two waves of tiles.
 static int pick_cg(int BN, int kblocks, long long tiles) {
-    static int minkb = -1;
+    static int minkb = -1, minbn = -1;
     if (minkb < 0) { const char* e = getenv("UB_PAIR_MINKB"); minkb = e ? atoi(e) : 16; }
-    return (pairs_enabled() && BN >= 128 && kblocks >= minkb && tiles >= 2LL * num_sms()) ? 2 : 1;
+    if (minbn < 0) { const char* e = getenv("UB_PAIR_MINBN"); minbn = e ? atoi(e) : 128; }
+    return (pairs_enabled() && BN >= minbn && kblocks >= minkb && tiles >= 2LL * num_sms()) ? 2 : 1;
 }
 
 template <int BN, int EPI, int CG>

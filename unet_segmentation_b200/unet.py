@@ -189,9 +189,16 @@ class _Plan:
         self.training = training
         handle = C.c_void_p()
         with torch.cuda.device(device):
-            check(self.lib.ub_plan_create_ex(C.byref(handle), n, cin, h, w, base, levels, n_classes,
-                                             1 if training else 0, 1 if bilinear else 0),
-                  "ub_plan_create")
+            args = (C.byref(handle), n, cin, h, w, base, levels, n_classes, 1 if training else 0,
+                    1 if bilinear else 0)
+            status = self.lib.ub_plan_create_ex(*args)
+            if status == -5:      # UB_ERR_NOMEM: the arena is cudaMalloc'ed beside torch's caching
+                import gc         # allocator — hand its cached, unused blocks back and retry once
+
+                gc.collect()
+                torch.cuda.empty_cache()
+                status = self.lib.ub_plan_create_ex(*args)
+            check(status, "ub_plan_create")
         self.handle = handle
         oh, ow = C.c_int(), C.c_int()
         check(self.lib.ub_plan_out_hw(handle, C.byref(oh), C.byref(ow)))
