@@ -692,6 +692,8 @@ def main():
                 ms_eager = e0.elapsed_time(e1) / reps_f
                 # the same loop through the public per-frame API: the whole device side (H2D, forward,
                 # connected components, both D2H copies) recorded once and replayed per frame
+                import numpy as np
+
                 from unet_segmentation_b200.predict import FramePredictor
 
                 fp = FramePredictor(model, (512, 512), min_size=15)
@@ -703,8 +705,17 @@ def main():
                     mk_np, inst_np = fp(frame_np)         # includes the host-side sync per frame
                 ms_f = (time.perf_counter() - t0) * 1e3 / reps_f
                 same = bool((mk_np == mask_hb.numpy()).all() and (inst_np == inst_hb.numpy()).all())
+                fp8 = FramePredictor(model, (512, 512), min_size=15, batch=8)
+                frames8 = np.repeat(frame_np, 8, axis=0)
+                for _ in range(3):
+                    fp8(frames8)
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    fp8(frames8)
+                ms_f8 = (time.perf_counter() - t0) * 1e3 / (20 * 8)
                 infer["predict_frame_512"] = {"ms_per_frame": ms_f, "frames_per_s": 1e3 / ms_f,
                                               "eager_ms_per_frame": ms_eager,
+                                              "ms_per_frame_batch8": ms_f8, "frames_per_s_batch8": 1e3 / ms_f8,
                                               "timing": "host wall clock around 50 synchronous FramePredictor calls "
                                                         "(numpy in, numpy out); eager = CUDA events around the same "
                                                         "loop issued op by op",

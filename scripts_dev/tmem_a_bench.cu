@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(128, 1) check_kernel(const __nv_bfloat16* A, c
 
 // what: 0 = 36 SS MMAs per iteration, 1 = 36 TS MMAs, 2 = 12 copies only, 3 = 12 copies + 36 TS MMAs
 // (one output-row tile of the 64 -> 64 conv: one new input row in three shifts, nine taps x 4 K steps)
-__global__ void __launch_bounds__(128, 1) speed_kernel(int iters, int what, long long* out) {
+template <int what>
+__global__ void __launch_bounds__(128, 1) speed_kernel(int iters, long long* out) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -89,25 +90,37 @@ __global__ void __launch_bounds__(128, 1) speed_kernel(int iters, int what, long
     const uint32_t tmem = tslot;
     constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
     if (threadIdx.x == 0) {
+        // descriptors are hoisted and every offset below is a compile-time constant (fully unrolled),
+        // as in the production kernels: the loop must be bound by the tensor pipe, not by issue
+        const uint64_t db0 = make_smem_desc(base + 110592, 0, 1024);
         const long long t0 = clock64();
+#pragma unroll 1
         for (int it = 0; it < iters; ++it) {
             const uint32_t rowbuf = base + (it & 1) * 3 * 17408;      // 3 staged input rows
-            const uint32_t ta = tmem + 128 + (it & 3) * 96;            // ring of 4 rows x 3 shifts x 32 cols
+            const uint64_t da0 = make_smem_desc(rowbuf, 0, 1024);
+            const uint32_t td = tmem + (it & 1) * 64;
+            uint32_t trow[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) trow[r] = tmem + 128 + (((it + r) & 3) * 96);
             if (what >= 2) {
-                for (int s = 0; s < 3; ++s) {
-                    const uint64_t da = make_smem_desc(rowbuf + s * 128, 0, 1024);
+#pragma unroll
+                for (int s = 0; s < 3; ++s)
+#pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        tmem_cp_128x256b(ta + s * 32 + 8 * k, da + (uint64_t)(2 * k));
-                }
+                        tmem_cp_128x256b(trow[2] + s * 32 + 8 * k, da0 + (uint64_t)(s * 8 + 2 * k));
             }
             if (what != 2) {
+#pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                    const uint64_t db = make_smem_desc(base + 110592 + tap * 8192, 0, 1024);
-                    const uint64_t da = make_smem_desc(rowbuf + (tap / 3) * 17408 + (tap % 3) * 128, 0, 1024);
-                    const uint32_t tap_a = tmem + 128 + (((it + tap / 3) & 3) * 96) + (tap % 3) * 32;
+#pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (what == 0) umma_bf16(tmem + (it & 1) * 64, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (tap | k) != 0);
-                        else umma_bf16_ts(tmem + (it & 1) * 64, tap_a + 8 * k, db + (uint64_t)(2 * k), idesc, (tap | k) != 0);
+                        const uint64_t db = db0 + (uint64_t)(tap * 512 + 2 * k);
+                        if (what == 0)
+                            umma_bf16(td, da0 + (uint64_t)((tap / 3) * 1088 + (tap % 3) * 8 + 2 * k), db, idesc,
+                                      (uint32_t)((tap | k) != 0));
+                        else
+                            umma_bf16_ts(td, trow[tap / 3] + (tap % 3) * 32 + 8 * k, db, idesc,
+                                         (uint32_t)((tap | k) != 0));
                     }
                 }
             }
@@ -134,7 +147,6 @@ int main() {
     cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(speed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     std::vector<float> hD(128 * 64);
     for (int mode = 0; mode < 2; ++mode)
         for (int shift = 0; shift < 3; ++shift) {
@@ -158,13 +170,16 @@ int main() {
     const char* names[4] = {"36 SS MMA (N=64)", "36 TS MMA (A in TMEM)", "12 tcgen05.cp 128x256b (48 KB)",
                             "12 tcgen05.cp + 36 TS MMA"};
     const int iters = 2000;
-    for (int what = 0; what < 4; ++what) {
-        for (int r = 0; r < 2; ++r) speed_kernel<<<1, 128, smem>>>(iters, what, dT);
+    auto run = [&](auto kern, int what) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        for (int r = 0; r < 2; ++r) kern<<<1, 128, smem>>>(iters, dT);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[2]; cudaMemcpy(h, dT, 16, cudaMemcpyDeviceToHost);
         printf("%-34s issue %7.1f cyc/tile, total %7.1f cyc/tile (MMA floor 1152)  %s\n", names[what],
                h[0] / (double)iters, h[1] / (double)iters, cudaGetErrorString(e));
-        if (e != cudaSuccess) return 1;
-    }
+        return e == cudaSuccess;
+    };
+    if (!run(speed_kernel<0>, 0) || !run(speed_kernel<1>, 1) || !run(speed_kernel<2>, 2) ||
+        !run(speed_kernel<3>, 3)) return 1;
     return 0;
 }

@@ -76,7 +76,7 @@ def test_double_conv_down_up_outconv_forwards(training):
     if training:    # batch statistics were used and the running buffers moved like torch's
         for name in ("inc.double_conv.1", "down1.maxpool_conv.1.double_conv.4", "up4.conv.double_conv.1"):
             a, b = dict(model.named_modules())[name], dict(twin.named_modules())[name]
-            assert int(a.num_batches_tracked) == int(b.num_batches_tracked) == 1, name
+            assert int(a.num_batches_tracked) == 1, name    # (F.batch_norm on the torch side does not count)
             assert rel_l2(a.running_mean, b.running_mean) < 1e-2, name
             assert rel_l2(a.running_var, b.running_var) < 1e-2, name
     # mismatched skip size fails like torch.cat would

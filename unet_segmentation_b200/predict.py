@@ -25,9 +25,14 @@ from .postprocess import get_instance_masks
 
 class FramePredictor:
     """``mask_u8, labels_u16 = FramePredictor(model, (H, W))(frame)`` — numpy in, numpy out (views of
-    pinned buffers that the next call overwrites; copy them to keep them)."""
+    pinned buffers that the next call overwrites; copy them to keep them).
 
-    def __init__(self, model, frame_hw: Tuple[int, int], min_size: int = 15, device=None):
+    ``batch`` > 1 handles that many frames per launch (input (batch, C, H, W), outputs (batch, h, w)):
+    one frame alone cannot fill 148 SMs — its bottleneck layers have 5 ... 17 tiles with K loops of
+    up to 9 216 — so frames of a sequence are best predicted a few at a time."""
+
+    def __init__(self, model, frame_hw: Tuple[int, int], min_size: int = 15, device=None,
+                 batch: int = 1):
         if model.training:
             raise RuntimeError("FramePredictor needs model.eval() (scripts/predict.py:70)")
         p = model.outc.conv.weight
@@ -38,8 +43,9 @@ class FramePredictor:
         self.device = torch.device(device) if device is not None else p.device
         h, w = frame_hw
         c = model.n_channels
-        self.frame_h = torch.empty(1, c, h, w, dtype=torch.float32).pin_memory()
-        self.x = torch.empty(1, c, h, w, dtype=torch.float32, device=self.device)
+        self.batch = int(batch)
+        self.frame_h = torch.empty(self.batch, c, h, w, dtype=torch.float32).pin_memory()
+        self.x = torch.empty(self.batch, c, h, w, dtype=torch.float32, device=self.device)
         self.graph = None
         self._weights_key = None
         self._pending = False
@@ -52,8 +58,9 @@ class FramePredictor:
     def _pipeline(self):
         self.x.copy_(self.frame_h, non_blocking=True)
         _, mask = self.model.predict_mask(self.x)
-        labels = get_instance_masks(mask[0], min_size=self.min_size)
-        return mask[0], labels
+        if self.batch == 1:
+            return mask[0], get_instance_masks(mask[0], min_size=self.min_size)
+        return mask, torch.stack([get_instance_masks(m, min_size=self.min_size) for m in mask])
 
     def _record(self):
         with torch.cuda.device(self.device):
@@ -79,7 +86,8 @@ class FramePredictor:
         self._record()
 
     def submit(self, frame) -> None:
-        """Enqueue one frame (numpy or CPU tensor, any shape that reshapes to (1, C, H, W))."""
+        """Enqueue one frame — or ``batch`` frames — (numpy or CPU tensor, any shape that reshapes to
+        (batch, C, H, W))."""
         if self._pending:         # the previous replay may still be reading the pinned input
             torch.cuda.current_stream(self.device).synchronize()
             self._pending = False
