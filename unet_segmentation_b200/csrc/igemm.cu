@@ -73,13 +73,19 @@ static bool pairs_enabled() {
     return on != 0;
 }
 
-// Pairs pay off for BN >= 128 (a 2-CTA MMA with N = 64 issues slower than two 1-CTA MMAs, measured)
-// with at least 16 k-blocks per tile (short-K tiles are epilogue-bound) and two waves of tiles.
+// Pairs pay off for BN >= 128 with at least 16 k-blocks per tile (short-K tiles are epilogue-bound) and
+// two waves of tiles. BN = 64: an M128 x N64 MMA reads 6 KB of shared memory for 32 cycles of math; a
+// pair reads 5 KB per CTA (each CTA stages half of the weight rows), which wins once the weights are
+// streamed per tile, i.e. for C_in >= 128 (18+ k-blocks: up4.a fprop 0.392 -> 0.330 ms, d1.a dgrad
+// 0.175 -> 0.157 ms at N = 16); the C_in = 64 layers keep the single-CTA resident-weight kernel, which
+// the pair form only equals. UB_PAIR_MINBN / UB_PAIR64_MINKB override.
 static int pick_cg(int BN, int kblocks, long long tiles) {
-    static int minkb = -1, minbn = -1;
+    static int minkb = -1, minbn = -1, minkb64 = -1;
     if (minkb < 0) { const char* e = getenv("UB_PAIR_MINKB"); minkb = e ? atoi(e) : 16; }
-    if (minbn < 0) { const char* e = getenv("UB_PAIR_MINBN"); minbn = e ? atoi(e) : 128; }
-    return (pairs_enabled() && BN >= minbn && kblocks >= minkb && tiles >= 2LL * num_sms()) ? 2 : 1;
+    if (minbn < 0) { const char* e = getenv("UB_PAIR_MINBN"); minbn = e ? atoi(e) : 64; }
+    if (minkb64 < 0) { const char* e = getenv("UB_PAIR64_MINKB"); minkb64 = e ? atoi(e) : 18; }
+    if (!pairs_enabled() || BN < minbn || tiles < 2LL * num_sms()) return 1;
+    return kblocks >= (BN == 64 ? minkb64 : minkb) ? 2 : 1;
 }
 
 template <int BN, int EPI, int CG>
@@ -220,11 +226,19 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
         q.qtiles = (Wo + 127) / 128;
         q.m_tiles = src0.N * Ho * q.qtiles;
         q.n_tiles = ncols / BN;
-        const int CG = pick_cg(BN, 9 * (q.cchunks0 + q.cchunks1), (long long)q.m_tiles * q.n_tiles);
-        // Cin = Cout = 64: weights resident in shared memory (UB_WRES=0 disables)
-        static int wres_on = -1;
+        int CG = pick_cg(BN, 9 * (q.cchunks0 + q.cchunks1), (long long)q.m_tiles * q.n_tiles);
+        // Cin = Cout = 64: weights resident in shared memory (UB_WRES=0 disables). The CTA-pair form of
+        // it (each CTA keeps half of the weight rows: 5 KB instead of 6 KB of operand reads per MMA) is
+        // built but OFF: measured 46 % slower (inc.b fprop 0.324 -> 0.472 ms, up4.b 0.173 -> 0.249 ms at
+        // N = 16) — a 256 x 64 pair MMA issues slower than two 128 x 64 ones (UB_WRES_PAIR=1 enables).
+        // The fused-head epilogue exists for CG = 1 only.
+        static int wres_on = -1, wres_pair = -1;
         if (wres_on < 0) { const char* e = getenv("UB_WRES"); wres_on = (e && !atoi(e)) ? 0 : 1; }
-        const bool wres = wres_on && BN == 64 && CG == 1 && q.cchunks0 + q.cchunks1 == 1 && q.n_tiles == 1;
+        if (wres_pair < 0) { const char* e = getenv("UB_WRES_PAIR"); wres_pair = (e && atoi(e)) ? 1 : 0; }
+        const bool wres = wres_on && BN == 64 && q.cchunks0 + q.cchunks1 == 1 && q.n_tiles == 1;
+        if (epi.kind == EPI_AFFINE_RELU_HEAD) CG = 1;
+        else if (wres)
+            CG = (wres_pair && pairs_enabled() && (long long)q.m_tiles >= 2LL * num_sms()) ? 2 : 1;
         int rr = make_tmap_rows(&mA0, src0, 130, 3);
         if (!rr && src1) rr = make_tmap_rows(&mA1, *src1, 130, 3);
         if (!src1) mA1 = mA0;
@@ -247,7 +261,10 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
             switch (BN) {
                 case 256: rc = launch_rowrun_bn<256, 2>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
                 case 128: rc = launch_rowrun_bn<128, 2>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
-                default: rc = launch_rowrun_bn<64, 2>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
+                default:
+                    if (wres) rc = launch_rowrun_bn<64, 2, true>(epi.kind, mA0, mA1, mB, q, grid, stream);
+                    else rc = launch_rowrun_bn<64, 2>(epi.kind, mA0, mA1, mB, q, grid, stream);
+                    break;
             }
         } else {
             switch (BN) {
@@ -277,7 +294,8 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
     p.m_tiles = (int)((M + 127) / 128);
     p.n_tiles = ncols / BN;
     // CTA pairs (256 x BN tiles) whenever there are at least two full waves of pair tiles
-    const int CG = pick_cg(BN, taps * (p.cchunks0 + p.cchunks1), (long long)p.m_tiles * p.n_tiles);
+    const int CG = epi.kind == EPI_AFFINE_RELU_HEAD
+                       ? 1 : pick_cg(BN, taps * (p.cchunks0 + p.cchunks1), (long long)p.m_tiles * p.n_tiles);
     r = make_tmap_weights(&mB, wB, (unsigned long long)ctot, (unsigned long long)ncols,
                           (unsigned long long)taps, (unsigned)(BN / CG), 1);
     if (r) { set_last_error("igemm: weight tensor map failed: %d", r); return UB_ERR_TMAP; }

@@ -56,7 +56,7 @@ struct RowRunCfg {
     static constexpr int STAT_BYTES = (BN == 64) ? 2304 : 4 * 2 * BN * 4;
     static constexpr int CONST_BYTES = 2 * BN * 4;   // per-column epilogue constants of the n tile
     static constexpr int SMEM_BYTES = SA * A_STAGE + B_AREA + BAR_BYTES + STAT_BYTES + CONST_BYTES + 1024;
-    static_assert(!WRES || (BN == 64 && CG == 1), "resident weights: BN = 64, single CTA");
+    static_assert(!WRES || BN == 64, "resident weights: BN = 64 (one 64-channel chunk)");
     static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
@@ -153,12 +153,14 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         int stage = 0;
         uint32_t phase = 0;
         const int nrow0 = n0 + (int)rank * Cfg::B_ROWS;
-        if (WRES) {   // all nine taps once: three boxes of (64 ch, 64 rows, 3 taps)
+        if (WRES) {   // all nine taps once: three boxes of (64 ch, B_ROWS rows, 3 taps); in a pair each
+                      // CTA keeps its half of the weight rows and both complete on the leader's barrier
+            const uint32_t fb = (CG == 2) ? mapa_rank(fullB(0), 0) : fullB(0);
             if (elect_one()) {
-                mbar_expect_tx(fullB(0), 9 * Cfg::B_TILE);
+                if (rank == 0) mbar_expect_tx(fullB(0), CG * 9 * Cfg::B_TILE);
 #pragma unroll
                 for (int tap = 0; tap < 9; tap += 3)
-                    tma_load_3d(b_base + tap * Cfg::B_TILE, &mapB, fullB(0), 0, nrow0, tap);
+                    tma_load_3d_cg<CG>(b_base + tap * Cfg::B_TILE, &mapB, fb, 0, nrow0, tap);
             }
             __syncwarp();
         } else
@@ -204,12 +206,12 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                         const uint64_t db = make_smem_desc(b_base + tap * Cfg::B_TILE, 0, 1024);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
+                            umma_bf16_cg<CG>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
                             acc = 1;
                         }
                     }
-                    umma_commit(emptyA(sa_i));
-                    umma_commit(tfull_bar(as));
+                    umma_commit_cg<CG>(emptyA(sa_i));
+                    umma_commit_cg<CG>(tfull_bar(as));
                 }
                 __syncwarp();
                 if (++sa_i == Cfg::SA) { sa_i = 0; pa ^= 1u; }
