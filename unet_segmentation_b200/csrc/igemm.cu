@@ -136,35 +136,35 @@ static int check_view(const View& v, const char* what) {
 }
 
 // ---- row-run variant (igemm_rr.cuh) -----------------------------------------------------------
-template <int BN, int EPI, int CG, bool WRES>
+template <int BN, int EPI, int CG, bool WRES, int ROWS>
 static int launch_rowrun_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const RowRunParams& p, int grid, cudaStream_t stream) {
-    using Cfg = RowRunCfg<BN, CG, WRES>;
+    using Cfg = RowRunCfg<BN, CG, WRES, ROWS>;
     static bool attr_set = false;
     if (!attr_set) {
-        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_rowrun_kernel<BN, EPI, CG, WRES>,
+        UB_CHECK_CUDA(cudaFuncSetAttribute(igemm_rowrun_kernel<BN, EPI, CG, WRES, ROWS>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    UB_CHECK_CUDA(ub_launch(igemm_rowrun_kernel<BN, EPI, CG, WRES>, dim3(grid),
+    UB_CHECK_CUDA(ub_launch(igemm_rowrun_kernel<BN, EPI, CG, WRES, ROWS>, dim3(grid),
                                    dim3(igemm_threads(BN)), Cfg::SMEM_BYTES, stream, CG, a0, a1, b, p));
     UB_POST_LAUNCH();
     return UB_OK;
 }
-template <int BN, int CG, bool WRES = false>
+template <int BN, int CG, bool WRES = false, int ROWS = 1>
 static int launch_rowrun_bn(int epi, const CUtensorMap& a0, const CUtensorMap& a1,
                             const CUtensorMap& b, const RowRunParams& p, int grid,
                             cudaStream_t stream) {
     switch (epi) {
         case EPI_CONV_STATS:
-            return launch_rowrun_t<BN, EPI_CONV_STATS, CG, WRES>(a0, a1, b, p, grid, stream);
-        case EPI_STORE: return launch_rowrun_t<BN, EPI_STORE, CG, WRES>(a0, a1, b, p, grid, stream);
+            return launch_rowrun_t<BN, EPI_CONV_STATS, CG, WRES, ROWS>(a0, a1, b, p, grid, stream);
+        case EPI_STORE: return launch_rowrun_t<BN, EPI_STORE, CG, WRES, ROWS>(a0, a1, b, p, grid, stream);
         case EPI_AFFINE_RELU:
-            return launch_rowrun_t<BN, EPI_AFFINE_RELU, CG, WRES>(a0, a1, b, p, grid, stream);
+            return launch_rowrun_t<BN, EPI_AFFINE_RELU, CG, WRES, ROWS>(a0, a1, b, p, grid, stream);
         case EPI_AFFINE_RELU_HEAD:
             if (BN == 64 && CG == 1)
-                return launch_rowrun_t<64, EPI_AFFINE_RELU_HEAD, 1, WRES>(a0, a1, b, p, grid, stream);
+                return launch_rowrun_t<64, EPI_AFFINE_RELU_HEAD, 1, WRES, ROWS>(a0, a1, b, p, grid, stream);
             break;
     }
     set_last_error("row-run: unsupported epilogue kind %d", epi);
@@ -224,8 +224,14 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
         q.N = src0.N; q.Ho = Ho; q.Wo = Wo; q.lower = lower;
         q.cchunks0 = src0.C / 64; q.cchunks1 = src1 ? src1->C / 64 : 0;
         q.qtiles = (Wo + 127) / 128;
-        q.m_tiles = src0.N * Ho * q.qtiles;
         q.n_tiles = ncols / BN;
+        // two output rows per tile for BN <= 128 (igemm_rr.cuh: halves the weight traffic through the
+        // shared-memory port and stages 4 input rows per 2 output rows); UB_RR_ROWS2=0 disables
+        static int rows2_on = -1;
+        if (rows2_on < 0) { const char* e = getenv("UB_RR_ROWS2"); rows2_on = (e && !atoi(e)) ? 0 : 1; }
+        const int ROWS = (rows2_on && BN <= 128 && Ho >= 2) ? 2 : 1;
+        q.HoT = (Ho + ROWS - 1) / ROWS;
+        q.m_tiles = src0.N * q.HoT * q.qtiles;
         int CG = pick_cg(BN, 9 * (q.cchunks0 + q.cchunks1), (long long)q.m_tiles * q.n_tiles);
         // Cin = Cout = 64: weights resident in shared memory (UB_WRES=0 disables). The CTA-pair form of
         // it (each CTA keeps half of the weight rows: 5 KB instead of 6 KB of operand reads per MMA) is
@@ -239,12 +245,12 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
         if (epi.kind == EPI_AFFINE_RELU_HEAD) CG = 1;
         else if (wres)
             CG = (wres_pair && pairs_enabled() && (long long)q.m_tiles >= 2LL * num_sms()) ? 2 : 1;
-        int rr = make_tmap_rows(&mA0, src0, 130, 3);
-        if (!rr && src1) rr = make_tmap_rows(&mA1, *src1, 130, 3);
+        int rr = make_tmap_rows(&mA0, src0, 130, (unsigned)(ROWS + 2));
+        if (!rr && src1) rr = make_tmap_rows(&mA1, *src1, 130, (unsigned)(ROWS + 2));
         if (!src1) mA1 = mA0;
         if (!rr) rr = make_tmap_weights(&mB, wB, (unsigned long long)ctot, (unsigned long long)ncols,
                                         (unsigned long long)taps, (unsigned)(BN / CG),
-                                        (unsigned)RowRunCfg<64>::btaps(BN, CG));
+                                        (unsigned)RowRunCfg<64>::btaps(BN, CG, ROWS));
         if (rr) { set_last_error("row-run: tensor map encoding failed: %d", rr); return UB_ERR_TMAP; }
         q.epi.M = (int)M; q.epi.out = epi.out; q.epi.ldo = epi.ldo; q.epi.bias = epi.bias;
         q.epi.scale = epi.scale; q.epi.shift = epi.shift; q.epi.stats = epi.stats;
@@ -257,25 +263,19 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
         const int grid = units * CG;
         if (info) { info->grid = grid; info->n_tiles = q.n_tiles; info->BN = BN; info->M = (int)M; }
         int rc;
-        if (CG == 2) {
-            switch (BN) {
-                case 256: rc = launch_rowrun_bn<256, 2>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
-                case 128: rc = launch_rowrun_bn<128, 2>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
-                default:
-                    if (wres) rc = launch_rowrun_bn<64, 2, true>(epi.kind, mA0, mA1, mB, q, grid, stream);
-                    else rc = launch_rowrun_bn<64, 2>(epi.kind, mA0, mA1, mB, q, grid, stream);
-                    break;
-            }
+#define UB_RR(BN_, CG_, WRES_, ROWS_) launch_rowrun_bn<BN_, CG_, WRES_, ROWS_>(epi.kind, mA0, mA1, mB, q, grid, stream)
+        if (BN == 256) rc = CG == 2 ? UB_RR(256, 2, false, 1) : UB_RR(256, 1, false, 1);
+        else if (BN == 128) {
+            if (ROWS == 2) rc = CG == 2 ? UB_RR(128, 2, false, 2) : UB_RR(128, 1, false, 2);
+            else rc = CG == 2 ? UB_RR(128, 2, false, 1) : UB_RR(128, 1, false, 1);
+        } else if (wres) {
+            if (ROWS == 2) rc = CG == 2 ? UB_RR(64, 2, true, 2) : UB_RR(64, 1, true, 2);
+            else rc = CG == 2 ? UB_RR(64, 2, true, 1) : UB_RR(64, 1, true, 1);
         } else {
-            switch (BN) {
-                case 256: rc = launch_rowrun_bn<256, 1>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
-                case 128: rc = launch_rowrun_bn<128, 1>(epi.kind, mA0, mA1, mB, q, grid, stream); break;
-                default:
-                    if (wres) rc = launch_rowrun_bn<64, 1, true>(epi.kind, mA0, mA1, mB, q, grid, stream);
-                    else rc = launch_rowrun_bn<64, 1>(epi.kind, mA0, mA1, mB, q, grid, stream);
-                    break;
-            }
+            if (ROWS == 2) rc = CG == 2 ? UB_RR(64, 2, false, 2) : UB_RR(64, 1, false, 2);
+            else rc = CG == 2 ? UB_RR(64, 2, false, 1) : UB_RR(64, 1, false, 1);
         }
+#undef UB_RR
         return rc;
     }
     int r = make_tmap_im2col(&mA0, src0, lower, upper, tstride, 128);

@@ -22,7 +22,8 @@ struct RowRunParams {
     int lower;            // input coordinate of tap (0,0) relative to the output pixel (0 / -2)
     int cchunks0, cchunks1;
     int qtiles;           // ceil(Wo / 128)
-    int m_tiles, n_tiles; // m_tiles = N * Ho * qtiles
+    int HoT;              // ceil(Ho / ROWS): a tile covers ROWS consecutive output rows
+    int m_tiles, n_tiles; // m_tiles = N * HoT * qtiles
     IgemmParams epi;      // epilogue fields (out, ldo, bias, scale, shift, stats); M = N*Ho*Wo
 };
 
@@ -34,22 +35,32 @@ struct RowRunParams {
 // resident in shared memory for the whole kernel instead of being re-staged for every tile — these
 // tiles are bound by shared-memory bandwidth (TMA writes + MMA operand reads), and the weights were
 // 21 % of it.
-template <int BN, int CG = 1, bool WRES = false>
+// ROWS = 2 (BN <= 128): a tile is TWO consecutive output rows of the same 128-pixel column range. One
+// A stage then holds four input rows (66.5 KB for two output rows instead of 2 x 50 KB) and every
+// staged weight tile feeds the MMAs of both rows, so the weights cross the shared-memory port once
+// per two output rows; the two rows accumulate side by side in tensor memory (2 x 2 x BN columns with
+// the double buffering). These layers are bound by that port (TMA writes + MMA operand reads share
+// 128 B/clk): per output row d1.a fprop moves 393 KB instead of 482 KB, up4.a 462 instead of 532.
+template <int BN, int CG = 1, bool WRES = false, int ROWS = 1>
 struct RowRunCfg {
-    static constexpr int btaps(int bn, int cg) { return bn <= 128 ? 3 : 1; }
-    static constexpr int BTAPS = btaps(BN, CG);
+    static constexpr int btaps(int bn, int cg, int rows = 1) {
+        return bn <= 128 ? ((rows == 2 && bn == 128 && cg == 1) ? 1 : 3) : 1;
+    }
+    static constexpr int BTAPS = btaps(BN, CG, ROWS);
     static constexpr int ROW_BYTES = 130 * 128;            // input rows are packed back to back
-    static constexpr int A_TX = 3 * ROW_BYTES;             // bytes one A stage receives (49920)
-    static constexpr int A_STAGE = 49 * 1024;              // 1024-aligned stage pitch
+    static constexpr int A_ROWS = ROWS + 2;
+    static constexpr int A_TX = A_ROWS * ROW_BYTES;        // bytes one A stage receives (49920 / 66560)
+    static constexpr int A_STAGE = (A_TX + 1023) / 1024 * 1024;   // 1024-aligned stage pitch
     static constexpr int B_ROWS = BN / CG;                 // weight rows staged by one CTA
     static constexpr int B_TILE = B_ROWS * 128;            // one tap: [B_ROWS][64] K-major
     static constexpr int B_STAGE = BTAPS * B_TILE;
     // Ring depths. A B stage of a BN = 128 pair is only 12 MMAs x 64 cycles = 768 cycles of cover
     // against ~1 us of TMA latency: with two stages the MMA warp waited for weights a third of the
     // time (role profile), so that ring gets four stages and the A ring, which had slack, two.
-    static constexpr int SA = (CG == 2) ? (BN == 64 ? 3 : 2) : ((BN == 64) ? 3 : 2);
+    static constexpr int SA = ROWS == 2 ? 2 : ((CG == 2) ? (BN == 64 ? 3 : 2) : ((BN == 64) ? 3 : 2));
     static constexpr int SB = WRES ? 1
-                                   : ((CG == 2) ? (BN == 256 ? 6 : 4) : ((BN == 64) ? 3 : (BN == 128 ? 2 : 3)));
+                              : ROWS == 2 ? ((BN == 128 && CG == 2) || (BN == 64 && CG == 1) ? 3 : 4)
+                                          : ((CG == 2) ? (BN == 256 ? 6 : 4) : ((BN == 64) ? 3 : (BN == 128 ? 2 : 3)));
     static constexpr int B_AREA = WRES ? 9 * B_TILE : SB * B_STAGE;
     static constexpr int BAR_BYTES = 256;
     // epilogue scratch: BN-statistics rows of the 4 lane quadrants, or the fused head's weights
@@ -57,16 +68,18 @@ struct RowRunCfg {
     static constexpr int CONST_BYTES = 2 * BN * 4;   // per-column epilogue constants of the n tile
     static constexpr int SMEM_BYTES = SA * A_STAGE + B_AREA + BAR_BYTES + STAT_BYTES + CONST_BYTES + 1024;
     static_assert(!WRES || BN == 64, "resident weights: BN = 64 (one 64-channel chunk)");
-    static constexpr uint32_t TMEM_COLS = 2 * BN;
+    static_assert(ROWS == 1 || (ROWS == 2 && BN <= 128), "two-row tiles: 2 x 2 x BN TMEM columns");
+    static constexpr uint32_t TMEM_COLS = 2 * ROWS * BN;
+    static_assert(SMEM_BYTES <= 227 * 1024, "row-run configuration exceeds shared memory");
 };
 
-template <int BN, int EPI, int CG, bool WRES>
+template <int BN, int EPI, int CG, bool WRES, int ROWS>
 __global__ void __launch_bounds__(igemm_threads(BN), 1)
 igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                     const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const RowRunParams p) {
     pdl_trigger();   // let the next kernel's CTAs be scheduled while this grid drains
-    using Cfg = RowRunCfg<BN, CG, WRES>;
+    using Cfg = RowRunCfg<BN, CG, WRES, ROWS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -121,7 +134,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
 
     // (whole warps run the role loops; see the note on elect_one() in igemm_kmajor_kernel)
     if (warp == 0) {
-        // ---------------- A producer: 3 input rows x 130 pixels x 64 channels per chunk ----------
+        // ---------------- A producer: ROWS + 2 input rows x 130 pixels x 64 channels per chunk ------
         int stage = 0;
         uint32_t phase = 0;
         for (int mu = m_first; mu < m_units; mu += m_step) {
@@ -129,17 +142,17 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             if (mt >= p.m_tiles) mt = p.m_tiles - 1;   // odd tail: reload a valid tile, rows masked
             const int qt = mt % p.qtiles;
             const int t = mt / p.qtiles;
-            const int pr = t % p.Ho;
-            const int n = t / p.Ho;
+            const int pr = (t % p.HoT) * ROWS;
+            const int n = t / p.HoT;
             const int w0 = qt * 128 + p.lower;
-            const int h0 = pr + p.lower;
+            const int h0 = pr + p.lower;   // rows past the tensor (odd Ho, last tile) are zero filled
             for (int cc = 0; cc < cchunks; ++cc) {
                 mbar_wait(emptyA(stage), phase ^ 1u);
                 const uint32_t sa = base + stage * Cfg::A_STAGE;
                 const uint32_t fb = (CG == 2) ? mapa_rank(fullA(stage), 0) : fullA(stage);
                 if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(fullA(stage), CG * Cfg::A_TX);
-                    if (cc < p.cchunks0)   // box (64, 130, 3, 1)
+                    if (cc < p.cchunks0)   // box (64, 130, ROWS + 2, 1)
                         tma_load_4d_cg<CG>(sa, &mapA0, fb, cc * 64, w0, h0, n);
                     else
                         tma_load_4d_cg<CG>(sa, &mapA1, fb, (cc - p.cchunks0) * 64, w0, h0, n);
@@ -191,23 +204,25 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         for (int mu = m_first; mu < m_units; mu += m_step) {
             mbar_wait(tempty_bar(as), aphase ^ 1u);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-            uint32_t acc = 0;
+            // accumulator of output row j of the tile: columns [(as * ROWS + j) * BN, + BN)
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * ROWS * BN);
             if (WRES) {
-                // one chunk, resident weights: all 36 MMAs of the tile behind a single wait
+                // one chunk, resident weights: all 36 * ROWS MMAs of the tile behind a single wait
                 mbar_wait(fullA(sa_i), pa);
                 tc_fence_after();
                 const uint32_t sa = base + sa_i * Cfg::A_STAGE;
                 if (elect_one()) {
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const uint64_t da = make_smem_desc(
-                            sa + (tap / 3) * Cfg::ROW_BYTES + (tap % 3) * 128, 0, 1024);
-                        const uint64_t db = make_smem_desc(b_base + tap * Cfg::B_TILE, 0, 1024);
+                    for (int j = 0; j < ROWS; ++j) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_bf16_cg<CG>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
-                            acc = 1;
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint64_t da = make_smem_desc(
+                                sa + (tap / 3 + j) * Cfg::ROW_BYTES + (tap % 3) * 128, 0, 1024);
+                            const uint64_t db = make_smem_desc(b_base + tap * Cfg::B_TILE, 0, 1024);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16_cg<CG>(tmem_d + (uint32_t)(j * BN), da + (uint64_t)(2 * k),
+                                                 db + (uint64_t)(2 * k), idesc, (uint32_t)((tap | k) != 0));
                         }
                     }
                     umma_commit_cg<CG>(emptyA(sa_i));
@@ -223,28 +238,29 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                 for (int tap = 0; tap < 9; tap += Cfg::BTAPS) {
                     mbar_wait(fullB(sb_i), pb);
                     tc_fence_after();
+                    const uint32_t first = (cc == 0 && tap == 0) ? 0u : 1u;   // 0: overwrite the accumulator
                     if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < Cfg::BTAPS; ++j) {
-                        const int r = (tap + j) / 3, sft = (tap + j) % 3;
-                        // tap (r, sft) = window of input row r shifted by sft pixels (128 B each)
-                        const uint64_t da =
-                            make_smem_desc(sa + r * Cfg::ROW_BYTES + sft * 128, 0, 1024);
-                        const uint64_t db =
-                            make_smem_desc(b_base + sb_i * Cfg::B_STAGE + j * Cfg::B_TILE, 0, 1024);
+                    for (int j = 0; j < ROWS; ++j) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_bf16_cg<CG>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k),
-                                             idesc, acc);
-                            acc = 1;
-                        }
+                    for (int jt = 0; jt < Cfg::BTAPS; ++jt) {
+                        const int r = (tap + jt) / 3, sft = (tap + jt) % 3;
+                        // tap (r, sft) of output row j = window of input row r + j shifted by sft pixels
+                        const uint64_t da =
+                            make_smem_desc(sa + (r + j) * Cfg::ROW_BYTES + sft * 128, 0, 1024);
+                        const uint64_t db =
+                            make_smem_desc(b_base + sb_i * Cfg::B_STAGE + jt * Cfg::B_TILE, 0, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_cg<CG>(tmem_d + (uint32_t)(j * BN), da + (uint64_t)(2 * k),
+                                             db + (uint64_t)(2 * k), idesc, first | (uint32_t)((jt | k) != 0));
+                    }
                     }
                     umma_commit_cg<CG>(emptyB(sb_i));
                     if (tap + Cfg::BTAPS >= 9) umma_commit_cg<CG>(emptyA(sa_i));
                     if (tap + Cfg::BTAPS >= 9 && cc == cchunks - 1) umma_commit_cg<CG>(tfull_bar(as));
                     }
                     __syncwarp();
-                    acc = 1;
                     if (++sb_i == Cfg::SB) { sb_i = 0; pb ^= 1u; }
                 }
                 if (++sa_i == Cfg::SA) { sa_i = 0; pa ^= 1u; }
@@ -267,14 +283,20 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
         for (int mu = m_first; mu < m_units; mu += m_step) {
             const int mt = mu * CG + (int)rank;
             const int qt = mt % p.qtiles;
-            const int t = mt / p.qtiles;      // = n * Ho + p
+            const int t = mt / p.qtiles;      // = n * HoT + (row pair)
+            const int pr = (t % p.HoT) * ROWS;
+            const int n = t / p.HoT;
             const int q = qt * 128 + row_in_tile;
-            const bool valid = q < p.Wo && mt < p.m_tiles;
-            const long long m = (long long)t * p.Wo + q;
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-            epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, cs, hs);
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) {
+                const bool valid = q < p.Wo && mt < p.m_tiles && pr + j < p.Ho;
+                const long long m = ((long long)n * p.Ho + pr + j) * p.Wo + q;
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                      (uint32_t)((as * ROWS + j) * BN);
+                epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, cs, hs);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
