@@ -209,6 +209,31 @@ def test_eval_forward_and_fused_mask_vs_oracle():
     assert agree_conf >= 0.999
 
 
+@pytest.mark.parametrize("size", [230, 231])
+def test_eval_forward_with_odd_feature_maps_vs_oracle(size):
+    """Eval path on sizes whose level-0 / level-1 maps are odd (230: 226 -> 113 -> 109 -> 54, 231: 227 -> 113; floor-mode
+    pooling drops the last row / column): the 2x2 max-pool fused into the two-row conv
+    epilogue must floor exactly like nn.MaxPool2d(2)."""
+    model, sd = make_model(seed=5)
+    gen = torch.Generator().manual_seed(11)
+    for k in [k for k in sd if k.endswith("running_mean")]:
+        nf = sd[k].numel()
+        sd[k] = (torch.randn(nf, generator=gen) * 0.1).cuda()
+        sd[k.replace("running_mean", "running_var")] = (0.5 + torch.rand(nf, generator=gen)).cuda()
+    model.load_state_dict(sd)
+    model.eval()
+    img, _, _ = unet_ref.synthetic_batch(2, size=size, seed=8, device="cuda")
+    with torch.no_grad():
+        ref = unet_ref.unet_forward(sd, img, training=False)
+        logits, mask = model.predict_mask(img)
+    torch.cuda.synchronize()
+    assert logits.shape == ref.shape
+    e = rel_l2(logits, ref)
+    print(f"\n[eval {size}^2, odd maps] logits rel-L2 {e:.3e}")
+    assert e < 2e-2
+    assert torch.equal(mask > 0, logits[:, 1] > logits[:, 0])
+
+
 def test_reference_style_training_loop_runs_and_learns():
     """The hot loop of scripts/train.py:104-135 with the drop-in classes (SGD lr 1e-4 -> 1e-2 here
     so that three steps show progress)."""

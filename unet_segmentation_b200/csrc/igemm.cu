@@ -232,7 +232,10 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
         const int ROWS = (rows2_on && BN <= 128 && Ho >= 2) ? 2 : 1;
         q.HoT = (Ho + ROWS - 1) / ROWS;
         q.m_tiles = src0.N * q.HoT * q.qtiles;
-        int CG = pick_cg(BN, 9 * (q.cchunks0 + q.cchunks1), (long long)q.m_tiles * q.n_tiles);
+        // (a two-row tile issues twice the MMAs per staged weight tile: it counts as twice as deep for
+        // the "pairs need long tiles" rule, which makes d1.a fprop and up4.a dgrad pairs: their
+        // single-CTA two-row form must stage weights one tap at a time to fit shared memory)
+        int CG = pick_cg(BN, 9 * (q.cchunks0 + q.cchunks1) * ROWS, (long long)q.m_tiles * q.n_tiles);
         // Cin = Cout = 64: weights resident in shared memory (UB_WRES=0 disables). The CTA-pair form of
         // it (each CTA keeps half of the weight rows: 5 KB instead of 6 KB of operand reads per MMA) is
         // built but OFF: measured 46 % slower (inc.b fprop 0.324 -> 0.472 ms, up4.b 0.173 -> 0.249 ms at
@@ -256,12 +259,20 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
         q.epi.scale = epi.scale; q.epi.shift = epi.shift; q.epi.stats = epi.stats;
         q.epi.head_w = epi.head_w; q.epi.head_b = epi.head_b; q.epi.head_logits = epi.head_logits;
         q.epi.head_mask = epi.head_mask; q.epi.head_nc = epi.head_nc; q.epi.head_hw = Ho * Wo;
+        static int fuse_pool = -1;
+        if (fuse_pool < 0) { const char* e = getenv("UB_FUSE_EVAL_POOL"); fuse_pool = (e && !atoi(e)) ? 0 : 1; }
+        const bool pool_fused = fuse_pool && ROWS == 2 && epi.kind == EPI_AFFINE_RELU && epi.pooled != nullptr;
+        q.epi.pooled = pool_fused ? epi.pooled : nullptr;
+        q.epi.pool_Ho = Ho; q.epi.pool_Wo = Wo;
         int units = (num_sms() / CG / q.n_tiles) * q.n_tiles;
         if (units <= 0) units = q.n_tiles;
         const long long tiles = (long long)((q.m_tiles + CG - 1) / CG) * q.n_tiles;
         if (units > tiles) units = (int)tiles;
         const int grid = units * CG;
-        if (info) { info->grid = grid; info->n_tiles = q.n_tiles; info->BN = BN; info->M = (int)M; }
+        if (info) {
+            info->grid = grid; info->n_tiles = q.n_tiles; info->BN = BN; info->M = (int)M;
+            info->pool_fused = pool_fused ? 1 : 0;
+        }
         int rc;
 #define UB_RR(BN_, CG_, WRES_, ROWS_) launch_rowrun_bn<BN_, CG_, WRES_, ROWS_>(epi.kind, mA0, mA1, mB, q, grid, stream)
         if (BN == 256) rc = CG == 2 ? UB_RR(256, 2, false, 1) : UB_RR(256, 1, false, 1);
@@ -314,7 +325,7 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
     const long long tiles = (long long)((p.m_tiles + CG - 1) / CG) * p.n_tiles;
     if (units > tiles) units = (int)tiles;
     const int grid = units * CG;
-    if (info) { info->grid = grid; info->n_tiles = p.n_tiles; info->BN = BN; info->M = (int)M; }
+    if (info) { info->grid = grid; info->n_tiles = p.n_tiles; info->BN = BN; info->M = (int)M; info->pool_fused = 0; }
     if (CG == 2) {
         switch (BN) {
             case 256: return launch_igemm_bn<256, 2>(epi.kind, mA0, mA1, mB, p, grid, stream);

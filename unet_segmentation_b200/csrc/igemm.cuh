@@ -42,6 +42,10 @@ struct IgemmParams {
     float* head_logits;
     unsigned char* head_mask;   // may be null
     int head_nc, head_hw;       // classes, pixels per image (Ho*Wo)
+    // EPI_AFFINE_RELU in the two-row row-run kernel: optional fused 2x2 floor max-pool (eval path),
+    // pooled [N][Ho/2][Wo/2][ldo] written next to the activation
+    __nv_bfloat16* pooled;
+    int pool_Ho, pool_Wo;       // extents of the conv output (= un-pooled activation)
     // EPI_CONVT: GEMM column = q*ct_cout + co, q = dy*2+dx; row = (n,h,w) of the input
     int ct_cout, ct_H, ct_W;
     long long ct_sN, ct_sH, ct_sW;  // element strides of the destination [N,2H,2W,*] view
@@ -260,6 +264,74 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                     if (p.head_mask)   // one class: sigmoid(z) > 0.5 == z > 0 (scripts/inference.py:39,85)
                         p.head_mask[m] = (p.head_nc >= 2 ? hacc[1] > hacc[0] : hacc[0] > 0.f) ? 255 : 0;
                 }
+}
+
+// Eval epilogue of a TWO-ROW tile with the 2x2 floor max-pool of the reference's Down block fused in
+// (nn.MaxPool2d(2), models/unet_model.py:28): folded BN + ReLU on both output rows of the tile, both
+// stored as the activation (it is the skip connection), and their 2x2 maxima — the vertical pair
+// lives in the same thread's two accumulators, the horizontal pair in the neighbouring lane — stored
+// to the pooled tensor. max commutes with the (monotone) bf16 rounding, so the result equals pooling
+// the stored activation.  trow0 / trow1: TMEM addresses of the two rows; m0: GEMM row of the thread in
+// output row `pr` (even), q its column.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_pool2(const IgemmParams& p, uint32_t trow0, uint32_t trow1,
+                                                    long long m0, int n, int pr, int q, bool valid0,
+                                                    bool valid1, int n0, int lane, int chalf,
+                                                    const float* cs) {
+    const bool pool_ok = valid1 && (q + 1 < p.pool_Wo) && ((q & 1) == 0);   // valid1 implies valid0
+#pragma unroll
+    for (int cl = 0; cl < EpiCfg<BN>::NCH; ++cl) {
+        const int c = chalf * EpiCfg<BN>::NCH + cl;
+        const int col0 = n0 + c * 32;
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(trow0 + (uint32_t)(c * 32), r0);
+        tmem_ld_32x32(trow1 + (uint32_t)(c * 32), r1);
+        tmem_ld_wait();
+        float mx[32];
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 a4 = reinterpret_cast<const float4*>(cs + c * 32)[i4];
+            const float4 b4 = reinterpret_cast<const float4*>(cs + BN + c * 32)[i4];
+            const float sc[4] = {a4.x, a4.y, a4.z, a4.w}, sh[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = 4 * i4 + e;
+                const float v0 = fmaxf(fmaf(__uint_as_float(r0[i]), sc[e], sh[e]), 0.f);
+                const float v1 = fmaxf(fmaf(__uint_as_float(r1[i]), sc[e], sh[e]), 0.f);
+                r0[i] = __float_as_uint(v0);
+                r1[i] = __float_as_uint(v1);
+                mx[i] = fmaxf(v0, v1);
+            }
+        }
+        if (valid0) {
+            uint4* d4 = reinterpret_cast<uint4*>(p.out + m0 * p.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                d4[j] = make_uint4(pack_bf16x2(__uint_as_float(r0[8 * j + 0]), __uint_as_float(r0[8 * j + 1])),
+                                   pack_bf16x2(__uint_as_float(r0[8 * j + 2]), __uint_as_float(r0[8 * j + 3])),
+                                   pack_bf16x2(__uint_as_float(r0[8 * j + 4]), __uint_as_float(r0[8 * j + 5])),
+                                   pack_bf16x2(__uint_as_float(r0[8 * j + 6]), __uint_as_float(r0[8 * j + 7])));
+        }
+        if (valid1) {
+            uint4* d4 = reinterpret_cast<uint4*>(p.out + (m0 + p.pool_Wo) * p.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                d4[j] = make_uint4(pack_bf16x2(__uint_as_float(r1[8 * j + 0]), __uint_as_float(r1[8 * j + 1])),
+                                   pack_bf16x2(__uint_as_float(r1[8 * j + 2]), __uint_as_float(r1[8 * j + 3])),
+                                   pack_bf16x2(__uint_as_float(r1[8 * j + 4]), __uint_as_float(r1[8 * j + 5])),
+                                   pack_bf16x2(__uint_as_float(r1[8 * j + 6]), __uint_as_float(r1[8 * j + 7])));
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+        if (pool_ok) {
+            const long long pm = ((long long)n * (p.pool_Ho >> 1) + (pr >> 1)) * (p.pool_Wo >> 1) + (q >> 1);
+            uint4* d4 = reinterpret_cast<uint4*>(p.pooled + pm * p.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                d4[j] = make_uint4(pack_bf16x2(mx[8 * j + 0], mx[8 * j + 1]), pack_bf16x2(mx[8 * j + 2], mx[8 * j + 3]),
+                                   pack_bf16x2(mx[8 * j + 4], mx[8 * j + 5]), pack_bf16x2(mx[8 * j + 6], mx[8 * j + 7]));
+        }
+    }
 }
 
 // Per-column epilogue constants of n tile [n0, n0+BN) -> shared memory (broadcast LDS.128 reads

@@ -289,6 +289,12 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             const int q = qt * 128 + row_in_tile;
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
+            if (ROWS == 2 && EPI == EPI_AFFINE_RELU && p.epi.pooled != nullptr) {
+                const bool v0 = q < p.Wo && mt < p.m_tiles && pr < p.Ho;
+                const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ROWS * BN);
+                epilogue_tile_pool2<BN>(p.epi, t0, t0 + (uint32_t)BN, ((long long)n * p.Ho + pr) * p.Wo + q,
+                                        n, pr, q, v0, v0 && pr + 1 < p.Ho, n0, lane, chalf, cs);
+            } else
 #pragma unroll
             for (int j = 0; j < ROWS; ++j) {
                 const bool valid = q < p.Wo && mt < p.m_tiles && pr + j < p.Ho;

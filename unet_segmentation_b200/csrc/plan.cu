@@ -548,11 +548,12 @@ static int conv_unit_forward(ub_plan* P, ConvUnit& u, const View& in0, const Vie
         e.head_w = P->params[np - 2]; e.head_b = P->params[np - 1];
         e.head_logits = P->fused_logits; e.head_mask = P->fused_mask; e.head_nc = P->NC;
     }
+    if (e.kind == EPI_AFFINE_RELU) e.pooled = pooled;   // fused where the selected kernel can (info.pool_fused)
     {
         ProfScope ps(P, CLS_FPROP, fl, by, s);
         UB_TRY(launch_igemm(in0, in1, 0, -2, 1, 9, 3, u.wf, u.Co, e, &u.info, s));
     }
-    if (pooled) {
+    if (pooled && !u.info.pool_fused) {
         ProfScope ps(P, CLS_BN_APPLY, 0, pix_out * u.Co * 2.5, s);
         return launch_maxpool2(u.a, pooled, N, u.Ho(), u.Wo(), u.Co, s);
     }

@@ -93,9 +93,14 @@ struct IgemmEpilogue {
     float* head_logits;
     unsigned char* head_mask;
     int head_nc;
+    // EPI_AFFINE_RELU: optional [N][Ho/2][Wo/2][ldo] destination of a fused 2x2 floor max-pool. The
+    // launcher fuses it where the kernel selected for the shape can (two-row row-run tiles) and says so
+    // in IgemmLaunchInfo::pool_fused; otherwise the caller runs launch_maxpool2.
+    __nv_bfloat16* pooled;
 };
 struct IgemmLaunchInfo {
     int grid, n_tiles, BN, M;
+    int pool_fused;
 };
 // A operand: im2col over src0 (and optionally src1 = second channel range of a zero-copy concat).
 // B operand: packed weights [ncols][taps*(C0+C1)] bf16, K-major.
