@@ -132,6 +132,42 @@ def test_choose_plan_minimises_modelled_time_and_never_loses_with_more_ranks():
     assert tiling.choose_plan(1024, 1024, 1)[:2] == (1212, 1)
 
 
+def test_tile_session_tables_cover_every_tile_once_and_leave_idle_ranks_empty():
+    """Host logic of the sharded overlap-tile path (tiling._TileSession): the (world, slots, 2) origin
+    table that drives ub_extract_tiles / ub_stitch_tiles holds every tile exactly once, round-robin
+    over the ranks in use, unused slots and idle ranks are marked with a negative row, slots come in
+    whole batches, and every rank derives the same table."""
+    import types
+
+    import torch
+
+    from unet_segmentation_b200 import tiling
+
+    model = types.SimpleNamespace(levels=5)
+    dev = torch.device("cpu")
+    for (h, w, tile_in, bt, world, used) in [(1024, 1024, 700, 8, 8, 4), (8192, 8192, 2236, 8, 8, 8),
+                                             (500, 420, 572, 2, 1, 1), (800, 800, 572, 4, 3, 3),
+                                             (1024, 1024, 444, 2, 8, 8), (300, 300, 252, 2, 4, 9)]:
+        tables = []
+        for rank in range(world):
+            s = tiling._TileSession(model, h, w, tile_in, bt, rank, world, used, dev)
+            tables.append(s.table)
+            assert s.slots % s.bt == 0 and s.table.shape == (world, s.slots, 2)
+            assert s.n_batches * s.bt >= len(s.mine)
+            assert torch.equal(s.my_table, s.table[rank])
+            if rank >= s.ranks_used:
+                assert s.mine == [] and s.n_batches == 0 and bool((s.my_table[:, 0] < 0).all())
+        assert all(torch.equal(t, tables[0]) for t in tables)
+        t = tables[0]
+        valid = t[t[:, :, 0] >= 0]
+        got = sorted((int(y), int(x)) for y, x in valid.tolist())
+        assert got == sorted(s.origins)                      # every tile once, none invented
+        assert s.ranks_used <= min(world, len(s.origins))
+        per_rank = (t[:, :, 0] >= 0).sum(1)
+        assert int(per_rank[:s.ranks_used].max() - per_rank[:s.ranks_used].min()) <= 1   # balanced
+        assert int(per_rank[s.ranks_used:].sum()) == 0
+
+
 def test_bf16_rounding_oracle_is_a_small_perturbation_of_the_fp32_oracle():
     """T2 oracle plumbing (oracle/unet_ref.py emulate_bf16): same graph, bf16 rounding at the conv
     operands except the first conv — close to, but not identical with, the fp32 restatement, and
