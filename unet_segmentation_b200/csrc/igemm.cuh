@@ -354,12 +354,13 @@ __device__ __forceinline__ void stage_epilogue_consts(const IgemmParams& p, int 
 // Head weights of EPI_AFFINE_RELU_HEAD -> shared memory: hs[c*64 + k] (c < 8), bias at hs[512 + c].
 template <int EPI>
 __device__ __forceinline__ void stage_head_weights(const IgemmParams& p, float* hs) {
-    if (EPI != EPI_AFFINE_RELU_HEAD) return;
-    for (int i = threadIdx.x; i < HEAD_EPI_MAX_CLASSES * 64; i += blockDim.x)
-        hs[i] = i < p.head_nc * 64 ? p.head_w[i] : 0.f;
-    for (int i = threadIdx.x; i < HEAD_EPI_MAX_CLASSES; i += blockDim.x)
-        hs[HEAD_EPI_MAX_CLASSES * 64 + i] = (p.head_b && i < p.head_nc) ? p.head_b[i] : 0.f;
-    __syncthreads();
+    if constexpr (EPI == EPI_AFFINE_RELU_HEAD) {
+        for (int i = threadIdx.x; i < HEAD_EPI_MAX_CLASSES * 64; i += blockDim.x)
+            hs[i] = i < p.head_nc * 64 ? p.head_w[i] : 0.f;
+        for (int i = threadIdx.x; i < HEAD_EPI_MAX_CLASSES; i += blockDim.x)
+            hs[HEAD_EPI_MAX_CLASSES * 64 + i] = (p.head_b && i < p.head_nc) ? p.head_b[i] : 0.f;
+        __syncthreads();
+    }
 }
 
 template <int BN, int EPI, int CG>
