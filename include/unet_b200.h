@@ -257,6 +257,18 @@ int ub_op_conv3x3_affine_relu_head(const ub_view* src0, const ub_view* src1, con
                                    const float* head_b, int n_classes, float* logits,
                                    uint8_t* mask, void* stream);
 int ub_op_conv3x3_dgrad(const ub_view* dy, const void* wd, int Ci, void* dx, void* stream);
+/* Data gradient whose epilogue also performs the REDUCE pass of the BatchNorm + ReLU backward of the
+ * layer that receives dx (nn.BatchNorm2d + nn.ReLU backward, models/unet_model.py:12-13,16-17): y = that
+ * layer's stored pre-BN output (bf16, the geometry of dx), scale / shift / mean = its batch-norm
+ * statistics. partial: ub_op_conv_stats_floats(Ci) floats; info4 describes the partial rows for
+ * ub_op_bn_relu_backward_fused, which then runs only the finalisation and the apply pass. */
+int ub_op_conv3x3_dgrad_bnred(const ub_view* dy, const void* wd, int Ci, void* dx, const void* y,
+                              const float* scale, const float* shift, const float* mean,
+                              float* partial, int* info4, void* stream);
+int ub_op_bn_relu_backward_fused(const void* y, int N, int H, int W, int C, const float* scale,
+                                 const float* shift, const float* mean, const float* rstd,
+                                 const ub_view* g, float* partial, const int* info4, float* dgamma,
+                                 float* dbeta, void* dy, void* stream);
 int64_t ub_op_wgrad_workspace_floats(int rows, int cols, int64_t pixels);
 /* dw[Co][C0+C1][3][3] fp32 = sum over pixels of x (concat of src0, src1) * dy[N][H-2][W-2][Co]. */
 int ub_op_conv3x3_wgrad(const ub_view* src0, const ub_view* src1, const void* dy, int Co,

@@ -152,6 +152,49 @@ def test_bn_relu_backward_at_layer_geometry(ops, cap, unit):
     assert rel_l2(dbeta, bv.grad) < GRAD_TOL and cosine(dbeta, bv.grad) >= COS_BAR
 
 
+FIRST_UNITS = [u for u in CONV_UNITS if u.endswith(".0")]      # receive the second unit's data gradient
+
+
+@pytest.mark.parametrize("unit", FIRST_UNITS)
+def test_fused_bn_backward_reduction_at_layer_geometry(ops, cap, unit):
+    """EPI_STORE_BNRED: the data gradient of a block's second conv, whose epilogue also reduces
+    sum dyh and sum dyh (y - mean) for the FIRST unit's BatchNorm + ReLU backward, against (a) the
+    unfused kernels (plain data gradient + stand-alone reduce pass) and (b) torch autograd — fed the
+    oracle's tensors at the real layer geometry (row-run two-row tiles, pair kernels, BN = 64 ... 256)."""
+    sd = cap["sd"]
+    nxt = unit[:-1] + "3"                                     # the second conv of the same block
+    bn = unit[:-1] + "1"
+    wt = bf(sd[f"{nxt}.weight"])
+    _, wd = ops.pack_conv3x3(wt)
+    gamma, beta = sd[f"{bn}.weight"] * 1.0, sd[f"{bn}.bias"] + 0.05
+    y = bf(cap[f"{unit}.y"])                                  # pre-BN output of the first unit
+    dy2 = cap[f"{nxt}.y.grad"]
+    dy2 = bf(dy2 / dy2.abs().max().clamp_min(1e-30))          # upstream of the second conv
+    mean = y.mean((0, 2, 3)); var = y.var((0, 2, 3), unbiased=False)
+    rstd = (var + 1e-5).rsqrt(); scale = gamma * rstd; shift = beta - mean * scale
+    y_n, dy2_n = ops.nhwc(y), ops.nhwc(dy2)
+    # fused
+    dx_f, partial, info = ops.conv3x3_dgrad_bnred(dy2_n, wd, y_n, scale, shift, mean)
+    dy_f, dg_f, db_f = ops.bn_relu_backward_fused(y_n, scale, shift, mean, rstd, dx_f, partial, info)
+    # unfused through the library
+    dx_u = ops.conv3x3_dgrad(dy2_n, wd)
+    dy_u, dg_u, db_u = ops.bn_relu_backward(y_n, scale, shift, mean, rstd, g=dx_u)
+    torch.cuda.synchronize()
+    assert torch.equal(dx_f, dx_u)                            # same tiles, same K order
+    assert rel_l2(dg_f, dg_u) < 1e-5 and rel_l2(db_f, db_u) < 1e-5     # summation order only
+    assert rel_l2(dy_f.float(), dy_u.float()) < 2e-3          # last bf16 bit where dgamma / dbeta differ
+    # torch: d(relu(bn(y))) with the upstream gradient the library's own data gradient produced
+    g_ref = ops.nchw(dx_u)
+    yv = y.clone().requires_grad_(True)
+    gv, bv = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    F.relu(F.batch_norm(yv, None, None, gv, bv, True, 0.1, 1e-5)).backward(g_ref)
+    print(f"\n[T0 fused BN-bwd reduce {unit}: {tuple(y.shape)}] dgamma {rel_l2(dg_f, gv.grad):.2e} cos "
+          f"{cosine(dg_f, gv.grad):.6f}  dbeta {rel_l2(db_f, bv.grad):.2e}  dY {rel_l2(ops.nchw(dy_f), yv.grad):.2e}")
+    assert rel_l2(dg_f, gv.grad) < GRAD_TOL and cosine(dg_f, gv.grad) >= COS_BAR
+    assert rel_l2(db_f, bv.grad) < GRAD_TOL and cosine(db_f, bv.grad) >= COS_BAR
+    assert rel_l2(ops.nchw(dy_f), yv.grad) < 6e-3
+
+
 @pytest.mark.parametrize("j", [1, 2, 3, 4])
 def test_conv_transpose_at_layer_geometry(ops, cap, j):
     """ConvTranspose2d(k=2, s=2) of up1..up4 (1024->512 at 24^2 ... 128->64 at 164^2): forward written

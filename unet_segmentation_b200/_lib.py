@@ -84,6 +84,9 @@ _SIGNATURES = {
     "ub_op_conv3x3_dgrad": (c_int, [_VP, _P, c_int, _P, _P]),
     "ub_op_upsample2x_forward": (c_int, [_VP, _P, _P]),
     "ub_op_upsample2x_backward": (c_int, [_VP, _P, _P]),
+    "ub_op_conv3x3_dgrad_bnred": (c_int, [_VP, _P, c_int, _P, _P, _P, _P, _P, _P, C.POINTER(c_int), _P]),
+    "ub_op_bn_relu_backward_fused": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _VP, _P,
+                                             C.POINTER(c_int), _P, _P, _P, _P]),
     "ub_op_wgrad_workspace_floats": (c_int64, [c_int, c_int, c_int64]),
     "ub_op_conv3x3_wgrad": (c_int, [_VP, _VP, _P, c_int, _P, c_int64, _P, _P]),
     "ub_op_convT_forward": (c_int, [_VP, _P, _P, c_int, _VP, _P]),

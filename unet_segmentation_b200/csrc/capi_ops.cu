@@ -140,6 +140,39 @@ int ub_op_conv3x3_dgrad(const ub_view* dy, const void* wd, int Ci, void* dx, voi
     return launch_igemm(to_view(dy), nullptr, -2, 0, 1, 9, 3, (const __nv_bfloat16*)wd, Ci, e,
                         nullptr, S(stream));
 }
+int ub_op_conv3x3_dgrad_bnred(const ub_view* dy, const void* wd, int Ci, void* dx, const void* y,
+                              const float* scale, const float* shift, const float* mean,
+                              float* partial, int* info, void* stream) {
+    UB_REQUIRE(dy && wd && dx && y && scale && shift && mean && partial && info,
+               "conv3x3_dgrad_bnred: null pointer");
+    IgemmEpilogue e;
+    memset(&e, 0, sizeof(e));
+    e.kind = EPI_STORE_BNRED; e.out = (__nv_bfloat16*)dx; e.ldo = Ci;
+    e.red_y = (const __nv_bfloat16*)y; e.scale = scale; e.shift = shift; e.red_mean = mean;
+    e.stats = partial;
+    IgemmLaunchInfo li;
+    memset(&li, 0, sizeof(li));
+    const int r = launch_igemm(to_view(dy), nullptr, -2, 0, 1, 9, 3, (const __nv_bfloat16*)wd, Ci, e,
+                               &li, S(stream));
+    if (r == 0) { info[0] = li.grid; info[1] = li.n_tiles; info[2] = li.BN; info[3] = li.M; }
+    return r;
+}
+int ub_op_bn_relu_backward_fused(const void* y, int N, int H, int W, int C, const float* scale,
+                                 const float* shift, const float* mean, const float* rstd,
+                                 const ub_view* g, float* partial, const int* info, float* dgamma,
+                                 float* dbeta, void* dy, void* stream) {
+    UB_REQUIRE(y && g && partial && info && dgamma && dbeta && dy, "bn_relu_backward_fused: null pointer");
+    BnBwdDesc d;
+    memset(&d, 0, sizeof(d));
+    d.y = (const __nv_bfloat16*)y; d.N = N; d.H = H; d.W = W; d.C = C;
+    d.scale = scale; d.shift = shift; d.mean = mean; d.rstd = rstd;
+    d.pool_skip = false; d.g = to_view(g);
+    d.partial = partial; d.dgamma = dgamma; d.dbeta = dbeta; d.dy = (__nv_bfloat16*)dy;
+    IgemmLaunchInfo li;
+    memset(&li, 0, sizeof(li));
+    li.grid = info[0]; li.n_tiles = info[1]; li.BN = info[2]; li.M = info[3];
+    return launch_bn_bwd(d, S(stream), &li);
+}
 int64_t ub_op_wgrad_workspace_floats(int rows, int cols, int64_t pixels) {
     return (int64_t)wgrad_ws_floats(rows, cols, pixels);
 }

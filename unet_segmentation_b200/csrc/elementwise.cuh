@@ -602,6 +602,31 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C,
     }
 }
 
+// Same, for partial rows written by a tensor-core epilogue (EPI_STORE_BNRED): stats[cta][2][BN], CTA b
+// covers channel tile (b % n_tiles) — the layout bn_finalize_kernel reads for the forward statistics.
+static __global__ void __launch_bounds__(1024)
+bn_bwd_finalize_tiled_kernel(const float* __restrict__ stats, int grid_ctas, int n_tiles, int BN, int C,
+                             const float* __restrict__ rstd, float* __restrict__ dgamma,
+                             float* __restrict__ dbeta) {
+    pdl_entry();
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double b = 0.0, g = 0.0;
+    if (c < C) {
+        const int tile = c / BN, col = c % BN;
+        const int rows = (grid_ctas - tile + n_tiles - 1) / n_tiles;
+        for (int r = threadIdx.y; r < rows; r += FIN_SLICES) {
+            const float* p = stats + (long long)(tile + r * n_tiles) * (2 * BN);
+            b += (double)p[col];
+            g += (double)p[BN + col];
+        }
+    }
+    finalize_combine(b, g);
+    if (threadIdx.y == 0 && c < C) {
+        dbeta[c] = (float)b;
+        dgamma[c] = (float)(g * (double)rstd[c]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Weight packing (fp32 torch layouts -> bf16 GEMM operands)
 // ---------------------------------------------------------------------------------------------

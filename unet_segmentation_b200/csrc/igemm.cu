@@ -112,6 +112,7 @@ static int launch_igemm_bn(int epi, const CUtensorMap& a0, const CUtensorMap& a1
     switch (epi) {
         case EPI_CONV_STATS: return launch_igemm_t<BN, EPI_CONV_STATS, CG>(a0, a1, b, p, grid, stream);
         case EPI_STORE: return launch_igemm_t<BN, EPI_STORE, CG>(a0, a1, b, p, grid, stream);
+        case EPI_STORE_BNRED: return launch_igemm_t<BN, EPI_STORE_BNRED, CG>(a0, a1, b, p, grid, stream);
         case EPI_AFFINE_RELU: return launch_igemm_t<BN, EPI_AFFINE_RELU, CG>(a0, a1, b, p, grid, stream);
         case EPI_CONVT: return launch_igemm_t<BN, EPI_CONVT, CG>(a0, a1, b, p, grid, stream);
         case EPI_AFFINE_RELU_HEAD:
@@ -160,6 +161,8 @@ static int launch_rowrun_bn(int epi, const CUtensorMap& a0, const CUtensorMap& a
         case EPI_CONV_STATS:
             return launch_rowrun_t<BN, EPI_CONV_STATS, CG, WRES, ROWS>(a0, a1, b, p, grid, stream);
         case EPI_STORE: return launch_rowrun_t<BN, EPI_STORE, CG, WRES, ROWS>(a0, a1, b, p, grid, stream);
+        case EPI_STORE_BNRED:
+            return launch_rowrun_t<BN, EPI_STORE_BNRED, CG, WRES, ROWS>(a0, a1, b, p, grid, stream);
         case EPI_AFFINE_RELU:
             return launch_rowrun_t<BN, EPI_AFFINE_RELU, CG, WRES, ROWS>(a0, a1, b, p, grid, stream);
         case EPI_AFFINE_RELU_HEAD:
@@ -195,6 +198,12 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
     if (!BN) {
         set_last_error("igemm: %d output columns is not a multiple of 64", ncols);
         return UB_ERR_UNSUPPORTED;
+    }
+    if (epi.kind == EPI_STORE_BNRED && (!epi.red_y || !epi.red_mean || !epi.scale || !epi.shift ||
+                                        !epi.stats || epi.ldo != ncols)) {
+        set_last_error("igemm: the fused BN-backward reduction needs y, mean, scale, shift, a partial "
+                       "buffer and a dense output (ldo == columns)");
+        return UB_ERR_ARG;
     }
     if (epi.kind == EPI_AFFINE_RELU_HEAD &&
         (ncols != 64 || epi.head_nc < 1 || epi.head_nc > HEAD_EPI_MAX_CLASSES || !epi.head_w ||
@@ -257,6 +266,7 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
         if (rr) { set_last_error("row-run: tensor map encoding failed: %d", rr); return UB_ERR_TMAP; }
         q.epi.M = (int)M; q.epi.out = epi.out; q.epi.ldo = epi.ldo; q.epi.bias = epi.bias;
         q.epi.scale = epi.scale; q.epi.shift = epi.shift; q.epi.stats = epi.stats;
+        q.epi.red_y = epi.red_y; q.epi.red_mean = epi.red_mean;
         q.epi.head_w = epi.head_w; q.epi.head_b = epi.head_b; q.epi.head_logits = epi.head_logits;
         q.epi.head_mask = epi.head_mask; q.epi.head_nc = epi.head_nc; q.epi.head_hw = Ho * Wo;
         static int fuse_pool = -1;
@@ -313,6 +323,7 @@ int launch_igemm(const View& src0, const View* src1, int lower, int upper, int t
     (void)K;
     p.out = epi.out; p.ldo = epi.ldo; p.bias = epi.bias; p.scale = epi.scale; p.shift = epi.shift;
     p.stats = epi.stats;
+    p.red_y = epi.red_y; p.red_mean = epi.red_mean;
     p.head_w = epi.head_w; p.head_b = epi.head_b; p.head_logits = epi.head_logits;
     p.head_mask = epi.head_mask; p.head_nc = epi.head_nc; p.head_hw = Ho * Wo;
     if (epi.kind == EPI_CONVT) {

@@ -18,8 +18,19 @@ namespace ub {
 // convolution and the z1 > z0 mask in the SAME epilogue — every epilogue thread holds one pixel's 64
 // activations, so the logits are 64 FMAs per class and the activation tensor is never written
 // (reference models/unet_model.py:56-63,145; scripts/predict.py:85-92).
+// EPI_STORE_BNRED (data gradients): EPI_STORE plus the REDUCE pass of the BatchNorm + ReLU backward of the
+// layer that receives this gradient (reference nn.BatchNorm2d / nn.ReLU backward, models/unet_model.py:
+// 12-13,16-17): the tile just computed IS the upstream gradient g of that layer, so the epilogue fetches
+// the layer's stored pre-BN output y at the same pixels, forms dyh = g * [y*scale + shift > 0] and
+// accumulates the per-channel sums  S1 = sum dyh,  S2 = sum dyh * (y - mean)  with the machinery of the
+// forward statistics (one deterministic partial row per CTA). The stand-alone reduce kernel — a full HBM
+// pass over (y, g), 4 B/element — is then skipped. g enters the sums as rounded to bf16, i.e. exactly
+// the value the apply pass reads back.
 enum : int { EPI_CONV_STATS = 0, EPI_STORE = 1, EPI_AFFINE_RELU = 2, EPI_CONVT = 3,
-             EPI_AFFINE_RELU_HEAD = 4 };
+             EPI_AFFINE_RELU_HEAD = 4, EPI_STORE_BNRED = 5 };
+template <int EPI> struct EpiTraits {
+    static constexpr bool SUMS = (EPI == EPI_CONV_STATS || EPI == EPI_STORE_BNRED);   // per-column sums
+};
 constexpr int HEAD_EPI_MAX_CLASSES = 8;
 
 struct IgemmParams {
@@ -35,7 +46,9 @@ struct IgemmParams {
     const float* bias;   // per GEMM column, may be null
     const float* scale;  // EPI_AFFINE_RELU: y = relu(acc*scale + shift)
     const float* shift;
-    float* stats;        // EPI_CONV_STATS: [gridDim.x][2][BN] per-CTA partial (sum, sumsq)
+    float* stats;        // EPI_CONV_STATS: [gridDim.x][2][BN] per-CTA partial (sum, sumsq); BNRED: (S1, S2)
+    const __nv_bfloat16* red_y;   // EPI_STORE_BNRED: pre-BN output of the receiving layer, [M][ldo]
+    const float* red_mean;        // EPI_STORE_BNRED: its batch mean per column (scale / shift above)
     // EPI_AFFINE_RELU_HEAD: head weights [nc][64] + bias [nc] (fp32), logits NCHW fp32, u8 mask
     const float* head_w;
     const float* head_b;
@@ -64,7 +77,7 @@ struct IgemmCfg {
     static constexpr int BAR_BYTES = 256;
     // epilogue scratch: BN-statistics rows of the 4 lane quadrants, or the fused head's weights
     static constexpr int STAT_BYTES = (BN == 64) ? 2304 : 4 * 2 * BN * 4;
-    static constexpr int CONST_BYTES = 2 * BN * 4;   // per-column epilogue constants of the n tile
+    static constexpr int CONST_BYTES = 3 * BN * 4;   // per-column epilogue constants of the n tile
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + CONST_BYTES + 1024;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
@@ -149,7 +162,8 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                                               float (&ssum)[EpiCfg<BN>::NCH],
                                               float (&ssq)[EpiCfg<BN>::NCH],
                                               StatRegs<BN, EPI>& sr, const float* cs,
-                                              const float* hs = nullptr) {
+                                              const float* hs = nullptr,
+                                              const uint4* ypre = nullptr) {
                 long long ct_row = 0;
                 if (EPI == EPI_CONVT) {
                     const int w = (int)(m % p.ct_W);
@@ -211,6 +225,11 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                             v[4 * i4 + 2] += a4.z; v[4 * i4 + 3] += a4.w;
                         }
                     }
+                    if (EPI == EPI_STORE_BNRED) {
+                        // g as it is stored (bf16), then dyh and dyh * (y - mean) from the prefetched y
+    #pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+                    }
                     if (valid && EPI != EPI_AFFINE_RELU_HEAD) {
                         __nv_bfloat16* dst;
                         if (EPI == EPI_CONVT) {
@@ -232,7 +251,29 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
                             d4[j] = o;
                         }
                     }
-                    if (EPI == EPI_CONV_STATS && StatRegs<BN, EPI>::ON) {
+                    if (EPI == EPI_STORE_BNRED) {
+                        float s2[32];
+    #pragma unroll
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 a4 = reinterpret_cast<const float4*>(cs + c * 32)[i4];
+                            const float4 b4 = reinterpret_cast<const float4*>(cs + BN + c * 32)[i4];
+                            const float4 m4 = reinterpret_cast<const float4*>(cs + 2 * BN + c * 32)[i4];
+                            const uint4 yr = ypre[cl * 4 + (i4 >> 1)];
+                            const uint32_t y01 = (i4 & 1) ? yr.z : yr.x, y23 = (i4 & 1) ? yr.w : yr.y;
+                            const float yv[4] = {bf16_lo(y01), bf16_hi(y01), bf16_lo(y23), bf16_hi(y23)};
+                            const float sc[4] = {a4.x, a4.y, a4.z, a4.w}, sh[4] = {b4.x, b4.y, b4.z, b4.w};
+                            const float mu[4] = {m4.x, m4.y, m4.z, m4.w};
+    #pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int i = 4 * i4 + e;
+                                const float dyh = (valid && fmaf(yv[e], sc[e], sh[e]) > 0.f) ? v[i] : 0.f;
+                                v[i] = dyh;
+                                s2[i] = dyh * (yv[e] - mu[e]);
+                            }
+                        }
+                        ssum[cl] += warp_column_sum(v, lane);
+                        ssq[cl] += warp_column_sum(s2, lane);
+                    } else if (EPI == EPI_CONV_STATS && StatRegs<BN, EPI>::ON) {
     #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const float x = valid ? v[i] : 0.f;
@@ -334,15 +375,33 @@ __device__ __forceinline__ void epilogue_tile_pool2(const IgemmParams& p, uint32
     }
 }
 
+// EPI_STORE_BNRED: fetch the y values of this thread's row (NCH chunks x 32 columns = NCH x 4 x 16 bytes)
+// BEFORE waiting for the accumulator, so that their HBM latency hides behind the tile's MMAs.
+template <int BN, int EPI>
+__device__ __forceinline__ void bnred_prefetch(const IgemmParams& p, long long m, bool valid, int n0,
+                                               int chalf, uint4 (&ypre)[EpiCfg<BN>::NCH * 4]) {
+    if constexpr (EPI == EPI_STORE_BNRED) {
+#pragma unroll
+        for (int cl = 0; cl < EpiCfg<BN>::NCH; ++cl) {
+            const int c = chalf * EpiCfg<BN>::NCH + cl;
+            const uint4* src = reinterpret_cast<const uint4*>(p.red_y + m * p.ldo + n0 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                ypre[cl * 4 + j] = valid ? __ldg(src + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
 // Per-column epilogue constants of n tile [n0, n0+BN) -> shared memory (broadcast LDS.128 reads
 // instead of 32-64 cached global loads per 32-column chunk and tile):
 //   cs[0..BN) = scale (AFFINE_RELU kinds) or bias (other kinds, 0 if absent), cs[BN..2BN) = shift.
 template <int BN, int EPI>
 __device__ __forceinline__ void stage_epilogue_consts(const IgemmParams& p, int n0, float* cs) {
     for (int i = threadIdx.x; i < BN; i += blockDim.x) {
-        if (EPI == EPI_AFFINE_RELU || EPI == EPI_AFFINE_RELU_HEAD) {
+        if (EPI == EPI_AFFINE_RELU || EPI == EPI_AFFINE_RELU_HEAD || EPI == EPI_STORE_BNRED) {
             cs[i] = p.scale[n0 + i];
             cs[BN + i] = p.shift[n0 + i];
+            if (EPI == EPI_STORE_BNRED) cs[2 * BN + i] = p.red_mean[n0 + i];
         } else {
             cs[i] = p.bias ? p.bias[n0 + i] : 0.f;
             cs[BN + i] = 0.f;
@@ -538,11 +597,13 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
         for (int mu = m_first; mu < m_units; mu += m_step) {
             const long long m = (long long)(mu * CG + (int)rank) * 128 + row_in_tile;
             const bool valid = m < p.M;
+            uint4 ypre[EPI == EPI_STORE_BNRED ? NCH * 4 : 1];
+            if constexpr (EPI == EPI_STORE_BNRED) bnred_prefetch<BN, EPI>(p, m, valid, n0, chalf, ypre);
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 
-            epilogue_tile<BN, EPI>(p, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, cs, hs);
+            epilogue_tile<BN, EPI>(p, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, cs, hs, ypre);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -552,7 +613,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
         finish_stat_regs<BN, EPI>(sr, lane, ssum, ssq);
-        if (EPI == EPI_CONV_STATS) {
+        if (EpiTraits<EPI>::SUMS) {
             // partial row of "virtual CTA" rank*nunits + unit: nunits % n_tiles == 0, so the channel
             // tile of a row is still (row index % n_tiles) for bn_finalize_kernel
             float* red = reinterpret_cast<float*>(gbase + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);

@@ -65,7 +65,7 @@ struct RowRunCfg {
     static constexpr int BAR_BYTES = 256;
     // epilogue scratch: BN-statistics rows of the 4 lane quadrants, or the fused head's weights
     static constexpr int STAT_BYTES = (BN == 64) ? 2304 : 4 * 2 * BN * 4;
-    static constexpr int CONST_BYTES = 2 * BN * 4;   // per-column epilogue constants of the n tile
+    static constexpr int CONST_BYTES = 3 * BN * 4;   // per-column epilogue constants of the n tile
     static constexpr int SMEM_BYTES = SA * A_STAGE + B_AREA + BAR_BYTES + STAT_BYTES + CONST_BYTES + 1024;
     static_assert(!WRES || BN == 64, "resident weights: BN = 64 (one 64-channel chunk)");
     static_assert(ROWS == 1 || (ROWS == 2 && BN <= 128), "two-row tiles: 2 x 2 x BN TMEM columns");
@@ -287,6 +287,13 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             const int pr = (t % p.HoT) * ROWS;
             const int n = t / p.HoT;
             const int q = qt * 128 + row_in_tile;
+            uint4 ypre[EPI == EPI_STORE_BNRED ? ROWS : 1][EPI == EPI_STORE_BNRED ? NCH * 4 : 1];
+            if constexpr (EPI == EPI_STORE_BNRED) {
+#pragma unroll
+                for (int j = 0; j < ROWS; ++j)
+                    bnred_prefetch<BN, EPI>(p.epi, ((long long)n * p.Ho + pr + j) * p.Wo + q,
+                                            q < p.Wo && mt < p.m_tiles && pr + j < p.Ho, n0, chalf, ypre[j]);
+            }
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
             if (ROWS == 2 && EPI == EPI_AFFINE_RELU && p.epi.pooled != nullptr) {
@@ -301,7 +308,8 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
                 const long long m = ((long long)n * p.Ho + pr + j) * p.Wo + q;
                 const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) +
                                       (uint32_t)((as * ROWS + j) * BN);
-                epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, cs, hs);
+                epilogue_tile<BN, EPI>(p.epi, trow, m, valid, n0, lane, chalf, ssum, ssq, sr, cs, hs,
+                                       ypre[EPI == EPI_STORE_BNRED ? j : 0]);
             }
             tc_fence_before();
             __syncwarp();
@@ -312,7 +320,7 @@ igemm_rowrun_kernel(const __grid_constant__ CUtensorMap mapA0,
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
         finish_stat_regs<BN, EPI>(sr, lane, ssum, ssq);
-        if (EPI == EPI_CONV_STATS) {
+        if (EpiTraits<EPI>::SUMS) {
             float* red = reinterpret_cast<float*>(gbase + Cfg::SA * Cfg::A_STAGE + Cfg::B_AREA +
                                                   Cfg::BAR_BYTES);
             write_cta_stats<BN>(red, p.epi.stats + (long long)((int)rank * nunits + unit) * (2 * BN),

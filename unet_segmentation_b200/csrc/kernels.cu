@@ -135,7 +135,7 @@ int launch_maxpool2(const __nv_bfloat16* a, __nv_bfloat16* pooled, int N, int H,
 
 size_t bn_bwd_partial_floats(int C) { return (size_t)num_sms() * 4 * 2 * C; }
 
-int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
+int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s, const IgemmLaunchInfo* fused) {
     UB_TRY(check_cg(d.C, "bn_bwd"));
     if ((long long)d.N * d.H * d.W * (d.C / 8) >= 0x7FFFFFFFLL) {
         set_last_error("bn_bwd: tensor too large for 32-bit indexing");
@@ -158,12 +158,19 @@ int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s) {
                                 : count * (d.C / 8);
     // one wave of resident CTAs (launch bounds: 3 per SM for the direct variant, 2 for the pooled one)
     const int blocks = red_blocks(items, d.pool_skip ? 2 : 3);
-    if (pix) UB_LAUNCH_NC((bn_bwd_kernel<true, false, true>), blocks, 256, 0, s, A);
-    else if (d.pool_skip) UB_LAUNCH_NC((bn_bwd_kernel<true, false>), blocks, 256, 0, s, A);
-    else UB_LAUNCH_NC((bn_bwd_kernel<false, false>), blocks, 256, 0, s, A);
-    UB_POST_LAUNCH();
-    UB_LAUNCH_NC(bn_bwd_finalize_kernel, (d.C + 31) / 32, dim3(32, FIN_SLICES), 0, s, d.partial, blocks, d.C, d.rstd, d.dgamma, d.dbeta);
-    UB_POST_LAUNCH();
+    if (fused) {
+        // reduce pass done by the producer of the upstream gradient (EPI_STORE_BNRED epilogue)
+        if (d.pool_skip) { set_last_error("bn_bwd: a fused reduction needs a direct upstream gradient"); return UB_ERR_ARG; }
+        UB_LAUNCH_NC(bn_bwd_finalize_tiled_kernel, (d.C + 31) / 32, dim3(32, FIN_SLICES), 0, s, d.partial, fused->grid, fused->n_tiles, fused->BN, d.C, d.rstd, d.dgamma, d.dbeta);
+        UB_POST_LAUNCH();
+    } else {
+        if (pix) UB_LAUNCH_NC((bn_bwd_kernel<true, false, true>), blocks, 256, 0, s, A);
+        else if (d.pool_skip) UB_LAUNCH_NC((bn_bwd_kernel<true, false>), blocks, 256, 0, s, A);
+        else UB_LAUNCH_NC((bn_bwd_kernel<false, false>), blocks, 256, 0, s, A);
+        UB_POST_LAUNCH();
+        UB_LAUNCH_NC(bn_bwd_finalize_kernel, (d.C + 31) / 32, dim3(32, FIN_SLICES), 0, s, d.partial, blocks, d.C, d.rstd, d.dgamma, d.dbeta);
+        UB_POST_LAUNCH();
+    }
     const int ablocks = ew_blocks(items);
     if (pix) UB_LAUNCH_NC((bn_bwd_kernel<true, true, true>), ablocks, 256, 0, s, A);
     else if (d.pool_skip) UB_LAUNCH_NC((bn_bwd_kernel<true, true>), ablocks, 256, 0, s, A);

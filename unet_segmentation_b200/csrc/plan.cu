@@ -91,6 +91,11 @@ struct ub_plan {
     // maps) is captured into a CUDA graph the second time ub_plan_forward sees the same (x, logits,
     // mask) pointers and parameter binding, and replayed afterwards: per-frame prediction
     // (scripts/predict.py:73-112) is otherwise bound by host launch work, not by the GPU.
+    // BN-backward reduce pass fused into the epilogue of the data-gradient kernel that produces the
+    // upstream gradient (EPI_STORE_BNRED): layout of the partial rows left in `scratch` by the transposed
+    // conv's data gradient at the end of a decoder stage, consumed by the first BN backward of the next
+    bool dx_fused = false;
+    IgemmLaunchInfo dx_info{};
     cudaGraphExec_t fwd_graph = nullptr;
     cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's may be the legacy stream)
     const float* g_x = nullptr;
@@ -723,7 +728,24 @@ static void wgrad_join(ub_plan* P, cudaStream_t s) {
     P->side_used = false;
 }
 
+// The fused reduction makes the data-gradient epilogue ~5x longer (y prefetch, mask, two column sums per
+// 32-column chunk). It is free only where a tile's MMAs outlast it, i.e. for long K: measured on the
+// N = 16 step, fusing EVERY eligible layer moved 0.48 ms out of the BN-backward class but added 0.80 ms
+// to the data gradients (the 128 / 64-column two-row tiles of the shallow layers become epilogue-bound),
+// so a layer is fused only from UB_BNRED_MINKB k-blocks of 64 per tile on (UB_FUSE_BNRED=0: never).
+static int bnred_min_kblocks() {
+    static const int v = [] {
+        const char* off = getenv("UB_FUSE_BNRED");
+        if (off && off[0] == '0') return 1 << 30;
+        const char* e = getenv("UB_BNRED_MINKB");
+        return e ? atoi(e) : 36;
+    }();
+    return v;
+}
+static bool fuse_bnred(int kblocks) { return kblocks >= bnred_min_kblocks(); }
+
 struct Upstream {
+    const IgemmLaunchInfo* fused = nullptr;   // reduce pass of the block's second unit already done
     bool pool_skip = false;
     View g{}, gp{}, gs{};
     int crop_h = 0, crop_w = 0;
@@ -748,8 +770,8 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
     const double po1 = (double)N * u1.Ho() * u1.Wo(), pi1 = (double)N * u1.Hin * u1.Win;
     const double fl1 = 2.0 * po1 * u1.Co * 9.0 * u1.Ci;
     {
-        ProfScope ps(P, CLS_BN_BWD, 0, po1 * u1.Co * 10.0, s);
-        UB_TRY(launch_bn_bwd(d, s));
+        ProfScope ps(P, CLS_BN_BWD, 0, po1 * u1.Co * (up.fused ? 6.0 : 10.0), s);
+        UB_TRY(launch_bn_bwd(d, s, up.fused));
     }
     View a0 = make_view(u0.a, N, u0.Ho(), u0.Wo(), u0.Co);
     {
@@ -760,13 +782,22 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
                             P->wgrad_ws_floats, grads[u1.p_w], ws, grads[u1.p_b], u1.Co,
                             grads[u0.p_b], u0.Co));
     }
+    // The data gradient of the second unit IS the upstream gradient of the first unit's BN + ReLU: its
+    // epilogue also does that layer's reduce pass (sum dyh, sum dyh (y - mean)) from the stored y.
+    const bool fuse0 = !u0.first && fuse_bnred(9 * u1.Co / 64);
+    IgemmLaunchInfo info0{};
     {
         IgemmEpilogue e;
         memset(&e, 0, sizeof(e));
         e.kind = EPI_STORE; e.out = b.da0; e.ldo = u1.Ci;
+        if (fuse0) {
+            e.kind = EPI_STORE_BNRED;
+            e.red_y = u0.y; e.scale = u0.scale; e.shift = u0.shift; e.red_mean = u0.mean;
+            e.stats = P->scratch;
+        }
         View dyv = make_view(u1.dy, N, u1.Ho(), u1.Wo(), u1.Co);
-        ProfScope ps(P, CLS_DGRAD, fl1, gemm_bytes(po1, u1.Co, u1.Ci, 9, pi1), s);
-        UB_TRY(launch_igemm(dyv, nullptr, -2, 0, 1, 9, 3, u1.wd, u1.Ci, e, nullptr, s));
+        ProfScope ps(P, CLS_DGRAD, fl1, gemm_bytes(po1, u1.Co, u1.Ci, 9, pi1) + (fuse0 ? 2.0 * pi1 * u1.Ci : 0.0), s);
+        UB_TRY(launch_igemm(dyv, nullptr, -2, 0, 1, 9, 3, u1.wd, u1.Ci, e, &info0, s));
     }
     // ---- first conv unit ----
     View g0 = make_view(b.da0, N, u0.Ho(), u0.Wo(), u0.Co);
@@ -788,8 +819,8 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
     const double po0 = (double)N * u0.Ho() * u0.Wo(), pi0 = (double)N * u0.Hin * u0.Win;
     const double fl0 = 2.0 * po0 * u0.Co * 9.0 * u0.Ci;
     {
-        ProfScope ps(P, CLS_BN_BWD, 0, po0 * u0.Co * 10.0, s);
-        UB_TRY(launch_bn_bwd(d, s));
+        ProfScope ps(P, CLS_BN_BWD, 0, po0 * u0.Co * (fuse0 ? 6.0 : 10.0), s);
+        UB_TRY(launch_bn_bwd(d, s, fuse0 ? &info0 : nullptr));
     }
     {
         cudaStream_t ws = wgrad_stream(P, s);
@@ -838,7 +869,9 @@ static int backward_stage_impl(ub_plan* P, int stage, const float* dlogits, floa
         } else {
             const UpT& nt = P->ups[j + 1];
             up.g = make_view(nt.dx, N, nt.Hin, nt.Win, nt.Ci);
+            if (P->dx_fused) up.fused = &P->dx_info;    // left by the previous stage's transposed conv
         }
+        P->dx_fused = false;
         UB_TRY(block_backward(P, b, up, grads, s));
         // transposed conv: the second channel range of d(concat) is d(up)
         const int cs = b.u[0].Ci - t.Co;  // skip channels
@@ -850,15 +883,24 @@ static int backward_stage_impl(ub_plan* P, int stage, const float* dlogits, floa
             ProfScope ps(P, CLS_CT_DGRAD, 0, 2.0 * m * 5, s);
             return launch_upsample2x_bwd(dup, t.dx, s);
         }
+        const ConvUnit& prev = j == 0 ? P->enc[L - 1].u[1] : P->dec[j - 1].u[1];
         IgemmEpilogue e;
         memset(&e, 0, sizeof(e));
         e.kind = EPI_STORE; e.out = t.dx; e.ldo = t.Ci;
+        const bool fuse_dx = fuse_bnred(4 * t.Co / 64);
+        if (fuse_dx) {
+            // t.dx is the upstream gradient of the previous block's second BN + ReLU (no pool, no skip
+            // in between): reduce pass in this epilogue, consumed by the next backward stage
+            e.kind = EPI_STORE_BNRED;
+            e.red_y = prev.y; e.scale = prev.scale; e.shift = prev.shift; e.red_mean = prev.mean;
+            e.stats = P->scratch;
+        }
         const double mt = (double)N * t.Hin * t.Win, flt = 2.0 * mt * 4 * t.Co * t.Ci;
         {
             ProfScope ps(P, CLS_CT_DGRAD, flt, gemm_bytes(mt, 4.0 * t.Co, t.Ci, 1, mt), s);
-            UB_TRY(launch_igemm(dup, nullptr, 0, -1, 2, 4, 2, t.wb, t.Ci, e, nullptr, s));
+            UB_TRY(launch_igemm(dup, nullptr, 0, -1, 2, 4, 2, t.wb, t.Ci, e, &P->dx_info, s));
         }
-        const ConvUnit& prev = j == 0 ? P->enc[L - 1].u[1] : P->dec[j - 1].u[1];
+        P->dx_fused = fuse_dx;
         cudaStream_t ws = wgrad_stream(P, s);   // after the data gradient that produced d(concat)
         ProfScope ps(P, CLS_CT_WGRAD, flt, 2.0 * mt * (4.0 * t.Co + t.Ci) + 16.0 * t.Co * t.Ci, ws);
         // the transposed-conv bias is removed by the following BatchNorm: zero gradient
@@ -871,6 +913,8 @@ static int backward_stage_impl(ub_plan* P, int stage, const float* dlogits, floa
     if (i == L - 1) {
         const UpT& t0 = P->ups[0];
         up.g = make_view(t0.dx, N, t0.Hin, t0.Win, t0.Ci);
+        if (P->dx_fused) up.fused = &P->dx_info;
+        P->dx_fused = false;
     } else {
         const Block& nx = P->enc[i + 1];
         const int j = L - 2 - i;

@@ -93,6 +93,12 @@ struct IgemmEpilogue {
     float* head_logits;
     unsigned char* head_mask;
     int head_nc;
+    // EPI_STORE_BNRED (data gradients): pre-BN output `red_y` ([M][ldo], the geometry of `out`) and batch
+    // mean of the layer that receives this gradient; its scale / shift go in `scale` / `shift`, the
+    // per-CTA partial sums (S1 = sum dyh, S2 = sum dyh (y - mean)) land in `stats` with the layout of the
+    // forward statistics (IgemmLaunchInfo describes it; launch_bn_bwd(..., fused) consumes it).
+    const __nv_bfloat16* red_y;
+    const float* red_mean;
     // EPI_AFFINE_RELU: optional [N][Ho/2][Wo/2][ldo] destination of a fused 2x2 floor max-pool. The
     // launcher fuses it where the kernel selected for the shape can (two-row row-run tiles) and says so
     // in IgemmLaunchInfo::pool_fused; otherwise the caller runs launch_maxpool2.
@@ -161,7 +167,10 @@ struct BnBwdDesc {
     __nv_bfloat16* dy;     // out [N,H,W,C]
 };
 size_t bn_bwd_partial_floats(int C);
-int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s);
+// `fused` (optional): the reduce pass already happened in the epilogue of the kernel that produced the
+// upstream gradient (EPI_STORE_BNRED); its partial rows are in d.partial with the layout `fused`
+// describes. Only the finalisation and the apply pass are launched then.
+int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s, const IgemmLaunchInfo* fused = nullptr);
 
 struct FirstConvDesc {
     const float* x;

@@ -157,6 +157,32 @@ def conv3x3_dgrad(dy, wd):
     return dx
 
 
+def conv3x3_dgrad_bnred(dy, wd, y, scale, shift, mean):
+    """Data gradient with the BN + ReLU backward REDUCE pass of the receiving layer fused into its
+    epilogue. Returns (dx, partial, info) — feed the latter two to ``bn_relu_backward_fused``."""
+    lib = _lib.load()
+    n, h, w, _ = dy.shape
+    ci = wd.shape[1]
+    dx = torch.empty(n, h + 2, w + 2, ci, dtype=torch.bfloat16, device=dy.device)
+    partial = torch.zeros(int(lib.ub_op_conv_stats_floats(ci)), dtype=torch.float32, device=dy.device)
+    info = (C.c_int * 4)()
+    check(lib.ub_op_conv3x3_dgrad_bnred(_vp(dy), _p(wd), ci, _p(dx), _p(y), _p(scale), _p(shift),
+                                        _p(mean), _p(partial), info, _stream()), "conv3x3_dgrad_bnred")
+    return dx, partial, info
+
+
+def bn_relu_backward_fused(y, scale, shift, mean, rstd, g, partial, info):
+    lib = _lib.load()
+    n, h, w, c = y.shape
+    dgamma = torch.empty(c, dtype=torch.float32, device=y.device)
+    dbeta = torch.empty_like(dgamma)
+    dy = torch.empty_like(y)
+    check(lib.ub_op_bn_relu_backward_fused(_p(y), n, h, w, c, _p(scale), _p(shift), _p(mean), _p(rstd),
+                                           _vp(g), _p(partial), info, _p(dgamma), _p(dbeta), _p(dy),
+                                           _stream()), "bn_relu_backward_fused")
+    return dy, dgamma, dbeta
+
+
 def conv3x3_wgrad(src0, src1, dy):
     lib = _lib.load()
     n, h, w, c0 = src0.shape
