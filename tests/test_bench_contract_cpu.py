@@ -78,3 +78,20 @@ def test_reference_loader_runs_the_unmodified_reference_files():
     sd = unet_ref.make_state_dict(1, 2, seed=0)
     assert all(torch.equal(sd[k], v) for k, v in m.state_dict().items())
     del mod
+
+
+def test_forward_flop_model_matches_the_survey_figures():
+    """bench.forward_flops (layer-by-layer FLOPs of one eval forward, the `executed_tflops` of the
+    inference block) against SURVEY §8d: 223.86 GFLOP per 512^2 image, 2.04 MFLOP per output pixel for
+    572 -> 388 tiles at stride 384, 1 359.1 GFLOP per 1084-tile; wide net: 4 745.7 GFLOP at 1024^2."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert abs(bench.forward_flops(512) / 1e9 - 223.860) < 0.01
+    assert abs(bench.forward_flops(572) / 384 ** 2 / 1e6 - 2.04) < 0.005
+    assert abs(bench.forward_flops(1084) / 1e9 - 1359.1) < 0.1
+    assert abs(bench.forward_flops(1024, base=128) / 1e9 - 4745.7) < 0.5
+    # training step = 3 x forward minus the first layer's data gradient (2 * 510^2 * 64 * 9 FLOP), SURVEY §8d
+    assert abs(3 * bench.forward_flops(512) - 2.0 * 510 ** 2 * 64 * 9 - bench.FLOP_PER_IMG_STEP) < 1e-4 * bench.FLOP_PER_IMG_STEP
