@@ -238,6 +238,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-infer", action="store_true")
+    ap.add_argument("--grad-wire", default=os.environ.get("UB_GRAD_WIRE", "fp32"), choices=["fp32", "bf16"],
+                    help="payload dtype of the data-parallel gradient all-reduce")
     ap.add_argument("--no-wide", action="store_true", help="skip the BASELINE configs[4] wide-U-Net step")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused = unet_segmentation_b200.optim.FusedSGD, torch = torch.optim.SGD")
@@ -277,7 +279,8 @@ def main():
     model.load_state_dict(unet_ref.make_state_dict(1, 2, seed=0))   # reference ctor + init_weights
     model = model.to(dev).train()
     parallel.broadcast_parameters(model)
-    reducer = parallel.StageGradAllReducer(model) if world > 1 else None
+    wire = {"fp32": None, "bf16": torch.bfloat16}[args.grad_wire]
+    reducer = parallel.StageGradAllReducer(model, wire_dtype=wire) if world > 1 else None
     criterion = WeightedCrossEntropyLoss()
     if args.optimizer == "fused":     # same update rule as scripts/train.py:97, one fused kernel
         from unet_segmentation_b200.optim import FusedSGD
@@ -525,7 +528,7 @@ def main():
             wide_model.load_state_dict(unet_ref.make_state_dict(1, 2, seed=0, base=128))
             wide_model = wide_model.to(dev).train()
             parallel.broadcast_parameters(wide_model)
-            wide_red = parallel.StageGradAllReducer(wide_model) if world > 1 else None
+            wide_red = parallel.StageGradAllReducer(wide_model, wire_dtype=wire) if world > 1 else None
             from unet_segmentation_b200.optim import FusedSGD as _FSGD
 
             wopt = _FSGD(wide_model, lr=1e-4, momentum=0.99)
@@ -751,7 +754,8 @@ def main():
                        "optimizer": ("SGD(lr=1e-4, momentum=0.99), FusedSGD (update + bf16 operand "
                                      "refresh in one kernel), inside the step" if args.optimizer == "fused"
                                      else "SGD(lr=1e-4, momentum=0.99) torch foreach, inside the step"),
-                       "bn": "per-rank batch statistics", "l2": "per-step working set 11 GB >> 126 MB L2",
+                       "bn": "per-rank batch statistics",
+                       "grad_allreduce": (f"9 per-stage NCCL all-reduces, {args.grad_wire} payload" if world > 1 else None), "l2": "per-step working set 11 GB >> 126 MB L2",
                        "streams": "weight gradients on an internal side stream, overlapping the "
                                   "BN-backward / data-gradient chain (kernel_breakdown is measured "
                                   "with that overlap off)",

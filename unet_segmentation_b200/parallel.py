@@ -56,8 +56,14 @@ class StageGradAllReducer:
     tensors (synchronous; used by the CPU tests of the host logic).
     """
 
-    def __init__(self, model: Optional[torch.nn.Module] = None, group=None):
+    def __init__(self, model: Optional[torch.nn.Module] = None, group=None,
+                 wire_dtype: Optional[torch.dtype] = None):
+        """``wire_dtype=torch.bfloat16`` sends the gradients over NVLink as bf16 (62 MB instead of
+        124 MB per step for the reference net): the collective kernels, which share the SMs with the
+        backward pass, run half as long. The averaged gradient is rounded to bf16 once more than with
+        the default fp32 payload (masters, momentum and the update stay fp32)."""
         self.group = group
+        self.wire_dtype = wire_dtype
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.comm_stream = None
         self.n_collectives = 0
@@ -88,7 +94,12 @@ class StageGradAllReducer:
                 if plan is not None:
                     plan.join_side(self.comm_stream)
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(flat_grads, op=dist.ReduceOp.AVG, group=self.group)
+                if self.wire_dtype is not None and self.wire_dtype != flat_grads.dtype:
+                    wire = flat_grads.to(self.wire_dtype)
+                    dist.all_reduce(wire, op=dist.ReduceOp.AVG, group=self.group)
+                    flat_grads.copy_(wire)
+                else:
+                    dist.all_reduce(flat_grads, op=dist.ReduceOp.AVG, group=self.group)
             flat_grads.record_stream(self.comm_stream)
         else:
             dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=self.group)
