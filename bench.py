@@ -240,6 +240,9 @@ def main():
     ap.add_argument("--no-infer", action="store_true")
     ap.add_argument("--grad-wire", default=os.environ.get("UB_GRAD_WIRE", "fp32"), choices=["fp32", "bf16"],
                     help="payload dtype of the data-parallel gradient all-reduce")
+    ap.add_argument("--stream-priority", type=int, default=None,
+                    help="run on a non-default torch stream of this priority (-1 = above the library's "
+                         "weight-gradient side stream) instead of the default stream")
     ap.add_argument("--no-wide", action="store_true", help="skip the BASELINE configs[4] wide-U-Net step")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused = unet_segmentation_b200.optim.FusedSGD, torch = torch.optim.SGD")
@@ -261,6 +264,8 @@ def main():
                          "(use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.stream_priority is not None:
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=args.stream_priority))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)

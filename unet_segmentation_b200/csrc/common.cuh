@@ -371,4 +371,28 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two IEEE fp32 operations, each lane
+// rounded exactly like fmaf / + on its own. A plain FFMA with three register operands issues every
+// second cycle per scheduler; the CUDA-core kernels whose inner loop is a 9-tap fp32 convolution
+// (first_conv.cuh) are bound by that, not by HBM. ptxas folds a {s, s} pair into the broadcast
+// operand form (`R.F32`), so a scalar multiplicand costs no extra move.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)),
+          "l"(*reinterpret_cast<const uint64_t*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 ffma2(float s, float2 b, float2 c) {
+    return ffma2(make_float2(s, s), b, c);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
 }  // namespace ub

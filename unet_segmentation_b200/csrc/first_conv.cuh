@@ -369,16 +369,19 @@ fc1_apply_kernel(const FirstConvArgs A) {
     const unsigned cg = threadIdx.x % CG;
     const unsigned Ho = A.H - 2, Wo = A.W - 2, W = A.W;
     const unsigned GW = (Wo + PX - 1) / PX;
-    float wr[9][8], sc[8], shb[8];
+    // channel pairs (2k, 2k+1) packed for FFMA2: same per-lane fmaf order as the scalar form
+    float2 wr[9][4], sc[4], shb[4];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) wr[tap][k] = A.w[(cg * 8 + k) * 9 + tap];
+        for (int k = 0; k < 4; ++k)
+            wr[tap][k] = make_float2(A.w[(cg * 8 + 2 * k) * 9 + tap], A.w[(cg * 8 + 2 * k + 1) * 9 + tap]);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = cg * 8 + k;
-        sc[k] = A.scale[c];
-        shb[k] = fmaf(A.bias ? A.bias[c] : 0.f, sc[k], A.shift[c]);
+    for (int k = 0; k < 4; ++k) {
+        const int c = cg * 8 + 2 * k;
+        sc[k] = make_float2(A.scale[c], A.scale[c + 1]);
+        shb[k] = make_float2(fmaf(A.bias ? A.bias[c] : 0.f, sc[k].x, A.shift[c]),
+                             fmaf(A.bias ? A.bias[c + 1] : 0.f, sc[k].y, A.shift[c + 1]));
     }
     const unsigned ngroups = (unsigned)A.N * Ho * GW;
     const unsigned gstride = gridDim.x * 256u / CG;
@@ -391,19 +394,23 @@ fc1_apply_kernel(const FirstConvArgs A) {
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
             if (wq0 + j < Wo) {
-                float y[8];
+                float2 y[4];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) y[k] = 0.f;
+                for (int k = 0; k < 4; ++k) y[k] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const float xv = xp[tap / 3][j + tap % 3];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) y[k] = fmaf(xv, wr[tap][k], y[k]);
+                    for (int k = 0; k < 4; ++k) y[k] = ffma2(xv, wr[tap][k], y[k]);
                 }
-                Vec8 o;
+                uint4 o;
+                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(fmaf(y[k], sc[k], shb[k]), 0.f);
-                *reinterpret_cast<uint4*>(A.a + (pq0 + j) * Co + cg * 8) = pack8(o);
+                for (int k = 0; k < 4; ++k) {
+                    const float2 v = ffma2(y[k], sc[k], shb[k]);
+                    ow[k] = pack_bf16x2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+                }
+                *reinterpret_cast<uint4*>(A.a + (pq0 + j) * Co + cg * 8) = o;
             }
         }
     }
@@ -419,12 +426,12 @@ fc1_bwd_kernel(const FirstConvArgs A, const double* __restrict__ cov) {
     const unsigned Ho = A.H - 2, Wo = A.W - 2, W = A.W;
     const unsigned GW = (Wo + PX - 1) / PX;
     const float c0 = (float)cov[0];
-    float G[9][8], db[8];
+    float2 G[9][4], db[4];   // channel pairs (2k, 2k+1): FFMA2 / FADD2, per-lane order as scalar
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        db[k] = 0.f;
+    for (int k = 0; k < 4; ++k) {
+        db[k] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int t = 0; t < 9; ++t) G[t][k] = 0.f;
+        for (int t = 0; t < 9; ++t) G[t][k] = make_float2(0.f, 0.f);
     }
     const unsigned ngroups = (unsigned)A.N * Ho * GW;
     const unsigned gstride = gridDim.x * 256u / CG;
@@ -446,15 +453,18 @@ fc1_bwd_kernel(const FirstConvArgs A, const double* __restrict__ cov) {
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
             if (wq0 + j < Wo) {
-                const Vec8 gv = unpack8(graw[j]);
-                const Vec8 av = unpack8(araw[j]);
+                const uint32_t* gw32 = reinterpret_cast<const uint32_t*>(&graw[j]);
+                const uint32_t* aw32 = reinterpret_cast<const uint32_t*>(&araw[j]);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float m = av.v[k] > 0.f ? gv.v[k] : 0.f;
-                    db[k] += m;
+                for (int k = 0; k < 4; ++k) {
+                    // a is a ReLU output (>= 0, never -0 or NaN from finite inputs): "> 0" on the
+                    // bf16 bit pattern of each half
+                    const float2 m = make_float2(bf16_lo(aw32[k]) > 0.f ? bf16_lo(gw32[k]) : 0.f,
+                                                 bf16_hi(aw32[k]) > 0.f ? bf16_hi(gw32[k]) : 0.f);
+                    db[k] = fadd2(db[k], m);
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap)
-                        G[tap][k] = fmaf(m, xp[tap / 3][j + tap % 3], G[tap][k]);
+                        G[tap][k] = ffma2(xp[tap / 3][j + tap % 3], m, G[tap][k]);
                 }
             }
         }
@@ -464,8 +474,9 @@ fc1_bwd_kernel(const FirstConvArgs A, const double* __restrict__ cov) {
     for (int k = 0; k < 8; ++k) {
         __syncthreads();
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) red[threadIdx.x * 10 + tap] = G[tap][k];
-        red[threadIdx.x * 10 + 9] = db[k];
+        for (int tap = 0; tap < 9; ++tap)
+            red[threadIdx.x * 10 + tap] = (k & 1) ? G[tap][k >> 1].y : G[tap][k >> 1].x;
+        red[threadIdx.x * 10 + 9] = (k & 1) ? db[k >> 1].y : db[k >> 1].x;
         __syncthreads();
         for (int j = threadIdx.x; j < CG * 10; j += blockDim.x) {
             const int g2 = j / 10, e = j % 10;

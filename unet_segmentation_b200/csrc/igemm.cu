@@ -365,13 +365,17 @@ static int wgrad_splits(int rows, int cols, long long mpix) {
     const int kpix = bn == 256 ? 64 : 128;
     const long long kblocks = (mpix + kpix - 1) / kpix;
     const long long smax = kblocks / 8 > 1 ? kblocks / 8 : 1;
+    // UB_WGRAD_MAXKB=n: at most n k-blocks per CTA (short-lived CTAs release their SM sooner to the
+    // data-gradient kernel they overlap with); 0 = only the wave rule below
+    static const int maxkb = [] { const char* e = getenv("UB_WGRAD_MAXKB"); return e ? atoi(e) : 0; }();
+    const long long smin = maxkb > 0 ? (kblocks + maxkb - 1) / maxkb : 1;
     // Pick the split count that minimises (number of CTA waves) x (k-blocks per CTA + fixed cost):
     // avoids e.g. 300 CTAs on 148 SMs (a third, nearly empty, wave).
     const double fixed = 24.0;  // prologue + fp32 epilogue of one CTA, in k-block units
     const int slots = num_sms() / cg;   // CTAs (or CTA pairs) resident at once
     long long best = 1;
     double best_cost = 1e30;
-    for (long long s = 1; s <= smax && s <= 256; ++s) {
+    for (long long s = smin < smax ? smin : smax; s <= smax && s <= 1024; ++s) {
         const long long ctas = (long long)units * s;
         const long long waves = (ctas + slots - 1) / slots;
         const double cost = (double)waves * ((double)((kblocks + s - 1) / s) + fixed);

@@ -171,7 +171,9 @@ int launch_bn_bwd(const BnBwdDesc& d, cudaStream_t s, const IgemmLaunchInfo* fus
         UB_LAUNCH_NC(bn_bwd_finalize_kernel, (d.C + 31) / 32, dim3(32, FIN_SLICES), 0, s, d.partial, blocks, d.C, d.rstd, d.dgamma, d.dbeta);
         UB_POST_LAUNCH();
     }
-    const int ablocks = ew_blocks(items);
+    // UB_BNBWD_APPLY_CTAS=n: CTAs per SM of the apply pass (default 8 = several waves)
+    static const int apply_ctas = [] { const char* e = getenv("UB_BNBWD_APPLY_CTAS"); return e ? atoi(e) : 8; }();
+    const int ablocks = ew_blocks(items, apply_ctas);
     if (pix) UB_LAUNCH_NC((bn_bwd_kernel<true, true, true>), ablocks, 256, 0, s, A);
     else if (d.pool_skip) UB_LAUNCH_NC((bn_bwd_kernel<true, true>), ablocks, 256, 0, s, A);
     else UB_LAUNCH_NC((bn_bwd_kernel<false, true>), ablocks, 256, 0, s, A);

@@ -143,11 +143,11 @@ struct ub_plan {
 };
 
 enum : int { CLS_FPROP = 0, CLS_DGRAD, CLS_WGRAD, CLS_CT_FPROP, CLS_CT_DGRAD, CLS_CT_WGRAD,
-             CLS_BN_APPLY, CLS_BN_BWD, CLS_FIRST, CLS_HEAD, CLS_COUNT };
+             CLS_BN_APPLY, CLS_BN_BWD, CLS_FIRST, CLS_HEAD, CLS_SGD, CLS_COUNT };
 
 static const char* const kClassNames[CLS_COUNT] = {
     "conv3x3_fprop", "conv3x3_dgrad", "conv3x3_wgrad", "convT_fprop", "convT_dgrad", "convT_wgrad",
-    "bn_apply_relu_pool", "bn_relu_backward", "first_conv_fp32", "head_1x1"};
+    "bn_apply_relu_pool", "bn_relu_backward", "first_conv_fp32", "head_1x1", "sgd_update"};
 static bool nvtx_on() {   // UB_NVTX=1: name every kernel class for `ncu --nvtx --print-nvtx-rename kernel`
     static const bool on = [] { const char* e = getenv("UB_NVTX"); return e && e[0] == '1'; }();
     return on;
@@ -744,6 +744,14 @@ static int bnred_min_kblocks() {
 }
 static bool fuse_bnred(int kblocks) { return kblocks >= bnred_min_kblocks(); }
 
+// UB_WGRAD_DEFER=1: enqueue a unit's weight gradient AFTER its data gradient, so that on the side
+// stream it becomes runnable together with the next (HBM-bound) BN-backward instead of competing with
+// the tensor-bound data gradient of the same unit.
+static bool wgrad_defer() {
+    static const bool v = [] { const char* e = getenv("UB_WGRAD_DEFER"); return e && e[0] == '1'; }();
+    return v;
+}
+
 struct Upstream {
     const IgemmLaunchInfo* fused = nullptr;   // reduce pass of the block's second unit already done
     bool pool_skip = false;
@@ -774,14 +782,16 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
         UB_TRY(launch_bn_bwd(d, s, up.fused));
     }
     View a0 = make_view(u0.a, N, u0.Ho(), u0.Wo(), u0.Co);
-    {
+    auto wgrad1 = [&]() -> int {
         cudaStream_t ws = wgrad_stream(P, s);
         ProfScope ps(P, CLS_WGRAD, fl1, 2.0 * (pi1 * u1.Ci + po1 * u1.Co) + 4.0 * 9 * u1.Ci * u1.Co, ws);
         // both conv biases of the block sit ahead of a BatchNorm: analytically zero gradients
-        UB_TRY(launch_wgrad(a0, nullptr, 0, -2, 1, 9, 3, u1.dy, u1.Co, u1.Co, P->wgrad_ws,
+        return launch_wgrad(a0, nullptr, 0, -2, 1, 9, 3, u1.dy, u1.Co, u1.Co, P->wgrad_ws,
                             P->wgrad_ws_floats, grads[u1.p_w], ws, grads[u1.p_b], u1.Co,
-                            grads[u0.p_b], u0.Co));
-    }
+                            grads[u0.p_b], u0.Co);
+    };
+    const bool defer = wgrad_defer();
+    if (!defer) UB_TRY(wgrad1());
     // The data gradient of the second unit IS the upstream gradient of the first unit's BN + ReLU: its
     // epilogue also does that layer's reduce pass (sum dyh, sum dyh (y - mean)) from the stored y.
     const bool fuse0 = !u0.first && fuse_bnred(9 * u1.Co / 64);
@@ -799,6 +809,7 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
         ProfScope ps(P, CLS_DGRAD, fl1, gemm_bytes(po1, u1.Co, u1.Ci, 9, pi1) + (fuse0 ? 2.0 * pi1 * u1.Ci : 0.0), s);
         UB_TRY(launch_igemm(dyv, nullptr, -2, 0, 1, 9, 3, u1.wd, u1.Ci, e, &info0, s));
     }
+    if (defer) UB_TRY(wgrad1());
     // ---- first conv unit ----
     View g0 = make_view(b.da0, N, u0.Ho(), u0.Wo(), u0.Co);
     if (u0.first) {
@@ -822,18 +833,23 @@ static int block_backward(ub_plan* P, Block& b, const Upstream& up, float* const
         ProfScope ps(P, CLS_BN_BWD, 0, po0 * u0.Co * (fuse0 ? 6.0 : 10.0), s);
         UB_TRY(launch_bn_bwd(d, s, fuse0 ? &info0 : nullptr));
     }
-    {
+    auto wgrad0 = [&]() -> int {
         cudaStream_t ws = wgrad_stream(P, s);
         ProfScope ps(P, CLS_WGRAD, fl0, 2.0 * (pi0 * u0.Ci + po0 * u0.Co) + 4.0 * 9 * u0.Ci * u0.Co, ws);
-        UB_TRY(launch_wgrad(b.in0, b.two ? &b.in1 : nullptr, 0, -2, 1, 9, 3, u0.dy, u0.Co, u0.Co,
-                            P->wgrad_ws, P->wgrad_ws_floats, grads[u0.p_w], ws));
+        return launch_wgrad(b.in0, b.two ? &b.in1 : nullptr, 0, -2, 1, 9, 3, u0.dy, u0.Co, u0.Co,
+                            P->wgrad_ws, P->wgrad_ws_floats, grads[u0.p_w], ws);
+    };
+    if (!defer) UB_TRY(wgrad0());
+    {
+        IgemmEpilogue e;
+        memset(&e, 0, sizeof(e));
+        e.kind = EPI_STORE; e.out = b.din; e.ldo = u0.Ci;
+        View dyv = make_view(u0.dy, N, u0.Ho(), u0.Wo(), u0.Co);
+        ProfScope ps(P, CLS_DGRAD, fl0, gemm_bytes(po0, u0.Co, u0.Ci, 9, pi0), s);
+        UB_TRY(launch_igemm(dyv, nullptr, -2, 0, 1, 9, 3, u0.wd, u0.Ci, e, nullptr, s));
     }
-    IgemmEpilogue e;
-    memset(&e, 0, sizeof(e));
-    e.kind = EPI_STORE; e.out = b.din; e.ldo = u0.Ci;
-    View dyv = make_view(u0.dy, N, u0.Ho(), u0.Wo(), u0.Co);
-    ProfScope ps(P, CLS_DGRAD, fl0, gemm_bytes(po0, u0.Co, u0.Ci, 9, pi0), s);
-    return launch_igemm(dyv, nullptr, -2, 0, 1, 9, 3, u0.wd, u0.Ci, e, nullptr, s);
+    if (defer) UB_TRY(wgrad0());
+    return 0;
 }
 
 static int backward_stage_impl(ub_plan* P, int stage, const float* dlogits, float* const* grads,
@@ -1001,12 +1017,21 @@ int ub_plan_sgd_step(ub_plan* P, const float* const* grads, float* const* moment
         tb.kind = SGD_CONVT_BIAS; tb.d0 = u.Co; tb.bias4 = u.bias4;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    // algorithmic bytes: p, grad, momentum read + p, momentum written (fp32) + two bf16 operand layouts
+    double total = 0.0, packed = 0.0;
+    for (int i = 0; i < np; ++i) {
+        total += (double)all[i].n;
+        if (all[i].kind == SGD_CONV3 || all[i].kind == SGD_CONVT) packed += (double)all[i].n;
+    }
+    static const int sgd_vec = [] { const char* e = getenv("UB_SGD_VEC"); return (e && e[0] == '0') ? 0 : 1; }();
+    ProfScope ps(P, CLS_SGD, 0.0, total * 4.0 * (momentum != 0.f ? 5.0 : 3.0) + packed * 4.0, s);
     for (int i0 = 0; i0 < np; i0 += SGD_MAX_TENSORS) {
         SgdBatch B;
         memset(&B, 0, sizeof(B));
         B.count = np - i0 < SGD_MAX_TENSORS ? np - i0 : SGD_MAX_TENSORS;
         B.lr = lr; B.momentum = momentum; B.dampening = dampening; B.weight_decay = weight_decay;
         B.nesterov = nesterov; B.first_step = first_step;
+        B.vec = sgd_vec;
         int blocks = 0;
         for (int j = 0; j < B.count; ++j) {
             B.t[j] = all[i0 + j];

@@ -29,6 +29,7 @@ struct SgdBatch {
     int count;
     float lr, momentum, dampening, weight_decay;
     int nesterov, first_step;
+    int vec;   // 16-byte accesses where the pointers allow it (UB_SGD_VEC=0: scalar path, for A/B runs)
 };
 
 __device__ __forceinline__ float sgd_update(float p, float g, float* buf_io, const SgdBatch& B) {
@@ -71,29 +72,74 @@ sgd_fused_kernel(const __grid_constant__ SgdBatch B) {
     const int tiles1 = d1 / 32;
     const int a0 = (blk / tiles1) * 32, b0 = (blk % tiles1) * 32;   // tile origin in (d0, d1)
     const int row_len = 32 * T;                                        // contiguous floats per d0 row
-    for (int idx = threadIdx.x; idx < 32 * row_len; idx += 256) {
-        const int l0 = idx / row_len, r = idx % row_len;
-        const int l1 = r / T, tap = r % T;
-        const long long gi = ((long long)(a0 + l0) * d1 + b0) * T + r;
-        float bv = t.buf ? t.buf[gi] : 0.f;
-        const float np = sgd_update(t.p[gi], t.g[gi], &bv, B);
-        t.p[gi] = np;
-        if (t.buf) t.buf[gi] = bv;
-        tile[(tap * 32 + l0) * 33 + l1] = __float2bfloat16_rn(np);
+    // 16-byte accesses: a tile row starts at ((a0+l0)*d1 + b0)*T floats, a multiple of 32 (d1, b0
+    // are multiples of 32), so only the base pointers decide the alignment.
+    const bool vec = B.vec && (((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
+                        reinterpret_cast<uintptr_t>(t.buf)) & 15u) == 0u);
+    if (vec) {
+        const int row4 = row_len / 4;
+        for (int idx = threadIdx.x; idx < 32 * row4; idx += 256) {
+            const int l0 = idx / row4, r = (idx % row4) * 4;
+            const long long gi = ((long long)(a0 + l0) * d1 + b0) * T + r;
+            const float4 pv = *reinterpret_cast<const float4*>(t.p + gi);
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(t.g + gi));
+            float4 bv = t.buf ? *reinterpret_cast<const float4*>(t.buf + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 np;
+            np.x = sgd_update(pv.x, gv.x, &bv.x, B);
+            np.y = sgd_update(pv.y, gv.y, &bv.y, B);
+            np.z = sgd_update(pv.z, gv.z, &bv.z, B);
+            np.w = sgd_update(pv.w, gv.w, &bv.w, B);
+            *reinterpret_cast<float4*>(t.p + gi) = np;
+            if (t.buf) *reinterpret_cast<float4*>(t.buf + gi) = bv;
+            const float nv[4] = {np.x, np.y, np.z, np.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int l1 = (r + e) / T, tap = (r + e) % T;
+                tile[(tap * 32 + l0) * 33 + l1] = __float2bfloat16_rn(nv[e]);
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < 32 * row_len; idx += 256) {
+            const int l0 = idx / row_len, r = idx % row_len;
+            const int l1 = r / T, tap = r % T;
+            const long long gi = ((long long)(a0 + l0) * d1 + b0) * T + r;
+            float bv = t.buf ? t.buf[gi] : 0.f;
+            const float np = sgd_update(t.p[gi], t.g[gi], &bv, B);
+            t.p[gi] = np;
+            if (t.buf) t.buf[gi] = bv;
+            tile[(tap * 32 + l0) * 33 + l1] = __float2bfloat16_rn(np);
+        }
     }
     __syncthreads();
+    // Both packed layouts are written as 16-byte pieces (8 bf16) of their 64-byte runs; the packed
+    // operand buffers are library allocations (256-byte aligned), rows are multiples of 32 elements.
+    const unsigned short* tl = reinterpret_cast<const unsigned short*>(tile);
     // outA[tap][d0][d1]: rows (tap, l0), 32 consecutive d1
-    for (int idx = threadIdx.x; idx < T * 32 * 32; idx += 256) {
-        const int l1 = idx % 32, l0 = (idx / 32) % 32, tap = idx / 1024;
-        if (t.outA)
-            t.outA[((long long)tap * d0 + a0 + l0) * d1 + b0 + l1] = tile[(tap * 32 + l0) * 33 + l1];
+    if (t.outA) {
+        for (int idx = threadIdx.x; idx < T * 32 * 4; idx += 256) {
+            const int q = idx % 4, l0 = (idx / 4) % 32, tap = idx / 128;
+            const unsigned short* src = tl + (tap * 32 + l0) * 33 + q * 8;
+            uint4 o;
+            o.x = src[0] | ((uint32_t)src[1] << 16);
+            o.y = src[2] | ((uint32_t)src[3] << 16);
+            o.z = src[4] | ((uint32_t)src[5] << 16);
+            o.w = src[6] | ((uint32_t)src[7] << 16);
+            *reinterpret_cast<uint4*>(t.outA + ((long long)tap * d0 + a0 + l0) * d1 + b0 + q * 8) = o;
+        }
     }
     // outB[tb][d1][d0]: rows (tb, l1), 32 consecutive d0
-    for (int idx = threadIdx.x; idx < T * 32 * 32; idx += 256) {
-        const int l0 = idx % 32, l1 = (idx / 32) % 32, tap = idx / 1024;
-        const int tb = t.kind == SGD_CONV3 ? T - 1 - tap : tap;
-        if (t.outB)
-            t.outB[((long long)tb * d1 + b0 + l1) * d0 + a0 + l0] = tile[(tap * 32 + l0) * 33 + l1];
+    if (t.outB) {
+        for (int idx = threadIdx.x; idx < T * 32 * 4; idx += 256) {
+            const int q = idx % 4, l1 = (idx / 4) % 32, tap = idx / 128;
+            const int tb = t.kind == SGD_CONV3 ? T - 1 - tap : tap;
+            const unsigned short* src = tl + (tap * 32 + q * 8) * 33 + l1;
+            uint4 o;
+            o.x = src[0 * 33] | ((uint32_t)src[1 * 33] << 16);
+            o.y = src[2 * 33] | ((uint32_t)src[3 * 33] << 16);
+            o.z = src[4 * 33] | ((uint32_t)src[5 * 33] << 16);
+            o.w = src[6 * 33] | ((uint32_t)src[7 * 33] << 16);
+            *reinterpret_cast<uint4*>(t.outB + ((long long)tb * d1 + b0 + l1) * d0 + a0 + q * 8) = o;
+        }
     }
 }
 
