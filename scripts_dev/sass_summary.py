@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "unet_segmentation_b200", "lib", "libunetb200.so")
 KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UTMALDG.IM2COL", "UTMASTG", "UTCCP", "UTCBAR",
-        "SYNCS", "HMMA", "STG.E.128", "LDG.E.128", "FFMA", "DFMA", "ATOM", "RED"]
+        "SYNCS", "HMMA", "STG.E.128", "LDG.E.128", "FFMA", "FFMA2", "DFMA", "ATOM", "RED"]
 
 
 def main():
@@ -46,7 +46,7 @@ def main():
         c = funcs[n]
         for k in KEYS:
             tot[k] += c[k]
-        shown = {k: c[k] for k in KEYS if c[k] and k not in ("FFMA", "LDG.E.128", "STG.E.128", "ATOM", "RED", "DFMA")}
+        shown = {k: c[k] for k in KEYS if c[k] and k not in ("FFMA", "FFMA2", "LDG.E.128", "STG.E.128", "ATOM", "RED", "DFMA")}
         short = (d.split(">(")[0] + ">") if ">(" in d else re.sub(r"\(.*", "", d)
         short = short.replace("ub::", "").replace("void ", "")
         if not shown:

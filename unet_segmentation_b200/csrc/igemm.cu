@@ -64,6 +64,7 @@ bool pdl_allow(bool gemm, unsigned blocks) {
     last_kind = kind;
     if (mode == 1) return true;
     if (mode == 2) return !(kind == 2 && prev == 1);
+    if (mode == 3) return kind == 0 || prev == 0;   // only the edges into / out of the tiny finalisation kernels
     return false;
 }
 // cta_group::2 pairs: on unless UB_PAIR=0

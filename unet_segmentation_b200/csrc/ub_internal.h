@@ -47,7 +47,7 @@ long long launch_count();
 
 // Kernel launch with programmatic dependent launch (see common.cuh: pdl_*) and an optional
 // 2-CTA cluster (cta_group::2 pairs). UB_PDL=0 launches with plain stream serialization.
-// pdl_allow(): may this launch start while its predecessor drains? (UB_PDL: 0 never, 1 always,
+// pdl_allow(): may this launch start while its predecessor drains? (UB_PDL: 0 never, 1 always, 3 = only edges next to a tiny kernel,
 // 2 = every edge except a tensor-core kernel following a large elementwise kernel, whose early
 // resident CTAs (352 threads, ~47 K registers, 200 KB smem) would cut the elementwise occupancy.)
 bool pdl_allow(bool gemm, unsigned blocks);
