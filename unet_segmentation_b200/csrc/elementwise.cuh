@@ -685,7 +685,7 @@ template <int T>
 static __global__ void __launch_bounds__(256 * WGR_SLICES)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long split_stride, int cols,
                     int RC, float* __restrict__ out, float* zero0, int nzero0, float* zero1,
-                    int nzero1) {
+                    int nzero1, int tn) {
     pdl_entry();
     __shared__ float sm[WGR_SLICES][32][8 * T + 1];
     const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
@@ -700,11 +700,15 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long split_st
     float acc[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.f;
-    const float* base = ws + (long long)(rc0 + ty) * cols + col0 + tx;
+    // workspace rows are (t / tn, rc), its columns (t % tn, col): tn = 1 is the plain tap-major layout,
+    // tn = 3 the shifted form (rows = filter row dy, column blocks = filter column dx)
+    const long long ldw = (long long)cols * tn;
+    const float* base = ws + (long long)(rc0 + ty) * ldw + col0 + tx;
     for (int k = tz; k < splits; k += WGR_SLICES) {
         const float* p = base + (long long)k * split_stride;
 #pragma unroll
-        for (int t = 0; t < T; ++t) acc[t] += __ldg(p + (long long)t * RC * cols);
+        for (int t = 0; t < T; ++t)
+            acc[t] += __ldg(p + (long long)(t / tn) * RC * ldw + (long long)(t % tn) * cols);
     }
 #pragma unroll
     for (int t = 0; t < T; ++t) sm[tz][tx][ty * T + t] = acc[t];

@@ -357,14 +357,22 @@ static int wgrad_cg(int cols) {
     const int bn = pick_bn(cols);
     return (pairs_enabled() && bn >= 128) ? 2 : 1;
 }
+static int wgrad_pick_splits(int units, long long kblocks, int cg);
+static int wgrad_shift_splits(int ctot, long long mpix);
 static int wgrad_splits(int rows, int cols, long long mpix) {
     const int bn = pick_bn(cols);
     if (!bn) return 1;
     const int cg = wgrad_cg(cols);
     const int m_tiles = (rows + 128 * cg - 1) / (128 * cg), n_tiles = cols / bn;
-    const int units = m_tiles * n_tiles;
     const int kpix = bn == 256 ? 64 : 128;
-    const long long kblocks = (mpix + kpix - 1) / kpix;
+    return wgrad_pick_splits(m_tiles * n_tiles, (mpix + kpix - 1) / kpix, cg);
+}
+// split count of the shifted form, from the OUTPUT pixel count so that the workspace query (which does
+// not know the row width) and the launch agree
+static int wgrad_shift_splits(int ctot, long long mpix) {
+    return wgrad_pick_splits((3 * ctot + 127) / 128, (mpix + 63) / 64, 1);
+}
+static int wgrad_pick_splits(int units, long long kblocks, int cg) {
     const long long smax = kblocks / 8 > 1 ? kblocks / 8 : 1;
     // UB_WGRAD_MAXKB=n: at most n k-blocks per CTA (short-lived CTAs release their SM sooner to the
     // data-gradient kernel they overlap with); 0 = only the wave rule below
@@ -386,7 +394,20 @@ static int wgrad_splits(int rows, int cols, long long mpix) {
 }
 size_t wgrad_ws_floats(int rows, int cols, long long mpix) {
     // sized for either tiling (UB_PAIR may differ between the size query and the launch only in tests)
-    return (size_t)wgrad_splits(rows, cols, mpix) * (size_t)rows * (size_t)cols;
+    size_t splits = (size_t)wgrad_splits(rows, cols, mpix);
+    if (cols == 64 && rows % (9 * 64) == 0) {   // 3x3 layer eligible for the shifted form
+        const size_t s2 = (size_t)wgrad_shift_splits(rows / 9, mpix);
+        if (s2 > splits) splits = s2;
+    }
+    return splits * (size_t)rows * (size_t)cols;
+}
+
+// "Shifted dY" form for 3x3 layers with 64 output channels (UB_WGRAD_SHIFT=0 disables): GEMM rows =
+// (filter row dy, input channel), GEMM columns = (filter column dx, output channel) = 192, reduction
+// over the INPUT-wide pixel grid; dW[dy][dx] = sum_u X[u + (dy, 0)] dY[u - (0, dx)].
+static bool wgrad_shift_enabled() {
+    static const bool v = [] { const char* e = getenv("UB_WGRAD_SHIFT"); return !(e && e[0] == '0'); }();
+    return v;
 }
 
 template <int BN, int CG>
@@ -422,6 +443,42 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
     const long long mpix = (long long)src0.N * Ho * Wo;
     const int ctot = src0.C + (src1 ? src1->C : 0);
     const int rows = taps * ctot;
+    if (taps == 9 && tapw == 3 && tstride == 1 && lower == 0 && upper == -2 && cols == 64 &&
+        wgrad_shift_enabled()) {
+        // ---- shifted form: one CTA computes a 128 x 192 tile, A read once for three filter columns ----
+        constexpr int KP = WgradCfg<192, 1>::KPIX;
+        const long long tpix = (long long)src0.N * Ho * src0.W;          // base pixels: input-wide rows
+        const int srows = 3 * ctot, m_tiles = (srows + 127) / 128;
+        const long long kblocks = (tpix + KP - 1) / KP;
+        const int splits = wgrad_shift_splits(ctot, mpix);
+        if ((size_t)splits * rows * cols <= ws_floats && tpix < 0x7FFFFFFFLL) {
+            CUtensorMap mA0, mA1, mB;
+            int r = make_tmap_im2col_wh(&mA0, src0, 0, 0, 0, -2, 1, (unsigned)KP);
+            if (!r && src1) r = make_tmap_im2col_wh(&mA1, *src1, 0, 0, 0, -2, 1, (unsigned)KP);
+            if (!src1) mA1 = mA0;
+            View dyv{};
+            dyv.ptr = B;
+            dyv.N = src0.N; dyv.H = Ho; dyv.W = Wo; dyv.C = cols;
+            dyv.sW = ldb; dyv.sH = (long long)Wo * ldb; dyv.sN = (long long)Ho * Wo * ldb;
+            if (!r) r = make_tmap_im2col_wh(&mB, dyv, -2, 0, 0, 0, 1, (unsigned)KP);
+            if (r) { set_last_error("wgrad: im2col tensor map (shifted form) failed: %d", r); return UB_ERR_TMAP; }
+            WgradParams p;
+            memset(&p, 0, sizeof(p));
+            p.Mpix = (int)tpix; p.Wo = src0.W; p.Ho = Ho; p.lower = 0; p.tstride = 1;
+            p.taps = 3; p.tapw = 1;   // A-side taps: filter rows only
+            p.cchunks0 = src0.C / 64; p.cchunks1 = src1 ? src1->C / 64 : 0;
+            p.a_chunks_total = srows / 64;
+            p.n_tiles = 1; p.splits = splits;
+            p.kblocks_total = (int)kblocks;
+            p.ws = ws; p.ldw = 192; p.split_stride = (long long)rows * cols;
+            UB_TRY((launch_wgrad_t<192, 1>(mA0, mA1, mB, p, dim3(m_tiles, splits), stream)));
+            const dim3 rgrid(cols / 32, ctot / 8);
+            UB_LAUNCH_NC((wgrad_reduce_kernel<9>), rgrid, dim3(32, 8, WGR_SLICES), 0, stream, ws, splits, p.split_stride, cols, ctot, out, zero0, nzero0, zero1, nzero1, 3);
+            UB_POST_LAUNCH();
+            return UB_OK;
+        }
+        // workspace sized by an older query: fall through to the tap-major form
+    }
     const int CG = wgrad_cg(cols);
     const int splits = wgrad_splits(rows, cols, mpix);
     if ((size_t)splits * rows * cols > ws_floats) {
@@ -467,9 +524,9 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
     UB_TRY(rc);
     const dim3 rgrid(cols / 32, ctot / 8);
     if (taps == 9)
-        UB_LAUNCH_NC((wgrad_reduce_kernel<9>), rgrid, dim3(32, 8, WGR_SLICES), 0, stream, ws, splits, p.split_stride, cols, ctot, out, zero0, nzero0, zero1, nzero1);
+        UB_LAUNCH_NC((wgrad_reduce_kernel<9>), rgrid, dim3(32, 8, WGR_SLICES), 0, stream, ws, splits, p.split_stride, cols, ctot, out, zero0, nzero0, zero1, nzero1, 1);
     else if (taps == 4)
-        UB_LAUNCH_NC((wgrad_reduce_kernel<4>), rgrid, dim3(32, 8, WGR_SLICES), 0, stream, ws, splits, p.split_stride, cols, ctot, out, zero0, nzero0, zero1, nzero1);
+        UB_LAUNCH_NC((wgrad_reduce_kernel<4>), rgrid, dim3(32, 8, WGR_SLICES), 0, stream, ws, splits, p.split_stride, cols, ctot, out, zero0, nzero0, zero1, nzero1, 1);
     else {
         set_last_error("wgrad: unsupported tap count %d", taps);
         return UB_ERR_UNSUPPORTED;

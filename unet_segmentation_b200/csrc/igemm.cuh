@@ -654,20 +654,31 @@ struct WgradCfg {
     // Pixels (GEMM K) per pipeline stage. One barrier wait + tcgen05 fence costs the MMA thread
     // ~230 cycles, so narrow tiles (BN <= 128, 48-64 cycles per MMA) take 128 pixels = 8 MMAs per
     // stage; BN = 256 is already execution-bound with 64.
-    static constexpr int KPIX = (BN == 256) ? 64 : 128;
+    // BN = 192 is the "shifted dY" form for 64-output-channel layers (see igemm_wgrad_kernel): three
+    // 64-column copies of dY displaced by 0 / 1 / 2 pixels along w share every read of the A operand.
+    static constexpr bool SHIFT = (BN == 192);
+    static constexpr int KPIX = (BN >= 192) ? 64 : 128;
     static constexpr int CHUNK_BYTES = KPIX * 128;   // one [KPIX pixels][64 channels] MN-major chunk
     static constexpr int A_BYTES = 2 * CHUNK_BYTES;  // per CTA: two 64-row chunks = 128 GEMM rows
     static constexpr int B_CHUNKS = BN / 64 / CG;    // per CTA: BN / CG columns of dY
     static constexpr int B_BYTES = B_CHUNKS * CHUNK_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (CG == 2) ? (BN == 256 ? 6 : 4)
-                                            : ((BN == 256) ? 4 : (BN == 128 ? 3 : 4));
+    static constexpr int STAGES = SHIFT ? 5
+                                  : (CG == 2) ? (BN == 256 ? 6 : 4)
+                                              : ((BN == 256) ? 4 : (BN == 128 ? 3 : 4));
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
-    static constexpr uint32_t TMEM_COLS = BN;
+    static constexpr uint32_t TMEM_COLS = SHIFT ? 256 : BN;   // allocations are powers of two
     static_assert(CG == 1 || BN >= 128, "a CTA pair splits dY by 64-channel chunks");
+    static_assert(!SHIFT || CG == 1, "the shifted form is a single-CTA kernel");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
+// BN = 192 ("shifted dY", WgradCfg::SHIFT): for a 3x3 layer with 64 output channels the plain form runs
+// M128 x N64 MMAs, each re-reading 4 KB of MN-major A from shared memory (64 B/clk) for 32 cycles of
+// math. Here the GEMM columns are (filter column dx, output channel): three copies of the dY tile
+// displaced by 0 / 1 / 2 pixels along w (im2col loads over the input-wide pixel grid, zero filled
+// outside dY), so one read of A serves three taps; the GEMM rows are (filter row dy, input channel).
 template <int BN, int CG>
 __global__ void __launch_bounds__(256, 1)
 igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
@@ -767,6 +778,23 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                         else
                             tma_load_im2col_cg<CG>(sa + role * Cfg::CHUNK_BYTES, &mapA1, fb,
                                                    (a_cc - p.cchunks0) * 64, cw, ch, n, a_offw, a_offh);
+                    }
+                    __syncwarp();
+                    q += Cfg::KPIX;
+                    while (q >= p.Wo) {
+                        q -= p.Wo;
+                        if (++pr == p.Ho) { pr = 0; ++n; }
+                    }
+                } else if (Cfg::SHIFT) {
+                    // B side, shifted form: mapB is an im2col map of dY whose base pixels run over the
+                    // INPUT-wide grid (w from -2, zero filled outside dY); chunk j is dY displaced by
+                    // j pixels to the right, i.e. tap column dx = j of the filter.
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(stage), tx);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            tma_load_im2col(sa + Cfg::A_BYTES + j * Cfg::CHUNK_BYTES, &mapB, fb, 0,
+                                            q - 2, pr, n, (uint16_t)(2 - j), (uint16_t)0);
                     }
                     __syncwarp();
                     q += Cfg::KPIX;

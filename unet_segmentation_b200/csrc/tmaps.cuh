@@ -122,14 +122,22 @@ inline int make_tmap_rows(CUtensorMap* out, const View& v, unsigned box_w, unsig
 //   valid 3x3 conv (fprop / wgrad activations): lower 0, upper -2
 //   its data gradient (full correlation over dY):  lower -2, upper 0
 //   2x2 stride-2 transposed conv backward:         lower 0, upper -1, tstride 2
+//   per-axis corners (make_tmap_im2col_wh): the "shifted dY" weight gradient walks the activations
+//   with (w: 0 / 0, h: 0 / -2) and dY with (w: -2 / 0, h: 0 / 0) — the same base-pixel grid for both.
+inline int make_tmap_im2col_wh(CUtensorMap* out, const View& v, int lower_w, int upper_w, int lower_h,
+                               int upper_h, int tstride, unsigned pixels);
 inline int make_tmap_im2col(CUtensorMap* out, const View& v, int lower, int upper, int tstride,
                             unsigned pixels) {
+    return make_tmap_im2col_wh(out, v, lower, upper, lower, upper, tstride, pixels);
+}
+inline int make_tmap_im2col_wh(CUtensorMap* out, const View& v, int lower_w, int upper_w, int lower_h,
+                               int upper_h, int tstride, unsigned pixels) {
     TmapApi& api = tmap_api();
     if (!api.ok) return -1;
     cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
     cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
-    int lo[2] = {lower, lower};
-    int up[2] = {upper, upper};
+    int lo[2] = {lower_w, lower_h};
+    int up[2] = {upper_w, upper_h};
     cuuint32_t estr[4] = {1, (cuuint32_t)tstride, (cuuint32_t)tstride, 1};
     CUresult r = api.im2col(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr),
                             dims, strides, lo, up, 64, pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
