@@ -417,6 +417,43 @@ def test_conv3x3_wgrad_wide_maps(ops, n, h, w, c0, c1, co):
     assert rel_l2(dw, ref) < F32_TOL and cosine(dw, ref) > 0.9999
 
 
+_WGRAD_FORMS_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+from unet_segmentation_b200 import ops
+g = torch.Generator(device="cuda").manual_seed(11)
+outs = []
+for (n, h, w, c0, c1) in [(2, 21, 77, 64, 0), (1, 9, 300, 64, 64), (3, 12, 12, 128, 0)]:
+    x0 = torch.randn(n, h, w, c0, device="cuda", generator=g).bfloat16()
+    x1 = torch.randn(n, h, w, c1, device="cuda", generator=g).bfloat16() if c1 else None
+    dy = torch.randn(n, h - 2, w - 2, 64, device="cuda", generator=g).bfloat16()
+    outs.append(ops.conv3x3_wgrad(x0, x1, dy).cpu())
+torch.save(outs, sys.argv[2])
+"""
+
+
+def test_conv3x3_wgrad_shifted_form_matches_tap_major_form(ops, tmp_path):
+    """The 64-output-channel weight gradient has two forms (igemm.cuh: 128 x 192 tiles with dY displaced
+    along w — the default — and the tap-major 128 x 64 tiles, UB_WGRAD_SHIFT=0). The switch is read once
+    per process, so each form runs in its own interpreter on the same seeded inputs; they differ only
+    in summation order."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "forms.py"
+    script.write_text(_WGRAD_FORMS_SCRIPT)
+    res = {}
+    for form in ("1", "0"):
+        out = tmp_path / f"dw_{form}.pt"
+        env = dict(os.environ, UB_WGRAD_SHIFT=form)
+        subprocess.run([sys.executable, str(script), root, str(out)], check=True, env=env, timeout=300)
+        res[form] = torch.load(out)
+    for a, b in zip(res["1"], res["0"]):
+        assert a.shape == b.shape
+        assert rel_l2(a, b) < 1e-5 and not torch.equal(a, torch.zeros_like(a))
+
+
 @pytest.mark.parametrize("n,h,w,ci,nc", [(1, 12, 12, 64, 2), (2, 20, 30, 64, 3), (1, 6, 130, 64, 2),
                                          (2, 9, 260, 128, 2)])
 def test_conv3x3_eval_fused_head(ops, n, h, w, ci, nc):
