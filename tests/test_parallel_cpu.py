@@ -52,6 +52,29 @@ def test_stage_grad_allreducer_averages_across_ranks():
         assert n_coll == 3 and nbytes == 40 * 4
 
 
+def _stage_reduce_bf16_wire(rank, world):
+    red = parallel.StageGradAllReducer(model=None, wire_dtype=torch.bfloat16)
+    flat = (torch.arange(40, dtype=torch.float32) + 0.123) * (rank + 1)
+    for s, (a, b) in enumerate([(25, 40), (0, 25)]):
+        red.on_stage(s, flat[a:b])
+    red.on_done()
+    return flat.tolist(), flat.dtype == torch.float32
+
+
+def test_stage_grad_allreducer_bf16_payload_keeps_fp32_masters():
+    """wire_dtype=bf16: each rank's slice is rounded to bf16, summed, averaged and rounded once more;
+    the caller's gradient buffer stays fp32 and every rank ends with identical values."""
+    out = _run(_stage_reduce_bf16_wire)
+    base = torch.arange(40, dtype=torch.float32) + 0.123
+    w = base.bfloat16() + (base * 2).bfloat16()                 # bf16 accumulation on the wire
+    expect = (w.float() / 2).bfloat16().float()
+    for flat, is_f32 in out:
+        assert is_f32
+        got = torch.tensor(flat)
+        assert torch.equal(got, expect)
+        assert float((got - base * 1.5).abs().max() / (base * 1.5).abs().max()) < 1e-2
+
+
 def _tile_gather(rank, world):
     n_tiles = 5
     mine = parallel.shard_indices(n_tiles, rank, world)

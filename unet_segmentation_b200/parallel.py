@@ -59,9 +59,11 @@ class StageGradAllReducer:
     def __init__(self, model: Optional[torch.nn.Module] = None, group=None,
                  wire_dtype: Optional[torch.dtype] = None):
         """``wire_dtype=torch.bfloat16`` sends the gradients over NVLink as bf16 (62 MB instead of
-        124 MB per step for the reference net): the collective kernels, which share the SMs with the
-        backward pass, run half as long. The averaged gradient is rounded to bf16 once more than with
-        the default fp32 payload (masters, momentum and the update stay fp32)."""
+        124 MB per step for the reference net). The averaged gradient is rounded to bf16 once more than
+        with the default fp32 payload (masters, momentum and the update stay fp32). Measured on an
+        8 x B200 NVSwitch box it is SLOWER than fp32 (14.72-14.75 vs 14.56-14.62 ms per step,
+        profiles/r02_grad_wire_ab.txt): the pack / unpack kernels cost more than the shorter
+        collective saves. Kept for links slower than NVLink 5; fp32 is the default."""
         self.group = group
         self.wire_dtype = wire_dtype
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -101,6 +103,10 @@ class StageGradAllReducer:
                 else:
                     dist.all_reduce(flat_grads, op=dist.ReduceOp.AVG, group=self.group)
             flat_grads.record_stream(self.comm_stream)
+        elif self.wire_dtype is not None and self.wire_dtype != flat_grads.dtype:
+            wire = flat_grads.to(self.wire_dtype)          # same rounding points as the CUDA path
+            dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=self.group)
+            flat_grads.copy_(wire.to(flat_grads.dtype).div_(self.world).to(self.wire_dtype))
         else:
             dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=self.group)
             flat_grads.div_(self.world)
