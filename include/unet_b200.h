@@ -269,6 +269,10 @@ int ub_op_bn_relu_backward_fused(const void* y, int N, int H, int W, int C, cons
                                  const float* shift, const float* mean, const float* rstd,
                                  const ub_view* g, float* partial, const int* info4, float* dgamma,
                                  float* dbeta, void* dy, void* stream);
+/* fp32 workspace (split-K partial tiles) of a weight gradient with `rows` = taps * C_in GEMM rows, `cols`
+ * = C_out columns over `pixels` output pixels; covers both forms of the 64-output-channel 3x3 case (tap-major
+ * 128 x 64 tiles and the "shifted" 128 x 192 tiles, csrc/igemm.cuh). A smaller buffer makes
+ * ub_op_conv3x3_wgrad fall back to the tap-major form or fail with UB_ERR_ARG. */
 int64_t ub_op_wgrad_workspace_floats(int rows, int cols, int64_t pixels);
 /* dw[Co][C0+C1][3][3] fp32 = sum over pixels of x (concat of src0, src1) * dy[N][H-2][W-2][Co]. */
 int ub_op_conv3x3_wgrad(const ub_view* src0, const ub_view* src1, const void* dy, int Co,
