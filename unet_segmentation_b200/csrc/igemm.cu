@@ -358,7 +358,7 @@ static int wgrad_cg(int cols) {
     return (pairs_enabled() && bn >= 128) ? 2 : 1;
 }
 static int wgrad_pick_splits(int units, long long kblocks, int cg);
-static int wgrad_shift_splits(int ctot, long long mpix);
+static int wgrad_shift_splits(int ctot, long long mpix, int cg);
 static int wgrad_splits(int rows, int cols, long long mpix) {
     const int bn = pick_bn(cols);
     if (!bn) return 1;
@@ -369,8 +369,12 @@ static int wgrad_splits(int rows, int cols, long long mpix) {
 }
 // split count of the shifted form, from the OUTPUT pixel count so that the workspace query (which does
 // not know the row width) and the launch agree
-static int wgrad_shift_splits(int ctot, long long mpix) {
-    return wgrad_pick_splits((3 * ctot + 127) / 128, (mpix + 63) / 64, 1);
+static bool wgrad_shift_pair_enabled() {   // the 128-output-channel pair form (UB_WGRAD_SHIFT128=0 disables)
+    static const bool v = [] { const char* e = getenv("UB_WGRAD_SHIFT128"); return !(e && e[0] == '0'); }();
+    return v && pairs_enabled();
+}
+static int wgrad_shift_splits(int ctot, long long mpix, int cg) {
+    return wgrad_pick_splits((3 * ctot + 128 * cg - 1) / (128 * cg), (mpix + 63) / 64, cg);
 }
 static int wgrad_pick_splits(int units, long long kblocks, int cg) {
     const long long smax = kblocks / 8 > 1 ? kblocks / 8 : 1;
@@ -395,8 +399,8 @@ static int wgrad_pick_splits(int units, long long kblocks, int cg) {
 size_t wgrad_ws_floats(int rows, int cols, long long mpix) {
     // sized for either tiling (UB_PAIR may differ between the size query and the launch only in tests)
     size_t splits = (size_t)wgrad_splits(rows, cols, mpix);
-    if (cols == 64 && rows % (9 * 64) == 0) {   // 3x3 layer eligible for the shifted form
-        const size_t s2 = (size_t)wgrad_shift_splits(rows / 9, mpix);
+    if ((cols == 64 || cols == 128) && rows % (9 * 64) == 0) {   // 3x3 layer eligible for a shifted form
+        const size_t s2 = (size_t)wgrad_shift_splits(rows / 9, mpix, cols == 128 ? 2 : 1);
         if (s2 > splits) splits = s2;
     }
     return splits * (size_t)rows * (size_t)cols;
@@ -443,14 +447,17 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
     const long long mpix = (long long)src0.N * Ho * Wo;
     const int ctot = src0.C + (src1 ? src1->C : 0);
     const int rows = taps * ctot;
-    if (taps == 9 && tapw == 3 && tstride == 1 && lower == 0 && upper == -2 && cols == 64 &&
-        wgrad_shift_enabled()) {
-        // ---- shifted form: one CTA computes a 128 x 192 tile, A read once for three filter columns ----
+    if (taps == 9 && tapw == 3 && tstride == 1 && lower == 0 && upper == -2 && wgrad_shift_enabled() &&
+        (cols == 64 || (cols == 128 && wgrad_shift_pair_enabled()))) {
+        // ---- shifted forms: a CTA computes a 128 x 192 tile (a pair 256 x 384), A staged once for
+        //      three filter columns ----
         constexpr int KP = WgradCfg<192, 1>::KPIX;
+        static_assert(WgradCfg<384, 2>::KPIX == KP, "one k-block size for both shifted forms");
+        const int scg = cols == 128 ? 2 : 1;
         const long long tpix = (long long)src0.N * Ho * src0.W;          // base pixels: input-wide rows
-        const int srows = 3 * ctot, m_tiles = (srows + 127) / 128;
+        const int srows = 3 * ctot, m_tiles = (srows + 128 * scg - 1) / (128 * scg);
         const long long kblocks = (tpix + KP - 1) / KP;
-        const int splits = wgrad_shift_splits(ctot, mpix);
+        const int splits = wgrad_shift_splits(ctot, mpix, scg);
         if ((size_t)splits * rows * cols <= ws_floats && tpix < 0x7FFFFFFFLL) {
             CUtensorMap mA0, mA1, mB;
             int r = make_tmap_im2col_wh(&mA0, src0, 0, 0, 0, -2, 1, (unsigned)KP);
@@ -470,8 +477,9 @@ int launch_wgrad(const View& src0, const View* src1, int lower, int upper, int t
             p.a_chunks_total = srows / 64;
             p.n_tiles = 1; p.splits = splits;
             p.kblocks_total = (int)kblocks;
-            p.ws = ws; p.ldw = 192; p.split_stride = (long long)rows * cols;
-            UB_TRY((launch_wgrad_t<192, 1>(mA0, mA1, mB, p, dim3(m_tiles, splits), stream)));
+            p.ws = ws; p.ldw = 3 * cols; p.split_stride = (long long)rows * cols;
+            if (scg == 2) UB_TRY((launch_wgrad_t<384, 2>(mA0, mA1, mB, p, dim3(m_tiles * 2, splits), stream)));
+            else UB_TRY((launch_wgrad_t<192, 1>(mA0, mA1, mB, p, dim3(m_tiles, splits), stream)));
             const dim3 rgrid(cols / 32, ctot / 8);
             UB_LAUNCH_NC((wgrad_reduce_kernel<9>), rgrid, dim3(32, 8, WGR_SLICES), 0, stream, ws, splits, p.split_stride, cols, ctot, out, zero0, nzero0, zero1, nzero1, 3);
             UB_POST_LAUNCH();

@@ -656,7 +656,10 @@ struct WgradCfg {
     // stage; BN = 256 is already execution-bound with 64.
     // BN = 192 is the "shifted dY" form for 64-output-channel layers (see igemm_wgrad_kernel): three
     // 64-column copies of dY displaced by 0 / 1 / 2 pixels along w share every read of the A operand.
-    static constexpr bool SHIFT = (BN == 192);
+    // BN = 384 is the same idea for 128 output channels as a CTA pair: an N = 256 MMA over dY displaced by
+    // 0 and 1 pixels (CTA r stages the copy displaced by r) plus an N = 128 MMA over the copy displaced by 2
+    // (CTA r stages channel chunk r of it), both fed by one staging of A.
+    static constexpr bool SHIFT = (BN == 192 || BN == 384);
     static constexpr int KPIX = (BN >= 192) ? 64 : 128;
     static constexpr int CHUNK_BYTES = KPIX * 128;   // one [KPIX pixels][64 channels] MN-major chunk
     static constexpr int A_BYTES = 2 * CHUNK_BYTES;  // per CTA: two 64-row chunks = 128 GEMM rows
@@ -668,9 +671,10 @@ struct WgradCfg {
                                               : ((BN == 256) ? 4 : (BN == 128 ? 3 : 4));
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
-    static constexpr uint32_t TMEM_COLS = SHIFT ? 256 : BN;   // allocations are powers of two
+    static constexpr uint32_t TMEM_COLS = BN == 192 ? 256 : (BN == 384 ? 512 : BN);   // powers of two
     static_assert(CG == 1 || BN >= 128, "a CTA pair splits dY by 64-channel chunks");
-    static_assert(!SHIFT || CG == 1, "the shifted form is a single-CTA kernel");
+    static_assert(!SHIFT || (BN == 192 && CG == 1) || (BN == 384 && CG == 2),
+                  "shifted forms: 192 columns on one CTA, 384 on a pair");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -790,11 +794,24 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                     // INPUT-wide grid (w from -2, zero filled outside dY); chunk j is dY displaced by
                     // j pixels to the right, i.e. tap column dx = j of the filter.
                     if (elect_one()) {
-                        mbar_expect_tx(full_bar(stage), tx);
+                        if (rank == 0) mbar_expect_tx(full_bar(stage), tx);
+                        const uint32_t sb0 = sa + Cfg::A_BYTES;
+                        if (BN == 192) {
 #pragma unroll
-                        for (int j = 0; j < 3; ++j)
-                            tma_load_im2col(sa + Cfg::A_BYTES + j * Cfg::CHUNK_BYTES, &mapB, fb, 0,
-                                            q - 2, pr, n, (uint16_t)(2 - j), (uint16_t)0);
+                            for (int j = 0; j < 3; ++j)
+                                tma_load_im2col_cg<CG>(sb0 + j * Cfg::CHUNK_BYTES, &mapB, fb, 0, q - 2, pr,
+                                                       n, (uint16_t)(2 - j), (uint16_t)0);
+                        } else {
+                            // pair: columns [128 r, 128 r + 128) of the N = 256 MMA = dY displaced by r
+                            // (both channel chunks); columns [64 r, 64 r + 64) of the N = 128 MMA =
+                            // channel chunk r of dY displaced by 2
+                            const uint16_t ow = (uint16_t)(2 - (int)rank);
+                            tma_load_im2col_cg<CG>(sb0, &mapB, fb, 0, q - 2, pr, n, ow, (uint16_t)0);
+                            tma_load_im2col_cg<CG>(sb0 + Cfg::CHUNK_BYTES, &mapB, fb, 64, q - 2, pr, n,
+                                                   ow, (uint16_t)0);
+                            tma_load_im2col_cg<CG>(sb0 + 2 * Cfg::CHUNK_BYTES, &mapB, fb, 64 * (int)rank,
+                                                   q - 2, pr, n, (uint16_t)0, (uint16_t)0);
+                        }
                     }
                     __syncwarp();
                     q += Cfg::KPIX;
@@ -816,7 +833,8 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
             }
         }
     } else if (warp == 1 && rank == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN, 1, 1);
+        constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN == 384 ? 256 : BN, 1, 1);
+        constexpr uint32_t idesc2 = make_idesc_bf16(128 * CG, 128, 1, 1);   // BN = 384: third filter column
         int stage = 0;
         uint32_t phase = 0;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -829,7 +847,13 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0,
                 for (int k = 0; k < Cfg::KPIX / 16; ++k) {  // 16 pixels = 16 rows of 128 B
                     const uint64_t da = make_smem_desc(sa + k * 2048, Cfg::CHUNK_BYTES, 1024);
                     const uint64_t db = make_smem_desc(sb + k * 2048, Cfg::CHUNK_BYTES, 1024);
-                    umma_bf16_cg<CG>(tmem_base, da, db, idesc, (uint32_t)((kb != kb_begin) || (k != 0)));
+                    const uint32_t acc = (uint32_t)((kb != kb_begin) || (k != 0));
+                    umma_bf16_cg<CG>(tmem_base, da, db, idesc, acc);
+                    if (BN == 384) {
+                        const uint64_t db2 = make_smem_desc(sb + 2 * Cfg::CHUNK_BYTES + k * 2048,
+                                                            Cfg::CHUNK_BYTES, 1024);
+                        umma_bf16_cg<CG>(tmem_base + 256u, da, db2, idesc2, acc);
+                    }
                 }
                 umma_commit_cg<CG>(empty_bar(stage));
             }
