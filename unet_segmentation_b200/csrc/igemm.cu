@@ -369,8 +369,11 @@ static int wgrad_splits(int rows, int cols, long long mpix) {
 }
 // split count of the shifted form, from the OUTPUT pixel count so that the workspace query (which does
 // not know the row width) and the launch agree
-static bool wgrad_shift_pair_enabled() {   // the 128-output-channel pair form (UB_WGRAD_SHIFT128=0 disables)
-    static const bool v = [] { const char* e = getenv("UB_WGRAD_SHIFT128"); return !(e && e[0] == '0'); }();
+// The 128-output-channel pair form is correct but not faster than the tap-major pair form on the reference
+// net (profiles/r02_wgrad_shifted.txt: d1.b 0.260 -> 0.272 ms, up3.b 0.119 -> 0.151 ms, up3.a 0.204 -> 0.197 ms;
+// the wide U-Net step gains 1 %): opt-in with UB_WGRAD_SHIFT128=1.
+static bool wgrad_shift_pair_enabled() {
+    static const bool v = [] { const char* e = getenv("UB_WGRAD_SHIFT128"); return e && e[0] == '1'; }();
     return v && pairs_enabled();
 }
 static int wgrad_shift_splits(int ctot, long long mpix, int cg) {
